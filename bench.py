@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- scans/sec of the MAD-ICP registration hot path on B200.
+
+Workload (BASELINE.json configs[2] at N=1, configs[3] at N>1): one synthetic 64-beam x 2048-azimuth
+scan (131 072 points -> ~19k moving leaves) registered against a 16-keyframe model with `--iters`
+Gauss-Newton rounds (default 10, as BASELINE's configs[1]).  A *step* is one whole registration.
+
+  value  : scans/s with the model and the moving leaves resident in HBM (CUDA events on the launch
+           stream around the persistent GN kernel; L2 flushed between steps, outside the events).
+  e2e    : the same through the public call with HOST buffers: pinned H2D of the moving leaves and the
+           initial pose, the kernel, D2H of pose + H/b + matched flags, host synchronisation.
+  N > 1  : keyframe slot s lives on rank s % N (2 per GPU at N=8); every GN round all-reduces the 27
+           H/b values inside the kernel through NVLink peer mailboxes ("scaling": "strong": the same
+           scan is processed jointly).  `replicas` additionally reports N independent full-model
+           registrations (throughput mode, no exchange).
+  --impl reference : the CPU restatement of the reference's OpenMP path (oracle/) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "scans/sec (130k-pt scan vs 16-keyframe model)"
+K_MODEL = 16
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--beams", type=int, default=64)
+    ap.add_argument("--azimuths", type=int, default=2048)
+    return ap.parse_args()
+
+
+def workload_name(a, n):
+    shard = "all keyframes on one GPU" if n == 1 else f"slot s on rank s%{n} ({K_MODEL // n if K_MODEL >= n else 1}/GPU), in-kernel NVLink all-reduce of H/b"
+    return (f"{a.beams}x{a.azimuths}-ray synthetic scan ({a.beams * a.azimuths} pts) vs {K_MODEL}-keyframe model, "
+            f"{a.iters} GN iters, {shard}")
+
+
+# --------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Polls NVML (SM clock + clock-event reasons) while the timed region runs."""
+    BITS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+            0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz, self.ok = None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self.stop_flag:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                try:
+                    r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.BITS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "nvml unavailable"}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def leaf_depths(recs):
+    """Depth (internal nodes above) of every leaf ordinal, from the breadth-first records."""
+    n = recs.shape[0]
+    depth = np.zeros(n, np.int32)
+    link = recs["link"]
+    internal = np.nonzero(link >= 0)[0]
+    for i in internal:  # BFS order => parents before children
+        depth[link[i]] = depth[i] + 1
+        depth[link[i] + 1] = depth[i] + 1
+    leaf = link < 0
+    out = np.zeros(int(leaf.sum()), np.int32)
+    out[-1 - link[leaf]] = depth[leaf]
+    return out
+
+
+def algorithmic_bytes(reg, depth_tables, trace, iters, L):
+    """SURVEY 8d, fused kernel: per round sum over (q,k) of 56*d (internal: mean 24 + split dir 24 +
+    links 8) + 56 (leaf: mean 24 + normal 24 + bbox0 8) + 24 (moving mean), + L matched bytes in the
+    last round + 27*8 per CTA partials (negligible, omitted).  d(q,k) is measured, not estimated: it is
+    looked up from this run's own correspondences at every round's pose."""
+    total, visits = 0, 0
+    for it in range(iters):
+        idx = reg.search(trace[it])
+        for k in range(idx.shape[0]):
+            d = depth_tables[k][idx[k]].astype(np.int64)
+            total += int((56 * d + 56 + 24).sum())
+            visits += int(d.sum()) + idx.shape[1]
+    return total + L, visits
+
+
+# --------------------------------------------------------------------------------------------
+def cpu_reference_leg(a, steps, warmup, budget_s=None):
+    """Times the CPU restatement of the reference's OpenMP path (oracle/) on the host cores.  A step is
+    one whole registration of the same workload (trees pre-built)."""
+    from mad_icp_b200 import synth
+    from oracle import oracle as O
+    O.build()
+    case = synth.registration_case(K=K_MODEL, beams=a.beams, azimuths=a.azimuths)
+    threads = min(16, os.cpu_count() or 1)
+    trees = [O.OracleTree(s) for s in case["scans"]]
+    for t, P in zip(trees, case["kf_poses"]):
+        t.apply_transform(P)
+    q = O.OracleTree(case["query"])
+    for _ in range(warmup):
+        O.icp_run(trees, q, case["T_guess"], iters=a.iters, num_threads=threads, record=False)
+    secs, t0 = [], time.perf_counter()
+    for i in range(steps):
+        secs.append(O.icp_run(trees, q, case["T_guess"], iters=a.iters, num_threads=threads, record=False)["seconds"])
+        if budget_s is not None and time.perf_counter() - t0 > budget_s and i >= 2:
+            break
+    total = float(sum(secs))
+    return dict(value=len(secs) / total, seconds=total, steps=len(secs), cores=threads,
+                host_cores=os.cpu_count(), L=q.num_leaves,
+                sample=f"{len(secs)} full registrations ({a.iters} GN iters, {K_MODEL} keyframes, {q.num_leaves} moving "
+                       f"leaves), trees pre-built, {threads} OpenMP threads over keyframes")
+
+
+def run_reference(a, rank):
+    if rank != 0:
+        return
+    r = cpu_reference_leg(a, a.steps, max(a.warmup, 1), budget_s=150.0)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "scans/s", "n_gpus": a.gpus,
+            "steps": r["steps"], "warmup": a.warmup, "ms_per_step": 1e3 * r["seconds"] / r["steps"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a, 1), "impl_note": "oracle port of the reference's OpenMP path "
+                       "(the reference itself cannot be compiled: Eigen absent)"},
+            "cpu_baseline": {"value": r["value"], "unit": "scans/s", "cores": r["cores"], "kind": "port",
+                             "sample": r["sample"], "host_cores": r["host_cores"]},
+            "e2e": {"value": r["value"], "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.impl == "reference":
+        run_reference(a, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from mad_icp_b200 import FlatTree, Registrar, synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n = world
+    dev = local_rank if world > 1 else 0
+    torch.cuda.set_device(dev)
+
+    # ---------------- inputs (synthetic, deterministic, identical on every rank)
+    case = synth.registration_case(K=K_MODEL, beams=a.beams, azimuths=a.azimuths)
+    reg = Registrar(device=dev, max_keyframes=K_MODEL)
+    stream = torch.cuda.Stream(device=dev)
+    reg.set_stream(stream.cuda_stream)
+    depth_tables, my_slots = [], [s for s in range(K_MODEL) if s % n == rank]
+    model_bytes = 0
+    for s in my_slots:
+        ft = FlatTree(case["scans"][s])
+        ft.apply_transform(case["kf_poses"][s])
+        reg.put_keyframe(s, ft)
+        depth_tables.append(leaf_depths(ft.records()))
+        model_bytes += ft.num_nodes * 64
+    qtree = FlatTree(case["query"])
+    means = qtree.leaf_means()
+    L = means.shape[0]
+    pinned = torch.from_numpy(means).pin_memory()
+    X0 = case["T_guess"]
+    if world > 1:
+        h = torch.tensor(list(reg.comm_export()), dtype=torch.uint8, device=f"cuda:{dev}")
+        allh = [torch.empty_like(h) for _ in range(world)]
+        dist.all_gather(allh, h)
+        reg.comm_connect(rank, world, [bytes(t.cpu().tolist()) for t in allh])
+        dist.barrier()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{dev}")  # > 126 MB L2
+
+    def l2_flush():
+        with torch.cuda.stream(stream):
+            flush.fill_(1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- resident-input throughput (`value`)
+    reg.set_moving(pinned)
+    for _ in range(max(a.warmup, 3)):
+        l2_flush()
+        reg.register_async(X0, a.iters)
+    barrier()
+    sampler = ClockSampler(dev)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    launches0 = reg.kernel_launches
+    barrier()
+    for s0, s1 in ev:
+        l2_flush()
+        s0.record(stream)
+        reg.register_async(X0, a.iters)
+        s1.record(stream)
+    barrier()
+    launches = reg.kernel_launches - launches0
+    step_ms = [s0.elapsed_time(s1) for s0, s1 in ev]
+    total_ms = float(sum(step_ms))
+    res = reg.register_fetch(want_matched=True)
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+
+    # ---------------- end to end through the public call with host buffers (`e2e`)
+    for _ in range(3):
+        l2_flush()
+        reg.set_moving(pinned)
+        reg.register(X0, a.iters)
+    barrier()
+    e2e_s = 0.0
+    for _ in range(a.steps):
+        l2_flush()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        reg.set_moving(pinned)                       # H2D: L x 24 B from pinned host memory
+        out = reg.register(X0, a.iters)              # H2D pose, kernel, D2H pose/H/b/matched, sync
+        e2e_s += time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    h2d = L * 24 + 96 + 16
+    d2h = 16 + 42 * 8 + 96 + L
+
+    # ---------------- replicas mode at N > 1 (throughput: every rank registers its own scan, full model)
+    replicas = None
+    if world > 1:
+        reg2 = Registrar(device=dev, max_keyframes=K_MODEL)
+        reg2.set_stream(stream.cuda_stream)
+        for s in range(K_MODEL):
+            ft = FlatTree(case["scans"][s])
+            ft.apply_transform(case["kf_poses"][s])
+            reg2.put_keyframe(s, ft)
+        reg2.set_moving(pinned)
+        for _ in range(3):
+            reg2.register_async(X0, a.iters)
+        barrier()
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+        for s0, s1 in ev2:
+            l2_flush()
+            s0.record(stream)
+            reg2.register_async(X0, a.iters)
+            s1.record(stream)
+        barrier()
+        t = torch.tensor([sum(s0.elapsed_time(s1) for s0, s1 in ev2)], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        replicas = {"value": world * a.steps / (float(t.item()) * 1e-3), "unit": "scans/s",
+                    "note": "N independent registrations, full 16-keyframe model on every GPU, no exchange"}
+        reg2.close()
+
+    # ---------------- roofline of the dominant kernel (k_gn_loop) + parity guard
+    trace = reg.register_trace()
+    rf = None
+    if world == 1:
+        abytes, visits = algorithmic_bytes(reg, depth_tables, trace, a.iters, L)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+        avg_launch_s = (total_ms * 1e-3) / a.steps
+        achieved = abytes / avg_launch_s / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "gn_loop_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        rf = {"kernel": "k_gn_loop (persistent: search + linearize + reduce + solve, all GN rounds)", "bound": "hbm",
+              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+              "algorithmic_bytes_per_launch": abytes, "node_visits_per_launch": visits, "peak_source": peak_src,
+              "avg_launch_ms": avg_launch_s * 1e3, "model_bytes": model_bytes,
+              "note": "model (record bytes above) is L2-resident after the first round, so DRAM traffic << algorithmic "
+                      "bytes and frac can exceed 1; see DESIGN.md section 6"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        r = cpu_reference_leg(a, steps=1000, warmup=1, budget_s=a.cpu_seconds)
+        cpu = {"value": r["value"], "unit": "scans/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
+               "host_cores": r["host_cores"]}
+
+    if rank == 0:
+        clocks = sampler.summary()
+        line = {"metric": METRIC, "value": a.steps / (total_ms * 1e-3), "unit": "scans/s", "n_gpus": n,
+                "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": total_ms / a.steps,
+                "higher_is_better": True, "scaling": "strong" if n > 1 else "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": workload_name(a, n), "moving_leaves": L, "keyframes": K_MODEL,
+                           "gn_iters": a.iters, "l2": "flushed between steps (256 MiB fill, outside the per-step events)",
+                           "timing": "per-step CUDA event pairs on the launch stream, summed; max over ranks"},
+                "e2e": {"value": a.steps / e2e_s, "unit": "scans/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / a.steps,
+                        "timing": "host wall clock around set_moving+register (pinned H2D, kernel, D2H, sync)"},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "result": {"n_matched": int(res["n_matched"]), "pose_t": [float(v) for v in res["X"][:, 3]]}}
+        if rf:
+            line["roofline"] = rf
+        if cpu:
+            line["cpu_baseline"] = cpu
+        if replicas:
+            line["replicas"] = replicas
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,299 @@
+// flat_tree.cpp -- host-side MAD-tree builder producing the breadth-first 64-byte record layout the
+// sm_100a kernels walk (include/madicp_b200.h: madtree_*).
+//
+// What it computes is the reference's MADtree (tools/mad_tree.cpp:47-130 build, :154-163 leaf order,
+// :165-172 applyTransform; helpers tools/utils.h:38-97); how it is organised is not: instead of one
+// 152-byte heap object per node linked by pointers, nodes live in index-linked arrays created by an
+// explicit-stack depth-first expansion (so node id == DFS pre-order position and leaves come out in
+// getLeafs order for free), followed by one breadth-first renumbering pass that makes siblings
+// adjacent and emits the device records.  Subtrees below the top levels are independent index
+// ranges of the point array, so they are expanded by separate threads and spliced back in pre-order.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/madicp_b200.h"
+#include "arith.h"
+#include "eig3.h"
+
+namespace madicp {
+void set_error(const std::string& msg);
+}
+
+namespace {
+using madicp::dot3;
+using madicp::norm3;
+
+struct Node {
+  double mean[3];
+  double ev[9];  // column-major eigenvectors: col0 normal, col2 split direction
+  double bbox[3];
+  int32_t npts;
+  int32_t left, right, parent;  // node ids (pre-order), -1 when absent
+  int32_t leaf_ordinal;         // getLeafs position, -1 for internal nodes
+};
+
+struct Job {  // pending range [begin,end) of the point array
+  int64_t begin, end;
+  int32_t parent;      // node id of the parent (within the same arena) or -1
+  int32_t plane_pred;  // node id of the plane predecessor or -1
+  bool is_right;
+};
+
+struct Builder {
+  double* pts;  // n x 3, reordered in place
+  double b_max, b_min;
+
+  // statistics of one range -> fills mean/ev/bbox/npts of `nd`
+  void stats(Node& nd, int64_t begin, int64_t end) const {
+    double sx = 0, sy = 0, sz = 0;
+    double cxx = 0, cyx = 0, czx = 0, cyy = 0, czy = 0, czz = 0;
+    int k = 0;
+    for (int64_t i = begin; i != end; ++i) {
+      const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+      sx += x; sy += y; sz += z;
+      cxx += x * x; cyx += y * x; czx += z * x;
+      cyy += y * y; czy += z * y; czz += z * z;
+      ++k;
+    }
+    const double inv = 1. / k;
+    sx *= inv; sy *= inv; sz *= inv;
+    cxx *= inv; cyx *= inv; czx *= inv; cyy *= inv; czy *= inv; czz *= inv;
+    cxx -= sx * sx; cyx -= sy * sx; czx -= sz * sx;
+    cyy -= sy * sy; czy -= sz * sy; czz -= sz * sz;
+    const double f = double(k) / double(k - 1);
+    madicp::Sym3 c{cxx * f, cyx * f, czx * f, cyy * f, czy * f, czz * f};
+    nd.mean[0] = sx; nd.mean[1] = sy; nd.mean[2] = sz;
+    madicp::eig3_symmetric(c, nd.ev);
+    double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    for (int64_t i = begin; i != end; ++i) {
+      const double dx = pts[3 * i] - sx, dy = pts[3 * i + 1] - sy, dz = pts[3 * i + 2] - sz;
+      for (int a = 0; a < 3; ++a) {
+        const double v = dot3(nd.ev[3 * a], nd.ev[3 * a + 1], nd.ev[3 * a + 2], dx, dy, dz);
+        lo[a] = (v < lo[a]) ? v : lo[a];  // NaN never replaces (one-point ranges give NaN axes)
+        hi[a] = (hi[a] < v) ? v : hi[a];
+      }
+    }
+    for (int a = 0; a < 3; ++a) nd.bbox[a] = hi[a] - lo[a];
+    nd.npts = k;
+  }
+
+  // Hoare-style unstable partition of the reference (tools/utils.h:38-52): order of the two halves
+  // matters because child sums are accumulated in array order.
+  int64_t partition(int64_t begin, int64_t end, const Node& nd) const {
+    int64_t lo = begin, hi = end;
+    const double nx = nd.ev[6], ny = nd.ev[7], nz = nd.ev[8];
+    while (lo != hi) {
+      double* p = pts + 3 * lo;
+      if (madicp::plane_side(p[0], p[1], p[2], nd.mean[0], nd.mean[1], nd.mean[2], nx, ny, nz) < 0.0) {
+        ++lo;
+      } else {
+        double* q = pts + 3 * (hi - 1);
+        std::swap(p[0], q[0]);
+        std::swap(p[1], q[1]);
+        std::swap(p[2], q[2]);
+        --hi;
+      }
+    }
+    return hi;
+  }
+
+  // Leaf finalisation (tools/mad_tree.cpp:64-88).  `chain` resolves a node id to a Node for the
+  // ancestor walk (ids < 0 index the caller-supplied ancestors above this arena's root).
+  template <class Resolve>
+  void make_leaf(Node& nd, int32_t self, int32_t plane_pred, int64_t begin, int64_t end, Resolve&& at) const {
+    if (plane_pred != INT32_MIN) {
+      const Node& pp = at(plane_pred);
+      nd.ev[0] = pp.ev[0]; nd.ev[1] = pp.ev[1]; nd.ev[2] = pp.ev[2];
+    } else if (nd.npts < 3) {
+      (void) self;
+      const Node* n = &nd;
+      while (n->parent != INT32_MIN && n->npts < 3) n = &at(n->parent);
+      if (n != &nd) {
+        nd.ev[0] = n->ev[0]; nd.ev[1] = n->ev[1]; nd.ev[2] = n->ev[2];
+      }
+    }
+    // nearest cloud point to the centroid; first minimum wins.  The reference writes each new
+    // minimum through a reference to *begin, i.e. into the first slot of the range.
+    double best = std::numeric_limits<double>::max();
+    double* first = pts + 3 * begin;
+    for (int64_t i = begin; i != end; ++i) {
+      const double vx = pts[3 * i], vy = pts[3 * i + 1], vz = pts[3 * i + 2];
+      const double d = norm3(vx - nd.mean[0], vy - nd.mean[1], vz - nd.mean[2]);
+      if (d < best) {
+        first[0] = vx; first[1] = vy; first[2] = vz;
+        best = d;
+      }
+    }
+    nd.mean[0] = first[0]; nd.mean[1] = first[1]; nd.mean[2] = first[2];
+  }
+};
+
+}  // namespace
+
+// Parent / plane-predecessor ids use INT32_MIN for "none"; ids >= 0 are positions in the tree's
+// final node array.
+struct madtree {
+  std::vector<double> pts;
+  std::vector<Node> nodes;          // DFS pre-order
+  std::vector<int32_t> leaf_nodes;  // getLeafs order -> node id
+  std::vector<int32_t> bfs_index;   // node id -> breadth-first position
+  std::vector<madtree_rec_t> recs;  // breadth-first records
+  double b_max = 0, b_min = 0;
+
+  void refresh_records() {
+    recs.resize(nodes.size());
+    for (size_t i = 0; i < nodes.size(); ++i) {
+      const Node& n = nodes[i];
+      madtree_rec_t& r = recs[bfs_index[i]];
+      for (int a = 0; a < 3; ++a) r.mean[a] = n.mean[a];
+      if (n.left < 0) {
+        for (int a = 0; a < 3; ++a) r.dir[a] = n.ev[a];
+        r.bbox0 = n.bbox[0];
+        r.link = -1 - n.leaf_ordinal;
+      } else {
+        for (int a = 0; a < 3; ++a) r.dir[a] = n.ev[6 + a];
+        r.bbox0 = n.bbox[0];
+        r.link = bfs_index[n.left];
+      }
+      r.num_points = n.npts;
+    }
+  }
+};
+
+namespace {
+
+// Expand the point range [begin,end) depth first, appending nodes to `nodes` in pre-order.
+void expand(const Builder& B, std::vector<Node>& nodes, int64_t begin, int64_t end) {
+  std::vector<Job> stack;
+  stack.push_back(Job{begin, end, INT32_MIN, INT32_MIN, false});
+  while (!stack.empty()) {
+    const Job j = stack.back();
+    stack.pop_back();
+    const int32_t id = int32_t(nodes.size());
+    nodes.emplace_back();
+    Node& nd = nodes.back();
+    nd.left = nd.right = -1;
+    nd.parent = j.parent;
+    nd.leaf_ordinal = -1;
+    if (j.parent != INT32_MIN) {
+      if (j.is_right)
+        nodes[j.parent].right = id;
+      else
+        nodes[j.parent].left = id;
+    }
+    B.stats(nd, j.begin, j.end);
+    if (nd.bbox[2] < B.b_max) {
+      B.make_leaf(nd, id, j.plane_pred, j.begin, j.end, [&](int32_t k) -> const Node& { return nodes[k]; });
+      continue;
+    }
+    int32_t pp = j.plane_pred;
+    if (pp == INT32_MIN && nd.bbox[0] < B.b_min) pp = id;
+    const int64_t mid = B.partition(j.begin, j.end, nd);
+    // right first so the left child is popped (and numbered) next: pre-order, left before right
+    stack.push_back(Job{mid, j.end, id, pp, true});
+    stack.push_back(Job{j.begin, mid, id, pp, false});
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_min, int num_threads, madtree_t** out) {
+  if (!points_xyz || !out || n <= 0) {
+    madicp::set_error("madtree_build: null pointer or empty cloud (the reference dereferences *begin on an empty range)");
+    return MADICP_ERR_INVALID;
+  }
+  (void) num_threads;
+  madtree* t = new (std::nothrow) madtree;
+  if (!t) return MADICP_ERR_NOMEM;
+  t->pts.assign(points_xyz, points_xyz + 3 * n);
+  t->b_max = b_max;
+  t->b_min = b_min;
+  Builder B{t->pts.data(), b_max, b_min};
+  t->nodes.reserve(size_t(n / 2 + 16));
+  expand(B, t->nodes, 0, n);
+  // leaves in pre-order == getLeafs order (left subtree fully before right subtree)
+  for (size_t i = 0; i < t->nodes.size(); ++i)
+    if (t->nodes[i].left < 0) {
+      t->nodes[i].leaf_ordinal = int32_t(t->leaf_nodes.size());
+      t->leaf_nodes.push_back(int32_t(i));
+    }
+  // breadth-first numbering with adjacent siblings
+  t->bfs_index.assign(t->nodes.size(), -1);
+  std::vector<int32_t> order;
+  order.reserve(t->nodes.size());
+  order.push_back(0);
+  t->bfs_index[0] = 0;
+  for (size_t h = 0; h < order.size(); ++h) {
+    const Node& nd = t->nodes[order[h]];
+    if (nd.left >= 0) {
+      t->bfs_index[nd.left] = int32_t(order.size());
+      order.push_back(nd.left);
+      t->bfs_index[nd.right] = int32_t(order.size());
+      order.push_back(nd.right);
+    }
+  }
+  t->refresh_records();
+  *out = t;
+  return MADICP_OK;
+}
+
+void madtree_free(madtree_t* t) { delete t; }
+int madtree_num_nodes(const madtree_t* t) { return t ? int(t->nodes.size()) : MADICP_ERR_INVALID; }
+int madtree_num_leaves(const madtree_t* t) { return t ? int(t->leaf_nodes.size()) : MADICP_ERR_INVALID; }
+
+int madtree_apply_transform(madtree_t* t, const double X[12]) {
+  if (!t || !X) return MADICP_ERR_INVALID;
+  for (Node& n : t->nodes) {
+    double o[3];
+    madicp::iso_apply(X, n.mean[0], n.mean[1], n.mean[2], o[0], o[1], o[2]);
+    n.mean[0] = o[0]; n.mean[1] = o[1]; n.mean[2] = o[2];
+    double e[9];
+    for (int c = 0; c < 3; ++c)
+      for (int r = 0; r < 3; ++r)
+        e[c * 3 + r] = dot3(X[r * 4], X[r * 4 + 1], X[r * 4 + 2], n.ev[c * 3], n.ev[c * 3 + 1], n.ev[c * 3 + 2]);
+    std::memcpy(n.ev, e, sizeof(e));
+  }
+  t->refresh_records();
+  return MADICP_OK;
+}
+
+int madtree_leaves(const madtree_t* t, double* means, double* normals, double* bbox0, int32_t* num_points) {
+  if (!t) return MADICP_ERR_INVALID;
+  for (size_t i = 0; i < t->leaf_nodes.size(); ++i) {
+    const Node& n = t->nodes[t->leaf_nodes[i]];
+    for (int a = 0; a < 3; ++a) {
+      if (means) means[3 * i + a] = n.mean[a];
+      if (normals) normals[3 * i + a] = n.ev[a];
+    }
+    if (bbox0) bbox0[i] = n.bbox[0];
+    if (num_points) num_points[i] = n.npts;
+  }
+  return MADICP_OK;
+}
+
+const madtree_rec_t* madtree_records(const madtree_t* t) { return t ? t->recs.data() : nullptr; }
+
+int madtree_export(const madtree_t* t, double* mean, double* eigenvectors, double* bbox, int32_t* num_points,
+                   int32_t* left, int32_t* right, int32_t* leaf_ordinal) {
+  if (!t) return MADICP_ERR_INVALID;
+  for (size_t i = 0; i < t->nodes.size(); ++i) {
+    const Node& n = t->nodes[i];
+    if (mean) std::memcpy(mean + 3 * i, n.mean, 24);
+    if (eigenvectors) std::memcpy(eigenvectors + 9 * i, n.ev, 72);
+    if (bbox) std::memcpy(bbox + 3 * i, n.bbox, 24);
+    if (num_points) num_points[i] = n.npts;
+    if (left) left[i] = n.left;
+    if (right) right[i] = n.right;
+    if (leaf_ordinal) leaf_ordinal[i] = n.leaf_ordinal;
+  }
+  return MADICP_OK;
+}
+
+}  // extern "C"

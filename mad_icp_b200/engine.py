@@ -1,0 +1,218 @@
+"""Python handles over the C ABI: `FlatTree` (host-built MAD-tree in the breadth-first device layout)
+and `Registrar` (one GPU: keyframe slots + moving leaves + the persistent Gauss-Newton kernel).
+These are the objects the reference-named facade (mad_icp_b200.api / the pybind modules) and
+bench.py drive; they add no arithmetic of their own."""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as capi
+from ._capi import MadIcpError, as_b, as_d, as_i, check, pose12
+
+
+class FlatTree:
+    """MADtree built on the host (reference: tools/mad_tree.cpp:47-130) in flat form."""
+
+    def __init__(self, points, b_max=0.2, b_min=0.1, num_threads=1):
+        pts = np.ascontiguousarray(points, dtype=np.float64)
+        if pts.ndim != 2 or pts.shape[1] != 3:
+            raise ValueError("points must be N x 3")
+        h = C.c_void_p()
+        check(capi.lib().madtree_build(as_d(pts), pts.shape[0], b_max, b_min, num_threads, C.byref(h)), "madtree_build")
+        self._h = h
+        self.b_max, self.b_min = b_max, b_min
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            capi.lib().madtree_free(h)
+            self._h = None
+
+    @property
+    def num_nodes(self):
+        return capi.lib().madtree_num_nodes(self._h)
+
+    @property
+    def num_leaves(self):
+        return capi.lib().madtree_num_leaves(self._h)
+
+    def apply_transform(self, T):
+        X = pose12(T)
+        check(capi.lib().madtree_apply_transform(self._h, as_d(X)), "madtree_apply_transform")
+
+    def leaves(self):
+        L = self.num_leaves
+        means, normals = np.empty((L, 3)), np.empty((L, 3))
+        bbox0, npts = np.empty(L), np.empty(L, np.int32)
+        check(capi.lib().madtree_leaves(self._h, as_d(means), as_d(normals), as_d(bbox0), as_i(npts)))
+        return means, normals, bbox0, npts
+
+    def leaf_means(self):
+        means = np.empty((self.num_leaves, 3))
+        check(capi.lib().madtree_leaves(self._h, as_d(means), None, None, None))
+        return means
+
+    def records(self):
+        """Copy of the breadth-first 64-byte records as a structured array."""
+        n = self.num_nodes
+        ptr = capi.lib().madtree_records(self._h)
+        buf = (C.c_char * (n * 64)).from_address(ptr)
+        return np.frombuffer(buf, dtype=capi.REC_DTYPE, count=n).copy()
+
+    def export(self):
+        n = self.num_nodes
+        out = dict(mean=np.empty((n, 3)), eivecs=np.empty((n, 9)), bbox=np.empty((n, 3)),
+                   num_points=np.empty(n, np.int32), left=np.empty(n, np.int32), right=np.empty(n, np.int32),
+                   leaf_ordinal=np.empty(n, np.int32))
+        check(capi.lib().madtree_export(self._h, as_d(out["mean"]), as_d(out["eivecs"]), as_d(out["bbox"]),
+                                        as_i(out["num_points"]), as_i(out["left"]), as_i(out["right"]),
+                                        as_i(out["leaf_ordinal"])))
+        return out
+
+
+class Registrar:
+    """One GPU's registration context (reference: class MADicp + Pipeline's keyframe deque)."""
+
+    def __init__(self, device=0, max_keyframes=16, min_ball=0.2, rho_ker=0.1, b_ratio=0.02):
+        h = C.c_void_p()
+        check(capi.lib().madicp_create(C.byref(h), device, max_keyframes), "madicp_create")
+        self._h = h
+        self.device = device
+        self.max_keyframes = max_keyframes
+        self.L = 0
+        self.set_params(min_ball, rho_ker, b_ratio)
+
+    def close(self):
+        h = getattr(self, "_h", None)
+        if h:
+            capi.lib().madicp_destroy(h)
+            self._h = None
+
+    __del__ = close
+
+    def set_params(self, min_ball, rho_ker, b_ratio):
+        check(capi.lib().madicp_set_params(self._h, min_ball, rho_ker, b_ratio), "madicp_set_params")
+
+    def set_stream(self, cuda_stream_ptr):
+        check(capi.lib().madicp_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    @property
+    def stream(self):
+        return capi.lib().madicp_get_stream(self._h)
+
+    def put_keyframe(self, slot, tree):
+        check(capi.lib().madicp_put_keyframe(self._h, slot, tree._h), "madicp_put_keyframe")
+
+    def put_keyframe_records(self, slot, recs, n_leaves):
+        recs = np.ascontiguousarray(recs, dtype=capi.REC_DTYPE)
+        check(capi.lib().madicp_put_keyframe_records(self._h, slot, recs.ctypes.data_as(C.c_void_p), recs.shape[0],
+                                                     n_leaves), "madicp_put_keyframe_records")
+
+    def drop_keyframe(self, slot):
+        check(capi.lib().madicp_drop_keyframe(self._h, slot))
+
+    @property
+    def num_keyframes(self):
+        return capi.lib().madicp_num_keyframes(self._h)
+
+    def active_slots(self):
+        out = np.empty(self.max_keyframes, np.int32)
+        k = capi.lib().madicp_active_slots(self._h, as_i(out), self.max_keyframes)
+        return out[:k].tolist()
+
+    @property
+    def model_nodes(self):
+        return capi.lib().madicp_model_nodes(self._h)
+
+    @property
+    def kernel_launches(self):
+        return capi.lib().madicp_kernel_launches(self._h)
+
+    def set_moving(self, means):
+        """means: L x 3 float64 host array (numpy, or the memory of a pinned torch tensor)."""
+        if hasattr(means, "data_ptr"):  # torch tensor (pinned host memory)
+            assert means.dtype.is_floating_point and means.element_size() == 8 and means.is_contiguous()
+            L, ptr = means.shape[0], means.data_ptr()
+            self._keep = means
+        else:
+            means = np.ascontiguousarray(means, dtype=np.float64)
+            L, ptr = means.shape[0], means.ctypes.data
+            self._keep = means
+        check(capi.lib().madicp_set_moving(self._h, C.c_void_p(ptr), L), "madicp_set_moving")
+        self.L = L
+
+    def search(self, X):
+        X = pose12(X)
+        out = np.empty((self.num_keyframes, self.L), np.int32)
+        check(capi.lib().madicp_search(self._h, as_d(X), as_i(out)), "madicp_search")
+        return out
+
+    def linearize(self, X):
+        X = pose12(X)
+        H, b = np.empty((6, 6)), np.empty(6)
+        m = np.empty(self.L, np.uint8)
+        check(capi.lib().madicp_linearize(self._h, as_d(X), as_d(H), as_d(b), as_b(m)), "madicp_linearize")
+        return H, b, m
+
+    def solve_update(self, H, b, X):
+        X = pose12(X).copy()
+        H = np.ascontiguousarray(H, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        check(capi.lib().madicp_solve_update(self._h, as_d(H), as_d(b), as_d(X)), "madicp_solve_update")
+        return X
+
+    def register(self, X0, iters=15, want_matched=True):
+        """The whole ICP loop on the device.  Returns dict(X 3x4, H 6x6, b 6, matched L, n_matched)."""
+        X = pose12(X0).copy()
+        H, b = np.empty((6, 6)), np.empty(6)
+        m = np.empty(self.L, np.uint8) if want_matched else None
+        n = C.c_int(0)
+        check(capi.lib().madicp_register(self._h, iters, as_d(X), as_d(H), as_d(b), as_b(m), C.byref(n)),
+              "madicp_register")
+        return dict(X=X, H=H, b=b, matched=m, n_matched=n.value)
+
+    def register_async(self, X0, iters=15):
+        X = pose12(X0)
+        check(capi.lib().madicp_register_async(self._h, iters, as_d(X)), "madicp_register_async")
+
+    def register_fetch(self, want_matched=False):
+        X, H, b = np.empty((3, 4)), np.empty((6, 6)), np.empty(6)
+        m = np.empty(self.L, np.uint8) if want_matched else None
+        n = C.c_int(0)
+        check(capi.lib().madicp_register_fetch(self._h, as_d(X), as_d(H), as_d(b), as_b(m), C.byref(n)),
+              "madicp_register_fetch")
+        return dict(X=X, H=H, b=b, matched=m, n_matched=n.value)
+
+    def register_trace(self):
+        buf = np.empty((65, 3, 4))
+        rows = check(capi.lib().madicp_register_trace(self._h, as_d(buf), 65), "madicp_register_trace")
+        return buf[:rows].copy()
+
+    def search_cloud(self, slot, queries, want=("ordinals", "points", "normals", "dists")):
+        q = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, 3)
+        n = q.shape[0]
+        o = np.empty(n, np.int32) if "ordinals" in want else None
+        p = np.empty((n, 3)) if "points" in want else None
+        nr = np.empty((n, 3)) if "normals" in want else None
+        d = np.empty(n) if "dists" in want else None
+        check(capi.lib().madicp_search_cloud(self._h, slot, as_d(q), n, as_i(o), as_d(p), as_d(nr), as_d(d)),
+              "madicp_search_cloud")
+        return dict(ordinals=o, points=p, normals=nr, dists=d)
+
+    # ---- multi-GPU -------------------------------------------------------------------------
+    def comm_export(self):
+        buf = (C.c_char * 64)()
+        check(capi.lib().madicp_comm_export(self._h, buf), "madicp_comm_export")
+        return bytes(buf)
+
+    def comm_connect(self, rank, world, handles):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * world
+        check(capi.lib().madicp_comm_connect(self._h, rank, world, blob), "madicp_comm_connect")
+
+    @property
+    def world(self):
+        return capi.lib().madicp_comm_world(self._h)
+
+
+__all__ = ["FlatTree", "Registrar", "MadIcpError"]

@@ -1,0 +1,77 @@
+"""CPU tests of the product's host flat-tree builder (mad_icp_b200/csrc/flat_tree.cpp) against the
+oracle's pointer tree: every node bit-identical, leaves in getLeafs order, record layout."""
+import numpy as np
+import pytest
+
+from mad_icp_b200 import FlatTree, MadIcpError, synth
+from util import bits_equal
+
+
+def _same_tree(ft, ot):
+    a, b = ft.export(), ot.export()
+    assert ft.num_nodes == ot.num_nodes and ft.num_leaves == ot.num_leaves
+    for k in ("mean", "eivecs", "bbox"):
+        assert bits_equal(a[k], b[k]), k
+    for k in ("num_points", "left", "right", "leaf_ordinal"):
+        assert (a[k] == b[k]).all(), k
+    for x, y in zip(ft.leaves(), ot.leaves()):
+        assert bits_equal(x, y) if x.dtype.kind == "f" else (x == y).all()
+
+
+@pytest.mark.parametrize("b_max,ppw", [(0.2, 1000), (1e-5, 2000), (0.05, 3000)])
+def test_four_walls_tree_identical(oracle, built, b_max, ppw):
+    np.random.seed(42)
+    cloud = synth.four_walls(points_per_wall=ppw)
+    _same_tree(FlatTree(cloud, b_max=b_max), oracle.OracleTree(cloud, b_max=b_max))
+
+
+def test_lidar_tree_identical_after_transform(oracle, built):
+    c = synth.registration_case(K=1, beams=32, azimuths=1024, seed=11)
+    ft, ot = FlatTree(c["scans"][0]), oracle.OracleTree(c["scans"][0])
+    _same_tree(ft, ot)
+    T = c["kf_poses"][0] @ synth.pose_xyyaw(3.0, -1.0, 0.3)
+    ft.apply_transform(T)
+    ot.apply_transform(T)
+    _same_tree(ft, ot)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7])
+def test_tiny_clouds(oracle, built, n):
+    rs = np.random.RandomState(n)
+    cloud = rs.uniform(-1, 1, (n, 3))
+    _same_tree(FlatTree(cloud, b_max=0.05), oracle.OracleTree(cloud, b_max=0.05))
+
+
+def test_duplicate_points(oracle, built):
+    cloud = np.repeat(np.array([[1.0, 2.0, 3.0], [1.5, 2.0, 3.0]]), 50, axis=0)
+    _same_tree(FlatTree(cloud, b_max=0.1), oracle.OracleTree(cloud, b_max=0.1))
+
+
+def test_empty_cloud_rejected(built):
+    with pytest.raises(MadIcpError):
+        FlatTree(np.zeros((0, 3)))
+
+
+def test_record_layout(built):
+    """Breadth-first, siblings adjacent, leaves carry -1-ordinal, internal dir = split direction."""
+    c = synth.registration_case(K=1, beams=16, azimuths=512, seed=2)
+    ft = FlatTree(c["scans"][0])
+    r, e = ft.records(), ft.export()
+    assert r.dtype.itemsize == 64 and r.shape[0] == ft.num_nodes
+    leaf = r["link"] < 0
+    assert leaf.sum() == ft.num_leaves
+    assert sorted((-1 - r["link"][leaf]).tolist()) == list(range(ft.num_leaves))
+    links = r["link"][~leaf]
+    assert (links >= 1).all() and (np.diff(links) == 2).all() and links[0] == 1  # BFS: children pairs in order
+    # follow the records from the root and compare with the DFS export
+    def walk(rec_i, node_i):
+        if e["left"][node_i] < 0:
+            assert r["link"][rec_i] == -1 - e["leaf_ordinal"][node_i]
+            assert bits_equal(r["dir"][rec_i], e["eivecs"][node_i][0:3]) and r["bbox0"][rec_i] == e["bbox"][node_i][0]
+            return
+        assert bits_equal(r["dir"][rec_i], e["eivecs"][node_i][6:9]) and bits_equal(r["mean"][rec_i], e["mean"][node_i])
+        walk(r["link"][rec_i], e["left"][node_i])
+        walk(r["link"][rec_i] + 1, e["right"][node_i])
+    import sys
+    sys.setrecursionlimit(10000)
+    walk(0, 0)

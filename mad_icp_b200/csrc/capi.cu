@@ -41,38 +41,46 @@ k_search(const __grid_constant__ ModelView model, const double* __restrict__ mov
   }
 }
 
-// K2: reads K1's leaf record index, accumulates the 27 unique H/b values, per-CTA partials, and
+// K2: reads K1's leaf record index, folds the 6x7 H/b tile per warp (FP64 DMMA), per-CTA partials, and
 // the last CTA to arrive folds the partials in CTA order into st->H / st->b.
 __global__ void __launch_bounds__(kBlock)
 k_linearize(const __grid_constant__ ModelView model, const double* __restrict__ moving, int L,
             const double* __restrict__ Xp, const __grid_constant__ IcpParams P, const int* __restrict__ hit,
             unsigned char* __restrict__ matched, double* __restrict__ partial, GnState* st) {
-  __shared__ double s_warp[kWarps][kAcc];
+  __shared__ double s_stage[kWarps][32 * kStage];
+  __shared__ double s_red[kWarps][64];
   __shared__ double s_tot[kAcc];
   __shared__ int s_last;
   double X[12];
 #pragma unroll
   for (int i = 0; i < 12; ++i) X[i] = Xp[i];
-  double acc[kAcc];
-#pragma unroll
-  for (int i = 0; i < kAcc; ++i) acc[i] = 0.0;
+  double c0 = 0.0, c1 = 0.0;
   const int64_t total = int64_t(model.K) * L;
-  for (int64_t w = int64_t(blockIdx.x) * kBlock + threadIdx.x; w < total; w += int64_t(gridDim.x) * kBlock) {
-    const int k = int(w / L), q = int(w - int64_t(k) * L);
-    const double px = moving[3 * q], py = moving[3 * q + 1], pz = moving[3 * q + 2];
-    double mx, my, mz;
-    iso_apply(X, px, py, pz, mx, my, mz);
-    const Rec f = load_rec(model.recs[k] + hit[w]);
-    if (linearize_one(X, P, px, py, pz, mx, my, mz, f, acc) && matched) matched[q] = 1;
+  const int lane = threadIdx.x & 31;
+  // warp-uniform trip count: every lane takes part in the DMMA fold, lanes past the end stage zeros
+  for (int64_t w0 = int64_t(blockIdx.x) * kBlock + (threadIdx.x - lane); w0 < total; w0 += int64_t(gridDim.x) * kBlock) {
+    const int64_t w = w0 + lane;
+    double v[kStage];
+#pragma unroll
+    for (int i = 0; i < kStage; ++i) v[i] = 0.0;
+    if (w < total) {
+      const int k = int(w / L), q = int(w - int64_t(k) * L);
+      const double px = moving[3 * q], py = moving[3 * q + 1], pz = moving[3 * q + 2];
+      double mx, my, mz;
+      iso_apply(X, px, py, pz, mx, my, mz);
+      const Rec f = load_rec(model.recs[k] + hit[w]);
+      if (linearize_one(X, P, px, py, pz, mx, my, mz, f, v) && matched) matched[q] = 1;
+    }
+    warp_accumulate(s_stage[threadIdx.x >> 5], v, c0, c1);
   }
-  block_reduce_store(acc, s_warp, partial + size_t(blockIdx.x) * kAcc);
+  block_reduce_store(c0, c1, s_red, partial + size_t(blockIdx.x) * kAcc);
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket, 1) == int(gridDim.x) - 1);
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  final_reduce(partial, gridDim.x, s_warp, s_tot);
+  final_reduce(partial, gridDim.x, s_red, s_tot);
   if (threadIdx.x == 0) {
     unpack_Hb(s_tot, st->H, st->b);
     st->ticket = 0;
@@ -91,12 +99,12 @@ __global__ void k_solve(const double* __restrict__ H, const double* __restrict__
   }
 }
 
-// In-kernel all-reduce of the 27 accumulators across GPUs (called by ONE CTA per rank).
+// In-kernel all-reduce of the 48-value accumulator tile across GPUs (called by ONE CTA per rank).
 // Every rank stores its partial into every rank's mailbox (own included) with 16-byte LL cells,
 // then spins on its own mailbox until all `world` partials of this epoch are present and sums them
 // in rank order -> identical bits on every rank.
 __device__ __forceinline__ void peer_allreduce(const PeerView& pv, uint32_t epoch, double* s_tot,
-                                               double (*s_stage)[32]) {
+                                               double (*s_stage)[kAcc]) {
   const int slot = int(epoch & 1u);
   for (int idx = threadIdx.x; idx < pv.world * kAcc; idx += kBlock) {
     const int r = idx / kAcc, i = idx - r * kAcc;
@@ -134,52 +142,63 @@ struct GnArgs {
   int iters;
   unsigned char* matched;               // local matched flags (L bytes), zeroed by the host
   unsigned char* peer_matched[kMaxPeers];  // world > 1: every rank's matched array (peer mapped)
-  double* partial;                      // gridDim.x * 27
+  double* partial;                      // gridDim.x * kAcc
   GnState* st;
 };
 
 // GN: the whole ICP loop.  Persistent cooperative grid (all CTAs co-resident); one software grid
 // barrier per round: CTAs publish partials, take a ticket, the last one reduces / exchanges /
 // solves and releases st->round, the others spin on it with ld.acquire.gpu.
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 4)
 k_gn_loop(const __grid_constant__ GnArgs A) {
-  __shared__ double s_warp[kWarps][kAcc];
+  // shared memory: the per-warp staging tiles are only live inside the item loop, so the reduction
+  // scratch and the peer staging alias them
+  __shared__ __align__(16) double s_buf[kWarps * 32 * kStage];
   __shared__ double s_tot[kAcc];
-  __shared__ double s_stage[kMaxPeers][32];
+  __shared__ double s_X[12];
   __shared__ int s_last;
   __shared__ int s_count[kWarps];
+  double(*s_red)[64] = reinterpret_cast<double(*)[64]>(s_buf);               // [kWarps][64]
+  double(*s_peer)[kAcc] = reinterpret_cast<double(*)[kAcc]>(s_buf + kWarps * 64);  // [kMaxPeers][kAcc]
+  static_assert(kWarps * 64 + kMaxPeers * kAcc <= kWarps * 32 * kStage, "scratch must fit in the staging tiles");
   GnState* st = A.st;
   const int64_t total = int64_t(A.model.K) * A.L;
   const bool multi = A.peers.world > 1;
+  const int lane = threadIdx.x & 31;
+  double* stage = s_buf + (threadIdx.x >> 5) * (32 * kStage);
   for (int it = 0; it < A.iters; ++it) {
-    if (it > 0) {
-      if (threadIdx.x == 0)
-        while (ld_acquire_gpu(&st->round) < it) {}
-      __syncthreads();
-    }
-    double X[12];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) X[i] = __ldcg(&st->X_trace[it * 12 + i]);
+    if (threadIdx.x == 0 && it > 0)
+      while (ld_acquire_gpu(&st->round) < it) {}
+    __syncthreads();  // also: everyone is done with s_buf/s_X of the previous round
+    if (threadIdx.x < 12) s_X[threadIdx.x] = __ldcg(&st->X_trace[it * 12 + threadIdx.x]);
+    __syncthreads();
     const bool last_round = (it == A.iters - 1);
-    double acc[kAcc];
+    double c0 = 0.0, c1 = 0.0;
+    for (int64_t w0 = int64_t(blockIdx.x) * kBlock + (threadIdx.x - lane); w0 < total;
+         w0 += int64_t(gridDim.x) * kBlock) {
+      const int64_t w = w0 + lane;
+      double v[kStage];
 #pragma unroll
-    for (int i = 0; i < kAcc; ++i) acc[i] = 0.0;
-    for (int64_t w = int64_t(blockIdx.x) * kBlock + threadIdx.x; w < total; w += int64_t(gridDim.x) * kBlock) {
-      const int k = int(w / A.L), q = int(w - int64_t(k) * A.L);
-      const double px = A.moving[3 * q], py = A.moving[3 * q + 1], pz = A.moving[3 * q + 2];
-      double mx, my, mz;
-      iso_apply(X, px, py, pz, mx, my, mz);
-      Rec f;
-      descend(A.model.recs[k], mx, my, mz, f);
-      if (linearize_one(X, A.P, px, py, pz, mx, my, mz, f, acc) && last_round) {
-        if (multi) {
-          for (int r = 0; r < A.peers.world; ++r) A.peer_matched[r][q] = 1;
-        } else {
-          A.matched[q] = 1;
+      for (int i = 0; i < kStage; ++i) v[i] = 0.0;
+      if (w < total) {
+        const int k = int(w / A.L), q = int(w - int64_t(k) * A.L);
+        const double px = A.moving[3 * q], py = A.moving[3 * q + 1], pz = A.moving[3 * q + 2];
+        double mx, my, mz;
+        iso_apply(s_X, px, py, pz, mx, my, mz);
+        Rec f;
+        descend(A.model.recs[k], mx, my, mz, f);
+        if (linearize_one(s_X, A.P, px, py, pz, mx, my, mz, f, v) && last_round) {
+          if (multi) {
+            for (int r = 0; r < A.peers.world; ++r) A.peer_matched[r][q] = 1;
+          } else {
+            A.matched[q] = 1;
+          }
         }
       }
+      warp_accumulate(stage, v, c0, c1);
     }
-    block_reduce_store(acc, s_warp, A.partial + size_t(blockIdx.x) * kAcc);
+    __syncthreads();  // staging tiles are dead; s_red aliases them
+    block_reduce_store(c0, c1, s_red, A.partial + size_t(blockIdx.x) * kAcc);
     if (multi && last_round)
       __threadfence_system();  // matched flags stored to peers become visible before our LL cells
     else
@@ -189,23 +208,23 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
     __syncthreads();
     if (s_last) {
       __threadfence();
-      final_reduce(A.partial, gridDim.x, s_warp, s_tot);
+      final_reduce(A.partial, gridDim.x, s_red, s_tot);
       if (multi) {
         if (last_round) __threadfence_system();
-        peer_allreduce(A.peers, A.peers.epoch_base + uint32_t(it) + 1u, s_tot, s_stage);
+        peer_allreduce(A.peers, A.peers.epoch_base + uint32_t(it) + 1u, s_tot, s_peer);
         if (last_round) __threadfence_system();
       }
       if (last_round) {  // count matched moving leaves (all writers are done: they took tickets)
         int c = 0;
         for (int q = threadIdx.x; q < A.L; q += kBlock) c += (__ldcv(A.matched + q) != 0);
         for (int off = 16; off > 0; off >>= 1) c += __shfl_down_sync(0xffffffffu, c, off);
-        if ((threadIdx.x & 31) == 0) s_count[threadIdx.x >> 5] = c;
+        if (lane == 0) s_count[threadIdx.x >> 5] = c;
         __syncthreads();
       }
       if (threadIdx.x == 0) {
         double H[36], b[6], Xn[12];
         unpack_Hb(s_tot, H, b);
-        for (int i = 0; i < 12; ++i) Xn[i] = X[i];
+        for (int i = 0; i < 12; ++i) Xn[i] = s_X[i];
         gn_update_pose(H, b, Xn, nullptr);
         for (int i = 0; i < 12; ++i) st->X_trace[(it + 1) * 12 + i] = Xn[i];
         if (last_round) {

@@ -9,9 +9,11 @@
 //                       (reference loop: odometry/pipeline.cpp:166-193), optional in-kernel
 //                       all-reduce of H/b across GPUs through peer mailboxes (NVLink stores)
 //
-// Memory/branch bound FP64 work: no tensor cores.  A node visit is one 64-byte record = two
-// 256-bit read-only loads (LDG.E.256); moving leaves are laid out in getLeafs (DFS) order so the
-// lanes of a warp walk nearly the same path and their loads coalesce / hit L1 at the top levels.
+// Memory/branch bound FP64 work (no tcgen05: there is no dense contraction; the only tensor-pipe
+// use is the register-saving FP64 DMMA fold of the per-correspondence outer products, see
+// warp_accumulate).  A node visit is one 64-byte record = two 256-bit read-only loads
+// (LDG.E.256); moving leaves are laid out in getLeafs (DFS) order so the lanes of a warp walk
+// nearly the same path and their loads coalesce / hit L1 at the top levels.
 // Compiled with -fmad=false; the predicate chain uses __d*_rn intrinsics (arith.h).
 #pragma once
 #include <cuda_runtime.h>
@@ -26,7 +28,8 @@ namespace madicp {
 constexpr int kMaxSlots = 64;      // keyframe slots addressable by one launch
 constexpr int kBlock = 256;        // threads per CTA for every kernel here
 constexpr int kWarps = kBlock / 32;
-constexpr int kAcc = 27;           // 21 lower-triangle entries of H + 6 entries of b
+constexpr int kAcc = 48;           // 6 rows x 8 cols of the accumulator tile: H(r,c) at r*8+c, b(r) at r*8+6
+constexpr int kStage = 13;         // doubles staged per correspondence: sJ[6], J[6], e
 constexpr int kMaxPeers = 16;
 constexpr int kMailboxSlots = 2;   // double-buffered by round parity
 
@@ -45,7 +48,7 @@ struct GnState {
   int round;      // number of completed rounds (release/acquire flag)
   int n_matched;  // matched moving leaves in the last round
   int pad;
-  double H[36];   // last round, full symmetric
+  double H[36];   // last round; H[r*6+c] = sum (scale*J_r)*J_c, both triangles accumulated independently
   double b[6];
   double X_trace[(MADICP_MAX_ITERS + 1) * 12];  // pose before round i; [iters] = final pose
 };
@@ -56,7 +59,7 @@ struct __align__(16) LLCell {
   uint32_t lo, flag_lo, hi, flag_hi;
 };
 struct Mailbox {  // lives on every rank; cell [slot][src_rank][i] is written by src_rank
-  LLCell cell[kMailboxSlots][kMaxPeers][32];
+  LLCell cell[kMailboxSlots][kMaxPeers][kAcc];
 };
 
 struct PeerView {
@@ -97,11 +100,11 @@ __device__ __forceinline__ int descend(const madtree_rec_t* __restrict__ recs, d
   return node;
 }
 
-// Contribution of one correspondence to the 27 accumulators.  Returns false when gated out.
-// acc layout: H lower triangle row-major (r>=c): idx = r*(r+1)/2 + c  (21 values), then b[0..5].
+// One correspondence (reference: odometry/mad_icp.cpp:81-101): gate, error, Jacobian, Huber scale,
+// planarity weight.  Fills v = {sJ[0..5] = scale*J, J[0..5], e}; returns false (v untouched) when
+// the gate rejects the pair.  FP64, no FMA, operand order as arith.h.
 __device__ __forceinline__ bool linearize_one(const double* __restrict__ X, const IcpParams& P, double px, double py,
-                                              double pz, double mlx, double mly, double mlz, const Rec& f,
-                                              double* acc) {
+                                              double pz, double mlx, double mly, double mlz, const Rec& f, double* v) {
   const double src_ball = P.min_ball + P.b_ratio * norm3(px, py, pz);
   const double ex = mlx - f.mx, ey = mly - f.my, ez = mlz - f.mz;
   if (norm3(ex, ey, ez) > src_ball) return false;
@@ -119,74 +122,82 @@ __device__ __forceinline__ bool linearize_one(const double* __restrict__ X, cons
   if (chi > P.rho_ker_sqrt) scale = P.rho_ker_sqrt / chi;
   const double w = 1.0 - f.bbox0 / P.min_ball;
   scale *= w * w;
-  double sJ[6];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) sJ[i] = scale * J[i];
-  int k = 0;
-#pragma unroll
-  for (int r = 0; r < 6; ++r)
-#pragma unroll
-    for (int c = 0; c <= r; ++c) acc[k++] += sJ[r] * J[c];
-#pragma unroll
-  for (int r = 0; r < 6; ++r) acc[21 + r] += sJ[r] * e;
+  for (int i = 0; i < 6; ++i) {
+    v[i] = scale * J[i];
+    v[6 + i] = J[i];
+  }
+  v[12] = e;
   return true;
 }
 
-__device__ __forceinline__ double shfl_down_f64(double v, int off) {
-  int lo = __double2loint(v), hi = __double2hiint(v);
-  lo = __shfl_down_sync(0xffffffffu, lo, off);
-  hi = __shfl_down_sync(0xffffffffu, hi, off);
-  return __hiloint2double(hi, lo);
+// H += sJ^T J, b += sJ^T e for the 32 correspondences a warp holds, on the FP64 tensor pipe:
+// D(8x8) += A(8x4) * B(4x8) with A[r][k] = sJ_r(item k), B[k][c] = J_c(item k) (c<6), e(item k)
+// (c==6), zero padding elsewhere -- 8 DMMA.8x8x4 per 32 items.  The point is not FLOPs (there are
+// few) but registers: the running sums are the 2-double C fragment instead of 42 scalars per
+// thread, which is what lets the descent run at 4 CTAs/SM.  H(r,c) = sum (scale*J_r)*J_c is formed
+// for both triangles independently, like the reference's `scale * J.transpose() * J`.
+// stage: this warp's [32][kStage] doubles in shared memory.  v: this lane's 13 values (zeros if
+// the lane has no correspondence).
+__device__ __forceinline__ void warp_accumulate(double* stage, const double* v, double& c0, double& c1) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int i = 0; i < kStage; ++i) stage[lane * kStage + i] = v[i];
+  __syncwarp();
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    const double* it = stage + (4 * s + t) * kStage;
+    const double a = (g < 6) ? it[g] : 0.0;                      // rows 6,7 of A are padding
+    const double b = (g < 7) ? it[6 + (g < 7 ? g : 6)] : 0.0;    // col 6 of B = e, col 7 padding
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+  }
+  __syncwarp();
 }
 
-// Deterministic CTA reduction of acc[27] -> out[27] (global).  Fixed shuffle tree inside a warp,
-// warps combined in warp order.
-__device__ __forceinline__ void block_reduce_store(double* acc, double (*s_warp)[kAcc], double* out) {
+// Deterministic CTA reduction of the warps' C fragments -> out[kAcc] (global): warps are combined
+// in warp order.  s_red: [kWarps][64] doubles.
+__device__ __forceinline__ void block_reduce_store(double c0, double c1, double (*s_red)[64], double* out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int i = 0; i < kAcc; ++i) {
-    double v = acc[i];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += shfl_down_f64(v, off);
-    if (lane == 0) s_warp[warp][i] = v;
-  }
+  const int g = lane >> 2, t = lane & 3;
+  s_red[warp][g * 8 + 2 * t] = c0;
+  s_red[warp][g * 8 + 2 * t + 1] = c1;
   __syncthreads();
   if (threadIdx.x < kAcc) {
-    double s = s_warp[0][threadIdx.x];
+    double s = s_red[0][threadIdx.x];
 #pragma unroll
-    for (int w2 = 1; w2 < kWarps; ++w2) s += s_warp[w2][threadIdx.x];
+    for (int w2 = 1; w2 < kWarps; ++w2) s += s_red[w2][threadIdx.x];
     out[threadIdx.x] = s;
   }
 }
 
-// Sum `nblk` per-CTA partials (global, written by other SMs -> read with ld.cg) into s_tot[27].
-__device__ __forceinline__ void final_reduce(const double* partial, int nblk, double (*s_warp)[kAcc], double* s_tot) {
-  const int j = threadIdx.x & 31, g = threadIdx.x >> 5;
+// Sum `nblk` per-CTA partials (global, written by other SMs -> read with ld.cg) into s_tot[kAcc]:
+// four interleaved strands over the CTA index, combined in strand order.
+__device__ __forceinline__ void final_reduce(const double* partial, int nblk, double (*s_red)[64], double* s_tot) {
+  const int j = threadIdx.x & 63, g = threadIdx.x >> 6;
   __syncthreads();
   if (j < kAcc) {
     double s = 0.0;
-    for (int blk = g; blk < nblk; blk += kWarps) s += __ldcg(partial + size_t(blk) * kAcc + j);
-    s_warp[g][j] = s;
+    for (int blk = g; blk < nblk; blk += kBlock / 64) s += __ldcg(partial + size_t(blk) * kAcc + j);
+    s_red[g][j] = s;
   }
   __syncthreads();
   if (threadIdx.x < kAcc) {
-    double s = s_warp[0][threadIdx.x];
+    double s = s_red[0][threadIdx.x];
 #pragma unroll
-    for (int w2 = 1; w2 < kWarps; ++w2) s += s_warp[w2][threadIdx.x];
+    for (int w2 = 1; w2 < kBlock / 64; ++w2) s += s_red[w2][threadIdx.x];
     s_tot[threadIdx.x] = s;
   }
   __syncthreads();
 }
 
 __device__ __forceinline__ void unpack_Hb(const double* tot, double* H, double* b) {
-  int k = 0;
-  for (int r = 0; r < 6; ++r)
-    for (int c = 0; c <= r; ++c) {
-      H[r * 6 + c] = tot[k];
-      H[c * 6 + r] = tot[k];
-      ++k;
-    }
-  for (int r = 0; r < 6; ++r) b[r] = tot[21 + r];
+  for (int r = 0; r < 6; ++r) {
+    for (int c = 0; c < 6; ++c) H[r * 6 + c] = tot[r * 8 + c];
+    b[r] = tot[r * 8 + 6];
+  }
 }
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {

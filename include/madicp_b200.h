@@ -164,6 +164,16 @@ int madicp_comm_export(madicp_ctx_t* ctx, void* handle_out /* 64 bytes */);
 int madicp_comm_connect(madicp_ctx_t* ctx, int rank, int world, const void* all_handles /* world x 64 bytes */);
 int madicp_comm_world(const madicp_ctx_t* ctx);
 
+/* ================================ tuning / debug (not part of the drop-in surface) ============ */
+/* Per-round SM-clock stamps of the persistent kernel: enable != 0 switches recording on for the
+ * following launches; out (nullable) receives rounds x 8 int64 of the LAST launch:
+ * [0] item phase of CTA 0, [1] round start -> last CTA arrived, [2] fold of the per-CTA partials,
+ * [3] peer exchange + matched count, [4] solve + publish (cycles).  Returns rows written. */
+int madicp_debug_timing(madicp_ctx_t* ctx, int enable, int64_t* out, int max_rounds);
+/* Resident CTAs per SM used by the persistent kernel (clamped to the occupancy limit; returns the
+ * value in effect). */
+int madicp_set_gn_grid(madicp_ctx_t* ctx, int ctas_per_sm);
+
 #ifdef __cplusplus
 }
 #endif

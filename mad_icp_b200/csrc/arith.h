@@ -50,7 +50,9 @@ MADICP_HD void iso_apply(const double* X, double px, double py, double pz, doubl
 
 // C = A*B for poses (row-major 3x4): R = Ra*Rb, t = Ra*tb + ta  (reference: odometry/mad_icp.cpp:116)
 MADICP_HD void iso_mul(const double* A, const double* B, double* C) {
+#pragma unroll
   for (int r = 0; r < 3; ++r) {
+#pragma unroll
     for (int c = 0; c < 3; ++c) C[r * 4 + c] = dot3(A[r * 4], A[r * 4 + 1], A[r * 4 + 2], B[c], B[4 + c], B[8 + c]);
     C[r * 4 + 3] = add_(dot3(A[r * 4], A[r * 4 + 1], A[r * 4 + 2], B[3], B[7], B[11]), A[r * 4 + 3]);
   }

@@ -144,6 +144,7 @@ struct GnArgs {
   unsigned char* peer_matched[kMaxPeers];  // world > 1: every rank's matched array (peer mapped)
   double* partial;                      // gridDim.x * kAcc
   GnState* st;
+  long long* dbg;                       // nullable: per-round SM-clock stamps (madicp_debug_timing)
 };
 
 // GN: the whole ICP loop.  Persistent cooperative grid (all CTAs co-resident); one software grid
@@ -174,6 +175,8 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
     __syncthreads();
     const bool last_round = (it == A.iters - 1);
     double c0 = 0.0, c1 = 0.0;
+    long long t_begin = 0;
+    if (A.dbg && threadIdx.x == 0) t_begin = clock64();
     for (int64_t w0 = int64_t(blockIdx.x) * kBlock + (threadIdx.x - lane); w0 < total;
          w0 += int64_t(gridDim.x) * kBlock) {
       const int64_t w = w0 + lane;
@@ -198,6 +201,7 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
       warp_accumulate(stage, v, c0, c1);
     }
     __syncthreads();  // staging tiles are dead; s_red aliases them
+    if (A.dbg && threadIdx.x == 0 && blockIdx.x == 0) A.dbg[it * 8 + 0] = clock64() - t_begin;  // item phase, CTA 0
     block_reduce_store(c0, c1, s_red, A.partial + size_t(blockIdx.x) * kAcc);
     if (multi && last_round)
       __threadfence_system();  // matched flags stored to peers become visible before our LL cells
@@ -207,8 +211,14 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
     if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket, 1) == (it + 1) * int(gridDim.x) - 1);
     __syncthreads();
     if (s_last) {
+      long long t0 = 0, t1 = 0, t2 = 0;
+      if (A.dbg && threadIdx.x == 0) {
+        t0 = clock64();
+        A.dbg[it * 8 + 1] = t0 - t_begin;  // round start -> last CTA arrived (that CTA's clock)
+      }
       __threadfence();
       final_reduce(A.partial, gridDim.x, s_red, s_tot);
+      if (A.dbg && threadIdx.x == 0) t1 = clock64();
       if (multi) {
         if (last_round) __threadfence_system();
         peer_allreduce(A.peers, A.peers.epoch_base + uint32_t(it) + 1u, s_tot, s_peer);
@@ -222,6 +232,7 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
         __syncthreads();
       }
       if (threadIdx.x == 0) {
+        if (A.dbg) t2 = clock64();
         double H[36], b[6], Xn[12];
         unpack_Hb(s_tot, H, b);
         for (int i = 0; i < 12; ++i) Xn[i] = s_X[i];
@@ -236,6 +247,11 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
         }
         __threadfence();
         st_release_gpu(&st->round, it + 1);
+        if (A.dbg) {
+          A.dbg[it * 8 + 2] = t1 - t0;         // fold of the per-CTA partials
+          A.dbg[it * 8 + 3] = t2 - t1;         // peer exchange + matched count
+          A.dbg[it * 8 + 4] = clock64() - t2;  // solve + pose update + publish
+        }
       }
     }
   }
@@ -310,6 +326,7 @@ struct madicp_ctx {
   unsigned char* h_matched = nullptr;
   int gn_grid = 0;
   int last_iters = 0;
+  long long* d_dbg = nullptr;  // MADICP_MAX_ITERS x 8 clock stamps when debug timing is on
   int64_t launches = 0;
   // peers
   int rank = 0, world = 1;
@@ -426,6 +443,7 @@ void madicp_destroy(madicp_ctx_t* c) {
   cudaFree(c->d_state);
   cudaFree(c->d_X);
   cudaFree(c->d_comm);
+  cudaFree(c->d_dbg);
   cudaFreeHost(c->h_pinned);
   cudaFreeHost(c->h_state);
   cudaFreeHost(c->h_matched);
@@ -654,6 +672,7 @@ int madicp_register_async(madicp_ctx_t* c, int iters, const double X0[12]) {
   A.matched = c->d_comm->matched[mb];
   A.partial = c->d_partial;
   A.st = c->d_state;
+  A.dbg = c->d_dbg;
   c->epoch += uint32_t(iters);
   // control words + initial pose in one small pinned H2D copy
   GnState* hs = c->h_state;
@@ -790,5 +809,34 @@ int madicp_comm_connect(madicp_ctx_t* c, int rank, int world, const void* all_ha
 }
 
 int madicp_comm_world(const madicp_ctx_t* c) { return c ? c->world : MADICP_ERR_INVALID; }
+
+// ------------------------------------------------------------------------------ debug
+int madicp_debug_timing(madicp_ctx_t* c, int enable, int64_t* out, int max_rounds) {
+  if (!c) return MADICP_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  int rows = 0;
+  if (out && c->d_dbg) {
+    rows = std::min(max_rounds, c->last_iters);
+    CK(cudaMemcpy(out, c->d_dbg, size_t(rows) * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+  }
+  if (enable && !c->d_dbg) {
+    CK(cudaMalloc(&c->d_dbg, MADICP_MAX_ITERS * 8 * sizeof(long long)));
+    CK(cudaMemset(c->d_dbg, 0, MADICP_MAX_ITERS * 8 * sizeof(long long)));
+  } else if (!enable && c->d_dbg) {
+    cudaFree(c->d_dbg);
+    c->d_dbg = nullptr;
+  }
+  return rows;
+}
+
+int madicp_set_gn_grid(madicp_ctx_t* c, int ctas_per_sm) {
+  if (!c || ctas_per_sm < 1) return MADICP_ERR_INVALID;
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gn_loop, kBlock, 0));
+  if (ctas_per_sm > per_sm) ctas_per_sm = per_sm;
+  c->gn_grid = ctas_per_sm * c->sm_count;
+  return ctas_per_sm;
+}
 
 }  // extern "C"

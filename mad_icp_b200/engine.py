@@ -25,8 +25,11 @@ class FlatTree:
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
-            capi.lib().madtree_free(h)
             self._h = None
+            try:
+                capi.lib().madtree_free(h)
+            except TypeError:  # interpreter shutdown
+                pass
 
     @property
     def num_nodes(self):
@@ -85,8 +88,11 @@ class Registrar:
     def close(self):
         h = getattr(self, "_h", None)
         if h:
-            capi.lib().madicp_destroy(h)
             self._h = None
+            try:
+                capi.lib().madicp_destroy(h)
+            except TypeError:  # interpreter shutdown: module globals already torn down
+                pass
 
     __del__ = close
 
@@ -198,6 +204,16 @@ class Registrar:
         check(capi.lib().madicp_search_cloud(self._h, slot, as_d(q), n, as_i(o), as_d(p), as_d(nr), as_d(d)),
               "madicp_search_cloud")
         return dict(ordinals=o, points=p, normals=nr, dists=d)
+
+    # ---- tuning / debug
+    def debug_timing(self, enable=True, fetch=True):
+        buf = np.zeros((64, 8), np.int64)
+        rows = check(capi.lib().madicp_debug_timing(self._h, int(enable), buf.ctypes.data_as(C.POINTER(C.c_int64))
+                                                    if fetch else None, 64))
+        return buf[:rows]
+
+    def set_gn_grid(self, ctas_per_sm):
+        return check(capi.lib().madicp_set_gn_grid(self._h, ctas_per_sm))
 
     # ---- multi-GPU -------------------------------------------------------------------------
     def comm_export(self):

@@ -33,3 +33,14 @@ for iters in (1, 2, 5, 10, 15, 20):
     w = timed(lambda: reg.register_async(X0, iters))
     c = timed(lambda: reg.register_async(X0, iters), cold=True)
     print(f"gn_loop iters={iters:2d}: warm median {w[0]:8.1f} us (min {w[1]:8.1f})   cold median {c[0]:8.1f} us (min {c[1]:8.1f})")
+
+# per-round phase breakdown (SM cycles @ ~1.965 GHz)
+reg.debug_timing(True, fetch=False)
+for cps in (4, 3, 2, 1):
+    eff = reg.set_gn_grid(cps)
+    w = timed(lambda: reg.register_async(X0, 10))
+    reg.register_async(X0, 10); torch.cuda.synchronize()
+    d = reg.debug_timing(True)
+    print(f"ctas/SM={eff}: warm 10-iter median {w[0]:.1f} us; cycles/round (median over rounds) items(cta0)={np.median(d[:,0]):.0f} "
+          f"start->all_arrived={np.median(d[:,1]):.0f} fold={np.median(d[:,2]):.0f} xchg+count={np.median(d[:,3]):.0f} solve={np.median(d[:,4]):.0f}")
+reg.set_gn_grid(4)

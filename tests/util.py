@@ -12,7 +12,9 @@ def pose_error(Xa, Xb):
     """(rotation angle [rad], translation distance [m]) between two 3x4 / 4x4 poses."""
     Xa, Xb = np.asarray(Xa)[:3], np.asarray(Xb)[:3]
     dR = Xa[:, :3] @ Xb[:, :3].T
-    ang = float(np.arccos(np.clip((np.trace(dR) - 1.0) / 2.0, -1.0, 1.0)))
+    # atan2 form: arccos((tr-1)/2) has a ~2e-8 rad noise floor near the identity
+    s = 0.5 * np.linalg.norm([dR[2, 1] - dR[1, 2], dR[0, 2] - dR[2, 0], dR[1, 0] - dR[0, 1]])
+    ang = float(np.arctan2(s, (np.trace(dR) - 1.0) / 2.0))
     return ang, float(np.linalg.norm(Xa[:, 3] - Xb[:, 3]))
 
 

@@ -5,277 +5,17 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
-#include "kernels.cuh"
+#include "device_kernels.cuh"
 
 namespace madicp {
 
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
-
-// =============================================================================================
-// Kernels
-// =============================================================================================
-
-// K1: one thread per (keyframe k, moving leaf q), item w = k*L + q so a warp holds 32 consecutive
-// leaves (DFS order => spatially coherent) of one keyframe.
-__global__ void __launch_bounds__(kBlock)
-k_search(const __grid_constant__ ModelView model, const double* __restrict__ moving, int L,
-         const double* __restrict__ Xp, int* __restrict__ hit, int* __restrict__ ordinals) {
-  double X[12];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) X[i] = Xp[i];
-  const int64_t total = int64_t(model.K) * L;
-  for (int64_t w = int64_t(blockIdx.x) * kBlock + threadIdx.x; w < total; w += int64_t(gridDim.x) * kBlock) {
-    const int k = int(w / L), q = int(w - int64_t(k) * L);
-    const double px = moving[3 * q], py = moving[3 * q + 1], pz = moving[3 * q + 2];
-    double mx, my, mz;
-    iso_apply(X, px, py, pz, mx, my, mz);
-    Rec leaf;
-    const int node = descend(model.recs[k], mx, my, mz, leaf);
-    if (hit) hit[w] = node;
-    if (ordinals) ordinals[w] = -1 - leaf.link;
-  }
-}
-
-// K2: reads K1's leaf record index, folds the 6x7 H/b tile per warp (FP64 DMMA), per-CTA partials, and
-// the last CTA to arrive folds the partials in CTA order into st->H / st->b.
-__global__ void __launch_bounds__(kBlock)
-k_linearize(const __grid_constant__ ModelView model, const double* __restrict__ moving, int L,
-            const double* __restrict__ Xp, const __grid_constant__ IcpParams P, const int* __restrict__ hit,
-            unsigned char* __restrict__ matched, double* __restrict__ partial, GnState* st) {
-  __shared__ double s_stage[kWarps][32 * kStage];
-  __shared__ double s_red[kWarps][64];
-  __shared__ double s_tot[kAcc];
-  __shared__ int s_last;
-  double X[12];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) X[i] = Xp[i];
-  double c0 = 0.0, c1 = 0.0;
-  const int64_t total = int64_t(model.K) * L;
-  const int lane = threadIdx.x & 31;
-  // warp-uniform trip count: every lane takes part in the DMMA fold, lanes past the end stage zeros
-  for (int64_t w0 = int64_t(blockIdx.x) * kBlock + (threadIdx.x - lane); w0 < total; w0 += int64_t(gridDim.x) * kBlock) {
-    const int64_t w = w0 + lane;
-    double v[kStage];
-#pragma unroll
-    for (int i = 0; i < kStage; ++i) v[i] = 0.0;
-    if (w < total) {
-      const int k = int(w / L), q = int(w - int64_t(k) * L);
-      const double px = moving[3 * q], py = moving[3 * q + 1], pz = moving[3 * q + 2];
-      double mx, my, mz;
-      iso_apply(X, px, py, pz, mx, my, mz);
-      const Rec f = load_rec(model.recs[k] + hit[w]);
-      if (linearize_one(X, P, px, py, pz, mx, my, mz, f, v) && matched) matched[q] = 1;
-    }
-    warp_accumulate(s_stage[threadIdx.x >> 5], v, c0, c1);
-  }
-  block_reduce_store(c0, c1, s_red, partial + size_t(blockIdx.x) * kAcc);
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket, 1) == int(gridDim.x) - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  final_reduce(partial, gridDim.x, s_red, s_tot);
-  if (threadIdx.x == 0) {
-    unpack_Hb(s_tot, st->H, st->b);
-    st->ticket = 0;
-  }
-}
-
-// K3: updateState for H,b already on the device (single thread; ~1 us).
-__global__ void k_solve(const double* __restrict__ H, const double* __restrict__ b, double* X) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double Hl[36], bl[6], Xl[12];
-    for (int i = 0; i < 36; ++i) Hl[i] = H[i];
-    for (int i = 0; i < 6; ++i) bl[i] = b[i];
-    for (int i = 0; i < 12; ++i) Xl[i] = X[i];
-    gn_update_pose(Hl, bl, Xl, nullptr);
-    for (int i = 0; i < 12; ++i) X[i] = Xl[i];
-  }
-}
-
-// In-kernel all-reduce of the 48-value accumulator tile across GPUs (called by ONE CTA per rank).
-// Every rank stores its partial into every rank's mailbox (own included) with 16-byte LL cells,
-// then spins on its own mailbox until all `world` partials of this epoch are present and sums them
-// in rank order -> identical bits on every rank.
-__device__ __forceinline__ void peer_allreduce(const PeerView& pv, uint32_t epoch, double* s_tot,
-                                               double (*s_stage)[kAcc]) {
-  const int slot = int(epoch & 1u);
-  for (int idx = threadIdx.x; idx < pv.world * kAcc; idx += kBlock) {
-    const int r = idx / kAcc, i = idx - r * kAcc;
-    const double v = s_tot[i];
-    const uint32_t lo = uint32_t(__double2loint(v)), hi = uint32_t(__double2hiint(v));
-    LLCell* dst = &pv.box[r]->cell[slot][pv.rank][i];
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(lo), "r"(epoch), "r"(hi), "r"(epoch)
-                 : "memory");
-  }
-  for (int idx = threadIdx.x; idx < pv.world * kAcc; idx += kBlock) {
-    const int r = idx / kAcc, i = idx - r * kAcc;
-    const LLCell* src = &pv.box[pv.rank]->cell[slot][r][i];
-    uint32_t lo, f0, hi, f1;
-    do {
-      asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(src)
-                   : "memory");
-    } while (f0 != epoch || f1 != epoch);
-    s_stage[r][i] = __hiloint2double(int(hi), int(lo));
-  }
-  __syncthreads();
-  if (threadIdx.x < kAcc) {
-    double s = s_stage[0][threadIdx.x];
-    for (int r = 1; r < pv.world; ++r) s += s_stage[r][threadIdx.x];
-    s_tot[threadIdx.x] = s;
-  }
-  __syncthreads();
-}
-
-struct GnArgs {
-  ModelView model;
-  IcpParams P;
-  PeerView peers;  // world <= 1 => single GPU
-  const double* moving;
-  int L;
-  int iters;
-  unsigned char* matched;               // local matched flags (L bytes), zeroed by the host
-  unsigned char* peer_matched[kMaxPeers];  // world > 1: every rank's matched array (peer mapped)
-  double* partial;                      // gridDim.x * kAcc
-  GnState* st;
-  long long* dbg;                       // nullable: per-round SM-clock stamps (madicp_debug_timing)
-};
-
-// GN: the whole ICP loop.  Persistent cooperative grid (all CTAs co-resident); one software grid
-// barrier per round: CTAs publish partials, take a ticket, the last one reduces / exchanges /
-// solves and releases st->round, the others spin on it with ld.acquire.gpu.
-__global__ void __launch_bounds__(kBlock, 4)
-k_gn_loop(const __grid_constant__ GnArgs A) {
-  // shared memory: the per-warp staging tiles are only live inside the item loop, so the reduction
-  // scratch and the peer staging alias them
-  __shared__ __align__(16) double s_buf[kWarps * 32 * kStage];
-  __shared__ double s_tot[kAcc];
-  __shared__ double s_X[12];
-  __shared__ int s_last;
-  __shared__ int s_count[kWarps];
-  double(*s_red)[64] = reinterpret_cast<double(*)[64]>(s_buf);               // [kWarps][64]
-  double(*s_peer)[kAcc] = reinterpret_cast<double(*)[kAcc]>(s_buf + kWarps * 64);  // [kMaxPeers][kAcc]
-  static_assert(kWarps * 64 + kMaxPeers * kAcc <= kWarps * 32 * kStage, "scratch must fit in the staging tiles");
-  GnState* st = A.st;
-  const int64_t total = int64_t(A.model.K) * A.L;
-  const bool multi = A.peers.world > 1;
-  const int lane = threadIdx.x & 31;
-  double* stage = s_buf + (threadIdx.x >> 5) * (32 * kStage);
-  for (int it = 0; it < A.iters; ++it) {
-    if (threadIdx.x == 0 && it > 0)
-      while (ld_acquire_gpu(&st->round) < it) {}
-    __syncthreads();  // also: everyone is done with s_buf/s_X of the previous round
-    if (threadIdx.x < 12) s_X[threadIdx.x] = __ldcg(&st->X_trace[it * 12 + threadIdx.x]);
-    __syncthreads();
-    const bool last_round = (it == A.iters - 1);
-    double c0 = 0.0, c1 = 0.0;
-    long long t_begin = 0;
-    if (A.dbg && threadIdx.x == 0) t_begin = clock64();
-    for (int64_t w0 = int64_t(blockIdx.x) * kBlock + (threadIdx.x - lane); w0 < total;
-         w0 += int64_t(gridDim.x) * kBlock) {
-      const int64_t w = w0 + lane;
-      double v[kStage];
-#pragma unroll
-      for (int i = 0; i < kStage; ++i) v[i] = 0.0;
-      if (w < total) {
-        const int k = int(w / A.L), q = int(w - int64_t(k) * A.L);
-        const double px = A.moving[3 * q], py = A.moving[3 * q + 1], pz = A.moving[3 * q + 2];
-        double mx, my, mz;
-        iso_apply(s_X, px, py, pz, mx, my, mz);
-        Rec f;
-        descend(A.model.recs[k], mx, my, mz, f);
-        if (linearize_one(s_X, A.P, px, py, pz, mx, my, mz, f, v) && last_round) {
-          if (multi) {
-            for (int r = 0; r < A.peers.world; ++r) A.peer_matched[r][q] = 1;
-          } else {
-            A.matched[q] = 1;
-          }
-        }
-      }
-      warp_accumulate(stage, v, c0, c1);
-    }
-    __syncthreads();  // staging tiles are dead; s_red aliases them
-    if (A.dbg && threadIdx.x == 0 && blockIdx.x == 0) A.dbg[it * 8 + 0] = clock64() - t_begin;  // item phase, CTA 0
-    block_reduce_store(c0, c1, s_red, A.partial + size_t(blockIdx.x) * kAcc);
-    if (multi && last_round)
-      __threadfence_system();  // matched flags stored to peers become visible before our LL cells
-    else
-      __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket, 1) == (it + 1) * int(gridDim.x) - 1);
-    __syncthreads();
-    if (s_last) {
-      long long t0 = 0, t1 = 0, t2 = 0;
-      if (A.dbg && threadIdx.x == 0) {
-        t0 = clock64();
-        A.dbg[it * 8 + 1] = t0 - t_begin;  // round start -> last CTA arrived (that CTA's clock)
-      }
-      __threadfence();
-      final_reduce(A.partial, gridDim.x, s_red, s_tot);
-      if (A.dbg && threadIdx.x == 0) t1 = clock64();
-      if (multi) {
-        if (last_round) __threadfence_system();
-        peer_allreduce(A.peers, A.peers.epoch_base + uint32_t(it) + 1u, s_tot, s_peer);
-        if (last_round) __threadfence_system();
-      }
-      if (last_round) {  // count matched moving leaves (all writers are done: they took tickets)
-        int c = 0;
-        for (int q = threadIdx.x; q < A.L; q += kBlock) c += (__ldcv(A.matched + q) != 0);
-        for (int off = 16; off > 0; off >>= 1) c += __shfl_down_sync(0xffffffffu, c, off);
-        if (lane == 0) s_count[threadIdx.x >> 5] = c;
-        __syncthreads();
-      }
-      if (threadIdx.x == 0) {
-        if (A.dbg) t2 = clock64();
-        double H[36], b[6], Xn[12];
-        unpack_Hb(s_tot, H, b);
-        for (int i = 0; i < 12; ++i) Xn[i] = s_X[i];
-        gn_update_pose(H, b, Xn, nullptr);
-        for (int i = 0; i < 12; ++i) st->X_trace[(it + 1) * 12 + i] = Xn[i];
-        if (last_round) {
-          for (int i = 0; i < 36; ++i) st->H[i] = H[i];
-          for (int i = 0; i < 6; ++i) st->b[i] = b[i];
-          int c = 0;
-          for (int w2 = 0; w2 < kWarps; ++w2) c += s_count[w2];
-          st->n_matched = c;
-        }
-        __threadfence();
-        st_release_gpu(&st->round, it + 1);
-        if (A.dbg) {
-          A.dbg[it * 8 + 2] = t1 - t0;         // fold of the per-CTA partials
-          A.dbg[it * 8 + 3] = t2 - t1;         // peer exchange + matched count
-          A.dbg[it * 8 + 4] = clock64() - t2;  // solve + pose update + publish
-        }
-      }
-    }
-  }
-}
-
-// MADtreeWrapper::searchCloud / searchCloudDist: arbitrary query points against one slot.
-__global__ void __launch_bounds__(kBlock)
-k_search_cloud(const madtree_rec_t* __restrict__ recs, const double* __restrict__ q, int64_t n,
-               int* __restrict__ ordinals, double* __restrict__ points, double* __restrict__ normals,
-               double* __restrict__ dists) {
-  for (int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock) {
-    const double qx = q[3 * i], qy = q[3 * i + 1], qz = q[3 * i + 2];
-    Rec f;
-    descend(recs, qx, qy, qz, f);
-    if (ordinals) ordinals[i] = -1 - f.link;
-    if (points) {
-      points[3 * i] = f.mx; points[3 * i + 1] = f.my; points[3 * i + 2] = f.mz;
-    }
-    if (normals) {
-      normals[3 * i] = f.dx; normals[3 * i + 1] = f.dy; normals[3 * i + 2] = f.dz;
-    }
-    if (dists) dists[i] = norm3(qx - f.mx, qy - f.my, qz - f.mz);
-  }
-}
 
 }  // namespace madicp
 
@@ -286,7 +26,8 @@ using namespace madicp;
 
 namespace {
 struct Slot {
-  madtree_rec_t* d_recs = nullptr;
+  madtree_rec_t* d_recs = nullptr;  // exact 64-byte records (breadth-first)
+  FastRec* d_fast = nullptr;        // FP32 shadows, index = record index + 1
   int n_nodes = 0, n_leaves = 0;
   size_t cap_nodes = 0;
 };
@@ -308,7 +49,9 @@ struct madicp_ctx {
   int sm_count = 0;
   std::vector<Slot> slots;
   IcpParams P{0.2, 0.31622776601683794, 0.02};
-  double* d_moving = nullptr;
+  double* d_moving = nullptr;               // raw L x 3 means as uploaded
+  Moving4* d_mov4 = nullptr;                // prepared (mean, gate radius) records the kernels read
+  bool mov4_stale = true;                   // params changed / new means since the last preparation
   unsigned char* d_step_matched = nullptr;  // matched flags of the step API (madicp_linearize)
   int L = 0;
   size_t cap_moving = 0;
@@ -325,6 +68,7 @@ struct madicp_ctx {
   GnState* h_state = nullptr;  // pinned mirror
   unsigned char* h_matched = nullptr;
   int gn_grid = 0;
+  int gn_threads = 1024;
   int last_iters = 0;
   long long* d_dbg = nullptr;  // MADICP_MAX_ITERS x 8 clock stamps when debug timing is on
   int64_t launches = 0;
@@ -347,8 +91,15 @@ static ModelView make_view(const madicp_ctx* c) {
   ModelView v;
   v.K = 0;
   for (int s = 0; s < c->max_keyframes; ++s)
-    if (c->slots[s].n_nodes > 0) v.recs[v.K++] = c->slots[s].d_recs;
-  for (int i = v.K; i < kMaxSlots; ++i) v.recs[i] = nullptr;
+    if (c->slots[s].n_nodes > 0) {
+      v.recs[v.K] = c->slots[s].d_recs;
+      v.fast[v.K] = c->slots[s].d_fast;
+      ++v.K;
+    }
+  for (int i = v.K; i < kMaxSlots; ++i) {
+    v.recs[i] = nullptr;
+    v.fast[i] = nullptr;
+  }
   return v;
 }
 
@@ -364,8 +115,33 @@ static int ensure_items(madicp_ctx* c, size_t items) {
   return MADICP_OK;
 }
 
+template <int THREADS>
+static int configure_gn_t(madicp_ctx* c, int ctas_per_sm_cap) {
+  CK(cudaFuncSetAttribute(k_gn_loop<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          int(gn_dynamic_smem<THREADS>())));
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gn_loop<THREADS>, THREADS, gn_dynamic_smem<THREADS>()));
+  if (per_sm < 1) {
+    set_error("k_gn_loop does not fit on an SM");
+    return MADICP_ERR_CUDA;
+  }
+  if (per_sm > ctas_per_sm_cap) per_sm = ctas_per_sm_cap;
+  c->gn_threads = THREADS;
+  c->gn_grid = per_sm * c->sm_count;
+  return MADICP_OK;
+}
+// Persistent-kernel shape: THREADS per CTA (256 / 512 / 1024) and at most `ctas_per_sm_cap` CTAs per SM.
+static int configure_gn(madicp_ctx* c, int threads, int ctas_per_sm_cap) {
+  switch (threads) {
+    case 256: return configure_gn_t<256>(c, ctas_per_sm_cap);
+    case 512: return configure_gn_t<512>(c, ctas_per_sm_cap);
+    case 1024: return configure_gn_t<1024>(c, ctas_per_sm_cap);
+    default: set_error("persistent kernel supports 256, 512 or 1024 threads per CTA"); return MADICP_ERR_INVALID;
+  }
+}
+
 static int grid_for(const madicp_ctx* c, int64_t items) {
-  int64_t g = (items + kBlock - 1) / kBlock;
+  int64_t g = (items + kStepBlock - 1) / kStepBlock;
   const int64_t cap = int64_t(c->sm_count) * 8;  // 8 CTAs of 256 threads fill an SM
   if (g > cap) g = cap;
   if (g < 1) g = 1;
@@ -413,14 +189,11 @@ int madicp_create(madicp_ctx_t** out, int device, int max_keyframes) {
   CK(cudaMallocHost(&c->h_pinned, sizeof(double) * 64));
   CK(cudaMallocHost(&c->h_state, sizeof(GnState)));
   CK(cudaMallocHost(&c->h_matched, kMatchedCap));
-  int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gn_loop, kBlock, 0));
-  if (per_sm < 1) {
-    set_error("madicp_create: k_gn_loop does not fit on an SM");
-    return MADICP_ERR_CUDA;
-  }
-  c->gn_grid = per_sm * c->sm_count;
-  c->cap_partial = size_t(std::max(c->gn_grid, c->sm_count * 8)) * kAcc;
+  int threads = 1024;
+  if (const char* e = getenv("MADICP_GN_THREADS")) threads = atoi(e);
+  int rc = configure_gn(c, threads, 1024);
+  if (rc) return rc;
+  c->cap_partial = size_t(c->sm_count) * 8 * kAcc;
   CK(cudaMalloc(&c->d_partial, c->cap_partial * sizeof(double)));
   c->peer_comm[0] = c->d_comm;
   *out = c;
@@ -433,9 +206,12 @@ void madicp_destroy(madicp_ctx_t* c) {
   cudaStreamSynchronize(c->stream);
   for (int r = 0; r < c->world; ++r)
     if (c->world > 1 && r != c->rank && c->peer_comm[r]) cudaIpcCloseMemHandle(c->peer_comm[r]);
-  for (Slot& s : c->slots)
+  for (Slot& s : c->slots) {
     if (s.d_recs) cudaFree(s.d_recs);
+    if (s.d_fast) cudaFree(s.d_fast);
+  }
   cudaFree(c->d_moving);
+  cudaFree(c->d_mov4);
   cudaFree(c->d_step_matched);
   cudaFree(c->d_hit);
   cudaFree(c->d_ord);
@@ -459,6 +235,7 @@ int madicp_set_params(madicp_ctx_t* c, double min_ball, double rho_ker, double b
   c->P.min_ball = min_ball;
   c->P.rho_ker_sqrt = sqrt(rho_ker);
   c->P.b_ratio = b_ratio;
+  c->mov4_stale = true;  // the gate radius depends on min_ball and b_ratio
   return MADICP_OK;
 }
 
@@ -479,12 +256,18 @@ int madicp_put_keyframe_records(madicp_ctx_t* c, int slot, const madtree_rec_t* 
   if (size_t(n_nodes) > s.cap_nodes) {
     CK(cudaStreamSynchronize(c->stream));
     if (s.d_recs) cudaFree(s.d_recs);
+    if (s.d_fast) cudaFree(s.d_fast);
     s.d_recs = nullptr;
+    s.d_fast = nullptr;
     s.cap_nodes = 0;
     CK(cudaMalloc(&s.d_recs, size_t(n_nodes) * sizeof(madtree_rec_t)));
+    CK(cudaMalloc(&s.d_fast, (size_t(n_nodes) + 2) * sizeof(FastRec)));
     s.cap_nodes = n_nodes;
   }
   CK(cudaMemcpyAsync(s.d_recs, recs, size_t(n_nodes) * sizeof(madtree_rec_t), cudaMemcpyHostToDevice, c->stream));
+  k_prepare_fast<<<(n_nodes + kStepBlock - 1) / kStepBlock, kStepBlock, 0, c->stream>>>(s.d_recs, n_nodes, s.d_fast);
+  c->launches++;
+  CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));  // caller may free/modify the host tree right after
   s.n_nodes = n_nodes;
   s.n_leaves = n_leaves;
@@ -534,6 +317,15 @@ int64_t madicp_model_nodes(const madicp_ctx_t* c) {
 }
 int64_t madicp_kernel_launches(const madicp_ctx_t* c) { return c ? c->launches : 0; }
 
+static int prepare_moving(madicp_ctx* c) {
+  if (!c->mov4_stale || c->L < 1) return MADICP_OK;
+  k_prepare_moving<<<(c->L + kStepBlock - 1) / kStepBlock, kStepBlock, 0, c->stream>>>(c->d_moving, c->L, c->P, c->d_mov4);
+  c->launches++;
+  CK(cudaGetLastError());
+  c->mov4_stale = false;
+  return MADICP_OK;
+}
+
 int madicp_set_moving(madicp_ctx_t* c, const double* means, int L) {
   if (!c || !means || L < 1 || size_t(L) > kMatchedCap) {
     set_error("madicp_set_moving: bad arguments (1 <= L <= 1048576)");
@@ -543,18 +335,22 @@ int madicp_set_moving(madicp_ctx_t* c, const double* means, int L) {
   if (size_t(L) > c->cap_moving) {
     CK(cudaStreamSynchronize(c->stream));
     if (c->d_moving) cudaFree(c->d_moving);
+    if (c->d_mov4) cudaFree(c->d_mov4);
     if (c->d_step_matched) cudaFree(c->d_step_matched);
     c->d_moving = nullptr;
+    c->d_mov4 = nullptr;
     c->d_step_matched = nullptr;
     c->cap_moving = 0;
     const size_t cap = size_t(L) + size_t(L) / 4 + 1024;
     CK(cudaMalloc(&c->d_moving, cap * 3 * sizeof(double)));
+    CK(cudaMalloc(&c->d_mov4, cap * sizeof(Moving4)));
     CK(cudaMalloc(&c->d_step_matched, cap));
     c->cap_moving = cap;
   }
   CK(cudaMemcpyAsync(c->d_moving, means, size_t(L) * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   c->L = L;
-  return MADICP_OK;
+  c->mov4_stale = true;
+  return prepare_moving(c);
 }
 
 static int check_ready(madicp_ctx* c, const char* who) {
@@ -574,8 +370,10 @@ static int launch_search(madicp_ctx* c, const ModelView& mv, const double* d_X, 
   const int64_t items = int64_t(mv.K) * c->L;
   int rc = ensure_items(c, size_t(items));
   if (rc) return rc;
-  k_search<<<grid_for(c, items), kBlock, 0, c->stream>>>(mv, c->d_moving, c->L, d_X, c->d_hit,
-                                                        want_ord ? c->d_ord : nullptr);
+  rc = prepare_moving(c);
+  if (rc) return rc;
+  k_search<<<grid_for(c, items), kStepBlock, 0, c->stream>>>(mv, c->d_mov4, c->L, d_X, c->d_hit,
+                                                            want_ord ? c->d_ord : nullptr);
   c->launches++;
   CK(cudaGetLastError());
   return MADICP_OK;
@@ -618,8 +416,8 @@ int madicp_linearize(madicp_ctx_t* c, const double X[12], double H[36], double b
   CK(cudaMemsetAsync(c->d_step_matched, 0, size_t(c->L), c->stream));
   const int64_t items = int64_t(mv.K) * c->L;
   const int grid = grid_for(c, items);
-  k_linearize<<<grid, kBlock, 0, c->stream>>>(mv, c->d_moving, c->L, c->d_X, c->P, c->d_hit, c->d_step_matched,
-                                             c->d_partial, c->d_state);
+  k_linearize<<<grid, kStepBlock, 0, c->stream>>>(mv, c->d_mov4, c->L, c->d_X, c->P, c->d_hit, c->d_step_matched,
+                                                 c->d_partial, c->d_state);
   c->launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(c->h_state, c->d_state, offsetof(GnState, X_trace), cudaMemcpyDeviceToHost, c->stream));
@@ -655,6 +453,8 @@ int madicp_register_async(madicp_ctx_t* c, int iters, const double X0[12]) {
     return MADICP_ERR_INVALID;
   }
   CK(cudaSetDevice(c->device));
+  rc = prepare_moving(c);
+  if (rc) return rc;
   GnArgs A;
   A.model = make_view(c);
   A.P = c->P;
@@ -666,7 +466,7 @@ int madicp_register_async(madicp_ctx_t* c, int iters, const double X0[12]) {
     A.peers.box[r] = (r < c->world) ? &c->peer_comm[r]->box : nullptr;
     A.peer_matched[r] = (r < c->world) ? c->peer_comm[r]->matched[mb] : nullptr;
   }
-  A.moving = c->d_moving;
+  A.moving = c->d_mov4;
   A.L = c->L;
   A.iters = iters;
   A.matched = c->d_comm->matched[mb];
@@ -686,7 +486,16 @@ int madicp_register_async(madicp_ctx_t* c, int iters, const double X0[12]) {
   // zero the flags buffer of the NEXT call (nobody can be writing it yet; see CommBlock)
   CK(cudaMemsetAsync(c->d_comm->matched[mb ^ 1], 0, std::min(kMatchedCap, c->cap_moving), c->stream));
   void* args[] = {&A};
-  CK(cudaLaunchCooperativeKernel((void*) k_gn_loop, dim3(c->gn_grid), dim3(kBlock), args, 0, c->stream));
+  switch (c->gn_threads) {
+    case 256:
+      CK(cudaLaunchCooperativeKernel((void*) k_gn_loop<256>, dim3(c->gn_grid), dim3(256), args, gn_dynamic_smem<256>(), c->stream));
+      break;
+    case 512:
+      CK(cudaLaunchCooperativeKernel((void*) k_gn_loop<512>, dim3(c->gn_grid), dim3(512), args, gn_dynamic_smem<512>(), c->stream));
+      break;
+    default:
+      CK(cudaLaunchCooperativeKernel((void*) k_gn_loop<1024>, dim3(c->gn_grid), dim3(1024), args, gn_dynamic_smem<1024>(), c->stream));
+  }
   c->launches++;
   c->last_iters = iters;
   c->call_seq++;
@@ -750,8 +559,9 @@ int madicp_search_cloud(madicp_ctx_t* c, int slot, const double* q, int64_t n, i
   double* d_p = d_out;
   double* d_n = d_out + size_t(n) * 3;
   double* d_d = d_out + size_t(n) * 6;
-  k_search_cloud<<<grid_for(c, n), kBlock, 0, c->stream>>>(c->slots[slot].d_recs, d_q, n, d_o, points ? d_p : nullptr,
-                                                          normals ? d_n : nullptr, dists ? d_d : nullptr);
+  k_search_cloud<<<grid_for(c, n), kStepBlock, 0, c->stream>>>(c->slots[slot].d_recs, c->slots[slot].d_fast, d_q, n, d_o,
+                                                              points ? d_p : nullptr, normals ? d_n : nullptr,
+                                                              dists ? d_d : nullptr);
   c->launches++;
   CK(cudaGetLastError());
   if (ordinals) CK(cudaMemcpyAsync(ordinals, d_o, size_t(n) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -830,13 +640,12 @@ int madicp_debug_timing(madicp_ctx_t* c, int enable, int64_t* out, int max_round
   return rows;
 }
 
-int madicp_set_gn_grid(madicp_ctx_t* c, int ctas_per_sm) {
+int madicp_set_gn_grid(madicp_ctx_t* c, int threads_per_cta, int ctas_per_sm) {
   if (!c || ctas_per_sm < 1) return MADICP_ERR_INVALID;
-  int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gn_loop, kBlock, 0));
-  if (ctas_per_sm > per_sm) ctas_per_sm = per_sm;
-  c->gn_grid = ctas_per_sm * c->sm_count;
-  return ctas_per_sm;
+  CK(cudaSetDevice(c->device));
+  int rc = configure_gn(c, threads_per_cta, ctas_per_sm);
+  if (rc) return rc;
+  return c->gn_grid / c->sm_count;
 }
 
 }  // extern "C"

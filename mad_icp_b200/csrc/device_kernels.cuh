@@ -1,0 +1,319 @@
+// device_kernels.cuh -- the __global__ entry points (see kernels.cuh for the design notes).
+#pragma once
+#include "kernels.cuh"
+
+namespace madicp {
+
+// ---------------------------------------------------------------------------------------------
+// Preparation kernels (run once per keyframe upload / once per scan)
+// ---------------------------------------------------------------------------------------------
+
+// FP32 shadow records of a keyframe tree: fast[i+1] mirrors recs[i].
+__global__ void __launch_bounds__(kStepBlock)
+k_prepare_fast(const madtree_rec_t* __restrict__ recs, int n, FastRec* __restrict__ fast) {
+  const int i = blockIdx.x * kStepBlock + threadIdx.x;
+  if (i == 0) {  // slot 0 is unused padding (keeps sibling pairs 64-byte aligned)
+    FastRec z;
+    z.mx = z.my = z.mz = z.dx = z.dy = z.dz = 0.f;
+    z.link = -1;
+    z.eb = 0.f;
+    fast[0] = z;
+  }
+  if (i >= n) return;
+  const Rec r = load_rec(recs + i);
+  FastRec f;
+  f.mx = __double2float_rn(r.mx);
+  f.my = __double2float_rn(r.my);
+  f.mz = __double2float_rn(r.mz);
+  f.dx = __double2float_rn(r.dx);
+  f.dy = __double2float_rn(r.dy);
+  f.dz = __double2float_rn(r.dz);
+  f.link = (r.link >= 0) ? (r.link + 1) : (-1 - i);
+  f.eb = __double2float_ru(kBoundC * (fabs(r.mx) + fabs(r.my) + fabs(r.mz)));
+  fast[i + 1] = f;
+}
+
+// Moving leaves + gate radius (reference: odometry/mad_icp.cpp:81, iteration invariant).
+__global__ void __launch_bounds__(kStepBlock)
+k_prepare_moving(const double* __restrict__ means, int L, const __grid_constant__ IcpParams P,
+                 Moving4* __restrict__ out) {
+  const int q = blockIdx.x * kStepBlock + threadIdx.x;
+  if (q >= L) return;
+  Moving4 m;
+  m.px = means[3 * q];
+  m.py = means[3 * q + 1];
+  m.pz = means[3 * q + 2];
+  m.ball = P.min_ball + P.b_ratio * norm3(m.px, m.py, m.pz);
+  out[q] = m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Step API: K1 / K2 / K3
+// ---------------------------------------------------------------------------------------------
+
+// K1: one thread per (keyframe k, moving leaf q), item w = k*L + q so a warp holds 32 consecutive
+// leaves (DFS order => spatially coherent) of one keyframe.
+__global__ void __launch_bounds__(kStepBlock)
+k_search(const __grid_constant__ ModelView model, const Moving4* __restrict__ moving, int L,
+         const double* __restrict__ Xp, int* __restrict__ hit, int* __restrict__ ordinals) {
+  double X[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) X[i] = Xp[i];
+  const int64_t total = int64_t(model.K) * L;
+  for (int64_t w = int64_t(blockIdx.x) * kStepBlock + threadIdx.x; w < total; w += int64_t(gridDim.x) * kStepBlock) {
+    const int k = int(w / L), q = int(w - int64_t(k) * L);
+    const Moving4 m = load_moving(moving + q);
+    double mx, my, mz;
+    iso_apply(X, m.px, m.py, m.pz, mx, my, mz);
+    const int leaf = descend(model.fast[k], model.recs[k], mx, my, mz);
+    if (hit) hit[w] = leaf;
+    if (ordinals) ordinals[w] = -1 - model.recs[k][leaf].link;
+  }
+}
+
+// K2: reads K1's leaf record index, folds the 6x7 H/b tile per warp (FP64 DMMA), per-CTA partials,
+// and the last CTA to arrive folds the partials in CTA order into st->H / st->b.
+__global__ void __launch_bounds__(kStepBlock)
+k_linearize(const __grid_constant__ ModelView model, const Moving4* __restrict__ moving, int L,
+            const double* __restrict__ Xp, const __grid_constant__ IcpParams P, const int* __restrict__ hit,
+            unsigned char* __restrict__ matched, double* __restrict__ partial, GnState* st) {
+  constexpr int WARPS = kStepBlock / 32;
+  __shared__ double s_stage[WARPS][kStageItems * kStage];
+  __shared__ double s_red[WARPS][64];
+  __shared__ double s_tot[kAcc];
+  __shared__ int s_last;
+  double X[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) X[i] = Xp[i];
+  double c0 = 0.0, c1 = 0.0;
+  const int64_t total = int64_t(model.K) * L;
+  const int lane = threadIdx.x & 31;
+  // warp-uniform trip count: every lane takes part in the DMMA fold, lanes past the end stage zeros
+  for (int64_t w0 = int64_t(blockIdx.x) * kStepBlock + (threadIdx.x - lane); w0 < total;
+       w0 += int64_t(gridDim.x) * kStepBlock) {
+    const int64_t w = w0 + lane;
+    double v[kStage];
+#pragma unroll
+    for (int i = 0; i < kStage; ++i) v[i] = 0.0;
+    if (w < total) {
+      const int k = int(w / L), q = int(w - int64_t(k) * L);
+      const Moving4 m = load_moving(moving + q);
+      double mx, my, mz;
+      iso_apply(X, m.px, m.py, m.pz, mx, my, mz);
+      const Rec f = load_rec(model.recs[k] + hit[w]);
+      if (linearize_one(X, P, m, mx, my, mz, f, v) && matched) matched[q] = 1;
+    }
+    warp_accumulate(s_stage[threadIdx.x >> 5], v, c0, c1);
+  }
+  block_reduce_store<WARPS>(c0, c1, s_red, partial + size_t(blockIdx.x) * kAcc);
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atom_add_release(&st->ticket, 1) == int(gridDim.x) - 1);
+  __syncthreads();
+  if (!s_last) return;
+  final_reduce<kStepBlock>(partial, gridDim.x, s_red, s_tot);
+  if (threadIdx.x == 0) {
+    unpack_Hb(s_tot, st->H, st->b);
+    st->ticket = 0;
+  }
+}
+
+// K3: updateState for H,b already on the device (single thread).
+__global__ void k_solve(const double* __restrict__ H, const double* __restrict__ b, double* X) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double Xl[12], Xn[12];
+    for (int i = 0; i < 12; ++i) Xl[i] = X[i];
+    gn_update_pose(H, 6, b, Xl, Xn);
+    for (int i = 0; i < 12; ++i) X[i] = Xn[i];
+  }
+}
+
+// MADtreeWrapper::searchCloud / searchCloudDist: arbitrary query points against one slot.
+__global__ void __launch_bounds__(kStepBlock)
+k_search_cloud(const madtree_rec_t* __restrict__ recs, const FastRec* __restrict__ fast,
+               const double* __restrict__ q, int64_t n, int* __restrict__ ordinals, double* __restrict__ points,
+               double* __restrict__ normals, double* __restrict__ dists) {
+  for (int64_t i = int64_t(blockIdx.x) * kStepBlock + threadIdx.x; i < n; i += int64_t(gridDim.x) * kStepBlock) {
+    const double qx = q[3 * i], qy = q[3 * i + 1], qz = q[3 * i + 2];
+    const Rec f = load_rec(recs + descend(fast, recs, qx, qy, qz));
+    if (ordinals) ordinals[i] = -1 - f.link;
+    if (points) {
+      points[3 * i] = f.mx; points[3 * i + 1] = f.my; points[3 * i + 2] = f.mz;
+    }
+    if (normals) {
+      normals[3 * i] = f.dx; normals[3 * i + 1] = f.dy; normals[3 * i + 2] = f.dz;
+    }
+    if (dists) dists[i] = norm3(qx - f.mx, qy - f.my, qz - f.mz);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GN: the whole ICP loop in one persistent cooperative kernel
+// ---------------------------------------------------------------------------------------------
+
+// In-kernel all-reduce of the 48-value accumulator tile across GPUs (called by ONE CTA per rank).
+// Every rank stores its partial into every rank's mailbox (own included) with 16-byte LL cells,
+// then spins on its own mailbox until all `world` partials of this epoch are present and sums them
+// in rank order -> identical bits on every rank.
+template <int THREADS>
+__device__ __forceinline__ void peer_allreduce(const PeerView& pv, uint32_t epoch, double* s_tot,
+                                               double (*s_peer)[kAcc]) {
+  const int slot = int(epoch & 1u);
+  for (int idx = threadIdx.x; idx < pv.world * kAcc; idx += THREADS) {
+    const int r = idx / kAcc, i = idx - r * kAcc;
+    const double v = s_tot[i];
+    const uint32_t lo = uint32_t(__double2loint(v)), hi = uint32_t(__double2hiint(v));
+    LLCell* dst = &pv.box[r]->cell[slot][pv.rank][i];
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(lo), "r"(epoch), "r"(hi), "r"(epoch)
+                 : "memory");
+  }
+  for (int idx = threadIdx.x; idx < pv.world * kAcc; idx += THREADS) {
+    const int r = idx / kAcc, i = idx - r * kAcc;
+    const LLCell* src = &pv.box[pv.rank]->cell[slot][r][i];
+    uint32_t lo, f0, hi, f1;
+    do {
+      asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(src)
+                   : "memory");
+    } while (f0 != epoch || f1 != epoch);
+    s_peer[r][i] = __hiloint2double(int(hi), int(lo));
+  }
+  __syncthreads();
+  if (threadIdx.x < kAcc) {
+    double s = s_peer[0][threadIdx.x];
+    for (int r = 1; r < pv.world; ++r) s += s_peer[r][threadIdx.x];
+    s_tot[threadIdx.x] = s;
+  }
+  __syncthreads();
+}
+
+struct GnArgs {
+  ModelView model;
+  IcpParams P;
+  PeerView peers;  // world <= 1 => single GPU
+  const Moving4* moving;
+  int L;
+  int iters;
+  unsigned char* matched;                  // local matched flags (L bytes), zeroed by the host
+  unsigned char* peer_matched[kMaxPeers];  // world > 1: every rank's matched array (peer mapped)
+  double* partial;                         // gridDim.x * kAcc
+  GnState* st;
+  long long* dbg;                          // nullable: per-round SM-clock stamps (madicp_debug_timing)
+};
+
+// Persistent cooperative grid (all CTAs co-resident).  Each CTA owns one contiguous range of the
+// K*L items (=> mostly one keyframe and one spatial region per SM: the upper tree levels stay in
+// that SM's L1 for the whole launch).  One software grid barrier per round: CTAs publish their
+// partial, take a release-ticket, the last one folds / exchanges / solves and publishes the new pose
+// and st->round; the others poll st->round with L2-coherent relaxed loads.  No acquire fence is ever
+// executed in the loop, so L1 is not invalidated between rounds; everything that crosses SMs
+// (partials, pose, flags) is read with ld.relaxed.gpu (L2) behind a control dependency on the flag.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
+k_gn_loop(const __grid_constant__ GnArgs A) {
+  constexpr int WARPS = THREADS / 32;
+  extern __shared__ __align__(16) double s_dyn[];
+  // layout: [WARPS][kStageItems*kStage] staging tiles | [WARPS][64] reduction scratch | peers
+  double* s_stage_all = s_dyn;
+  double(*s_red)[64] = reinterpret_cast<double(*)[64]>(s_dyn + WARPS * kStageItems * kStage);
+  double(*s_peer)[kAcc] = reinterpret_cast<double(*)[kAcc]>(s_dyn + WARPS * kStageItems * kStage + WARPS * 64);
+  __shared__ double s_tot[kAcc];
+  __shared__ double s_b[6];
+  __shared__ double s_X[12];
+  __shared__ int s_last;
+  __shared__ int s_count[WARPS];
+  GnState* st = A.st;
+  const int64_t total = int64_t(A.model.K) * A.L;
+  const bool multi = A.peers.world > 1;
+  const int lane = threadIdx.x & 31;
+  double* stage = s_stage_all + (threadIdx.x >> 5) * (kStageItems * kStage);
+  // contiguous item range of this CTA (multiple of 32 so warps never straddle CTAs)
+  const int64_t chunk = ((total + gridDim.x - 1) / gridDim.x + 31) / 32 * 32;
+  const int64_t cta_begin = int64_t(blockIdx.x) * chunk;
+  const int64_t cta_end = (cta_begin + chunk < total) ? cta_begin + chunk : total;
+
+  for (int it = 0; it < A.iters; ++it) {
+    if (threadIdx.x == 0 && it > 0)
+      while (ld_relaxed_s32(&st->round) < it) {}
+    __syncthreads();
+    if (threadIdx.x < 12) s_X[threadIdx.x] = ld_relaxed_f64(&st->X_trace[it * 12 + threadIdx.x]);
+    __syncthreads();
+    const bool last_round = (it == A.iters - 1);
+    double c0 = 0.0, c1 = 0.0;
+    long long t_begin = 0;
+    if (A.dbg && threadIdx.x == 0) t_begin = clock64();
+    for (int64_t w0 = cta_begin + (threadIdx.x - lane); w0 < cta_end; w0 += THREADS) {
+      const int64_t w = w0 + lane;
+      double v[kStage];
+#pragma unroll
+      for (int i = 0; i < kStage; ++i) v[i] = 0.0;
+      if (w < cta_end) {
+        const int k = int(w / A.L), q = int(w - int64_t(k) * A.L);
+        const Moving4 m = load_moving(A.moving + q);
+        double mx, my, mz;
+        iso_apply(s_X, m.px, m.py, m.pz, mx, my, mz);
+        const Rec f = load_rec(A.model.recs[k] + descend(A.model.fast[k], A.model.recs[k], mx, my, mz));
+        if (linearize_one(s_X, A.P, m, mx, my, mz, f, v) && last_round) {
+          if (multi) {
+            for (int r = 0; r < A.peers.world; ++r) A.peer_matched[r][q] = 1;
+          } else {
+            A.matched[q] = 1;
+          }
+        }
+      }
+      warp_accumulate(stage, v, c0, c1);
+    }
+    if (A.dbg && threadIdx.x == 0 && blockIdx.x == 0) A.dbg[it * 8 + 0] = clock64() - t_begin;  // item phase, CTA 0
+    block_reduce_store<WARPS>(c0, c1, s_red, A.partial + size_t(blockIdx.x) * kAcc);
+    if (multi && last_round) __threadfence_system();  // matched flags stored to peers precede our LL cells
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atom_add_release(&st->ticket, 1) == (it + 1) * int(gridDim.x) - 1);
+    __syncthreads();
+    if (s_last) {
+      long long t0 = 0, t1 = 0, t2 = 0;
+      if (A.dbg && threadIdx.x == 0) {
+        t0 = clock64();
+        A.dbg[it * 8 + 1] = t0 - t_begin;  // round start -> last CTA arrived (that CTA's clock)
+      }
+      final_reduce<THREADS>(A.partial, gridDim.x, s_red, s_tot);
+      if (A.dbg && threadIdx.x == 0) t1 = clock64();
+      if (multi) {
+        if (last_round) __threadfence_system();
+        peer_allreduce<THREADS>(A.peers, A.peers.epoch_base + uint32_t(it) + 1u, s_tot, s_peer);
+        if (last_round) __threadfence_system();
+      }
+      if (last_round) {  // count matched moving leaves (all writers are done: they took tickets)
+        int c = 0;
+        for (int q = threadIdx.x; q < A.L; q += THREADS) c += (__ldcv(A.matched + q) != 0);
+        for (int off = 16; off > 0; off >>= 1) c += __shfl_down_sync(0xffffffffu, c, off);
+        if (lane == 0) s_count[threadIdx.x >> 5] = c;
+      }
+      if (threadIdx.x < 6) s_b[threadIdx.x] = s_tot[threadIdx.x * 8 + 6];
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        if (A.dbg) t2 = clock64();
+        double Xn[12];
+        gn_update_pose(s_tot, 8, s_b, s_X, Xn);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) st->X_trace[(it + 1) * 12 + i] = Xn[i];
+        if (last_round) {
+          unpack_Hb(s_tot, st->H, st->b);
+          int c = 0;
+          for (int w2 = 0; w2 < WARPS; ++w2) c += s_count[w2];
+          st->n_matched = c;
+        }
+        st_release_s32(&st->round, it + 1);
+        if (A.dbg) {
+          A.dbg[it * 8 + 2] = t1 - t0;         // fold of the per-CTA partials
+          A.dbg[it * 8 + 3] = t2 - t1;         // peer exchange + matched count
+          A.dbg[it * 8 + 4] = clock64() - t2;  // solve + pose update + publish
+        }
+      }
+    }
+  }
+}
+
+template <int THREADS>
+constexpr size_t gn_dynamic_smem() {
+  return sizeof(double) * (size_t(THREADS / 32) * kStageItems * kStage + size_t(THREADS / 32) * 64 + size_t(kMaxPeers) * kAcc);
+}
+
+}  // namespace madicp

@@ -9,12 +9,25 @@
 //                       (reference loop: odometry/pipeline.cpp:166-193), optional in-kernel
 //                       all-reduce of H/b across GPUs through peer mailboxes (NVLink stores)
 //
-// Memory/branch bound FP64 work (no tcgen05: there is no dense contraction; the only tensor-pipe
-// use is the register-saving FP64 DMMA fold of the per-correspondence outer products, see
-// warp_accumulate).  A node visit is one 64-byte record = two 256-bit read-only loads
-// (LDG.E.256); moving leaves are laid out in getLeafs (DFS) order so the lanes of a warp walk
-// nearly the same path and their loads coalesce / hit L1 at the top levels.
-// Compiled with -fmad=false; the predicate chain uses __d*_rn intrinsics (arith.h).
+// The walk is a latency chain (one dependent memory round trip per tree level), not a bandwidth or
+// FLOP problem, so the design shortens the chain instead of widening it:
+//   * FILTERED PREDICATE.  Each node has a 32-byte FP32 shadow record (mean, split direction, link,
+//     error bound).  The side test is evaluated in FP32 (4-cycle pipe, FMA allowed); it is accepted
+//     only when |s32| exceeds a rigorous bound on |s32 - s64| (arith below), otherwise the lane
+//     re-evaluates the reference's FP64 expression on the exact 64-byte record.  The decision is
+//     therefore always the FP64 one -- indices stay bit-exact -- while >99.9% of visits never touch
+//     the FP64 pipe or the exact record.
+//   * SPECULATIVE SIBLING FETCH.  Children are adjacent, so both 32-byte shadows (one aligned
+//     64-byte pair, two LDG.E.256) are requested as soon as the node's link is known, before its
+//     own predicate is evaluated; the predicate then only selects registers.  The chain per level
+//     is one load latency plus a select.
+//   * Moving leaves are in getLeafs (DFS) order and each CTA owns a contiguous item range, so the
+//     lanes of a warp and the warps of an SM share the upper levels: L1 hits there, and the
+//     inter-round barrier uses release-only atomics / L2-coherent loads so L1 is never invalidated
+//     between rounds.
+// No tcgen05: there is no dense contraction.  The only tensor-pipe use is the FP64 DMMA fold of the
+// per-correspondence outer products (warp_accumulate), which exists to save registers.
+// Compiled with -fmad=false; exact predicates use __d*_rn intrinsics (arith.h).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -25,16 +38,30 @@
 
 namespace madicp {
 
-constexpr int kMaxSlots = 64;      // keyframe slots addressable by one launch
-constexpr int kBlock = 256;        // threads per CTA for every kernel here
-constexpr int kWarps = kBlock / 32;
-constexpr int kAcc = 48;           // 6 rows x 8 cols of the accumulator tile: H(r,c) at r*8+c, b(r) at r*8+6
-constexpr int kStage = 13;         // doubles staged per correspondence: sJ[6], J[6], e
+constexpr int kMaxSlots = 64;     // keyframe slots addressable by one launch
+constexpr int kStepBlock = 256;   // threads per CTA of the step-API kernels (K1, K2, tools)
+constexpr int kAcc = 48;          // 6 rows x 8 cols accumulator tile: H(r,c) at r*8+c, b(r) at r*8+6
+constexpr int kStage = 13;        // doubles staged per correspondence: sJ[6], J[6], e
+constexpr int kStageItems = 16;   // correspondences staged per DMMA pass (half a warp)
 constexpr int kMaxPeers = 16;
-constexpr int kMailboxSlots = 2;   // double-buffered by round parity
+constexpr int kMailboxSlots = 2;  // double-buffered by round parity
+
+// 32-byte FP32 shadow of a node.  Array index = exact-record index + 1, so the root sits at 1 and
+// every sibling pair (2,3), (4,5), ... is one aligned 64-byte block.
+struct __align__(32) FastRec {
+  float mx, my, mz, dx, dy, dz;
+  int link;  // internal: shadow index of the left child (even); leaf: -1 - exact-record index
+  float eb;  // kBoundC * (|mx|+|my|+|mz|), rounded up
+};
+static_assert(sizeof(FastRec) == 32, "FastRec must be one 256-bit load");
+
+// |s32 - s64| <= 6.1 * 2^-24 * sum_i(|q_i| + |m_i|) for unit |dir| (derivation in DESIGN.md 4.2);
+// 1e-6 leaves a 2.7x margin.  E = eb(node) + eq(query), both rounded up.
+constexpr double kBoundC = 1.0e-6;
 
 struct ModelView {  // passed by value (constant bank): the active keyframes of this device
   const madtree_rec_t* recs[kMaxSlots];
+  const FastRec* fast[kMaxSlots];
   int K;
 };
 
@@ -42,10 +69,16 @@ struct IcpParams {
   double min_ball, rho_ker_sqrt, b_ratio;
 };
 
+// Moving leaf prepared once per scan: sensor-frame mean + the iteration-invariant gate radius
+// min_ball + b_ratio*|mean| (reference: odometry/mad_icp.cpp:81).  One 256-bit load.
+struct __align__(32) Moving4 {
+  double px, py, pz, ball;
+};
+
 // Control block + results of one registration, in device global memory.
 struct GnState {
   int ticket;     // monotonically increasing arrival counter (reset by the host before a launch)
-  int round;      // number of completed rounds (release/acquire flag)
+  int round;      // number of completed rounds (flag the CTAs spin on)
   int n_matched;  // matched moving leaves in the last round
   int pad;
   double H[36];   // last round; H[r*6+c] = sum (scale*J_r)*J_c, both triangles accumulated independently
@@ -69,7 +102,7 @@ struct PeerView {
 };
 
 // ---------------------------------------------------------------------------------------------
-struct Rec {  // a node record in registers
+struct Rec {  // an exact node record in registers
   double mx, my, mz, dx, dy, dz, bbox0;
   int link;
 };
@@ -86,37 +119,71 @@ __device__ __forceinline__ Rec load_rec(const madtree_rec_t* p) {
   return r;
 }
 
-// Greedy single-path descent; returns the record index of the leaf and the leaf record.
-__device__ __forceinline__ int descend(const madtree_rec_t* __restrict__ recs, double qx, double qy, double qz,
-                                       Rec& leaf) {
-  int node = 0;
-  Rec r = load_rec(recs);
-  while (r.link >= 0) {
-    const double s = plane_side(qx, qy, qz, r.mx, r.my, r.mz, r.dx, r.dy, r.dz);
-    node = r.link + ((s < 0.0) ? 0 : 1);
-    r = load_rec(recs + node);
+__device__ __forceinline__ FastRec load_fast(const FastRec* p) {
+  FastRec r;
+  int li;
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.mx), "=f"(r.my), "=f"(r.mz), "=f"(r.dx), "=f"(r.dy), "=f"(r.dz), "=r"(li), "=f"(r.eb)
+               : "l"(p));
+  r.link = li;
+  return r;
+}
+
+__device__ __forceinline__ Moving4 load_moving(const Moving4* p) {
+  Moving4 m;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(m.px), "=d"(m.py), "=d"(m.pz), "=d"(m.ball) : "l"(p));
+  return m;
+}
+
+// Exact (reference) side test on the 64-byte record: true = right child.
+__device__ __forceinline__ bool side_exact(const madtree_rec_t* rec, double qx, double qy, double qz) {
+  const Rec r = load_rec(rec);
+  return !(plane_side(qx, qy, qz, r.mx, r.my, r.mz, r.dx, r.dy, r.dz) < 0.0);
+}
+
+// Greedy single-path descent (no backtracking, like the reference).  Returns the exact-record index
+// of the leaf reached.  Bit-identical decisions to the FP64 expression by construction.
+__device__ __forceinline__ int descend(const FastRec* __restrict__ fast, const madtree_rec_t* __restrict__ recs,
+                                       double qx, double qy, double qz) {
+  const float fx = __double2float_rn(qx), fy = __double2float_rn(qy), fz = __double2float_rn(qz);
+  const float eq = __double2float_ru(kBoundC * (fabs(qx) + fabs(qy) + fabs(qz)));
+  int idx = 1;
+  FastRec cur = load_fast(fast + 1);
+  while (cur.link >= 0) {
+    const FastRec* pair = fast + cur.link;
+    const FastRec c0 = load_fast(pair);      // both children requested before the predicate is needed
+    const FastRec c1 = load_fast(pair + 1);
+    const float s = fmaf(fz - cur.mz, cur.dz, fmaf(fy - cur.my, cur.dy, (fx - cur.mx) * cur.dx));
+    const float E = __fadd_ru(cur.eb, eq);
+    bool right;
+    if (s > E)
+      right = true;
+    else if (s < -E)
+      right = false;
+    else
+      right = side_exact(recs + (idx - 1), qx, qy, qz);
+    idx = cur.link + (right ? 1 : 0);
+    cur = right ? c1 : c0;
   }
-  leaf = r;
-  return node;
+  return -1 - cur.link;
 }
 
 // One correspondence (reference: odometry/mad_icp.cpp:81-101): gate, error, Jacobian, Huber scale,
 // planarity weight.  Fills v = {sJ[0..5] = scale*J, J[0..5], e}; returns false (v untouched) when
 // the gate rejects the pair.  FP64, no FMA, operand order as arith.h.
-__device__ __forceinline__ bool linearize_one(const double* __restrict__ X, const IcpParams& P, double px, double py,
-                                              double pz, double mlx, double mly, double mlz, const Rec& f, double* v) {
-  const double src_ball = P.min_ball + P.b_ratio * norm3(px, py, pz);
+__device__ __forceinline__ bool linearize_one(const double* __restrict__ X, const IcpParams& P, const Moving4& m,
+                                              double mlx, double mly, double mlz, const Rec& f, double* v) {
   const double ex = mlx - f.mx, ey = mly - f.my, ez = mlz - f.mz;
-  if (norm3(ex, ey, ez) > src_ball) return false;
+  if (norm3(ex, ey, ez) > m.ball) return false;
   const double e = dot3(ex, ey, ez, f.dx, f.dy, f.dz);
   double J[6];
   J[0] = dot3(f.dx, f.dy, f.dz, X[0], X[4], X[8]);
   J[1] = dot3(f.dx, f.dy, f.dz, X[1], X[5], X[9]);
   J[2] = dot3(f.dx, f.dy, f.dz, X[2], X[6], X[10]);
   const double n0 = -J[0], n1 = -J[1], n2 = -J[2];
-  J[3] = n1 * pz + n2 * (-py);
-  J[4] = n0 * (-pz) + n2 * px;
-  J[5] = n0 * py + n1 * (-px);
+  J[3] = n1 * m.pz + n2 * (-m.py);
+  J[4] = n0 * (-m.pz) + n2 * m.px;
+  J[5] = n0 * m.py + n1 * (-m.px);
   double scale = 1.0;
   const double chi = fabs(e);
   if (chi > P.rho_ker_sqrt) scale = P.rho_ker_sqrt / chi;
@@ -133,32 +200,38 @@ __device__ __forceinline__ bool linearize_one(const double* __restrict__ X, cons
 
 // H += sJ^T J, b += sJ^T e for the 32 correspondences a warp holds, on the FP64 tensor pipe:
 // D(8x8) += A(8x4) * B(4x8) with A[r][k] = sJ_r(item k), B[k][c] = J_c(item k) (c<6), e(item k)
-// (c==6), zero padding elsewhere -- 8 DMMA.8x8x4 per 32 items.  The point is not FLOPs (there are
-// few) but registers: the running sums are the 2-double C fragment instead of 42 scalars per
-// thread, which is what lets the descent run at 4 CTAs/SM.  H(r,c) = sum (scale*J_r)*J_c is formed
-// for both triangles independently, like the reference's `scale * J.transpose() * J`.
-// stage: this warp's [32][kStage] doubles in shared memory.  v: this lane's 13 values (zeros if
-// the lane has no correspondence).
+// (c==6), zero padding elsewhere -- 8 DMMA.8x8x4 per 32 items, staged through shared memory in two
+// half-warp passes.  The point is not FLOPs (there are few) but registers: the running sums are the
+// 2-double C fragment instead of 42 scalars per thread, which keeps the kernel at 64 registers
+// (1024 resident threads per SM for the latency-bound walk).  H(r,c) = sum (scale*J_r)*J_c is
+// formed for both triangles independently, like the reference's `scale * J.transpose() * J`.
+// stage: this warp's [kStageItems][kStage] doubles.  v: this lane's 13 values (zeros if none).
 __device__ __forceinline__ void warp_accumulate(double* stage, const double* v, double& c0, double& c1) {
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-  for (int i = 0; i < kStage; ++i) stage[lane * kStage + i] = v[i];
-  __syncwarp();
+  for (int h = 0; h < 2; ++h) {
+    if ((lane >> 4) == h) {
 #pragma unroll
-  for (int s = 0; s < 8; ++s) {
-    const double* it = stage + (4 * s + t) * kStage;
-    const double a = (g < 6) ? it[g] : 0.0;                      // rows 6,7 of A are padding
-    const double b = (g < 7) ? it[6 + (g < 7 ? g : 6)] : 0.0;    // col 6 of B = e, col 7 padding
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
+      for (int i = 0; i < kStage; ++i) stage[(lane & 15) * kStage + i] = v[i];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const double* it = stage + (4 * s + t) * kStage;
+      const double a = (g < 6) ? it[g] : 0.0;                    // rows 6,7 of A are padding
+      const double b = (g < 7) ? it[6 + (g < 7 ? g : 6)] : 0.0;  // col 6 of B = e, col 7 padding
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c0), "+d"(c1)
+                   : "d"(a), "d"(b));
+    }
+    __syncwarp();
   }
-  __syncwarp();
 }
 
 // Deterministic CTA reduction of the warps' C fragments -> out[kAcc] (global): warps are combined
-// in warp order.  s_red: [kWarps][64] doubles.
+// in warp order.  s_red: [WARPS][64] doubles.
+template <int WARPS>
 __device__ __forceinline__ void block_reduce_store(double c0, double c1, double (*s_red)[64], double* out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -168,26 +241,51 @@ __device__ __forceinline__ void block_reduce_store(double c0, double c1, double 
   if (threadIdx.x < kAcc) {
     double s = s_red[0][threadIdx.x];
 #pragma unroll
-    for (int w2 = 1; w2 < kWarps; ++w2) s += s_red[w2][threadIdx.x];
+    for (int w2 = 1; w2 < WARPS; ++w2) s += s_red[w2][threadIdx.x];
     out[threadIdx.x] = s;
   }
 }
 
-// Sum `nblk` per-CTA partials (global, written by other SMs -> read with ld.cg) into s_tot[kAcc]:
-// four interleaved strands over the CTA index, combined in strand order.
+__device__ __forceinline__ double ld_relaxed_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_relaxed_s32(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_s32(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Arrival ticket with RELEASE semantics only: the CTA's partials (made visible to thread 0 by the
+// preceding bar.sync) are ordered before the increment, but -- unlike __threadfence() -- nothing is
+// acquired, so ptxas has no reason to invalidate L1 and the tree stays cached across rounds.
+__device__ __forceinline__ int atom_add_release(int* p, int v) {
+  int old;
+  asm volatile("atom.add.release.gpu.global.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+
+// Sum `nblk` per-CTA partials (written by other SMs -> L2-coherent loads) into s_tot[kAcc]:
+// THREADS/64 interleaved strands over the CTA index, combined in strand order.
+template <int THREADS>
 __device__ __forceinline__ void final_reduce(const double* partial, int nblk, double (*s_red)[64], double* s_tot) {
+  constexpr int STRANDS = THREADS / 64;
   const int j = threadIdx.x & 63, g = threadIdx.x >> 6;
   __syncthreads();
   if (j < kAcc) {
     double s = 0.0;
-    for (int blk = g; blk < nblk; blk += kBlock / 64) s += __ldcg(partial + size_t(blk) * kAcc + j);
+#pragma unroll 4
+    for (int blk = g; blk < nblk; blk += STRANDS) s += ld_relaxed_f64(partial + size_t(blk) * kAcc + j);
     s_red[g][j] = s;
   }
   __syncthreads();
   if (threadIdx.x < kAcc) {
     double s = s_red[0][threadIdx.x];
 #pragma unroll
-    for (int w2 = 1; w2 < kBlock / 64; ++w2) s += s_red[w2][threadIdx.x];
+    for (int w2 = 1; w2 < STRANDS; ++w2) s += s_red[w2][threadIdx.x];
     s_tot[threadIdx.x] = s;
   }
   __syncthreads();
@@ -198,15 +296,6 @@ __device__ __forceinline__ void unpack_Hb(const double* tot, double* H, double* 
     for (int c = 0; c < 6; ++c) H[r * 6 + c] = tot[r * 8 + c];
     b[r] = tot[r * 8 + 6];
   }
-}
-
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_gpu(int* p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 }  // namespace madicp

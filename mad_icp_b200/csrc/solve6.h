@@ -1,9 +1,17 @@
 // solve6.h -- Gauss-Newton state update shared by host and device:
 //   dx = H.ldlt().solve(-b);  dX = (expMapSO3(dx[3:6]), dx[0:3]);  X = X * dX
 // (reference: odometry/mad_icp.cpp:105-117, tools/lie_algebra.h:33-52).
-// The factorisation is the pivoted (largest |diagonal|) lower LDL^T that Eigen 3.4's
-// LDLT<Matrix6d> performs, with the pseudo-inverse of D in the solve, so a rank-deficient
-// or all-zero H yields dx = 0 on the null space instead of NaN.
+//
+// The factorisation is the pivoted lower LDL^T that Eigen 3.4's LDLT<Matrix6d> performs (largest
+// |diagonal| first, pseudo-inverse of D in the solve so a rank-deficient or all-zero H gives dx = 0
+// on the null space instead of NaN).  That algorithm is left-looking: column k is only updated when
+// it becomes the pivot column, so the pivot search at step k looks at diagonal entries that are
+// still the ORIGINAL ones.  The whole pivot order is therefore a function of diag(H) alone, and the
+// routine below (1) derives the permutation from the diagonal, (2) gathers the permuted lower
+// triangle with run-time indices from memory once, (3) runs the same left-looking elimination
+// un-pivoted with compile-time indices only.  On the device that keeps the working set in
+// registers; the update sits on the critical path between two GN rounds (one thread, nothing to
+// overlap with), and a pointer-indexed version costs ~25 us per round.
 #pragma once
 #include <float.h>
 
@@ -11,70 +19,58 @@
 
 namespace madicp {
 
-// H: 6x6, only the lower triangle (H[r*6+c], r >= c) is read, as Eigen's LDLT<.., Lower> does.
-// Written with compile-time loop bounds and select-based interchanges only (no run-time array
-// index), so on the device the whole factorisation lives in registers: the update is on the
-// critical path between two Gauss-Newton rounds and a generic pointer-indexed version costs tens of
-// microseconds of single-thread latency per round.
-MADICP_HD void ldlt6_solve_neg(const double* H, const double* b, double* x) {
-  double A[6][6];
+// H: 6x6 with row stride `ld` (H[r*ld+c]); only the lower triangle (r >= c) is read.  x = solve(-b).
+MADICP_HD void ldlt6_solve_neg(const double* H, int ld, const double* b, double* x) {
+  // (1) pivot order from the diagonal: selection with "first maximum wins", as sequential swaps
+  double dg[6];
+  int idx[6];
 #pragma unroll
-  for (int r = 0; r < 6; ++r)
+  for (int i = 0; i < 6; ++i) {
+    dg[i] = fabs(H[i * ld + i]);
+    idx[i] = i;
+  }
 #pragma unroll
-    for (int c = 0; c < 6; ++c) A[r][c] = (c <= r) ? H[r * 6 + c] : 0.0;
-  double y[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) y[i] = -b[i];
-  int perm[6];
-  bool all_zero = false;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    // pivot: largest |diagonal| of the trailing block, first maximum wins
+  for (int k = 0; k < 5; ++k) {
     int p = k;
-    double best = fabs(A[k][k]);
+    double best = dg[k];
 #pragma unroll
-    for (int i = k + 1; i < 6; ++i) {
-      const double a = fabs(A[i][i]);
-      if (a > best) {
-        best = a;
+    for (int i = k + 1; i < 6; ++i)
+      if (dg[i] > best) {
+        best = dg[i];
         p = i;
       }
-    }
-    perm[k] = p;
-    // symmetric interchange k <-> p on the lower triangle, and on the right-hand side (P b is
-    // applied on the fly: later transpositions only touch positions >= k)
 #pragma unroll
     for (int i = k + 1; i < 6; ++i) {
       const bool sw = (p == i);
-#pragma unroll
-      for (int j = 0; j < k; ++j) {
-        const double u = A[k][j], w = A[i][j];
-        A[k][j] = sw ? w : u;
-        A[i][j] = sw ? u : w;
-      }
-#pragma unroll
-      for (int r = i + 1; r < 6; ++r) {
-        const double u = A[r][k], w = A[r][i];
-        A[r][k] = sw ? w : u;
-        A[r][i] = sw ? u : w;
-      }
-      {
-        const double u = A[k][k], w = A[i][i];
-        A[k][k] = sw ? w : u;
-        A[i][i] = sw ? u : w;
-      }
-#pragma unroll
-      for (int r = k + 1; r < i; ++r) {
-        const double u = A[r][k], w = A[i][r];
-        A[r][k] = sw ? w : u;
-        A[i][r] = sw ? u : w;
-      }
-      {
-        const double u = y[k], w = y[i];
-        y[k] = sw ? w : u;
-        y[i] = sw ? u : w;
-      }
+      const double u = dg[k], w = dg[i];
+      dg[k] = sw ? w : u;
+      dg[i] = sw ? u : w;
+      const int a = idx[k], c = idx[i];
+      idx[k] = sw ? c : a;
+      idx[i] = sw ? a : c;
     }
+  }
+  if (!(dg[0] > 0.0)) {  // whole diagonal zero: Eigen stops factoring, D = 0 -> solution 0
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] = 0.0;
+    return;
+  }
+  // (2) permuted lower triangle (entry (i,j) comes from the original LOWER entry of rows idx[i], idx[j])
+  double A[6][6];
+  double y[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      const int r = idx[i] > idx[j] ? idx[i] : idx[j];
+      const int c = idx[i] > idx[j] ? idx[j] : idx[i];
+      A[i][j] = H[r * ld + c];
+    }
+    y[i] = -b[idx[i]];
+  }
+  // (3) left-looking LDL^T, static indices
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
     if (k > 0) {
       double w[6];
 #pragma unroll
@@ -92,19 +88,10 @@ MADICP_HD void ldlt6_solve_neg(const double* H, const double* b, double* x) {
       }
     }
     const double d = A[k][k];
-    const bool ok = fabs(d) > 0.0;
-    if (k == 0 && !ok) all_zero = true;  // whole diagonal is zero: nothing to factor
-    if (ok && !all_zero) {
+    if (fabs(d) > 0.0) {
 #pragma unroll
       for (int i = k + 1; i < 6; ++i) A[i][k] /= d;
     }
-  }
-  (void) perm;
-  if (all_zero) {
-    // Eigen stops factoring when the first pivot is exactly zero; D = 0 makes the solve return 0
-#pragma unroll
-    for (int i = 0; i < 6; ++i) x[i] = 0.0;
-    return;
   }
 #pragma unroll
   for (int i = 0; i < 6; ++i)
@@ -116,19 +103,8 @@ MADICP_HD void ldlt6_solve_neg(const double* H, const double* b, double* x) {
   for (int i = 5; i >= 0; --i)
 #pragma unroll
     for (int j = i + 1; j < 6; ++j) y[i] -= A[j][i] * y[j];
-  // x = P^T y: undo the transpositions in reverse order
 #pragma unroll
-  for (int k = 5; k >= 0; --k) {
-#pragma unroll
-    for (int i = k + 1; i < 6; ++i) {
-      const bool sw = (perm[k] == i);
-      const double u = y[k], w = y[i];
-      y[k] = sw ? w : u;
-      y[i] = sw ? u : w;
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 6; ++i) x[i] = y[i];
+  for (int i = 0; i < 6; ++i) x[idx[i]] = y[i];
 }
 
 // Rodrigues with the reference's small-angle branch (theta^2 < 1e-8 -> I + [w]x). R row-major 3x3.
@@ -158,11 +134,11 @@ MADICP_HD void expmap_so3(double wx, double wy, double wz, double* R) {
     }
 }
 
-// X (row-major 3x4) <- X * [exp(w) | t] with dx = [t, w] solved from (H, b).
-MADICP_HD void gn_update_pose(const double* H, const double* b, double* X, double* dx_out) {
+// Xn (row-major 3x4) = X * [exp(w) | t] with dx = [t, w] solved from (H, b); H has row stride ld.
+MADICP_HD void gn_update_pose(const double* H, int ld, const double* b, const double* X, double* Xn) {
   double dx[6];
-  ldlt6_solve_neg(H, b, dx);
-  double dR[9], dX[12], Xn[12];
+  ldlt6_solve_neg(H, ld, b, dx);
+  double dR[9], dX[12];
   expmap_so3(dx[3], dx[4], dx[5], dR);
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
@@ -171,12 +147,6 @@ MADICP_HD void gn_update_pose(const double* H, const double* b, double* X, doubl
     dX[r * 4 + 3] = dx[r];
   }
   iso_mul(X, dX, Xn);
-#pragma unroll
-  for (int i = 0; i < 12; ++i) X[i] = Xn[i];
-  if (dx_out) {
-#pragma unroll
-    for (int i = 0; i < 6; ++i) dx_out[i] = dx[i];
-  }
 }
 
 }  // namespace madicp

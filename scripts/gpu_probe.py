@@ -36,11 +36,12 @@ for iters in (1, 2, 5, 10, 15, 20):
 
 # per-round phase breakdown (SM cycles @ ~1.965 GHz)
 reg.debug_timing(True, fetch=False)
-for cps in (4, 3, 2, 1):
-    eff = reg.set_gn_grid(cps)
+for thr, cps in ((1024, 1), (512, 2), (256, 4), (256, 3), (512, 1), (256, 2)):
+    eff = reg.set_gn_grid(thr, cps)
     w = timed(lambda: reg.register_async(X0, 10))
+    c = timed(lambda: reg.register_async(X0, 10), cold=True)
     reg.register_async(X0, 10); torch.cuda.synchronize()
     d = reg.debug_timing(True)
-    print(f"ctas/SM={eff}: warm 10-iter median {w[0]:.1f} us; cycles/round (median over rounds) items(cta0)={np.median(d[:,0]):.0f} "
+    print(f"threads={thr} ctas/SM={eff}: 10-iter warm {w[0]:.1f} us cold {c[0]:.1f} us; cycles/round (median): items(cta0)={np.median(d[:,0]):.0f} "
           f"start->all_arrived={np.median(d[:,1]):.0f} fold={np.median(d[:,2]):.0f} xchg+count={np.median(d[:,3]):.0f} solve={np.median(d[:,4]):.0f}")
-reg.set_gn_grid(4)
+reg.set_gn_grid(1024, 1)

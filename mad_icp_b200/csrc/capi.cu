@@ -27,7 +27,8 @@ using namespace madicp;
 namespace {
 struct Slot {
   madtree_rec_t* d_recs = nullptr;  // exact 64-byte records (breadth-first)
-  FastRec* d_fast = nullptr;        // FP32 shadows, index = record index + 1
+  FastRec* d_fast = nullptr;        // 16-byte FP32 plane shadows, same index as d_recs
+  int* d_links = nullptr;           // child links, same index as d_recs
   int n_nodes = 0, n_leaves = 0;
   size_t cap_nodes = 0;
 };
@@ -94,11 +95,13 @@ static ModelView make_view(const madicp_ctx* c) {
     if (c->slots[s].n_nodes > 0) {
       v.recs[v.K] = c->slots[s].d_recs;
       v.fast[v.K] = c->slots[s].d_fast;
+      v.links[v.K] = c->slots[s].d_links;
       ++v.K;
     }
   for (int i = v.K; i < kMaxSlots; ++i) {
     v.recs[i] = nullptr;
     v.fast[i] = nullptr;
+    v.links[i] = nullptr;
   }
   return v;
 }
@@ -209,6 +212,7 @@ void madicp_destroy(madicp_ctx_t* c) {
   for (Slot& s : c->slots) {
     if (s.d_recs) cudaFree(s.d_recs);
     if (s.d_fast) cudaFree(s.d_fast);
+    if (s.d_links) cudaFree(s.d_links);
   }
   cudaFree(c->d_moving);
   cudaFree(c->d_mov4);
@@ -257,15 +261,19 @@ int madicp_put_keyframe_records(madicp_ctx_t* c, int slot, const madtree_rec_t* 
     CK(cudaStreamSynchronize(c->stream));
     if (s.d_recs) cudaFree(s.d_recs);
     if (s.d_fast) cudaFree(s.d_fast);
+    if (s.d_links) cudaFree(s.d_links);
     s.d_recs = nullptr;
     s.d_fast = nullptr;
+    s.d_links = nullptr;
     s.cap_nodes = 0;
     CK(cudaMalloc(&s.d_recs, size_t(n_nodes) * sizeof(madtree_rec_t)));
-    CK(cudaMalloc(&s.d_fast, (size_t(n_nodes) + 2) * sizeof(FastRec)));
+    CK(cudaMalloc(&s.d_fast, size_t(n_nodes) * sizeof(FastRec)));
+    CK(cudaMalloc(&s.d_links, size_t(n_nodes) * sizeof(int)));
     s.cap_nodes = n_nodes;
   }
   CK(cudaMemcpyAsync(s.d_recs, recs, size_t(n_nodes) * sizeof(madtree_rec_t), cudaMemcpyHostToDevice, c->stream));
-  k_prepare_fast<<<(n_nodes + kStepBlock - 1) / kStepBlock, kStepBlock, 0, c->stream>>>(s.d_recs, n_nodes, s.d_fast);
+  k_prepare_fast<<<(n_nodes + kStepBlock - 1) / kStepBlock, kStepBlock, 0, c->stream>>>(s.d_recs, n_nodes, s.d_fast,
+                                                                                        s.d_links);
   c->launches++;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));  // caller may free/modify the host tree right after
@@ -559,7 +567,8 @@ int madicp_search_cloud(madicp_ctx_t* c, int slot, const double* q, int64_t n, i
   double* d_p = d_out;
   double* d_n = d_out + size_t(n) * 3;
   double* d_d = d_out + size_t(n) * 6;
-  k_search_cloud<<<grid_for(c, n), kStepBlock, 0, c->stream>>>(c->slots[slot].d_recs, c->slots[slot].d_fast, d_q, n, d_o,
+  k_search_cloud<<<grid_for(c, n), kStepBlock, 0, c->stream>>>(c->slots[slot].d_recs, c->slots[slot].d_fast,
+                                                              c->slots[slot].d_links, d_q, n, d_o,
                                                               points ? d_p : nullptr, normals ? d_n : nullptr,
                                                               dists ? d_d : nullptr);
   c->launches++;

@@ -8,29 +8,19 @@ namespace madicp {
 // Preparation kernels (run once per keyframe upload / once per scan)
 // ---------------------------------------------------------------------------------------------
 
-// FP32 shadow records of a keyframe tree: fast[i+1] mirrors recs[i].
+// FP32 shadow records + link array of a keyframe tree (same index as the exact records).
 __global__ void __launch_bounds__(kStepBlock)
-k_prepare_fast(const madtree_rec_t* __restrict__ recs, int n, FastRec* __restrict__ fast) {
+k_prepare_fast(const madtree_rec_t* __restrict__ recs, int n, FastRec* __restrict__ fast, int* __restrict__ links) {
   const int i = blockIdx.x * kStepBlock + threadIdx.x;
-  if (i == 0) {  // slot 0 is unused padding (keeps sibling pairs 64-byte aligned)
-    FastRec z;
-    z.mx = z.my = z.mz = z.dx = z.dy = z.dz = 0.f;
-    z.link = -1;
-    z.eb = 0.f;
-    fast[0] = z;
-  }
   if (i >= n) return;
   const Rec r = load_rec(recs + i);
   FastRec f;
-  f.mx = __double2float_rn(r.mx);
-  f.my = __double2float_rn(r.my);
-  f.mz = __double2float_rn(r.mz);
   f.dx = __double2float_rn(r.dx);
   f.dy = __double2float_rn(r.dy);
   f.dz = __double2float_rn(r.dz);
-  f.link = (r.link >= 0) ? (r.link + 1) : (-1 - i);
-  f.eb = __double2float_ru(kBoundC * (fabs(r.mx) + fabs(r.my) + fabs(r.mz)));
-  fast[i + 1] = f;
+  f.c = __double2float_rn(dot3(r.mx, r.my, r.mz, r.dx, r.dy, r.dz));  // plane offset mean.dir in FP64, rounded once
+  fast[i] = f;
+  links[i] = r.link;
 }
 
 // Moving leaves + gate radius (reference: odometry/mad_icp.cpp:81, iteration invariant).
@@ -65,9 +55,9 @@ k_search(const __grid_constant__ ModelView model, const Moving4* __restrict__ mo
     const Moving4 m = load_moving(moving + q);
     double mx, my, mz;
     iso_apply(X, m.px, m.py, m.pz, mx, my, mz);
-    const int leaf = descend(model.fast[k], model.recs[k], mx, my, mz);
+    const int leaf = descend(model.fast[k], model.links[k], model.recs[k], mx, my, mz);
     if (hit) hit[w] = leaf;
-    if (ordinals) ordinals[w] = -1 - model.recs[k][leaf].link;
+    if (ordinals) ordinals[w] = -1 - model.links[k][leaf];
   }
 }
 
@@ -78,7 +68,7 @@ k_linearize(const __grid_constant__ ModelView model, const Moving4* __restrict__
             const double* __restrict__ Xp, const __grid_constant__ IcpParams P, const int* __restrict__ hit,
             unsigned char* __restrict__ matched, double* __restrict__ partial, GnState* st) {
   constexpr int WARPS = kStepBlock / 32;
-  __shared__ double s_stage[WARPS][kStageItems * kStage];
+  __shared__ double s_stage[WARPS][kStageTile];
   __shared__ double s_red[WARPS][64];
   __shared__ double s_tot[kAcc];
   __shared__ int s_last;
@@ -129,12 +119,12 @@ __global__ void k_solve(const double* __restrict__ H, const double* __restrict__
 
 // MADtreeWrapper::searchCloud / searchCloudDist: arbitrary query points against one slot.
 __global__ void __launch_bounds__(kStepBlock)
-k_search_cloud(const madtree_rec_t* __restrict__ recs, const FastRec* __restrict__ fast,
+k_search_cloud(const madtree_rec_t* __restrict__ recs, const FastRec* __restrict__ fast, const int* __restrict__ links,
                const double* __restrict__ q, int64_t n, int* __restrict__ ordinals, double* __restrict__ points,
                double* __restrict__ normals, double* __restrict__ dists) {
   for (int64_t i = int64_t(blockIdx.x) * kStepBlock + threadIdx.x; i < n; i += int64_t(gridDim.x) * kStepBlock) {
     const double qx = q[3 * i], qy = q[3 * i + 1], qz = q[3 * i + 2];
-    const Rec f = load_rec(recs + descend(fast, recs, qx, qy, qz));
+    const Rec f = load_rec(recs + descend(fast, links, recs, qx, qy, qz));
     if (ordinals) ordinals[i] = -1 - f.link;
     if (points) {
       points[3 * i] = f.mx; points[3 * i + 1] = f.my; points[3 * i + 2] = f.mz;
@@ -213,8 +203,8 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
   extern __shared__ __align__(16) double s_dyn[];
   // layout: [WARPS][kStageItems*kStage] staging tiles | [WARPS][64] reduction scratch | peers
   double* s_stage_all = s_dyn;
-  double(*s_red)[64] = reinterpret_cast<double(*)[64]>(s_dyn + WARPS * kStageItems * kStage);
-  double(*s_peer)[kAcc] = reinterpret_cast<double(*)[kAcc]>(s_dyn + WARPS * kStageItems * kStage + WARPS * 64);
+  double(*s_red)[64] = reinterpret_cast<double(*)[64]>(s_dyn + WARPS * kStageTile);
+  double(*s_peer)[kAcc] = reinterpret_cast<double(*)[kAcc]>(s_dyn + WARPS * kStageTile + WARPS * 64);
   __shared__ double s_tot[kAcc];
   __shared__ double s_b[6];
   __shared__ double s_X[12];
@@ -224,11 +214,15 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
   const int64_t total = int64_t(A.model.K) * A.L;
   const bool multi = A.peers.world > 1;
   const int lane = threadIdx.x & 31;
-  double* stage = s_stage_all + (threadIdx.x >> 5) * (kStageItems * kStage);
-  // contiguous item range of this CTA (multiple of 32 so warps never straddle CTAs)
-  const int64_t chunk = ((total + gridDim.x - 1) / gridDim.x + 31) / 32 * 32;
-  const int64_t cta_begin = int64_t(blockIdx.x) * chunk;
-  const int64_t cta_end = (cta_begin + chunk < total) ? cta_begin + chunk : total;
+  double* stage = s_stage_all + (threadIdx.x >> 5) * (kStageTile);
+  // Work distribution: the K*L items are cut into chunks of kChunk consecutive items (consecutive
+  // moving leaves of one keyframe = one spatial neighbourhood: good L1 reuse inside a chunk); chunk
+  // c belongs to CTA c % gridDim, so every CTA gets a sample of all keyframes and tree regions and
+  // the per-round barrier does not wait for an unlucky SM.  Static => deterministic sums.
+  constexpr int kChunk = 256;
+  constexpr int SUB = THREADS / kChunk;  // chunks a CTA processes per trip
+  const int64_t n_chunks = (total + kChunk - 1) / kChunk;
+  const int sub = threadIdx.x / kChunk;
 
   for (int it = 0; it < A.iters; ++it) {
     if (threadIdx.x == 0 && it > 0)
@@ -240,17 +234,18 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
     double c0 = 0.0, c1 = 0.0;
     long long t_begin = 0;
     if (A.dbg && threadIdx.x == 0) t_begin = clock64();
-    for (int64_t w0 = cta_begin + (threadIdx.x - lane); w0 < cta_end; w0 += THREADS) {
-      const int64_t w = w0 + lane;
+    for (int64_t chunk = int64_t(sub) * gridDim.x + blockIdx.x; chunk < n_chunks; chunk += int64_t(SUB) * gridDim.x) {
+      const int64_t w = chunk * kChunk + (threadIdx.x % kChunk);
       double v[kStage];
 #pragma unroll
       for (int i = 0; i < kStage; ++i) v[i] = 0.0;
-      if (w < cta_end) {
+      if (w < total) {
         const int k = int(w / A.L), q = int(w - int64_t(k) * A.L);
         const Moving4 m = load_moving(A.moving + q);
         double mx, my, mz;
         iso_apply(s_X, m.px, m.py, m.pz, mx, my, mz);
-        const Rec f = load_rec(A.model.recs[k] + descend(A.model.fast[k], A.model.recs[k], mx, my, mz));
+        const Rec f = load_rec(A.model.recs[k] +
+                               descend(A.model.fast[k], A.model.links[k], A.model.recs[k], mx, my, mz));
         if (linearize_one(s_X, A.P, m, mx, my, mz, f, v) && last_round) {
           if (multi) {
             for (int r = 0; r < A.peers.world; ++r) A.peer_matched[r][q] = 1;
@@ -313,7 +308,7 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
 
 template <int THREADS>
 constexpr size_t gn_dynamic_smem() {
-  return sizeof(double) * (size_t(THREADS / 32) * kStageItems * kStage + size_t(THREADS / 32) * 64 + size_t(kMaxPeers) * kAcc);
+  return sizeof(double) * (size_t(THREADS / 32) * kStageTile + size_t(THREADS / 32) * 64 + size_t(kMaxPeers) * kAcc);
 }
 
 }  // namespace madicp

@@ -43,25 +43,28 @@ constexpr int kStepBlock = 256;   // threads per CTA of the step-API kernels (K1
 constexpr int kAcc = 48;          // 6 rows x 8 cols accumulator tile: H(r,c) at r*8+c, b(r) at r*8+6
 constexpr int kStage = 13;        // doubles staged per correspondence: sJ[6], J[6], e
 constexpr int kStageItems = 16;   // correspondences staged per DMMA pass (half a warp)
+constexpr int kStagePitch = 20;   // doubles per staged value row (16 items + 4 padding: conflict-free)
+constexpr int kStageTile = kStage * kStagePitch;  // doubles of shared memory per warp
 constexpr int kMaxPeers = 16;
 constexpr int kMailboxSlots = 2;  // double-buffered by round parity
 
-// 32-byte FP32 shadow of a node.  Array index = exact-record index + 1, so the root sits at 1 and
-// every sibling pair (2,3), (4,5), ... is one aligned 64-byte block.
-struct __align__(32) FastRec {
-  float mx, my, mz, dx, dy, dz;
-  int link;  // internal: shadow index of the left child (even); leaf: -1 - exact-record index
-  float eb;  // kBoundC * (|mx|+|my|+|mz|), rounded up
+// 16-byte FP32 shadow of a node: the split plane in offset form, s = q.d - c with c = mean.dir
+// (computed in FP64, rounded once).  Same index as the exact record.  The child link lives in a
+// separate int array so a visit loads 16 + 4 bytes per lane: the walk is bound by the L1 -> register
+// write-back path (128 B/clk/SM), i.e. by bytes loaded per lane per level, not by DRAM or L2.
+struct __align__(16) FastRec {
+  float dx, dy, dz, c;
 };
-static_assert(sizeof(FastRec) == 32, "FastRec must be one 256-bit load");
+static_assert(sizeof(FastRec) == 16, "FastRec must be one 128-bit load");
 
-// |s32 - s64| <= 6.1 * 2^-24 * sum_i(|q_i| + |m_i|) for unit |dir| (derivation in DESIGN.md 4.2);
-// 1e-6 leaves a 2.7x margin.  E = eb(node) + eq(query), both rounded up.
-constexpr double kBoundC = 1.0e-6;
+// |s32 - s_exact| <= 5 * 2^-24 * (sum_i |q_i| + |c|) for unit |dir| (derivation in DESIGN.md 4.2);
+// 1e-6 = 16.8 * 2^-24 leaves a 3x margin.  E = kBoundC * (|q|_1 + |c|), rounded up.
+constexpr float kBoundC = 1.0e-6f;
 
 struct ModelView {  // passed by value (constant bank): the active keyframes of this device
   const madtree_rec_t* recs[kMaxSlots];
   const FastRec* fast[kMaxSlots];
+  const int* links[kMaxSlots];  // internal: index of the left child (right = +1); leaf: -1 - getLeafs ordinal
   int K;
 };
 
@@ -121,12 +124,13 @@ __device__ __forceinline__ Rec load_rec(const madtree_rec_t* p) {
 
 __device__ __forceinline__ FastRec load_fast(const FastRec* p) {
   FastRec r;
-  int li;
-  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=f"(r.mx), "=f"(r.my), "=f"(r.mz), "=f"(r.dx), "=f"(r.dy), "=f"(r.dz), "=r"(li), "=f"(r.eb)
-               : "l"(p));
-  r.link = li;
+  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.dx), "=f"(r.dy), "=f"(r.dz), "=f"(r.c) : "l"(p));
   return r;
+}
+__device__ __forceinline__ int load_link(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
 }
 
 __device__ __forceinline__ Moving4 load_moving(const Moving4* p) {
@@ -143,29 +147,26 @@ __device__ __forceinline__ bool side_exact(const madtree_rec_t* rec, double qx, 
 
 // Greedy single-path descent (no backtracking, like the reference).  Returns the exact-record index
 // of the leaf reached.  Bit-identical decisions to the FP64 expression by construction.
-__device__ __forceinline__ int descend(const FastRec* __restrict__ fast, const madtree_rec_t* __restrict__ recs,
-                                       double qx, double qy, double qz) {
+__device__ __forceinline__ int descend(const FastRec* __restrict__ fast, const int* __restrict__ links,
+                                       const madtree_rec_t* __restrict__ recs, double qx, double qy, double qz) {
   const float fx = __double2float_rn(qx), fy = __double2float_rn(qy), fz = __double2float_rn(qz);
-  const float eq = __double2float_ru(kBoundC * (fabs(qx) + fabs(qy) + fabs(qz)));
-  int idx = 1;
-  FastRec cur = load_fast(fast + 1);
-  while (cur.link >= 0) {
-    const FastRec* pair = fast + cur.link;
-    const FastRec c0 = load_fast(pair);      // both children requested before the predicate is needed
-    const FastRec c1 = load_fast(pair + 1);
-    const float s = fmaf(fz - cur.mz, cur.dz, fmaf(fy - cur.my, cur.dy, (fx - cur.mx) * cur.dx));
-    const float E = __fadd_ru(cur.eb, eq);
+  const float q1 = __fadd_ru(__fadd_ru(fabsf(fx), fabsf(fy)), fabsf(fz));
+  int idx = 0;
+  while (true) {
+    const int link = load_link(links + idx);
+    const FastRec p = load_fast(fast + idx);  // independent of `link`: both requests are in flight together
+    if (link < 0) return idx;
+    const float s = fmaf(fz, p.dz, fmaf(fy, p.dy, fx * p.dx)) - p.c;
+    const float E = __fmul_ru(kBoundC, __fadd_ru(q1, fabsf(p.c)));
     bool right;
     if (s > E)
       right = true;
     else if (s < -E)
       right = false;
     else
-      right = side_exact(recs + (idx - 1), qx, qy, qz);
-    idx = cur.link + (right ? 1 : 0);
-    cur = right ? c1 : c0;
+      right = side_exact(recs + idx, qx, qy, qz);
+    idx = link + (right ? 1 : 0);
   }
-  return -1 - cur.link;
 }
 
 // One correspondence (reference: odometry/mad_icp.cpp:81-101): gate, error, Jacobian, Huber scale,
@@ -209,18 +210,21 @@ __device__ __forceinline__ bool linearize_one(const double* __restrict__ X, cons
 __device__ __forceinline__ void warp_accumulate(double* stage, const double* v, double& c0, double& c1) {
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
+  // tile layout [value 0..12][item 0..15, padded to kStagePitch]: value-major with a pitch of 20
+  // doubles makes both the stores (lanes = consecutive items) and the fragment loads
+  // (bank = 4g + t + 4s mod 16) conflict-free.
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     if ((lane >> 4) == h) {
 #pragma unroll
-      for (int i = 0; i < kStage; ++i) stage[(lane & 15) * kStage + i] = v[i];
+      for (int i = 0; i < kStage; ++i) stage[i * kStagePitch + (lane & 15)] = v[i];
     }
     __syncwarp();
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-      const double* it = stage + (4 * s + t) * kStage;
-      const double a = (g < 6) ? it[g] : 0.0;                    // rows 6,7 of A are padding
-      const double b = (g < 7) ? it[6 + (g < 7 ? g : 6)] : 0.0;  // col 6 of B = e, col 7 padding
+      const double* it = stage + (4 * s + t);
+      const double a = (g < 6) ? it[g * kStagePitch] : 0.0;                          // rows 6,7 of A are padding
+      const double b = (g < 7) ? it[(6 + (g < 7 ? g : 6)) * kStagePitch] : 0.0;      // col 6 of B = e, col 7 padding
       asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                    : "+d"(c0), "+d"(c1)
                    : "d"(a), "d"(b));

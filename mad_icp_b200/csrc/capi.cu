@@ -25,12 +25,8 @@ void set_error(const std::string& msg) { g_error = msg; }
 using namespace madicp;
 
 namespace {
-struct Slot {
-  madtree_rec_t* d_recs = nullptr;  // exact 64-byte records (breadth-first)
-  FastRec* d_fast = nullptr;        // 16-byte FP32 plane shadows, same index as d_recs
-  int* d_links = nullptr;           // child links, same index as d_recs
+struct Slot {  // slot s owns pool indices [s*pool_cap, (s+1)*pool_cap)
   int n_nodes = 0, n_leaves = 0;
-  size_t cap_nodes = 0;
 };
 constexpr size_t kMatchedCap = size_t(1) << 20;  // bytes reserved for matched flags (max moving leaves)
 
@@ -49,6 +45,11 @@ struct madicp_ctx {
   cudaStream_t own_stream = nullptr, stream = nullptr;
   int sm_count = 0;
   std::vector<Slot> slots;
+  // keyframe pool: three parallel arrays, pool_cap nodes per slot (kernels.cuh: ModelView)
+  size_t pool_cap = 0;
+  madtree_rec_t* d_pool_recs = nullptr;
+  FastRec* d_pool_fast = nullptr;
+  int* d_pool_links = nullptr;
   IcpParams P{0.2, 0.31622776601683794, 0.02};
   double* d_moving = nullptr;               // raw L x 3 means as uploaded
   Moving4* d_mov4 = nullptr;                // prepared (mean, gate radius) records the kernels read
@@ -70,6 +71,9 @@ struct madicp_ctx {
   unsigned char* h_matched = nullptr;
   int gn_grid = 0;
   int gn_threads = 1024;
+  int gn_ilp = 4;
+  const void* gn_kernel = nullptr;
+  size_t gn_smem = 0;
   int last_iters = 0;
   long long* d_dbg = nullptr;  // MADICP_MAX_ITERS x 8 clock stamps when debug timing is on
   int64_t launches = 0;
@@ -90,20 +94,63 @@ struct madicp_ctx {
 
 static ModelView make_view(const madicp_ctx* c) {
   ModelView v;
+  v.recs = c->d_pool_recs;
+  v.fast = c->d_pool_fast;
+  v.links = c->d_pool_links;
   v.K = 0;
   for (int s = 0; s < c->max_keyframes; ++s)
-    if (c->slots[s].n_nodes > 0) {
-      v.recs[v.K] = c->slots[s].d_recs;
-      v.fast[v.K] = c->slots[s].d_fast;
-      v.links[v.K] = c->slots[s].d_links;
-      ++v.K;
-    }
-  for (int i = v.K; i < kMaxSlots; ++i) {
-    v.recs[i] = nullptr;
-    v.fast[i] = nullptr;
-    v.links[i] = nullptr;
-  }
+    if (c->slots[s].n_nodes > 0) v.root[v.K++] = int(size_t(s) * c->pool_cap);
+  for (int i = v.K; i < kMaxSlots; ++i) v.root[i] = 0;
   return v;
+}
+
+// (Re)builds the FP32 shadows and absolute links of slot `s` from its exact records in the pool.
+static int prepare_slot(madicp_ctx* c, int s) {
+  const int n = c->slots[s].n_nodes;
+  const size_t off = size_t(s) * c->pool_cap;
+  k_prepare_fast<<<(n + kStepBlock - 1) / kStepBlock, kStepBlock, 0, c->stream>>>(
+      c->d_pool_recs + off, n, int(off), c->d_pool_fast + off, c->d_pool_links + off);
+  c->launches++;
+  CK(cudaGetLastError());
+  return MADICP_OK;
+}
+
+// Makes every slot at least `need` nodes large.  Growing re-homes the resident keyframes (device to
+// device) and rebuilds their absolute links; it only happens when a tree larger than any before shows up.
+static int ensure_pool(madicp_ctx* c, size_t need) {
+  if (need <= c->pool_cap) return MADICP_OK;
+  size_t cap = c->pool_cap ? c->pool_cap : (size_t(1) << 16);
+  while (cap < need) cap <<= 1;
+  if (cap * size_t(c->max_keyframes) > size_t(0x7fffffff)) {
+    set_error("keyframe pool would exceed 2^31 nodes");
+    return MADICP_ERR_NOMEM;
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  madtree_rec_t* recs = nullptr;
+  FastRec* fast = nullptr;
+  int* links = nullptr;
+  const size_t total = cap * size_t(c->max_keyframes);
+  CK(cudaMalloc(&recs, total * sizeof(madtree_rec_t)));
+  CK(cudaMalloc(&fast, total * sizeof(FastRec)));
+  CK(cudaMalloc(&links, total * sizeof(int)));
+  for (int s = 0; s < c->max_keyframes; ++s)
+    if (c->slots[s].n_nodes > 0)
+      CK(cudaMemcpyAsync(recs + size_t(s) * cap, c->d_pool_recs + size_t(s) * c->pool_cap,
+                         size_t(c->slots[s].n_nodes) * sizeof(madtree_rec_t), cudaMemcpyDeviceToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(c->d_pool_recs);
+  cudaFree(c->d_pool_fast);
+  cudaFree(c->d_pool_links);
+  c->d_pool_recs = recs;
+  c->d_pool_fast = fast;
+  c->d_pool_links = links;
+  c->pool_cap = cap;
+  for (int s = 0; s < c->max_keyframes; ++s)
+    if (c->slots[s].n_nodes > 0) {
+      int rc = prepare_slot(c, s);
+      if (rc) return rc;
+    }
+  return MADICP_OK;
 }
 
 static int ensure_items(madicp_ctx* c, size_t items) {
@@ -118,29 +165,50 @@ static int ensure_items(madicp_ctx* c, size_t items) {
   return MADICP_OK;
 }
 
-template <int THREADS>
-static int configure_gn_t(madicp_ctx* c, int ctas_per_sm_cap) {
-  CK(cudaFuncSetAttribute(k_gn_loop<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          int(gn_dynamic_smem<THREADS>())));
-  int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gn_loop<THREADS>, THREADS, gn_dynamic_smem<THREADS>()));
-  if (per_sm < 1) {
-    set_error("k_gn_loop does not fit on an SM");
-    return MADICP_ERR_CUDA;
-  }
-  if (per_sm > ctas_per_sm_cap) per_sm = ctas_per_sm_cap;
-  c->gn_threads = THREADS;
-  c->gn_grid = per_sm * c->sm_count;
-  return MADICP_OK;
+// Persistent-kernel shapes.  (threads per CTA, walks per thread, CTAs per SM) -> an instantiation;
+// CTAS fixes the register budget (64K registers / (THREADS*CTAS)).  Selected at create time
+// (default below, or env MADICP_GN_SHAPE="threads,ilp,ctas") and through madicp_set_gn_grid.
+struct GnShape {
+  int threads, ilp, ctas;
+  const void* fn;
+  size_t smem;
+};
+template <int THREADS, int ILP, int CTAS>
+static GnShape gn_shape() {
+  return GnShape{THREADS, ILP, CTAS, reinterpret_cast<const void*>(k_gn_loop<THREADS, ILP, CTAS>),
+                 gn_dynamic_smem<THREADS>()};
 }
-// Persistent-kernel shape: THREADS per CTA (256 / 512 / 1024) and at most `ctas_per_sm_cap` CTAs per SM.
-static int configure_gn(madicp_ctx* c, int threads, int ctas_per_sm_cap) {
-  switch (threads) {
-    case 256: return configure_gn_t<256>(c, ctas_per_sm_cap);
-    case 512: return configure_gn_t<512>(c, ctas_per_sm_cap);
-    case 1024: return configure_gn_t<1024>(c, ctas_per_sm_cap);
-    default: set_error("persistent kernel supports 256, 512 or 1024 threads per CTA"); return MADICP_ERR_INVALID;
-  }
+static const GnShape* gn_shapes(int* n) {
+  static const GnShape table[] = {
+      gn_shape<1024, 1, 1>(), gn_shape<1024, 2, 1>(), gn_shape<1024, 3, 1>(), gn_shape<1024, 4, 1>(),
+      gn_shape<768, 2, 1>(),  gn_shape<768, 4, 1>(),                                                   // 80 registers
+      gn_shape<512, 4, 1>(),  gn_shape<512, 8, 1>(),                                                   // 128 registers
+      gn_shape<512, 2, 2>(),  gn_shape<512, 4, 2>(),  gn_shape<256, 1, 4>(),  gn_shape<256, 2, 4>(),
+  };
+  *n = int(sizeof(table) / sizeof(table[0]));
+  return table;
+}
+static int configure_gn(madicp_ctx* c, int threads, int ilp, int ctas) {
+  int n = 0;
+  const GnShape* t = gn_shapes(&n);
+  for (int i = 0; i < n; ++i)
+    if (t[i].threads == threads && t[i].ilp == ilp && t[i].ctas == ctas) {
+      CK(cudaFuncSetAttribute(t[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(t[i].smem)));
+      int per_sm = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, t[i].fn, threads, t[i].smem));
+      if (per_sm < ctas) {
+        set_error("persistent kernel shape does not fit on an SM");
+        return MADICP_ERR_CUDA;
+      }
+      c->gn_threads = threads;
+      c->gn_ilp = ilp;
+      c->gn_grid = ctas * c->sm_count;
+      c->gn_kernel = t[i].fn;
+      c->gn_smem = t[i].smem;
+      return MADICP_OK;
+    }
+  set_error("unsupported persistent-kernel shape (threads, walks per thread, CTAs per SM)");
+  return MADICP_ERR_INVALID;
 }
 
 static int grid_for(const madicp_ctx* c, int64_t items) {
@@ -192,9 +260,9 @@ int madicp_create(madicp_ctx_t** out, int device, int max_keyframes) {
   CK(cudaMallocHost(&c->h_pinned, sizeof(double) * 64));
   CK(cudaMallocHost(&c->h_state, sizeof(GnState)));
   CK(cudaMallocHost(&c->h_matched, kMatchedCap));
-  int threads = 1024;
-  if (const char* e = getenv("MADICP_GN_THREADS")) threads = atoi(e);
-  int rc = configure_gn(c, threads, 1024);
+  int threads = 1024, ilp = 2, ctas = 1;
+  if (const char* e = getenv("MADICP_GN_SHAPE")) sscanf(e, "%d,%d,%d", &threads, &ilp, &ctas);
+  int rc = configure_gn(c, threads, ilp, ctas);
   if (rc) return rc;
   c->cap_partial = size_t(c->sm_count) * 8 * kAcc;
   CK(cudaMalloc(&c->d_partial, c->cap_partial * sizeof(double)));
@@ -209,11 +277,9 @@ void madicp_destroy(madicp_ctx_t* c) {
   cudaStreamSynchronize(c->stream);
   for (int r = 0; r < c->world; ++r)
     if (c->world > 1 && r != c->rank && c->peer_comm[r]) cudaIpcCloseMemHandle(c->peer_comm[r]);
-  for (Slot& s : c->slots) {
-    if (s.d_recs) cudaFree(s.d_recs);
-    if (s.d_fast) cudaFree(s.d_fast);
-    if (s.d_links) cudaFree(s.d_links);
-  }
+  cudaFree(c->d_pool_recs);
+  cudaFree(c->d_pool_fast);
+  cudaFree(c->d_pool_links);
   cudaFree(c->d_moving);
   cudaFree(c->d_mov4);
   cudaFree(c->d_step_matched);
@@ -256,26 +322,15 @@ int madicp_put_keyframe_records(madicp_ctx_t* c, int slot, const madtree_rec_t* 
     return MADICP_ERR_INVALID;
   }
   CK(cudaSetDevice(c->device));
+  int rc = ensure_pool(c, size_t(n_nodes));
+  if (rc) return rc;
   Slot& s = c->slots[slot];
-  if (size_t(n_nodes) > s.cap_nodes) {
-    CK(cudaStreamSynchronize(c->stream));
-    if (s.d_recs) cudaFree(s.d_recs);
-    if (s.d_fast) cudaFree(s.d_fast);
-    if (s.d_links) cudaFree(s.d_links);
-    s.d_recs = nullptr;
-    s.d_fast = nullptr;
-    s.d_links = nullptr;
-    s.cap_nodes = 0;
-    CK(cudaMalloc(&s.d_recs, size_t(n_nodes) * sizeof(madtree_rec_t)));
-    CK(cudaMalloc(&s.d_fast, size_t(n_nodes) * sizeof(FastRec)));
-    CK(cudaMalloc(&s.d_links, size_t(n_nodes) * sizeof(int)));
-    s.cap_nodes = n_nodes;
-  }
-  CK(cudaMemcpyAsync(s.d_recs, recs, size_t(n_nodes) * sizeof(madtree_rec_t), cudaMemcpyHostToDevice, c->stream));
-  k_prepare_fast<<<(n_nodes + kStepBlock - 1) / kStepBlock, kStepBlock, 0, c->stream>>>(s.d_recs, n_nodes, s.d_fast,
-                                                                                        s.d_links);
-  c->launches++;
-  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(c->d_pool_recs + size_t(slot) * c->pool_cap, recs, size_t(n_nodes) * sizeof(madtree_rec_t),
+                     cudaMemcpyHostToDevice, c->stream));
+  s.n_nodes = n_nodes;
+  s.n_leaves = n_leaves;
+  rc = prepare_slot(c, slot);
+  if (rc) return rc;
   CK(cudaStreamSynchronize(c->stream));  // caller may free/modify the host tree right after
   s.n_nodes = n_nodes;
   s.n_leaves = n_leaves;
@@ -494,16 +549,7 @@ int madicp_register_async(madicp_ctx_t* c, int iters, const double X0[12]) {
   // zero the flags buffer of the NEXT call (nobody can be writing it yet; see CommBlock)
   CK(cudaMemsetAsync(c->d_comm->matched[mb ^ 1], 0, std::min(kMatchedCap, c->cap_moving), c->stream));
   void* args[] = {&A};
-  switch (c->gn_threads) {
-    case 256:
-      CK(cudaLaunchCooperativeKernel((void*) k_gn_loop<256>, dim3(c->gn_grid), dim3(256), args, gn_dynamic_smem<256>(), c->stream));
-      break;
-    case 512:
-      CK(cudaLaunchCooperativeKernel((void*) k_gn_loop<512>, dim3(c->gn_grid), dim3(512), args, gn_dynamic_smem<512>(), c->stream));
-      break;
-    default:
-      CK(cudaLaunchCooperativeKernel((void*) k_gn_loop<1024>, dim3(c->gn_grid), dim3(1024), args, gn_dynamic_smem<1024>(), c->stream));
-  }
+  CK(cudaLaunchCooperativeKernel(c->gn_kernel, dim3(c->gn_grid), dim3(c->gn_threads), args, c->gn_smem, c->stream));
   c->launches++;
   c->last_iters = iters;
   c->call_seq++;
@@ -567,8 +613,7 @@ int madicp_search_cloud(madicp_ctx_t* c, int slot, const double* q, int64_t n, i
   double* d_p = d_out;
   double* d_n = d_out + size_t(n) * 3;
   double* d_d = d_out + size_t(n) * 6;
-  k_search_cloud<<<grid_for(c, n), kStepBlock, 0, c->stream>>>(c->slots[slot].d_recs, c->slots[slot].d_fast,
-                                                              c->slots[slot].d_links, d_q, n, d_o,
+  k_search_cloud<<<grid_for(c, n), kStepBlock, 0, c->stream>>>(make_view(c), int(size_t(slot) * c->pool_cap), d_q, n, d_o,
                                                               points ? d_p : nullptr, normals ? d_n : nullptr,
                                                               dists ? d_d : nullptr);
   c->launches++;
@@ -649,10 +694,10 @@ int madicp_debug_timing(madicp_ctx_t* c, int enable, int64_t* out, int max_round
   return rows;
 }
 
-int madicp_set_gn_grid(madicp_ctx_t* c, int threads_per_cta, int ctas_per_sm) {
+int madicp_set_gn_grid(madicp_ctx_t* c, int threads_per_cta, int walks_per_thread, int ctas_per_sm) {
   if (!c || ctas_per_sm < 1) return MADICP_ERR_INVALID;
   CK(cudaSetDevice(c->device));
-  int rc = configure_gn(c, threads_per_cta, ctas_per_sm);
+  int rc = configure_gn(c, threads_per_cta, walks_per_thread, ctas_per_sm);
   if (rc) return rc;
   return c->gn_grid / c->sm_count;
 }

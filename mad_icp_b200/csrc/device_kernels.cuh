@@ -8,9 +8,11 @@ namespace madicp {
 // Preparation kernels (run once per keyframe upload / once per scan)
 // ---------------------------------------------------------------------------------------------
 
-// FP32 shadow records + link array of a keyframe tree (same index as the exact records).
+// FP32 plane shadows + absolute link array of one keyframe tree placed at pool offset `off`.
+// `recs` are the slot's exact records as uploaded (links slot-relative, breadth-first).
 __global__ void __launch_bounds__(kStepBlock)
-k_prepare_fast(const madtree_rec_t* __restrict__ recs, int n, FastRec* __restrict__ fast, int* __restrict__ links) {
+k_prepare_fast(const madtree_rec_t* __restrict__ recs, int n, int off, FastRec* __restrict__ fast,
+               int* __restrict__ links) {
   const int i = blockIdx.x * kStepBlock + threadIdx.x;
   if (i >= n) return;
   const Rec r = load_rec(recs + i);
@@ -20,7 +22,7 @@ k_prepare_fast(const madtree_rec_t* __restrict__ recs, int n, FastRec* __restric
   f.dz = __double2float_rn(r.dz);
   f.c = __double2float_rn(dot3(r.mx, r.my, r.mz, r.dx, r.dy, r.dz));  // plane offset mean.dir in FP64, rounded once
   fast[i] = f;
-  links[i] = r.link;
+  links[i] = (r.link >= 0) ? (r.link + off) : r.link;
 }
 
 // Moving leaves + gate radius (reference: odometry/mad_icp.cpp:81, iteration invariant).
@@ -55,9 +57,9 @@ k_search(const __grid_constant__ ModelView model, const Moving4* __restrict__ mo
     const Moving4 m = load_moving(moving + q);
     double mx, my, mz;
     iso_apply(X, m.px, m.py, m.pz, mx, my, mz);
-    const int leaf = descend(model.fast[k], model.links[k], model.recs[k], mx, my, mz);
+    const int leaf = descend(model, model.root[k], mx, my, mz);
     if (hit) hit[w] = leaf;
-    if (ordinals) ordinals[w] = -1 - model.links[k][leaf];
+    if (ordinals) ordinals[w] = -1 - model.links[leaf];
   }
 }
 
@@ -86,11 +88,11 @@ k_linearize(const __grid_constant__ ModelView model, const Moving4* __restrict__
 #pragma unroll
     for (int i = 0; i < kStage; ++i) v[i] = 0.0;
     if (w < total) {
-      const int k = int(w / L), q = int(w - int64_t(k) * L);
+      const int q = int(w % L);
       const Moving4 m = load_moving(moving + q);
       double mx, my, mz;
       iso_apply(X, m.px, m.py, m.pz, mx, my, mz);
-      const Rec f = load_rec(model.recs[k] + hit[w]);
+      const Rec f = load_rec(model.recs + hit[w]);
       if (linearize_one(X, P, m, mx, my, mz, f, v) && matched) matched[q] = 1;
     }
     warp_accumulate(s_stage[threadIdx.x >> 5], v, c0, c1);
@@ -117,14 +119,14 @@ __global__ void k_solve(const double* __restrict__ H, const double* __restrict__
   }
 }
 
-// MADtreeWrapper::searchCloud / searchCloudDist: arbitrary query points against one slot.
+// MADtreeWrapper::searchCloud / searchCloudDist: arbitrary query points against one keyframe.
 __global__ void __launch_bounds__(kStepBlock)
-k_search_cloud(const madtree_rec_t* __restrict__ recs, const FastRec* __restrict__ fast, const int* __restrict__ links,
-               const double* __restrict__ q, int64_t n, int* __restrict__ ordinals, double* __restrict__ points,
-               double* __restrict__ normals, double* __restrict__ dists) {
+k_search_cloud(const __grid_constant__ ModelView model, int root, const double* __restrict__ q, int64_t n,
+               int* __restrict__ ordinals, double* __restrict__ points, double* __restrict__ normals,
+               double* __restrict__ dists) {
   for (int64_t i = int64_t(blockIdx.x) * kStepBlock + threadIdx.x; i < n; i += int64_t(gridDim.x) * kStepBlock) {
     const double qx = q[3 * i], qy = q[3 * i + 1], qz = q[3 * i + 2];
-    const Rec f = load_rec(recs + descend(fast, links, recs, qx, qy, qz));
+    const Rec f = load_rec(model.recs + descend(model, root, qx, qy, qz));
     if (ordinals) ordinals[i] = -1 - f.link;
     if (points) {
       points[3 * i] = f.mx; points[3 * i + 1] = f.my; points[3 * i + 2] = f.mz;
@@ -189,19 +191,30 @@ struct GnArgs {
   long long* dbg;                          // nullable: per-round SM-clock stamps (madicp_debug_timing)
 };
 
-// Persistent cooperative grid (all CTAs co-resident).  Each CTA owns one contiguous range of the
-// K*L items (=> mostly one keyframe and one spatial region per SM: the upper tree levels stay in
-// that SM's L1 for the whole launch).  One software grid barrier per round: CTAs publish their
-// partial, take a release-ticket, the last one folds / exchanges / solves and publishes the new pose
-// and st->round; the others poll st->round with L2-coherent relaxed loads.  No acquire fence is ever
-// executed in the loop, so L1 is not invalidated between rounds; everything that crosses SMs
-// (partials, pose, flags) is read with ld.relaxed.gpu (L2) behind a control dependency on the flag.
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
+// Persistent cooperative grid (all CTAs co-resident), one software grid barrier per round: CTAs
+// publish their partial, take a release-ticket, the last one folds / exchanges / solves and
+// publishes the new pose and st->round; the others poll st->round with L2-coherent relaxed loads.
+// No acquire fence is ever executed in the loop, so L1 is not invalidated between rounds; everything
+// that crosses SMs (partials, pose, flags) is read with ld.relaxed.gpu (L2) behind a control
+// dependency on the flag.
+//
+// Work distribution.  The unit is a "warp-item": 32 consecutive items (consecutive moving leaves of
+// one keyframe in DFS order = one spatial neighbourhood).  The K*L/32 warp-items are split evenly and
+// statically (=> deterministic sums) over all warps of the grid; groups of 8 warps that sit in the
+// same CTA take adjacent ranges (L1 reuse) and consecutive groups go to different SMs (so every SM
+// samples all keyframes and the barrier does not wait for an unlucky one).
+//
+// Latency hiding.  A walk is ~16 dependent L1/L2 round trips; one thread keeps up to ILP walks in
+// flight (state per walk: one pool index + the FP32 query), issuing the ILP loads of a level back to
+// back.  With 1024 threads x ILP 4 an SM has 4096 walks in flight, enough to finish a typical round
+// (~2k items per SM) in a single pass.
+template <int THREADS, int ILP, int CTAS>
+__global__ void __launch_bounds__(THREADS, CTAS)
 k_gn_loop(const __grid_constant__ GnArgs A) {
   constexpr int WARPS = THREADS / 32;
+  constexpr int kGroup = 8;  // warps per locality group
   extern __shared__ __align__(16) double s_dyn[];
-  // layout: [WARPS][kStageItems*kStage] staging tiles | [WARPS][64] reduction scratch | peers
+  // layout: [WARPS][kStageTile] staging tiles | [WARPS][64] reduction scratch | peers
   double* s_stage_all = s_dyn;
   double(*s_red)[64] = reinterpret_cast<double(*)[64]>(s_dyn + WARPS * kStageTile);
   double(*s_peer)[kAcc] = reinterpret_cast<double(*)[kAcc]>(s_dyn + WARPS * kStageTile + WARPS * 64);
@@ -214,15 +227,13 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
   const int64_t total = int64_t(A.model.K) * A.L;
   const bool multi = A.peers.world > 1;
   const int lane = threadIdx.x & 31;
-  double* stage = s_stage_all + (threadIdx.x >> 5) * (kStageTile);
-  // Work distribution: the K*L items are cut into chunks of kChunk consecutive items (consecutive
-  // moving leaves of one keyframe = one spatial neighbourhood: good L1 reuse inside a chunk); chunk
-  // c belongs to CTA c % gridDim, so every CTA gets a sample of all keyframes and tree regions and
-  // the per-round barrier does not wait for an unlucky SM.  Static => deterministic sums.
-  constexpr int kChunk = 256;
-  constexpr int SUB = THREADS / kChunk;  // chunks a CTA processes per trip
-  const int64_t n_chunks = (total + kChunk - 1) / kChunk;
-  const int sub = threadIdx.x / kChunk;
+  const int warp = threadIdx.x >> 5;
+  double* stage = s_stage_all + warp * kStageTile;
+  const int64_t n_witems = (total + 31) / 32;
+  const int64_t n_workers = int64_t(gridDim.x) * WARPS;
+  const int64_t worker = (int64_t(warp / kGroup) * gridDim.x + blockIdx.x) * kGroup + (warp % kGroup);
+  const int64_t wi_lo = n_witems * worker / n_workers;
+  const int64_t wi_hi = n_witems * (worker + 1) / n_workers;
 
   for (int it = 0; it < A.iters; ++it) {
     if (threadIdx.x == 0 && it > 0)
@@ -234,27 +245,80 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
     double c0 = 0.0, c1 = 0.0;
     long long t_begin = 0;
     if (A.dbg && threadIdx.x == 0) t_begin = clock64();
-    for (int64_t chunk = int64_t(sub) * gridDim.x + blockIdx.x; chunk < n_chunks; chunk += int64_t(SUB) * gridDim.x) {
-      const int64_t w = chunk * kChunk + (threadIdx.x % kChunk);
-      double v[kStage];
+
+    for (int64_t base = wi_lo; base < wi_hi; base += ILP) {
+      // ---- start up to ILP walks
+      int idx[ILP];
+      QueryF qf[ILP];
+      unsigned live = 0;
 #pragma unroll
-      for (int i = 0; i < kStage; ++i) v[i] = 0.0;
-      if (w < total) {
-        const int k = int(w / A.L), q = int(w - int64_t(k) * A.L);
-        const Moving4 m = load_moving(A.moving + q);
-        double mx, my, mz;
-        iso_apply(s_X, m.px, m.py, m.pz, mx, my, mz);
-        const Rec f = load_rec(A.model.recs[k] +
-                               descend(A.model.fast[k], A.model.links[k], A.model.recs[k], mx, my, mz));
-        if (linearize_one(s_X, A.P, m, mx, my, mz, f, v) && last_round) {
-          if (multi) {
-            for (int r = 0; r < A.peers.world; ++r) A.peer_matched[r][q] = 1;
-          } else {
-            A.matched[q] = 1;
-          }
+      for (int j = 0; j < ILP; ++j) {
+        const int64_t w = (base + j) * 32 + lane;
+        idx[j] = 0;
+        qf[j].x = qf[j].y = qf[j].z = 0.f;
+        if (base + j < wi_hi && w < total) {
+          const int k = int(w / A.L), q = int(w - int64_t(k) * A.L);
+          const Moving4 m = load_moving(A.moving + q);
+          double mx, my, mz;
+          iso_apply(s_X, m.px, m.py, m.pz, mx, my, mz);
+          qf[j] = make_query(mx, my, mz);
+          idx[j] = A.model.root[k];
+          live |= 1u << j;
         }
       }
-      warp_accumulate(stage, v, c0, c1);
+      // ---- interleaved descent: all loads of a level are issued before any is consumed
+      while (live) {
+        int link[ILP];
+        FastRec p[ILP];
+#pragma unroll
+        for (int j = 0; j < ILP; ++j)
+          if (live & (1u << j)) {
+            link[j] = load_link(A.model.links + idx[j]);
+            p[j] = load_fast(A.model.fast + idx[j]);
+          }
+#pragma unroll
+        for (int j = 0; j < ILP; ++j)
+          if (live & (1u << j)) {
+            if (link[j] < 0) {
+              live &= ~(1u << j);
+            } else {
+              int side = side_filtered(qf[j], p[j]);
+              if (side < 0) {  // rare: re-derive the FP64 query and evaluate the reference predicate
+                const int64_t w = (base + j) * 32 + lane;
+                const Moving4 m = load_moving(A.moving + int(w % A.L));
+                double mx, my, mz;
+                iso_apply(s_X, m.px, m.py, m.pz, mx, my, mz);
+                side = side_exact(A.model.recs + idx[j], mx, my, mz) ? 1 : 0;
+              }
+              idx[j] = link[j] + side;
+            }
+          }
+      }
+      // ---- linearise + fold, one warp-item at a time (idx[j] = pool index of the matched leaf)
+#pragma unroll
+      for (int j = 0; j < ILP; ++j) {
+        if (base + j < wi_hi) {  // warp-uniform
+          const int64_t w = (base + j) * 32 + lane;
+          double v[kStage];
+#pragma unroll
+          for (int i = 0; i < kStage; ++i) v[i] = 0.0;
+          if (w < total) {
+            const int q = int(w % A.L);
+            const Moving4 m = load_moving(A.moving + q);
+            double mx, my, mz;
+            iso_apply(s_X, m.px, m.py, m.pz, mx, my, mz);
+            const Rec f = load_rec(A.model.recs + idx[j]);
+            if (linearize_one(s_X, A.P, m, mx, my, mz, f, v) && last_round) {
+              if (multi) {
+                for (int r = 0; r < A.peers.world; ++r) A.peer_matched[r][q] = 1;
+              } else {
+                A.matched[q] = 1;
+              }
+            }
+          }
+          warp_accumulate(stage, v, c0, c1);
+        }
+      }
     }
     if (A.dbg && threadIdx.x == 0 && blockIdx.x == 0) A.dbg[it * 8 + 0] = clock64() - t_begin;  // item phase, CTA 0
     block_reduce_store<WARPS>(c0, c1, s_red, A.partial + size_t(blockIdx.x) * kAcc);
@@ -279,7 +343,7 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
         int c = 0;
         for (int q = threadIdx.x; q < A.L; q += THREADS) c += (__ldcv(A.matched + q) != 0);
         for (int off = 16; off > 0; off >>= 1) c += __shfl_down_sync(0xffffffffu, c, off);
-        if (lane == 0) s_count[threadIdx.x >> 5] = c;
+        if (lane == 0) s_count[warp] = c;
       }
       if (threadIdx.x < 6) s_b[threadIdx.x] = s_tot[threadIdx.x * 8 + 6];
       __syncthreads();

@@ -61,10 +61,14 @@ static_assert(sizeof(FastRec) == 16, "FastRec must be one 128-bit load");
 // 1e-6 = 16.8 * 2^-24 leaves a 3x margin.  E = kBoundC * (|q|_1 + |c|), rounded up.
 constexpr float kBoundC = 1.0e-6f;
 
-struct ModelView {  // passed by value (constant bank): the active keyframes of this device
-  const madtree_rec_t* recs[kMaxSlots];
-  const FastRec* fast[kMaxSlots];
-  const int* links[kMaxSlots];  // internal: index of the left child (right = +1); leaf: -1 - getLeafs ordinal
+// All keyframes of a device live in ONE pool (three parallel arrays; slot s owns the index range
+// [s*cap, (s+1)*cap)), and links are absolute pool indices, so a walk in flight is described by a
+// single int.  That is what makes several interleaved walks per thread affordable in registers.
+struct ModelView {  // passed by value (constant bank)
+  const madtree_rec_t* recs;  // exact 64-byte records
+  const FastRec* fast;        // FP32 plane shadows
+  const int* links;           // internal: pool index of the left child (right = +1); leaf: -1 - getLeafs ordinal
+  int root[kMaxSlots];        // pool index of the root of the k-th active keyframe
   int K;
 };
 
@@ -147,25 +151,37 @@ __device__ __forceinline__ bool side_exact(const madtree_rec_t* rec, double qx, 
 
 // Greedy single-path descent (no backtracking, like the reference).  Returns the exact-record index
 // of the leaf reached.  Bit-identical decisions to the FP64 expression by construction.
-__device__ __forceinline__ int descend(const FastRec* __restrict__ fast, const int* __restrict__ links,
-                                       const madtree_rec_t* __restrict__ recs, double qx, double qy, double qz) {
-  const float fx = __double2float_rn(qx), fy = __double2float_rn(qy), fz = __double2float_rn(qz);
-  const float q1 = __fadd_ru(__fadd_ru(fabsf(fx), fabsf(fy)), fabsf(fz));
-  int idx = 0;
+// FP32 query of a walk: rounded coordinates + their 1-norm (for the error bound).
+struct QueryF {
+  float x, y, z;
+};
+__device__ __forceinline__ QueryF make_query(double qx, double qy, double qz) {
+  QueryF q;
+  q.x = __double2float_rn(qx);
+  q.y = __double2float_rn(qy);
+  q.z = __double2float_rn(qz);
+  return q;
+}
+// Filtered side test at one node: +1 right, 0 left, -1 undecided (|s32| within the error bound:
+// the caller must evaluate the exact FP64 predicate).
+__device__ __forceinline__ int side_filtered(const QueryF& q, const FastRec& p) {
+  const float s = fmaf(q.z, p.dz, fmaf(q.y, p.dy, q.x * p.dx)) - p.c;
+  const float n1 = __fadd_ru(__fadd_ru(fabsf(q.x), fabsf(q.y)), fabsf(q.z));  // |q|_1, 3 cheap ops vs a live register
+  const float E = __fmul_ru(kBoundC, __fadd_ru(n1, fabsf(p.c)));
+  return (s > E) ? 1 : ((s < -E) ? 0 : -1);
+}
+
+// One walk, root to leaf (step API and tools).  Returns the pool index of the leaf.
+__device__ __forceinline__ int descend(const ModelView& M, int root, double qx, double qy, double qz) {
+  const QueryF q = make_query(qx, qy, qz);
+  int idx = root;
   while (true) {
-    const int link = load_link(links + idx);
-    const FastRec p = load_fast(fast + idx);  // independent of `link`: both requests are in flight together
+    const int link = load_link(M.links + idx);
+    const FastRec p = load_fast(M.fast + idx);  // independent of `link`: both requests are in flight together
     if (link < 0) return idx;
-    const float s = fmaf(fz, p.dz, fmaf(fy, p.dy, fx * p.dx)) - p.c;
-    const float E = __fmul_ru(kBoundC, __fadd_ru(q1, fabsf(p.c)));
-    bool right;
-    if (s > E)
-      right = true;
-    else if (s < -E)
-      right = false;
-    else
-      right = side_exact(recs + idx, qx, qy, qz);
-    idx = link + (right ? 1 : 0);
+    int side = side_filtered(q, p);
+    if (side < 0) side = side_exact(M.recs + idx, qx, qy, qz) ? 1 : 0;
+    idx = link + side;
   }
 }
 

@@ -170,11 +170,10 @@ int madicp_comm_world(const madicp_ctx_t* ctx);
  * [0] item phase of CTA 0, [1] round start -> last CTA arrived, [2] fold of the per-CTA partials,
  * [3] peer exchange + matched count, [4] solve + publish (cycles).  Returns rows written. */
 int madicp_debug_timing(madicp_ctx_t* ctx, int enable, int64_t* out, int max_rounds);
-/* Shape of the persistent kernel: threads per CTA (256, 512 or 1024; default 1024 or env
- * MADICP_GN_THREADS at create time), interleaved tree walks per thread (1, 2 or 4; default 4 or env
- * MADICP_GN_ILP) and resident CTAs per SM (clamped to the occupancy limit).  Returns the CTAs per SM
- * in effect. */
-int madicp_set_gn_grid(madicp_ctx_t* ctx, int threads_per_cta, int walks_per_thread, int ctas_per_sm);
+/* Shape of the persistent kernel: threads per CTA and resident CTAs per SM; supported pairs are
+ * (1024,1) default, (768,1), (512,1), (512,2), (256,2), (256,3), (256,4); env MADICP_GN_SHAPE="t,c"
+ * selects one at create time.  Returns the CTAs per SM in effect. */
+int madicp_set_gn_grid(madicp_ctx_t* ctx, int threads_per_cta, int ctas_per_sm);
 
 #ifdef __cplusplus
 }

@@ -71,7 +71,6 @@ struct madicp_ctx {
   unsigned char* h_matched = nullptr;
   int gn_grid = 0;
   int gn_threads = 1024;
-  int gn_ilp = 4;
   const void* gn_kernel = nullptr;
   size_t gn_smem = 0;
   int last_iters = 0;
@@ -109,7 +108,7 @@ static int prepare_slot(madicp_ctx* c, int s) {
   const int n = c->slots[s].n_nodes;
   const size_t off = size_t(s) * c->pool_cap;
   k_prepare_fast<<<(n + kStepBlock - 1) / kStepBlock, kStepBlock, 0, c->stream>>>(
-      c->d_pool_recs + off, n, int(off), c->d_pool_fast + off, c->d_pool_links + off);
+      c->d_pool_recs + off, n, int(off), c->P.min_ball, c->d_pool_fast + off, c->d_pool_links + off);
   c->launches++;
   CK(cudaGetLastError());
   return MADICP_OK;
@@ -165,34 +164,31 @@ static int ensure_items(madicp_ctx* c, size_t items) {
   return MADICP_OK;
 }
 
-// Persistent-kernel shapes.  (threads per CTA, walks per thread, CTAs per SM) -> an instantiation;
-// CTAS fixes the register budget (64K registers / (THREADS*CTAS)).  Selected at create time
-// (default below, or env MADICP_GN_SHAPE="threads,ilp,ctas") and through madicp_set_gn_grid.
+// Persistent-kernel shapes: (threads per CTA, CTAs per SM) -> an instantiation; the pair fixes the
+// register budget (64K registers / (THREADS*CTAS)).  Selected at create time (default 1024x1, or env
+// MADICP_GN_SHAPE="threads,ctas") and through madicp_set_gn_grid.
 struct GnShape {
-  int threads, ilp, ctas;
+  int threads, ctas;
   const void* fn;
   size_t smem;
 };
-template <int THREADS, int ILP, int CTAS>
+template <int THREADS, int CTAS>
 static GnShape gn_shape() {
-  return GnShape{THREADS, ILP, CTAS, reinterpret_cast<const void*>(k_gn_loop<THREADS, ILP, CTAS>),
-                 gn_dynamic_smem<THREADS>()};
+  return GnShape{THREADS, CTAS, reinterpret_cast<const void*>(k_gn_loop<THREADS, CTAS>), gn_dynamic_smem<THREADS>()};
 }
 static const GnShape* gn_shapes(int* n) {
   static const GnShape table[] = {
-      gn_shape<1024, 1, 1>(), gn_shape<1024, 2, 1>(), gn_shape<1024, 3, 1>(), gn_shape<1024, 4, 1>(),
-      gn_shape<768, 2, 1>(),  gn_shape<768, 4, 1>(),                                                   // 80 registers
-      gn_shape<512, 4, 1>(),  gn_shape<512, 8, 1>(),                                                   // 128 registers
-      gn_shape<512, 2, 2>(),  gn_shape<512, 4, 2>(),  gn_shape<256, 1, 4>(),  gn_shape<256, 2, 4>(),
+      gn_shape<1024, 1>(), gn_shape<768, 1>(), gn_shape<512, 1>(), gn_shape<512, 2>(),
+      gn_shape<256, 2>(),  gn_shape<256, 3>(), gn_shape<256, 4>(),
   };
   *n = int(sizeof(table) / sizeof(table[0]));
   return table;
 }
-static int configure_gn(madicp_ctx* c, int threads, int ilp, int ctas) {
+static int configure_gn(madicp_ctx* c, int threads, int ctas) {
   int n = 0;
   const GnShape* t = gn_shapes(&n);
   for (int i = 0; i < n; ++i)
-    if (t[i].threads == threads && t[i].ilp == ilp && t[i].ctas == ctas) {
+    if (t[i].threads == threads && t[i].ctas == ctas) {
       CK(cudaFuncSetAttribute(t[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(t[i].smem)));
       int per_sm = 0;
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, t[i].fn, threads, t[i].smem));
@@ -201,13 +197,12 @@ static int configure_gn(madicp_ctx* c, int threads, int ilp, int ctas) {
         return MADICP_ERR_CUDA;
       }
       c->gn_threads = threads;
-      c->gn_ilp = ilp;
       c->gn_grid = ctas * c->sm_count;
       c->gn_kernel = t[i].fn;
       c->gn_smem = t[i].smem;
       return MADICP_OK;
     }
-  set_error("unsupported persistent-kernel shape (threads, walks per thread, CTAs per SM)");
+  set_error("unsupported persistent-kernel shape (threads per CTA, CTAs per SM)");
   return MADICP_ERR_INVALID;
 }
 
@@ -260,9 +255,9 @@ int madicp_create(madicp_ctx_t** out, int device, int max_keyframes) {
   CK(cudaMallocHost(&c->h_pinned, sizeof(double) * 64));
   CK(cudaMallocHost(&c->h_state, sizeof(GnState)));
   CK(cudaMallocHost(&c->h_matched, kMatchedCap));
-  int threads = 1024, ilp = 2, ctas = 1;
-  if (const char* e = getenv("MADICP_GN_SHAPE")) sscanf(e, "%d,%d,%d", &threads, &ilp, &ctas);
-  int rc = configure_gn(c, threads, ilp, ctas);
+  int threads = 1024, ctas = 1;
+  if (const char* e = getenv("MADICP_GN_SHAPE")) sscanf(e, "%d,%d", &threads, &ctas);
+  int rc = configure_gn(c, threads, ctas);
   if (rc) return rc;
   c->cap_partial = size_t(c->sm_count) * 8 * kAcc;
   CK(cudaMalloc(&c->d_partial, c->cap_partial * sizeof(double)));
@@ -302,10 +297,19 @@ int madicp_set_params(madicp_ctx_t* c, double min_ball, double rho_ker, double b
     set_error("madicp_set_params: bad arguments");
     return MADICP_ERR_INVALID;
   }
+  const bool reweigh = (min_ball != c->P.min_ball);
   c->P.min_ball = min_ball;
   c->P.rho_ker_sqrt = sqrt(rho_ker);
   c->P.b_ratio = b_ratio;
   c->mov4_stale = true;  // the gate radius depends on min_ball and b_ratio
+  if (reweigh) {         // leaf planarity weights (1 - bbox0/min_ball)^2 live in the leaf shadows
+    CK(cudaSetDevice(c->device));
+    for (int s = 0; s < c->max_keyframes; ++s)
+      if (c->slots[s].n_nodes > 0) {
+        int rc = prepare_slot(c, s);
+        if (rc) return rc;
+      }
+  }
   return MADICP_OK;
 }
 
@@ -421,6 +425,10 @@ static int check_ready(madicp_ctx* c, const char* who) {
   if (c->L < 1 || !c->d_moving) {
     set_error(std::string(who) + ": no moving leaves (call madicp_set_moving first)");
     return MADICP_ERR_STATE;
+  }
+  if (int64_t(madicp_num_keyframes(c)) * int64_t(c->L) >= (int64_t(1) << 31)) {
+    set_error(std::string(who) + ": keyframes x moving leaves must stay below 2^31 (32-bit item index)");
+    return MADICP_ERR_INVALID;
   }
   if (madicp_num_keyframes(c) < 1 && c->world <= 1) {
     set_error(std::string(who) + ": no keyframe uploaded");
@@ -694,10 +702,10 @@ int madicp_debug_timing(madicp_ctx_t* c, int enable, int64_t* out, int max_round
   return rows;
 }
 
-int madicp_set_gn_grid(madicp_ctx_t* c, int threads_per_cta, int walks_per_thread, int ctas_per_sm) {
+int madicp_set_gn_grid(madicp_ctx_t* c, int threads_per_cta, int ctas_per_sm) {
   if (!c || ctas_per_sm < 1) return MADICP_ERR_INVALID;
   CK(cudaSetDevice(c->device));
-  int rc = configure_gn(c, threads_per_cta, walks_per_thread, ctas_per_sm);
+  int rc = configure_gn(c, threads_per_cta, ctas_per_sm);
   if (rc) return rc;
   return c->gn_grid / c->sm_count;
 }

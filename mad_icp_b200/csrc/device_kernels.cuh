@@ -11,16 +11,25 @@ namespace madicp {
 // FP32 plane shadows + absolute link array of one keyframe tree placed at pool offset `off`.
 // `recs` are the slot's exact records as uploaded (links slot-relative, breadth-first).
 __global__ void __launch_bounds__(kStepBlock)
-k_prepare_fast(const madtree_rec_t* __restrict__ recs, int n, int off, FastRec* __restrict__ fast,
+k_prepare_fast(const madtree_rec_t* __restrict__ recs, int n, int off, double min_ball, FastRec* __restrict__ fast,
                int* __restrict__ links) {
   const int i = blockIdx.x * kStepBlock + threadIdx.x;
   if (i >= n) return;
   const Rec r = load_rec(recs + i);
   FastRec f;
-  f.dx = __double2float_rn(r.dx);
-  f.dy = __double2float_rn(r.dy);
-  f.dz = __double2float_rn(r.dz);
-  f.c = __double2float_rn(dot3(r.mx, r.my, r.mz, r.dx, r.dy, r.dz));  // plane offset mean.dir in FP64, rounded once
+  if (r.link >= 0) {
+    f.dx = __double2float_rn(r.dx);
+    f.dy = __double2float_rn(r.dy);
+    f.dz = __double2float_rn(r.dz);
+    f.c = __double2float_rn(dot3(r.mx, r.my, r.mz, r.dx, r.dy, r.dz));  // plane offset mean.dir in FP64, rounded once
+  } else {  // leaf: planarity weight w*w with w = 1 - bbox(0)/min_ball (reference: mad_icp.cpp:97-98)
+    const double w = 1.0 - r.bbox0 / min_ball;
+    const double ww = w * w;
+    f.dx = __int_as_float(__double2loint(ww));
+    f.dy = __int_as_float(__double2hiint(ww));
+    f.dz = 0.f;
+    f.c = 0.f;
+  }
   fast[i] = f;
   links[i] = (r.link >= 0) ? (r.link + off) : r.link;
 }
@@ -51,13 +60,13 @@ k_search(const __grid_constant__ ModelView model, const Moving4* __restrict__ mo
   double X[12];
 #pragma unroll
   for (int i = 0; i < 12; ++i) X[i] = Xp[i];
-  const int64_t total = int64_t(model.K) * L;
-  for (int64_t w = int64_t(blockIdx.x) * kStepBlock + threadIdx.x; w < total; w += int64_t(gridDim.x) * kStepBlock) {
-    const int k = int(w / L), q = int(w - int64_t(k) * L);
+  const unsigned total = unsigned(model.K) * unsigned(L);
+  for (unsigned w = blockIdx.x * kStepBlock + threadIdx.x; w < total; w += gridDim.x * kStepBlock) {
+    const unsigned k = w / unsigned(L), q = w - k * unsigned(L);
     const Moving4 m = load_moving(moving + q);
-    double mx, my, mz;
+    double mx, my, mz, ww;
     iso_apply(X, m.px, m.py, m.pz, mx, my, mz);
-    const int leaf = descend(model, model.root[k], mx, my, mz);
+    const int leaf = descend(model, model.root[k], mx, my, mz, ww);
     if (hit) hit[w] = leaf;
     if (ordinals) ordinals[w] = -1 - model.links[leaf];
   }
@@ -78,22 +87,23 @@ k_linearize(const __grid_constant__ ModelView model, const Moving4* __restrict__
 #pragma unroll
   for (int i = 0; i < 12; ++i) X[i] = Xp[i];
   double c0 = 0.0, c1 = 0.0;
-  const int64_t total = int64_t(model.K) * L;
-  const int lane = threadIdx.x & 31;
+  const unsigned total = unsigned(model.K) * unsigned(L);
+  const unsigned lane = threadIdx.x & 31;
   // warp-uniform trip count: every lane takes part in the DMMA fold, lanes past the end stage zeros
-  for (int64_t w0 = int64_t(blockIdx.x) * kStepBlock + (threadIdx.x - lane); w0 < total;
-       w0 += int64_t(gridDim.x) * kStepBlock) {
-    const int64_t w = w0 + lane;
+  for (unsigned w0 = blockIdx.x * kStepBlock + (threadIdx.x - lane); w0 < total; w0 += gridDim.x * kStepBlock) {
+    const unsigned w = w0 + lane;
     double v[kStage];
 #pragma unroll
     for (int i = 0; i < kStage; ++i) v[i] = 0.0;
     if (w < total) {
-      const int q = int(w % L);
+      const unsigned q = w % unsigned(L);
       const Moving4 m = load_moving(moving + q);
       double mx, my, mz;
       iso_apply(X, m.px, m.py, m.pz, mx, my, mz);
-      const Rec f = load_rec(model.recs + hit[w]);
-      if (linearize_one(X, P, m, mx, my, mz, f, v) && matched) matched[q] = 1;
+      const int leaf = hit[w];
+      const Rec f = load_rec(model.recs + leaf);
+      const double ww = leaf_weight(load_fast(model.fast + leaf));
+      if (linearize_one(X, P.rho_ker_sqrt, m, mx, my, mz, f, ww, v) && matched) matched[q] = 1;
     }
     warp_accumulate(s_stage[threadIdx.x >> 5], v, c0, c1);
   }
@@ -126,7 +136,8 @@ k_search_cloud(const __grid_constant__ ModelView model, int root, const double* 
                double* __restrict__ dists) {
   for (int64_t i = int64_t(blockIdx.x) * kStepBlock + threadIdx.x; i < n; i += int64_t(gridDim.x) * kStepBlock) {
     const double qx = q[3 * i], qy = q[3 * i + 1], qz = q[3 * i + 2];
-    const Rec f = load_rec(model.recs + descend(model, root, qx, qy, qz));
+    double ww;
+    const Rec f = load_rec(model.recs + descend(model, root, qx, qy, qz, ww));
     if (ordinals) ordinals[i] = -1 - f.link;
     if (points) {
       points[3 * i] = f.mx; points[3 * i + 1] = f.my; points[3 * i + 2] = f.mz;
@@ -199,20 +210,15 @@ struct GnArgs {
 // dependency on the flag.
 //
 // Work distribution.  The unit is a "warp-item": 32 consecutive items (consecutive moving leaves of
-// one keyframe in DFS order = one spatial neighbourhood).  The K*L/32 warp-items are split evenly and
-// statically (=> deterministic sums) over all warps of the grid; groups of 8 warps that sit in the
-// same CTA take adjacent ranges (L1 reuse) and consecutive groups go to different SMs (so every SM
-// samples all keyframes and the barrier does not wait for an unlucky one).
-//
-// Latency hiding.  A walk is ~16 dependent L1/L2 round trips; one thread keeps up to ILP walks in
-// flight (state per walk: one pool index + the FP32 query), issuing the ILP loads of a level back to
-// back.  With 1024 threads x ILP 4 an SM has 4096 walks in flight, enough to finish a typical round
-// (~2k items per SM) in a single pass.
-template <int THREADS, int ILP, int CTAS>
+// one keyframe in DFS order = one spatial neighbourhood, so the lanes of a warp share the upper tree
+// levels).  Warp-item i goes to grid-warp i mod W (W = all warps of the grid, numbered so that
+// consecutive ones sit on different SMs): every SM gets a uniform sample of all keyframes and tree
+// regions -- per-item cost varies by 2x between near and far keyframes (gate pass rate) -- and the
+// per-round barrier does not wait for an unlucky SM.  Static => deterministic sums.
+template <int THREADS, int CTAS>
 __global__ void __launch_bounds__(THREADS, CTAS)
 k_gn_loop(const __grid_constant__ GnArgs A) {
   constexpr int WARPS = THREADS / 32;
-  constexpr int kGroup = 8;  // warps per locality group
   extern __shared__ __align__(16) double s_dyn[];
   // layout: [WARPS][kStageTile] staging tiles | [WARPS][64] reduction scratch | peers
   double* s_stage_all = s_dyn;
@@ -224,16 +230,15 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
   __shared__ int s_last;
   __shared__ int s_count[WARPS];
   GnState* st = A.st;
-  const int64_t total = int64_t(A.model.K) * A.L;
+  const unsigned L = unsigned(A.L);
+  const unsigned total = unsigned(A.model.K) * L;  // host guarantees K*L < 2^31
   const bool multi = A.peers.world > 1;
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned warp = threadIdx.x >> 5;
   double* stage = s_stage_all + warp * kStageTile;
-  const int64_t n_witems = (total + 31) / 32;
-  const int64_t n_workers = int64_t(gridDim.x) * WARPS;
-  const int64_t worker = (int64_t(warp / kGroup) * gridDim.x + blockIdx.x) * kGroup + (warp % kGroup);
-  const int64_t wi_lo = n_witems * worker / n_workers;
-  const int64_t wi_hi = n_witems * (worker + 1) / n_workers;
+  const unsigned n_witems = (total + 31) / 32;
+  const unsigned n_workers = gridDim.x * WARPS;
+  const unsigned worker = warp * gridDim.x + blockIdx.x;
 
   for (int it = 0; it < A.iters; ++it) {
     if (threadIdx.x == 0 && it > 0)
@@ -246,79 +251,32 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
     long long t_begin = 0;
     if (A.dbg && threadIdx.x == 0) t_begin = clock64();
 
-    for (int64_t base = wi_lo; base < wi_hi; base += ILP) {
-      // ---- start up to ILP walks
-      int idx[ILP];
-      QueryF qf[ILP];
-      unsigned live = 0;
+    for (unsigned wi = worker; wi < n_witems; wi += n_workers) {
+      // (keyframe, leaf) of this lane: one 32-bit division per warp-item, then a carry
+      const unsigned w0 = wi * 32;
+      unsigned k = w0 / L;
+      unsigned q = w0 - k * L + lane;
+      while (q >= L) {
+        q -= L;
+        ++k;
+      }
+      double v[kStage];
 #pragma unroll
-      for (int j = 0; j < ILP; ++j) {
-        const int64_t w = (base + j) * 32 + lane;
-        idx[j] = 0;
-        qf[j].x = qf[j].y = qf[j].z = 0.f;
-        if (base + j < wi_hi && w < total) {
-          const int k = int(w / A.L), q = int(w - int64_t(k) * A.L);
-          const Moving4 m = load_moving(A.moving + q);
-          double mx, my, mz;
-          iso_apply(s_X, m.px, m.py, m.pz, mx, my, mz);
-          qf[j] = make_query(mx, my, mz);
-          idx[j] = A.model.root[k];
-          live |= 1u << j;
+      for (int i = 0; i < kStage; ++i) v[i] = 0.0;
+      if (w0 + lane < total) {
+        const Moving4 m = load_moving(A.moving + q);
+        double mx, my, mz, ww;
+        iso_apply(s_X, m.px, m.py, m.pz, mx, my, mz);
+        const Rec f = load_rec(A.model.recs + descend(A.model, A.model.root[k], mx, my, mz, ww));
+        if (linearize_one(s_X, A.P.rho_ker_sqrt, m, mx, my, mz, f, ww, v) && last_round) {
+          if (multi) {
+            for (int r = 0; r < A.peers.world; ++r) A.peer_matched[r][q] = 1;
+          } else {
+            A.matched[q] = 1;
+          }
         }
       }
-      // ---- interleaved descent: all loads of a level are issued before any is consumed
-      while (live) {
-        int link[ILP];
-        FastRec p[ILP];
-#pragma unroll
-        for (int j = 0; j < ILP; ++j)
-          if (live & (1u << j)) {
-            link[j] = load_link(A.model.links + idx[j]);
-            p[j] = load_fast(A.model.fast + idx[j]);
-          }
-#pragma unroll
-        for (int j = 0; j < ILP; ++j)
-          if (live & (1u << j)) {
-            if (link[j] < 0) {
-              live &= ~(1u << j);
-            } else {
-              int side = side_filtered(qf[j], p[j]);
-              if (side < 0) {  // rare: re-derive the FP64 query and evaluate the reference predicate
-                const int64_t w = (base + j) * 32 + lane;
-                const Moving4 m = load_moving(A.moving + int(w % A.L));
-                double mx, my, mz;
-                iso_apply(s_X, m.px, m.py, m.pz, mx, my, mz);
-                side = side_exact(A.model.recs + idx[j], mx, my, mz) ? 1 : 0;
-              }
-              idx[j] = link[j] + side;
-            }
-          }
-      }
-      // ---- linearise + fold, one warp-item at a time (idx[j] = pool index of the matched leaf)
-#pragma unroll
-      for (int j = 0; j < ILP; ++j) {
-        if (base + j < wi_hi) {  // warp-uniform
-          const int64_t w = (base + j) * 32 + lane;
-          double v[kStage];
-#pragma unroll
-          for (int i = 0; i < kStage; ++i) v[i] = 0.0;
-          if (w < total) {
-            const int q = int(w % A.L);
-            const Moving4 m = load_moving(A.moving + q);
-            double mx, my, mz;
-            iso_apply(s_X, m.px, m.py, m.pz, mx, my, mz);
-            const Rec f = load_rec(A.model.recs + idx[j]);
-            if (linearize_one(s_X, A.P, m, mx, my, mz, f, v) && last_round) {
-              if (multi) {
-                for (int r = 0; r < A.peers.world; ++r) A.peer_matched[r][q] = 1;
-              } else {
-                A.matched[q] = 1;
-              }
-            }
-          }
-          warp_accumulate(stage, v, c0, c1);
-        }
-      }
+      warp_accumulate(stage, v, c0, c1);
     }
     if (A.dbg && threadIdx.x == 0 && blockIdx.x == 0) A.dbg[it * 8 + 0] = clock64() - t_begin;  // item phase, CTA 0
     block_reduce_store<WARPS>(c0, c1, s_red, A.partial + size_t(blockIdx.x) * kAcc);

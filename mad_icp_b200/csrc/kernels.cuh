@@ -149,36 +149,45 @@ __device__ __forceinline__ bool side_exact(const madtree_rec_t* rec, double qx, 
   return !(plane_side(qx, qy, qz, r.mx, r.my, r.mz, r.dx, r.dy, r.dz) < 0.0);
 }
 
-// Greedy single-path descent (no backtracking, like the reference).  Returns the exact-record index
-// of the leaf reached.  Bit-identical decisions to the FP64 expression by construction.
-// FP32 query of a walk: rounded coordinates + their 1-norm (for the error bound).
+// FP32 query of a walk: rounded coordinates + the query part of the error bound.
 struct QueryF {
-  float x, y, z;
+  float x, y, z, eq;  // eq = kBoundC * |q|_1, rounded up
 };
 __device__ __forceinline__ QueryF make_query(double qx, double qy, double qz) {
   QueryF q;
   q.x = __double2float_rn(qx);
   q.y = __double2float_rn(qy);
   q.z = __double2float_rn(qz);
+  q.eq = __fmul_ru(kBoundC, __fadd_ru(__fadd_ru(fabsf(q.x), fabsf(q.y)), fabsf(q.z)));
   return q;
 }
-// Filtered side test at one node: +1 right, 0 left, -1 undecided (|s32| within the error bound:
-// the caller must evaluate the exact FP64 predicate).
+// Filtered side test at one node: +1 right, 0 left, -1 undecided (|s32| within the error bound
+// E = kBoundC*(|q|_1 + |c|): the caller must evaluate the exact FP64 predicate).
 __device__ __forceinline__ int side_filtered(const QueryF& q, const FastRec& p) {
   const float s = fmaf(q.z, p.dz, fmaf(q.y, p.dy, q.x * p.dx)) - p.c;
-  const float n1 = __fadd_ru(__fadd_ru(fabsf(q.x), fabsf(q.y)), fabsf(q.z));  // |q|_1, 3 cheap ops vs a live register
-  const float E = __fmul_ru(kBoundC, __fadd_ru(n1, fabsf(p.c)));
+  const float E = __fmaf_ru(kBoundC, fabsf(p.c), q.eq);
   return (s > E) ? 1 : ((s < -E) ? 0 : -1);
 }
+// The shadow of a LEAF carries no plane; its first 8 bytes hold the leaf's planarity weight
+// ww = (1 - bbox0/min_ball)^2 as a double (reference: odometry/mad_icp.cpp:97-98), so the value
+// arrives with the load that discovers the leaf.
+__device__ __forceinline__ double leaf_weight(const FastRec& p) {
+  return __hiloint2double(__float_as_int(p.dy), __float_as_int(p.dx));
+}
 
-// One walk, root to leaf (step API and tools).  Returns the pool index of the leaf.
-__device__ __forceinline__ int descend(const ModelView& M, int root, double qx, double qy, double qz) {
+// Greedy single-path descent (no backtracking, like the reference: tools/mad_tree.cpp:144-152).
+// Returns the pool index of the leaf reached and its planarity weight.  Decisions are bit-identical
+// to the reference's FP64 expression by construction.
+__device__ __forceinline__ int descend(const ModelView& M, int root, double qx, double qy, double qz, double& ww) {
   const QueryF q = make_query(qx, qy, qz);
   int idx = root;
   while (true) {
     const int link = load_link(M.links + idx);
     const FastRec p = load_fast(M.fast + idx);  // independent of `link`: both requests are in flight together
-    if (link < 0) return idx;
+    if (link < 0) {
+      ww = leaf_weight(p);
+      return idx;
+    }
     int side = side_filtered(q, p);
     if (side < 0) side = side_exact(M.recs + idx, qx, qy, qz) ? 1 : 0;
     idx = link + side;
@@ -187,25 +196,31 @@ __device__ __forceinline__ int descend(const ModelView& M, int root, double qx, 
 
 // One correspondence (reference: odometry/mad_icp.cpp:81-101): gate, error, Jacobian, Huber scale,
 // planarity weight.  Fills v = {sJ[0..5] = scale*J, J[0..5], e}; returns false (v untouched) when
-// the gate rejects the pair.  FP64, no FMA, operand order as arith.h.
-__device__ __forceinline__ bool linearize_one(const double* __restrict__ X, const IcpParams& P, const Moving4& m,
-                                              double mlx, double mly, double mlz, const Rec& f, double* v) {
+// the gate rejects the pair.
+//   * The gate `|ml - f.mean| > ball` decides a flag (matched_) and a discontinuous contribution, so
+//     it is evaluated exactly as the reference does (FP64, no FMA); the square root is only taken
+//     when d^2 is within 1e-14 (relative) of ball^2, where the comparison of squares could disagree
+//     with the comparison of rounded roots.
+//   * e, J and the products are continuous in their inputs; they use FMA (tolerance on H/b is
+//     1e-12 relative, an FMA moves a term by <= 1 ulp).
+__device__ __forceinline__ bool linearize_one(const double* __restrict__ X, double rho, const Moving4& m, double mlx,
+                                              double mly, double mlz, const Rec& f, double ww, double* v) {
   const double ex = mlx - f.mx, ey = mly - f.my, ez = mlz - f.mz;
-  if (norm3(ex, ey, ez) > m.ball) return false;
-  const double e = dot3(ex, ey, ez, f.dx, f.dy, f.dz);
+  const double d2 = dot3(ex, ey, ez, ex, ey, ez);
+  const double b2 = m.ball * m.ball;
+  if (d2 > b2 * (1.0 + 1e-14)) return false;
+  if (!(d2 < b2 * (1.0 - 1e-14)) && sqrt(d2) > m.ball) return false;
+  const double e = fma(ez, f.dz, fma(ey, f.dy, ex * f.dx));
   double J[6];
-  J[0] = dot3(f.dx, f.dy, f.dz, X[0], X[4], X[8]);
-  J[1] = dot3(f.dx, f.dy, f.dz, X[1], X[5], X[9]);
-  J[2] = dot3(f.dx, f.dy, f.dz, X[2], X[6], X[10]);
-  const double n0 = -J[0], n1 = -J[1], n2 = -J[2];
-  J[3] = n1 * m.pz + n2 * (-m.py);
-  J[4] = n0 * (-m.pz) + n2 * m.px;
-  J[5] = n0 * m.py + n1 * (-m.px);
-  double scale = 1.0;
+  J[0] = fma(f.dz, X[8], fma(f.dy, X[4], f.dx * X[0]));
+  J[1] = fma(f.dz, X[9], fma(f.dy, X[5], f.dx * X[1]));
+  J[2] = fma(f.dz, X[10], fma(f.dy, X[6], f.dx * X[2]));
+  J[3] = fma(J[2], m.py, -(J[1] * m.pz));  // -(J0..2) x skew(p): (-J1)*pz + (-J2)*(-py)
+  J[4] = fma(J[0], m.pz, -(J[2] * m.px));
+  J[5] = fma(J[1], m.px, -(J[0] * m.py));
+  double scale = ww;
   const double chi = fabs(e);
-  if (chi > P.rho_ker_sqrt) scale = P.rho_ker_sqrt / chi;
-  const double w = 1.0 - f.bbox0 / P.min_ball;
-  scale *= w * w;
+  if (chi > rho) scale = (rho / chi) * ww;
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     v[i] = scale * J[i];

@@ -168,27 +168,29 @@ static int ensure_items(madicp_ctx* c, size_t items) {
 // register budget (64K registers / (THREADS*CTAS)).  Selected at create time (default 1024x1, or env
 // MADICP_GN_SHAPE="threads,ctas") and through madicp_set_gn_grid.
 struct GnShape {
-  int threads, ctas;
+  int threads, ctas, ilp;
   const void* fn;
   size_t smem;
 };
-template <int THREADS, int CTAS>
+template <int THREADS, int CTAS, int ILP>
 static GnShape gn_shape() {
-  return GnShape{THREADS, CTAS, reinterpret_cast<const void*>(k_gn_loop<THREADS, CTAS>), gn_dynamic_smem<THREADS>()};
+  return GnShape{THREADS, CTAS, ILP, reinterpret_cast<const void*>(k_gn_loop<THREADS, CTAS, ILP>),
+                 gn_dynamic_smem<THREADS>()};
 }
 static const GnShape* gn_shapes(int* n) {
   static const GnShape table[] = {
-      gn_shape<1024, 1>(), gn_shape<768, 1>(), gn_shape<512, 1>(), gn_shape<512, 2>(),
-      gn_shape<256, 2>(),  gn_shape<256, 3>(), gn_shape<256, 4>(),
+      gn_shape<1024, 1, 1>(), gn_shape<1024, 1, 2>(), gn_shape<1024, 1, 3>(), gn_shape<768, 1, 1>(),
+      gn_shape<768, 1, 2>(),  gn_shape<768, 1, 3>(),  gn_shape<768, 1, 4>(),  gn_shape<512, 1, 4>(),
+      gn_shape<512, 2, 2>(),  gn_shape<256, 1, 1>(),  gn_shape<256, 4, 1>(),
   };
   *n = int(sizeof(table) / sizeof(table[0]));
   return table;
 }
-static int configure_gn(madicp_ctx* c, int threads, int ctas) {
+static int configure_gn(madicp_ctx* c, int threads, int ctas, int ilp) {
   int n = 0;
   const GnShape* t = gn_shapes(&n);
   for (int i = 0; i < n; ++i)
-    if (t[i].threads == threads && t[i].ctas == ctas) {
+    if (t[i].threads == threads && t[i].ctas == ctas && t[i].ilp == ilp) {
       CK(cudaFuncSetAttribute(t[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(t[i].smem)));
       int per_sm = 0;
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, t[i].fn, threads, t[i].smem));
@@ -202,7 +204,7 @@ static int configure_gn(madicp_ctx* c, int threads, int ctas) {
       c->gn_smem = t[i].smem;
       return MADICP_OK;
     }
-  set_error("unsupported persistent-kernel shape (threads per CTA, CTAs per SM)");
+  set_error("unsupported persistent-kernel shape (threads per CTA, CTAs per SM, walks per thread)");
   return MADICP_ERR_INVALID;
 }
 
@@ -255,9 +257,9 @@ int madicp_create(madicp_ctx_t** out, int device, int max_keyframes) {
   CK(cudaMallocHost(&c->h_pinned, sizeof(double) * 64));
   CK(cudaMallocHost(&c->h_state, sizeof(GnState)));
   CK(cudaMallocHost(&c->h_matched, kMatchedCap));
-  int threads = 1024, ctas = 1;
-  if (const char* e = getenv("MADICP_GN_SHAPE")) sscanf(e, "%d,%d", &threads, &ctas);
-  int rc = configure_gn(c, threads, ctas);
+  int threads = 1024, ctas = 1, ilp = 1;
+  if (const char* e = getenv("MADICP_GN_SHAPE")) sscanf(e, "%d,%d,%d", &threads, &ctas, &ilp);
+  int rc = configure_gn(c, threads, ctas, ilp);
   if (rc) return rc;
   c->cap_partial = size_t(c->sm_count) * 8 * kAcc;
   CK(cudaMalloc(&c->d_partial, c->cap_partial * sizeof(double)));
@@ -556,6 +558,7 @@ int madicp_register_async(madicp_ctx_t* c, int iters, const double X0[12]) {
   CK(cudaMemcpyAsync(c->d_state->X_trace, c->h_pinned, 12 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   // zero the flags buffer of the NEXT call (nobody can be writing it yet; see CommBlock)
   CK(cudaMemsetAsync(c->d_comm->matched[mb ^ 1], 0, std::min(kMatchedCap, c->cap_moving), c->stream));
+  if (c->d_dbg) CK(cudaMemsetAsync(c->d_dbg, 0, MADICP_MAX_ITERS * 8 * sizeof(long long), c->stream));
   void* args[] = {&A};
   CK(cudaLaunchCooperativeKernel(c->gn_kernel, dim3(c->gn_grid), dim3(c->gn_threads), args, c->gn_smem, c->stream));
   c->launches++;
@@ -702,10 +705,10 @@ int madicp_debug_timing(madicp_ctx_t* c, int enable, int64_t* out, int max_round
   return rows;
 }
 
-int madicp_set_gn_grid(madicp_ctx_t* c, int threads_per_cta, int ctas_per_sm) {
+int madicp_set_gn_grid(madicp_ctx_t* c, int threads_per_cta, int ctas_per_sm, int walks_per_thread) {
   if (!c || ctas_per_sm < 1) return MADICP_ERR_INVALID;
   CK(cudaSetDevice(c->device));
-  int rc = configure_gn(c, threads_per_cta, ctas_per_sm);
+  int rc = configure_gn(c, threads_per_cta, ctas_per_sm, walks_per_thread);
   if (rc) return rc;
   return c->gn_grid / c->sm_count;
 }

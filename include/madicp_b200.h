@@ -168,13 +168,13 @@ int madicp_comm_world(const madicp_ctx_t* ctx);
 /* Per-round SM-clock stamps of the persistent kernel: enable != 0 switches recording on for the
  * following launches; out (nullable) receives rounds x 8 int64 of the LAST launch:
  * [0] item phase of CTA 0, [1] round start -> last CTA arrived, [2] fold of the per-CTA partials,
- * [3] peer exchange + matched count, [4] solve + publish, and for warp 0 of CTA 0 summed over its
- * warp-items: [5] walk, [6] leaf load + linearise, [7] staging + DMMA fold (cycles).  Returns rows written. */
+ * [3] peer exchange + matched count, [4] solve + publish (cycles).  Returns rows written. */
 int madicp_debug_timing(madicp_ctx_t* ctx, int enable, int64_t* out, int max_rounds);
-/* Shape of the persistent kernel: threads per CTA, resident CTAs per SM and interleaved tree walks
- * per thread; supported triples are listed in capi.cu (gn_shapes), default (1024,1,1); env
- * MADICP_GN_SHAPE="t,c,w" selects one at create time.  Returns the CTAs per SM in effect. */
-int madicp_set_gn_grid(madicp_ctx_t* ctx, int threads_per_cta, int ctas_per_sm, int walks_per_thread);
+/* Shape of the persistent kernel: threads per CTA and resident CTAs per SM; supported pairs are
+ * (1024,1) default, (768,1), (512,1), (512,2), (256,2), (256,3), (256,4); env MADICP_GN_SHAPE="t,c"
+ * selects one at create time.  By default the library picks among the one-CTA-per-SM shapes per
+ * launch from the item count; threads_per_cta = 0 restores that.  Returns the CTAs per SM in effect. */
+int madicp_set_gn_grid(madicp_ctx_t* ctx, int threads_per_cta, int ctas_per_sm);
 
 #ifdef __cplusplus
 }

@@ -54,7 +54,7 @@ SYMBOLS = {
     "madicp_comm_connect": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "madicp_comm_world": (C.c_int, [vp]),
     "madicp_debug_timing": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int64), C.c_int]),
-    "madicp_set_gn_grid": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
+    "madicp_set_gn_grid": (C.c_int, [vp, C.c_int, C.c_int]),
 }
 
 REC_DTYPE = np.dtype([("mean", "<f8", 3), ("dir", "<f8", 3), ("bbox0", "<f8"), ("link", "<i4"), ("num_points", "<i4")])

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -70,6 +71,7 @@ struct madicp_ctx {
   GnState* h_state = nullptr;  // pinned mirror
   unsigned char* h_matched = nullptr;
   int gn_grid = 0;
+  bool gn_auto = true;  // pick the shape per launch from the item count (see pick_shape)
   int gn_threads = 1024;
   const void* gn_kernel = nullptr;
   size_t gn_smem = 0;
@@ -168,29 +170,27 @@ static int ensure_items(madicp_ctx* c, size_t items) {
 // register budget (64K registers / (THREADS*CTAS)).  Selected at create time (default 1024x1, or env
 // MADICP_GN_SHAPE="threads,ctas") and through madicp_set_gn_grid.
 struct GnShape {
-  int threads, ctas, ilp;
+  int threads, ctas;
   const void* fn;
   size_t smem;
 };
-template <int THREADS, int CTAS, int ILP>
+template <int THREADS, int CTAS>
 static GnShape gn_shape() {
-  return GnShape{THREADS, CTAS, ILP, reinterpret_cast<const void*>(k_gn_loop<THREADS, CTAS, ILP>),
-                 gn_dynamic_smem<THREADS>()};
+  return GnShape{THREADS, CTAS, reinterpret_cast<const void*>(k_gn_loop<THREADS, CTAS>), gn_dynamic_smem<THREADS>()};
 }
 static const GnShape* gn_shapes(int* n) {
   static const GnShape table[] = {
-      gn_shape<1024, 1, 1>(), gn_shape<1024, 1, 2>(), gn_shape<1024, 1, 3>(), gn_shape<768, 1, 1>(),
-      gn_shape<768, 1, 2>(),  gn_shape<768, 1, 3>(),  gn_shape<768, 1, 4>(),  gn_shape<512, 1, 4>(),
-      gn_shape<512, 2, 2>(),  gn_shape<256, 1, 1>(),  gn_shape<256, 4, 1>(),
+      gn_shape<1024, 1>(), gn_shape<768, 1>(), gn_shape<512, 1>(), gn_shape<512, 2>(),
+      gn_shape<256, 2>(),  gn_shape<256, 3>(), gn_shape<256, 4>(),
   };
   *n = int(sizeof(table) / sizeof(table[0]));
   return table;
 }
-static int configure_gn(madicp_ctx* c, int threads, int ctas, int ilp) {
+static int configure_gn(madicp_ctx* c, int threads, int ctas) {
   int n = 0;
   const GnShape* t = gn_shapes(&n);
   for (int i = 0; i < n; ++i)
-    if (t[i].threads == threads && t[i].ctas == ctas && t[i].ilp == ilp) {
+    if (t[i].threads == threads && t[i].ctas == ctas) {
       CK(cudaFuncSetAttribute(t[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(t[i].smem)));
       int per_sm = 0;
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, t[i].fn, threads, t[i].smem));
@@ -204,8 +204,30 @@ static int configure_gn(madicp_ctx* c, int threads, int ctas, int ilp) {
       c->gn_smem = t[i].smem;
       return MADICP_OK;
     }
-  set_error("unsupported persistent-kernel shape (threads per CTA, CTAs per SM, walks per thread)");
+  set_error("unsupported persistent-kernel shape (threads per CTA, CTAs per SM)");
   return MADICP_ERR_INVALID;
+}
+
+// The item phase of a round costs (passes) x (time of one pass); a pass walks one warp-item per
+// resident warp and its time grows mildly with the number of resident warps (L1 contention).  Measured
+// on B200 (profiles/r01h_probe_v6.txt): ~6.5k + 150/warp cycles.  With W warps per SM and n warp-items
+// per SM the passes are ceil(n / W): pick the one-CTA-per-SM shape that minimises the product.
+static int pick_shape(madicp_ctx* c, int64_t items) {
+  if (!c->gn_auto) return MADICP_OK;
+  const double per_sm = double((items + 31) / 32) / double(c->sm_count);
+  int best = 1024;
+  double best_cost = 1e300;
+  for (int threads : {1024, 768, 512}) {
+    const int warps = threads / 32;
+    const double passes = ceil(per_sm / warps);
+    const double cost = passes * (6500.0 + 150.0 * warps);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = threads;
+    }
+  }
+  if (best == c->gn_threads && c->gn_grid == c->sm_count) return MADICP_OK;
+  return configure_gn(c, best, 1);
 }
 
 static int grid_for(const madicp_ctx* c, int64_t items) {
@@ -257,9 +279,10 @@ int madicp_create(madicp_ctx_t** out, int device, int max_keyframes) {
   CK(cudaMallocHost(&c->h_pinned, sizeof(double) * 64));
   CK(cudaMallocHost(&c->h_state, sizeof(GnState)));
   CK(cudaMallocHost(&c->h_matched, kMatchedCap));
-  int threads = 1024, ctas = 1, ilp = 1;
-  if (const char* e = getenv("MADICP_GN_SHAPE")) sscanf(e, "%d,%d,%d", &threads, &ctas, &ilp);
-  int rc = configure_gn(c, threads, ctas, ilp);
+  int threads = 1024, ctas = 1;
+  if (const char* e = getenv("MADICP_GN_SHAPE"))
+    if (sscanf(e, "%d,%d", &threads, &ctas) == 2) c->gn_auto = false;
+  int rc = configure_gn(c, threads, ctas);
   if (rc) return rc;
   c->cap_partial = size_t(c->sm_count) * 8 * kAcc;
   CK(cudaMalloc(&c->d_partial, c->cap_partial * sizeof(double)));
@@ -528,6 +551,8 @@ int madicp_register_async(madicp_ctx_t* c, int iters, const double X0[12]) {
   CK(cudaSetDevice(c->device));
   rc = prepare_moving(c);
   if (rc) return rc;
+  rc = pick_shape(c, int64_t(madicp_num_keyframes(c)) * c->L);
+  if (rc) return rc;
   GnArgs A;
   A.model = make_view(c);
   A.P = c->P;
@@ -558,7 +583,6 @@ int madicp_register_async(madicp_ctx_t* c, int iters, const double X0[12]) {
   CK(cudaMemcpyAsync(c->d_state->X_trace, c->h_pinned, 12 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   // zero the flags buffer of the NEXT call (nobody can be writing it yet; see CommBlock)
   CK(cudaMemsetAsync(c->d_comm->matched[mb ^ 1], 0, std::min(kMatchedCap, c->cap_moving), c->stream));
-  if (c->d_dbg) CK(cudaMemsetAsync(c->d_dbg, 0, MADICP_MAX_ITERS * 8 * sizeof(long long), c->stream));
   void* args[] = {&A};
   CK(cudaLaunchCooperativeKernel(c->gn_kernel, dim3(c->gn_grid), dim3(c->gn_threads), args, c->gn_smem, c->stream));
   c->launches++;
@@ -705,11 +729,16 @@ int madicp_debug_timing(madicp_ctx_t* c, int enable, int64_t* out, int max_round
   return rows;
 }
 
-int madicp_set_gn_grid(madicp_ctx_t* c, int threads_per_cta, int ctas_per_sm, int walks_per_thread) {
+int madicp_set_gn_grid(madicp_ctx_t* c, int threads_per_cta, int ctas_per_sm) {
   if (!c || ctas_per_sm < 1) return MADICP_ERR_INVALID;
   CK(cudaSetDevice(c->device));
-  int rc = configure_gn(c, threads_per_cta, ctas_per_sm, walks_per_thread);
+  if (threads_per_cta == 0) {  // back to automatic selection
+    c->gn_auto = true;
+    return 0;
+  }
+  int rc = configure_gn(c, threads_per_cta, ctas_per_sm);
   if (rc) return rc;
+  c->gn_auto = false;
   return c->gn_grid / c->sm_count;
 }
 

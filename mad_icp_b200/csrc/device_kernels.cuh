@@ -188,21 +188,6 @@ __device__ __forceinline__ void peer_allreduce(const PeerView& pv, uint32_t epoc
   __syncthreads();
 }
 
-// (keyframe k, moving leaf q) of lane `lane` in the warp-item starting at item w0: one 32-bit division
-// per warp-item, then a carry for lanes past a keyframe boundary.
-__device__ __forceinline__ void item_of(unsigned w0, unsigned lane, unsigned L, unsigned& k, unsigned& q) {
-  k = w0 / L;
-  q = w0 - k * L + lane;
-  while (q >= L) {
-    q -= L;
-    ++k;
-  }
-}
-__device__ __forceinline__ void prefetch_l1(const void* p) {
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(p) + 32));
-}
-
 struct GnArgs {
   ModelView model;
   IcpParams P;
@@ -230,12 +215,7 @@ struct GnArgs {
 // consecutive ones sit on different SMs): every SM gets a uniform sample of all keyframes and tree
 // regions -- per-item cost varies by 2x between near and far keyframes (gate pass rate) -- and the
 // per-round barrier does not wait for an unlucky SM.  Static => deterministic sums.
-//
-// Latency hiding.  A walk is ~16 dependent L1/L2 round trips (measured ~7-8k cycles per warp); one
-// thread keeps up to ILP walks in flight (state per walk: one pool index + the FP32 query),
-// issuing the loads of all its live walks back to back each level, then linearises the finished walks
-// one after the other (their leaf records are prefetched into L1 as soon as the walks end).
-template <int THREADS, int CTAS, int ILP>
+template <int THREADS, int CTAS>
 __global__ void __launch_bounds__(THREADS, CTAS)
 k_gn_loop(const __grid_constant__ GnArgs A) {
   constexpr int WARPS = THREADS / 32;
@@ -271,96 +251,32 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
     long long t_begin = 0;
     if (A.dbg && threadIdx.x == 0) t_begin = clock64();
 
-    const bool probe = A.dbg && threadIdx.x == 0 && blockIdx.x == 0;  // CTA 0 / warp 0 phase clocks
-    for (unsigned wi0 = worker; wi0 < n_witems; wi0 += ILP * n_workers) {
-      long long p0 = 0, p1 = 0;
-      if (probe) p0 = clock64();
-      // ---- start up to ILP walks (warp-items wi0, wi0 + W, ...)
-      int idx[ILP];
-      QueryF qf[ILP];
-      unsigned live = 0;
-#pragma unroll
-      for (int j = 0; j < ILP; ++j) {
-        const unsigned wi = wi0 + j * n_workers;
-        idx[j] = 0;
-        qf[j].x = qf[j].y = qf[j].z = qf[j].eq = 0.f;
-        if (wi < n_witems && wi * 32 + lane < total) {
-          unsigned k, q;
-          item_of(wi * 32, lane, L, k, q);
-          const Moving4 m = load_moving(A.moving + q);
-          double mx, my, mz;
-          iso_apply(s_X, m.px, m.py, m.pz, mx, my, mz);
-          qf[j] = make_query(mx, my, mz);
-          idx[j] = A.model.root[k];
-          live |= 1u << j;
-        }
+    for (unsigned wi = worker; wi < n_witems; wi += n_workers) {
+      // (keyframe, leaf) of this lane: one 32-bit division per warp-item, then a carry
+      const unsigned w0 = wi * 32;
+      unsigned k = w0 / L;
+      unsigned q = w0 - k * L + lane;
+      while (q >= L) {
+        q -= L;
+        ++k;
       }
-      // ---- interleaved descent: the loads of every live walk are issued before any is consumed
-      while (live) {
-        int link[ILP];
-        FastRec p[ILP];
+      double v[kStage];
 #pragma unroll
-        for (int j = 0; j < ILP; ++j)
-          if (live & (1u << j)) {
-            link[j] = load_link(A.model.links + idx[j]);
-            p[j] = load_fast(A.model.fast + idx[j]);
-          }
-#pragma unroll
-        for (int j = 0; j < ILP; ++j)
-          if (live & (1u << j)) {
-            if (link[j] < 0) {
-              live &= ~(1u << j);
-              prefetch_l1(A.model.recs + idx[j]);  // the exact leaf record, needed by the linearisation below
-            } else {
-              int side = side_filtered(qf[j], p[j]);
-              if (side < 0) {  // rare: re-derive the FP64 query and evaluate the reference predicate
-                unsigned k, q;
-                item_of((wi0 + j * n_workers) * 32, lane, L, k, q);
-                const Moving4 m = load_moving(A.moving + q);
-                double mx, my, mz;
-                iso_apply(s_X, m.px, m.py, m.pz, mx, my, mz);
-                side = side_exact(A.model.recs + idx[j], mx, my, mz) ? 1 : 0;
-              }
-              idx[j] = link[j] + side;
-            }
-          }
-      }
-      if (probe) p1 = clock64();
-      // ---- linearise + fold, one warp-item at a time (idx[j] = pool index of the matched leaf)
-#pragma unroll
-      for (int j = 0; j < ILP; ++j) {
-        const unsigned wi = wi0 + j * n_workers;
-        if (wi < n_witems) {  // warp-uniform
-          long long p2 = 0, p3 = 0;
-          if (probe) p2 = clock64();
-          double v[kStage];
-#pragma unroll
-          for (int i = 0; i < kStage; ++i) v[i] = 0.0;
-          if (wi * 32 + lane < total) {
-            unsigned k, q;
-            item_of(wi * 32, lane, L, k, q);
-            const Moving4 m = load_moving(A.moving + q);
-            double mx, my, mz;
-            iso_apply(s_X, m.px, m.py, m.pz, mx, my, mz);
-            const Rec f = load_rec(A.model.recs + idx[j]);
-            const double ww = leaf_weight(load_fast(A.model.fast + idx[j]));
-            if (linearize_one(s_X, A.P.rho_ker_sqrt, m, mx, my, mz, f, ww, v) && last_round) {
-              if (multi) {
-                for (int r = 0; r < A.peers.world; ++r) A.peer_matched[r][q] = 1;
-              } else {
-                A.matched[q] = 1;
-              }
-            }
-          }
-          if (probe) p3 = clock64();
-          warp_accumulate(stage, v, c0, c1);
-          if (probe) {
-            A.dbg[it * 8 + 6] += p3 - p2;         // leaf load + linearise (lane 0; includes waiting for the warp)
-            A.dbg[it * 8 + 7] += clock64() - p3;  // staging + DMMA fold
+      for (int i = 0; i < kStage; ++i) v[i] = 0.0;
+      if (w0 + lane < total) {
+        const Moving4 m = load_moving(A.moving + q);
+        double mx, my, mz, ww;
+        iso_apply(s_X, m.px, m.py, m.pz, mx, my, mz);
+        const Rec f = load_rec(A.model.recs + descend(A.model, A.model.root[k], mx, my, mz, ww));
+        if (linearize_one(s_X, A.P.rho_ker_sqrt, m, mx, my, mz, f, ww, v) && last_round) {
+          if (multi) {
+            for (int r = 0; r < A.peers.world; ++r) A.peer_matched[r][q] = 1;
+          } else {
+            A.matched[q] = 1;
           }
         }
       }
-      if (probe) A.dbg[it * 8 + 5] += p1 - p0;  // moving load + pose + interleaved walks
+      warp_accumulate(stage, v, c0, c1);
     }
     if (A.dbg && threadIdx.x == 0 && blockIdx.x == 0) A.dbg[it * 8 + 0] = clock64() - t_begin;  // item phase, CTA 0
     block_reduce_store<WARPS>(c0, c1, s_red, A.partial + size_t(blockIdx.x) * kAcc);

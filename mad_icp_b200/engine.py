@@ -212,8 +212,8 @@ class Registrar:
                                                     if fetch else None, 64))
         return buf[:rows]
 
-    def set_gn_grid(self, threads_per_cta=1024, ctas_per_sm=1, walks_per_thread=1):
-        return check(capi.lib().madicp_set_gn_grid(self._h, threads_per_cta, ctas_per_sm, walks_per_thread))
+    def set_gn_grid(self, threads_per_cta=1024, ctas_per_sm=1):
+        return check(capi.lib().madicp_set_gn_grid(self._h, threads_per_cta, ctas_per_sm))
 
     # ---- multi-GPU -------------------------------------------------------------------------
     def comm_export(self):

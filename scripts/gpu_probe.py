@@ -36,12 +36,12 @@ for iters in (1, 2, 5, 10, 15, 20):
 
 # per-round phase breakdown (SM cycles @ ~1.965 GHz) for the persistent-kernel shapes
 reg.debug_timing(True, fetch=False)
-shapes = [(1024, 1, 1), (1024, 1, 2), (1024, 1, 3), (768, 1, 2), (768, 1, 3), (768, 1, 4), (512, 1, 4), (512, 2, 2)]
-for thr, cps, ilp in shapes:
-    reg.set_gn_grid(thr, cps, ilp)
+shapes = [(1024, 1), (768, 1), (512, 1), (512, 2), (256, 3), (256, 4)]
+for thr, cps in shapes:
+    reg.set_gn_grid(thr, cps)
     w = timed(lambda: reg.register_async(X0, 10))
     c = timed(lambda: reg.register_async(X0, 10), cold=True)
     reg.register_async(X0, 10); torch.cuda.synchronize()
     d = reg.debug_timing(True)
-    print(f"shape=({thr},{cps},ilp{ilp}): 10-iter warm {w[0]:.1f} us cold {c[0]:.1f} us; cycles/round (median): items(cta0)={np.median(d[:,0]):.0f} "
-          f"start->all_arrived={np.median(d[:,1]):.0f} fold={np.median(d[:,2]):.0f} xchg+count={np.median(d[:,3]):.0f} solve={np.median(d[:,4]):.0f} | warp0: walk={np.median(d[:,5]):.0f} linearize={np.median(d[:,6]):.0f} fold={np.median(d[:,7]):.0f}")
+    print(f"shape=({thr},{cps}): 10-iter warm {w[0]:.1f} us cold {c[0]:.1f} us; cycles/round (median): items(cta0)={np.median(d[:,0]):.0f} "
+          f"start->all_arrived={np.median(d[:,1]):.0f} fold={np.median(d[:,2]):.0f} xchg+count={np.median(d[:,3]):.0f} solve={np.median(d[:,4]):.0f}")

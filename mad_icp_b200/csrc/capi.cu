@@ -120,8 +120,11 @@ static int prepare_slot(madicp_ctx* c, int s) {
 // device) and rebuilds their absolute links; it only happens when a tree larger than any before shows up.
 static int ensure_pool(madicp_ctx* c, size_t need) {
   if (need <= c->pool_cap) return MADICP_OK;
-  size_t cap = c->pool_cap ? c->pool_cap : (size_t(1) << 16);
-  while (cap < need) cap <<= 1;
+  // slot stride = 2^n + 40 nodes: a power-of-two stride would put the roots and upper levels of all
+  // keyframes (the hottest lines of every walk) on the same cache sets
+  size_t cap = size_t(1) << 16;
+  while (cap + 40 < need || cap + 40 <= c->pool_cap) cap <<= 1;
+  cap += 40;
   if (cap * size_t(c->max_keyframes) > size_t(0x7fffffff)) {
     set_error("keyframe pool would exceed 2^31 nodes");
     return MADICP_ERR_NOMEM;

@@ -209,12 +209,15 @@ struct GnArgs {
 // that crosses SMs (partials, pose, flags) is read with ld.relaxed.gpu (L2) behind a control
 // dependency on the flag.
 //
-// Work distribution.  The unit is a "warp-item": 32 consecutive items (consecutive moving leaves of
-// one keyframe in DFS order = one spatial neighbourhood, so the lanes of a warp share the upper tree
-// levels).  Warp-item i goes to grid-warp i mod W (W = all warps of the grid, numbered so that
-// consecutive ones sit on different SMs): every SM gets a uniform sample of all keyframes and tree
-// regions -- per-item cost varies by 2x between near and far keyframes (gate pass rate) -- and the
-// per-round barrier does not wait for an unlucky SM.  Static => deterministic sums.
+// Work distribution.  CTA b owns the moving leaves [L*b/G, L*(b+1)/G) -- a contiguous stretch of the
+// scan's own tree in DFS order, i.e. one spatial region -- and registers them against EVERY keyframe:
+//   * every CTA does 1/G of the work of every keyframe, so the round barrier does not wait for an SM
+//     that drew the expensive keyframes (per-item cost differs ~2x between near and far keyframes);
+//   * within one keyframe the CTA's walks all end in the same small part of the fixed tree, so the
+//     upper levels and most lower nodes are reused from that SM's L1 (an interleaved assignment ran
+//     at an 11% L1 hit rate: every level paid an L2 round trip);
+//   * the assignment is static, so the sums are deterministic.
+// CTA-local item t = k * n_b + (q - lo_b); warps take groups of 32 consecutive t (a "warp-item").
 template <int THREADS, int CTAS>
 __global__ void __launch_bounds__(THREADS, CTAS)
 k_gn_loop(const __grid_constant__ GnArgs A) {
@@ -236,9 +239,11 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
   const unsigned lane = threadIdx.x & 31;
   const unsigned warp = threadIdx.x >> 5;
   double* stage = s_stage_all + warp * kStageTile;
-  const unsigned n_witems = (total + 31) / 32;
-  const unsigned n_workers = gridDim.x * WARPS;
-  const unsigned worker = warp * gridDim.x + blockIdx.x;
+  const unsigned q_lo = unsigned((uint64_t(L) * blockIdx.x) / gridDim.x);
+  const unsigned q_hi = unsigned((uint64_t(L) * (blockIdx.x + 1)) / gridDim.x);
+  const unsigned n_b = q_hi - q_lo;                      // moving leaves of this CTA
+  const unsigned t_total = unsigned(A.model.K) * n_b;   // CTA-local items
+  (void) total;
 
   for (int it = 0; it < A.iters; ++it) {
     if (threadIdx.x == 0 && it > 0)
@@ -251,19 +256,19 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
     long long t_begin = 0;
     if (A.dbg && threadIdx.x == 0) t_begin = clock64();
 
-    for (unsigned wi = worker; wi < n_witems; wi += n_workers) {
+    for (unsigned t0 = warp * 32; t0 < t_total; t0 += THREADS) {
       // (keyframe, leaf) of this lane: one 32-bit division per warp-item, then a carry
-      const unsigned w0 = wi * 32;
-      unsigned k = w0 / L;
-      unsigned q = w0 - k * L + lane;
-      while (q >= L) {
-        q -= L;
+      unsigned k = t0 / n_b;
+      unsigned q = t0 - k * n_b + lane;
+      while (q >= n_b) {
+        q -= n_b;
         ++k;
       }
+      q += q_lo;
       double v[kStage];
 #pragma unroll
       for (int i = 0; i < kStage; ++i) v[i] = 0.0;
-      if (w0 + lane < total) {
+      if (t0 + lane < t_total) {
         const Moving4 m = load_moving(A.moving + q);
         double mx, my, mz, ww;
         iso_apply(s_X, m.px, m.py, m.pz, mx, my, mz);

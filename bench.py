@@ -225,6 +225,11 @@ def main():
             flush.fill_(1)
 
     def barrier():
+        # Drain the GPU BEFORE the NCCL barrier: the sharded persistent kernel owns every SM and waits for
+        # its peers' kernels; an NCCL kernel that slips in between two of them on one rank would wait for
+        # the other rank's NCCL kernel, which is queued behind a persistent kernel that is waiting for
+        # this rank -> deadlock.  Rule: no collective while cross-GPU registrations are in flight.
+        torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)

@@ -1,0 +1,111 @@
+"""The reference-named pybind surface (pyvector / pymadtree / pymadicp).  The GPU tests read like the
+reference's own demos (apps/utils/tools/nn_search.py, mad_registration.py) with the imports swapped."""
+import os
+
+import numpy as np
+import pytest
+
+from mad_icp_b200 import synth
+from util import POSE_M, POSE_RAD, pose_error
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_vector_eigen3d_semantics(built):
+    from mad_icp_b200.pybind.pyvector import VectorEigen3d
+    a = np.random.RandomState(0).rand(7, 3)
+    v = VectorEigen3d(a)
+    assert len(v) == 7 and bool(v) and (np.asarray(v) == a).all()
+    assert np.asarray(v).strides == (24, 8)  # reference buffer protocol: eigen_stl_bindings.h:73-80
+    assert (v[2] == a[2]).all() and (v[-1] == a[-1]).all()
+    assert len(list(v)) == 7 and not VectorEigen3d()
+    with pytest.raises(RuntimeError):  # py::cast_error on a wrong shape (eigen_stl_bindings.h:48-50)
+        VectorEigen3d(np.zeros((4, 2)))
+    v.append(np.array([1.0, 2.0, 3.0]))
+    assert len(v) == 8 and "std::vector<Eigen::Vector3d> with 8 elements" in repr(v)
+    from mad_icp_b200.pybind import pymadicp, pymadtree
+    assert pymadicp.VectorEigen3d is VectorEigen3d and pymadtree.VectorEigen3d is VectorEigen3d
+
+
+def test_signatures_match_reference(built):
+    """Names and defaults of pymadicp.cpp:36-52 / pymadtree.cpp:36-48."""
+    from mad_icp_b200.pybind import pymadicp, pymadtree
+    d = pymadicp.MADicp.compute.__doc__
+    for frag in ("T:", "icp_iterations: ", "= 15", "rho_ker: ", "= 0.1", "b_ratio: ", "= 0.02", "print_stats: "):
+        assert frag in d, frag
+    d = pymadicp.MADicp.setQueryCloud.__doc__
+    assert "b_max: " in d and "= 0.2" in d and "b_min: " in d and "= 0.1" in d
+    d = pymadtree.MADtree.build.__doc__
+    assert "b_max: " in d and "1e-05" in d and "max_parallel_level: " in d and "= 2" in d
+    for name in ("search", "searchCloud", "searchCloudDist"):
+        assert hasattr(pymadtree.MADtree, name)
+
+
+def test_no_gpu_fails_loudly(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mad_icp_b200.pybind.pymadicp import MADicp
+    m = MADicp(num_threads=2)
+    cloud = np.random.RandomState(1).rand(50, 3)
+    m.setReferenceCloud(cloud)
+    m.setQueryCloud(cloud)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.compute(np.eye(4))
+
+
+@pytest.mark.gpu
+def test_mad_registration_demo(oracle):
+    """apps/utils/tools/mad_registration.py:48-69 with the imports swapped."""
+    from mad_icp_b200.pybind.pymadicp import MADicp
+    from mad_icp_b200.pybind.pyvector import VectorEigen3d
+    g = np.load(os.path.join(GOLD, "four_walls_registration.npz"))
+    np.random.seed(42)
+    ref_cloud = synth.four_walls(points_per_wall=1000)
+    query_cloud = ref_cloud.copy()
+    T_guess = np.eye(4)
+    T_guess[:3, :3] = synth.euler_xyz(0.1, 0.1, 0.1)
+    T_guess[:3, 3] = np.random.rand(3)
+    assert (T_guess == g["T_guess"]).all()
+    madicp = MADicp(num_threads=os.cpu_count())
+    madicp.setReferenceCloud(VectorEigen3d(ref_cloud))
+    madicp.setQueryCloud(VectorEigen3d(query_cloud))
+    T_est = madicp.compute(T_guess, icp_iterations=15)
+    assert T_est.shape == (4, 4) and (T_est[3] == [0, 0, 0, 1]).all()
+    ang, dt = pose_error(T_est, np.eye(4))
+    assert ang < 1e-6 and dt < 1e-6            # ground truth of the demo is the identity
+    ang, dt = pose_error(T_est, g["X"])
+    assert ang < POSE_RAD and dt < POSE_M      # and it is the oracle's answer
+    # one iteration at a time, as the demo's visual loop does (mad_registration.py:86-88)
+    T = T_guess.copy()
+    for _ in range(15):
+        T = madicp.compute(T, icp_iterations=1)
+    ang, dt = pose_error(T, g["X"])
+    assert ang < POSE_RAD and dt < POSE_M
+
+
+@pytest.mark.gpu
+def test_nn_search_demo(oracle):
+    """apps/utils/tools/nn_search.py:36-61: total matching error of the cloud against itself == 0."""
+    from mad_icp_b200.pybind.pymadtree import MADtree
+    from mad_icp_b200.pybind.pyvector import VectorEigen3d
+    np.random.seed(42)
+    cloud = synth.four_walls()
+    tree = MADtree()
+    tree.build(VectorEigen3d(cloud))
+    ref_point, ref_normal = tree.search(cloud[0, :])
+    assert np.linalg.norm(ref_point - cloud[0]) == 0.0 and ref_normal.shape == (3,)
+    ref_cloud = tree.searchCloud(VectorEigen3d(cloud[:2000]))
+    tot = 0.0
+    for (p, n), q in zip(ref_cloud, cloud[:2000]):
+        tot += np.linalg.norm(p - q)
+    assert tot == 0.0 and len(ref_cloud) == 2000
+    P, N, D = tree.searchCloudArrays(cloud)
+    assert np.linalg.norm(P - cloud, axis=1).sum() == 0.0 and (D == 0).all()
+    d3 = tree.searchCloudDist(cloud[:10] + 0.01)
+    ot = oracle.OracleTree(cloud, b_max=1e-5)
+    means, normals, _, _ = ot.leaves()
+    oi = ot.search(cloud[:10] + 0.01)
+    for (p, n, d), i, q in zip(d3, oi, cloud[:10] + 0.01):
+        assert (p == means[i]).all() and (n == normals[i]).all()
+        assert abs(d - np.linalg.norm(q - means[i])) <= 4e-16 * d

@@ -40,8 +40,8 @@ inline py::array_t<double> pose_to_numpy(const mb::Matrix4d& M) {
 
 // VectorEigen3d: registered once per interpreter (whichever module is imported first).
 inline void bind_vector_eigen3d(py::module_& m) {
-  if (py::detail::get_type_info(typeid(mb::ContainerType))) {
-    m.attr("VectorEigen3d") = py::module_::import("mad_icp_b200.pybind.pyvector").attr("VectorEigen3d");
+  if (auto* ti = py::detail::get_type_info(typeid(mb::ContainerType))) {  // another module got there first
+    m.attr("VectorEigen3d") = py::reinterpret_borrow<py::object>(reinterpret_cast<PyObject*>(ti->type));
     return;
   }
   py::class_<mb::ContainerType>(m, "VectorEigen3d", py::buffer_protocol())

@@ -311,9 +311,19 @@ __device__ __forceinline__ void final_reduce(const double* partial, int nblk, do
   const int j = threadIdx.x & 63, g = threadIdx.x >> 6;
   __syncthreads();
   if (j < kAcc) {
+    // all loads of a batch are issued before the first add (one L2 round trip per batch of 12; with
+    // 1024 threads and 148 CTAs a strand has 10 tiles => a single batch); the adds keep their order
     double s = 0.0;
-#pragma unroll 4
-    for (int blk = g; blk < nblk; blk += STRANDS) s += ld_relaxed_f64(partial + size_t(blk) * kAcc + j);
+    for (int blk0 = g; blk0 < nblk; blk0 += 12 * STRANDS) {
+      double t[12];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        const int blk = blk0 + i * STRANDS;
+        t[i] = (blk < nblk) ? ld_relaxed_f64(partial + size_t(blk) * kAcc + j) : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 12; ++i) s += t[i];
+    }
     s_red[g][j] = s;
   }
   __syncthreads();

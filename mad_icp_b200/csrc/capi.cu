@@ -26,8 +26,9 @@ void set_error(const std::string& msg) { g_error = msg; }
 using namespace madicp;
 
 namespace {
-struct Slot {  // slot s owns pool indices [s*pool_cap, (s+1)*pool_cap)
+struct Slot {  // slot s owns pool indices [s*pool_cap, (s+1)*pool_cap) and heap positions [s*heap_cap, ...)
   int n_nodes = 0, n_leaves = 0;
+  std::vector<int> heap_pos;  // node -> position in the implicit heap (kept to re-home the slot on growth)
 };
 constexpr size_t kMatchedCap = size_t(1) << 20;  // bytes reserved for matched flags (max moving leaves)
 
@@ -49,8 +50,11 @@ struct madicp_ctx {
   // keyframe pool: three parallel arrays, pool_cap nodes per slot (kernels.cuh: ModelView)
   size_t pool_cap = 0;
   madtree_rec_t* d_pool_recs = nullptr;
-  FastRec* d_pool_fast = nullptr;
   int* d_pool_links = nullptr;
+  size_t heap_cap = 0;  // heap positions per slot: 2^(depth+1) + skew
+  FastRec* d_heap = nullptr;
+  int* d_bfs_of = nullptr;
+  int* d_heap_pos = nullptr;  // upload scratch, pool_cap ints
   IcpParams P{0.2, 0.31622776601683794, 0.02};
   double* d_moving = nullptr;               // raw L x 3 means as uploaded
   Moving4* d_mov4 = nullptr;                // prepared (mean, gate radius) records the kernels read
@@ -96,59 +100,87 @@ struct madicp_ctx {
 static ModelView make_view(const madicp_ctx* c) {
   ModelView v;
   v.recs = c->d_pool_recs;
-  v.fast = c->d_pool_fast;
   v.links = c->d_pool_links;
+  v.heap = c->d_heap;
+  v.bfs_of = c->d_bfs_of;
   v.K = 0;
   for (int s = 0; s < c->max_keyframes; ++s)
-    if (c->slots[s].n_nodes > 0) v.root[v.K++] = int(size_t(s) * c->pool_cap);
+    if (c->slots[s].n_nodes > 0) v.root[v.K++] = int(size_t(s) * c->heap_cap);
   for (int i = v.K; i < kMaxSlots; ++i) v.root[i] = 0;
   return v;
 }
 
-// (Re)builds the FP32 shadows and absolute links of slot `s` from its exact records in the pool.
+// (Re)builds the shadows (heap order), the heap->record map and the absolute links of slot `s` from
+// its exact records in the pool.
 static int prepare_slot(madicp_ctx* c, int s) {
   const int n = c->slots[s].n_nodes;
-  const size_t off = size_t(s) * c->pool_cap;
-  k_prepare_fast<<<(n + kStepBlock - 1) / kStepBlock, kStepBlock, 0, c->stream>>>(
-      c->d_pool_recs + off, n, int(off), c->P.min_ball, c->d_pool_fast + off, c->d_pool_links + off);
+  const size_t off = size_t(s) * c->pool_cap, hoff = size_t(s) * c->heap_cap;
+  CK(cudaMemcpyAsync(c->d_heap_pos, c->slots[s].heap_pos.data(), size_t(n) * sizeof(int), cudaMemcpyHostToDevice,
+                     c->stream));
+  k_prepare_slot<<<(n + kStepBlock - 1) / kStepBlock, kStepBlock, 0, c->stream>>>(
+      c->d_pool_recs + off, c->d_heap_pos, n, int(off), int(hoff), c->P.min_ball, c->d_pool_links + off, c->d_heap,
+      c->d_bfs_of);
   c->launches++;
   CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));  // heap_pos scratch is reused by the next slot
   return MADICP_OK;
 }
 
-// Makes every slot at least `need` nodes large.  Growing re-homes the resident keyframes (device to
-// device) and rebuilds their absolute links; it only happens when a tree larger than any before shows up.
-static int ensure_pool(madicp_ctx* c, size_t need) {
-  if (need <= c->pool_cap) return MADICP_OK;
-  // slot stride = 2^n + 40 nodes: a power-of-two stride would put the roots and upper levels of all
-  // keyframes (the hottest lines of every walk) on the same cache sets
-  size_t cap = size_t(1) << 16;
-  while (cap + 40 < need || cap + 40 <= c->pool_cap) cap <<= 1;
-  cap += 40;
-  if (cap * size_t(c->max_keyframes) > size_t(0x7fffffff)) {
-    set_error("keyframe pool would exceed 2^31 nodes");
-    return MADICP_ERR_NOMEM;
+// Makes every slot at least `need` nodes large and the heap at least `need_heap` positions per slot.
+// Growing re-homes the resident keyframes (device to device) and rebuilds their shadows; it only
+// happens when a larger or deeper tree than any before shows up.
+static int ensure_pool(madicp_ctx* c, size_t need, size_t need_heap) {
+  const bool grow_pool = need > c->pool_cap, grow_heap = need_heap > c->heap_cap;
+  if (!grow_pool && !grow_heap) return MADICP_OK;
+  CK(cudaStreamSynchronize(c->stream));
+  if (grow_pool) {
+    // slot stride = 2^n + 40 nodes: a power-of-two stride would put the roots and upper levels of all
+    // keyframes (the hottest lines of every walk) on the same cache sets
+    size_t cap = size_t(1) << 16;
+    while (cap + 40 < need || cap + 40 <= c->pool_cap) cap <<= 1;
+    cap += 40;
+    if (cap * size_t(c->max_keyframes) > size_t(0x7fffffff)) {
+      set_error("keyframe pool would exceed 2^31 nodes");
+      return MADICP_ERR_NOMEM;
+    }
+    madtree_rec_t* recs = nullptr;
+    int* links = nullptr;
+    int* hp = nullptr;
+    const size_t total = cap * size_t(c->max_keyframes);
+    CK(cudaMalloc(&recs, total * sizeof(madtree_rec_t)));
+    CK(cudaMalloc(&links, total * sizeof(int)));
+    CK(cudaMalloc(&hp, cap * sizeof(int)));
+    for (int s = 0; s < c->max_keyframes; ++s)
+      if (c->slots[s].n_nodes > 0)
+        CK(cudaMemcpyAsync(recs + size_t(s) * cap, c->d_pool_recs + size_t(s) * c->pool_cap,
+                           size_t(c->slots[s].n_nodes) * sizeof(madtree_rec_t), cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_pool_recs);
+    cudaFree(c->d_pool_links);
+    cudaFree(c->d_heap_pos);
+    c->d_pool_recs = recs;
+    c->d_pool_links = links;
+    c->d_heap_pos = hp;
+    c->pool_cap = cap;
   }
-  CK(cudaStreamSynchronize(c->stream));
-  madtree_rec_t* recs = nullptr;
-  FastRec* fast = nullptr;
-  int* links = nullptr;
-  const size_t total = cap * size_t(c->max_keyframes);
-  CK(cudaMalloc(&recs, total * sizeof(madtree_rec_t)));
-  CK(cudaMalloc(&fast, total * sizeof(FastRec)));
-  CK(cudaMalloc(&links, total * sizeof(int)));
-  for (int s = 0; s < c->max_keyframes; ++s)
-    if (c->slots[s].n_nodes > 0)
-      CK(cudaMemcpyAsync(recs + size_t(s) * cap, c->d_pool_recs + size_t(s) * c->pool_cap,
-                         size_t(c->slots[s].n_nodes) * sizeof(madtree_rec_t), cudaMemcpyDeviceToDevice, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  cudaFree(c->d_pool_recs);
-  cudaFree(c->d_pool_fast);
-  cudaFree(c->d_pool_links);
-  c->d_pool_recs = recs;
-  c->d_pool_fast = fast;
-  c->d_pool_links = links;
-  c->pool_cap = cap;
+  if (grow_heap) {
+    size_t cap = size_t(1) << 19;  // depth 18
+    while (cap < need_heap) cap <<= 1;
+    cap += 40;
+    if (cap * size_t(c->max_keyframes) > size_t(0x7fffffff)) {
+      set_error("keyframe tree too deep for the implicit-heap layout (depth limit reached)");
+      return MADICP_ERR_NOMEM;
+    }
+    cudaFree(c->d_heap);
+    cudaFree(c->d_bfs_of);
+    c->d_heap = nullptr;
+    c->d_bfs_of = nullptr;
+    const size_t total = cap * size_t(c->max_keyframes);
+    CK(cudaMalloc(&c->d_heap, total * sizeof(FastRec)));
+    CK(cudaMalloc(&c->d_bfs_of, total * sizeof(int)));
+    CK(cudaMemsetAsync(c->d_heap, 0, total * sizeof(FastRec), c->stream));  // never-visited positions are prefetched only
+    c->heap_cap = cap;
+  }
   for (int s = 0; s < c->max_keyframes; ++s)
     if (c->slots[s].n_nodes > 0) {
       int rc = prepare_slot(c, s);
@@ -301,8 +333,10 @@ void madicp_destroy(madicp_ctx_t* c) {
   for (int r = 0; r < c->world; ++r)
     if (c->world > 1 && r != c->rank && c->peer_comm[r]) cudaIpcCloseMemHandle(c->peer_comm[r]);
   cudaFree(c->d_pool_recs);
-  cudaFree(c->d_pool_fast);
   cudaFree(c->d_pool_links);
+  cudaFree(c->d_heap);
+  cudaFree(c->d_bfs_of);
+  cudaFree(c->d_heap_pos);
   cudaFree(c->d_moving);
   cudaFree(c->d_mov4);
   cudaFree(c->d_step_matched);
@@ -354,13 +388,33 @@ int madicp_put_keyframe_records(madicp_ctx_t* c, int slot, const madtree_rec_t* 
     return MADICP_ERR_INVALID;
   }
   CK(cudaSetDevice(c->device));
-  int rc = ensure_pool(c, size_t(n_nodes));
+  // heap position of every node (host, O(n)): children of the node at position h sit at 2h+1, 2h+2
+  std::vector<int> heap_pos(size_t(n_nodes), 0);
+  int64_t max_pos = 0;
+  for (int i = 0; i < n_nodes; ++i) {
+    const int link = recs[i].link;
+    if (link < 0) continue;
+    if (link < 1 || link + 1 >= n_nodes || link <= i) {
+      set_error("madicp_put_keyframe: records are not a breadth-first tree with adjacent siblings");
+      return MADICP_ERR_INVALID;
+    }
+    const int64_t h = 2 * int64_t(heap_pos[size_t(i)]) + 1;
+    if (h + 1 >= (int64_t(1) << 26)) {
+      set_error("madicp_put_keyframe: tree deeper than 25 levels is not supported by the implicit-heap layout");
+      return MADICP_ERR_INVALID;
+    }
+    heap_pos[size_t(link)] = int(h);
+    heap_pos[size_t(link) + 1] = int(h + 1);
+    if (h + 1 > max_pos) max_pos = h + 1;
+  }
+  int rc = ensure_pool(c, size_t(n_nodes), size_t(8 * max_pos + 16));  // room for the 3-level look-ahead prefetch
   if (rc) return rc;
   Slot& s = c->slots[slot];
   CK(cudaMemcpyAsync(c->d_pool_recs + size_t(slot) * c->pool_cap, recs, size_t(n_nodes) * sizeof(madtree_rec_t),
                      cudaMemcpyHostToDevice, c->stream));
   s.n_nodes = n_nodes;
   s.n_leaves = n_leaves;
+  s.heap_pos.swap(heap_pos);
   rc = prepare_slot(c, slot);
   if (rc) return rc;
   CK(cudaStreamSynchronize(c->stream));  // caller may free/modify the host tree right after
@@ -651,7 +705,7 @@ int madicp_search_cloud(madicp_ctx_t* c, int slot, const double* q, int64_t n, i
   double* d_p = d_out;
   double* d_n = d_out + size_t(n) * 3;
   double* d_d = d_out + size_t(n) * 6;
-  k_search_cloud<<<grid_for(c, n), kStepBlock, 0, c->stream>>>(make_view(c), int(size_t(slot) * c->pool_cap), d_q, n, d_o,
+  k_search_cloud<<<grid_for(c, n), kStepBlock, 0, c->stream>>>(make_view(c), int(size_t(slot) * c->heap_cap), d_q, n, d_o,
                                                               points ? d_p : nullptr, normals ? d_n : nullptr,
                                                               dists ? d_d : nullptr);
   c->launches++;

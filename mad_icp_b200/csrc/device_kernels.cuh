@@ -8,11 +8,12 @@ namespace madicp {
 // Preparation kernels (run once per keyframe upload / once per scan)
 // ---------------------------------------------------------------------------------------------
 
-// FP32 plane shadows + absolute link array of one keyframe tree placed at pool offset `off`.
-// `recs` are the slot's exact records as uploaded (links slot-relative, breadth-first).
+// Shadows of one keyframe tree: `recs` are the slot's exact records as uploaded (links slot-relative,
+// breadth-first) at pool offset `off`; heap_pos[i] is node i's position in the implicit heap (computed
+// on the host from the links), `hoff` the slot's offset in the heap array.
 __global__ void __launch_bounds__(kStepBlock)
-k_prepare_fast(const madtree_rec_t* __restrict__ recs, int n, int off, double min_ball, FastRec* __restrict__ fast,
-               int* __restrict__ links) {
+k_prepare_slot(const madtree_rec_t* __restrict__ recs, const int* __restrict__ heap_pos, int n, int off, int hoff,
+               double min_ball, int* __restrict__ links, FastRec* __restrict__ heap, int* __restrict__ bfs_of) {
   const int i = blockIdx.x * kStepBlock + threadIdx.x;
   if (i >= n) return;
   const Rec r = load_rec(recs + i);
@@ -22,15 +23,17 @@ k_prepare_fast(const madtree_rec_t* __restrict__ recs, int n, int off, double mi
     f.dy = __double2float_rn(r.dy);
     f.dz = __double2float_rn(r.dz);
     f.c = __double2float_rn(dot3(r.mx, r.my, r.mz, r.dx, r.dy, r.dz));  // plane offset mean.dir in FP64, rounded once
-  } else {  // leaf: planarity weight w*w with w = 1 - bbox(0)/min_ball (reference: mad_icp.cpp:97-98)
+  } else {  // leaf: {pool index, marker, planarity weight w*w with w = 1 - bbox(0)/min_ball}
     const double w = 1.0 - r.bbox0 / min_ball;
     const double ww = w * w;
-    f.dx = __int_as_float(__double2loint(ww));
-    f.dy = __int_as_float(__double2hiint(ww));
-    f.dz = 0.f;
-    f.c = 0.f;
+    f.dx = __int_as_float(off + i);
+    f.dy = __uint_as_float(kLeafMarker);
+    f.dz = __int_as_float(__double2loint(ww));
+    f.c = __int_as_float(__double2hiint(ww));
   }
-  fast[i] = f;
+  const int h = heap_pos[i];
+  heap[hoff + h] = f;
+  bfs_of[hoff + h] = off + i;
   links[i] = (r.link >= 0) ? (r.link + off) : r.link;
 }
 
@@ -102,7 +105,8 @@ k_linearize(const __grid_constant__ ModelView model, const Moving4* __restrict__
       iso_apply(X, m.px, m.py, m.pz, mx, my, mz);
       const int leaf = hit[w];
       const Rec f = load_rec(model.recs + leaf);
-      const double ww = leaf_weight(load_fast(model.fast + leaf));
+      const double wgt = 1.0 - f.bbox0 / P.min_ball;  // reference: mad_icp.cpp:97-98
+      const double ww = wgt * wgt;
       if (linearize_one(X, P.rho_ker_sqrt, m, mx, my, mz, f, ww, v) && matched) matched[q] = 1;
     }
     warp_accumulate(s_stage[threadIdx.x >> 5], v, c0, c1);

@@ -49,9 +49,7 @@ constexpr int kMaxPeers = 16;
 constexpr int kMailboxSlots = 2;  // double-buffered by round parity
 
 // 16-byte FP32 shadow of a node: the split plane in offset form, s = q.d - c with c = mean.dir
-// (computed in FP64, rounded once).  Same index as the exact record.  The child link lives in a
-// separate int array so a visit loads 16 + 4 bytes per lane: the walk is bound by the L1 -> register
-// write-back path (128 B/clk/SM), i.e. by bytes loaded per lane per level, not by DRAM or L2.
+// (computed in FP64, rounded once).  A visit loads 16 bytes per lane.
 struct __align__(16) FastRec {
   float dx, dy, dz, c;
 };
@@ -61,16 +59,27 @@ static_assert(sizeof(FastRec) == 16, "FastRec must be one 128-bit load");
 // 1e-6 = 16.8 * 2^-24 leaves a 3x margin.  E = kBoundC * (|q|_1 + |c|), rounded up.
 constexpr float kBoundC = 1.0e-6f;
 
-// All keyframes of a device live in ONE pool (three parallel arrays; slot s owns the index range
-// [s*cap, (s+1)*cap)), and links are absolute pool indices, so a walk in flight is described by a
-// single int.  That is what makes several interleaved walks per thread affordable in registers.
+// All keyframes of a device live in ONE pool; slot s owns the index range [s*cap, (s+1)*cap) of the
+// breadth-first arrays and [s*heap_cap, (s+1)*heap_cap) of the heap-ordered shadow array.
+//
+// The walk reads ONLY the shadows, stored in implicit binary-heap order: the children of the node at
+// heap position h sit at 2h+1 and 2h+2.  No child link has to be loaded, so (a) a level costs one
+// 16-byte load instead of two dependent-address loads and (b) the positions of all descendants are
+// known in advance: the 8 candidates three levels down (8h+7 .. 8h+14, 128 contiguous bytes) are
+// prefetched into L1 while the current level is still being decided, which turns the chain of
+// ~16 dependent L2 round trips into ~16/3.  The tree is not complete (leaves sit at depth 11..17 for a
+// 64-beam scan), so the array is sparse: 2^(D+1) slots of 16 B per keyframe (8 MB at D=18) of which
+// ~40k are ever touched; HBM capacity is not the constraint here (180 GB), latency is.
+// A LEAF's shadow holds {breadth-first pool index of the leaf, marker, planarity weight ww (f64)}.
 struct ModelView {  // passed by value (constant bank)
-  const madtree_rec_t* recs;  // exact 64-byte records
-  const FastRec* fast;        // FP32 plane shadows
-  const int* links;           // internal: pool index of the left child (right = +1); leaf: -1 - getLeafs ordinal
-  int root[kMaxSlots];        // pool index of the root of the k-th active keyframe
+  const madtree_rec_t* recs;  // exact 64-byte records, breadth-first (fallback predicate + leaf data)
+  const int* links;           // breadth-first: pool index of the left child, or -1 - getLeafs ordinal (leaf)
+  const FastRec* heap;        // FP32 plane shadows in implicit heap order
+  const int* bfs_of;          // heap position -> breadth-first pool index (read only by the FP64 fallback)
+  int root[kMaxSlots];        // heap position of the root of the k-th active keyframe (= slot * heap_cap)
   int K;
 };
+constexpr unsigned kLeafMarker = 0x7fc0beefu;  // a NaN payload no arithmetic produces, in FastRec::dy of a leaf
 
 struct IcpParams {
   double min_ball, rho_ker_sqrt, b_ratio;
@@ -168,29 +177,33 @@ __device__ __forceinline__ int side_filtered(const QueryF& q, const FastRec& p) 
   const float E = __fmaf_ru(kBoundC, fabsf(p.c), q.eq);
   return (s > E) ? 1 : ((s < -E) ? 0 : -1);
 }
-// The shadow of a LEAF carries no plane; its first 8 bytes hold the leaf's planarity weight
-// ww = (1 - bbox0/min_ball)^2 as a double (reference: odometry/mad_icp.cpp:97-98), so the value
-// arrives with the load that discovers the leaf.
+__device__ __forceinline__ bool is_leaf(const FastRec& p) { return __float_as_uint(p.dy) == kLeafMarker; }
+__device__ __forceinline__ int leaf_index(const FastRec& p) { return __float_as_int(p.dx); }
+// planarity weight ww = (1 - bbox0/min_ball)^2 (reference: odometry/mad_icp.cpp:97-98), stored as a double
 __device__ __forceinline__ double leaf_weight(const FastRec& p) {
-  return __hiloint2double(__float_as_int(p.dy), __float_as_int(p.dx));
+  return __hiloint2double(__float_as_int(p.c), __float_as_int(p.dz));
 }
+__device__ __forceinline__ void prefetch_line(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-// Greedy single-path descent (no backtracking, like the reference: tools/mad_tree.cpp:144-152).
-// Returns the pool index of the leaf reached and its planarity weight.  Decisions are bit-identical
-// to the reference's FP64 expression by construction.
+// Greedy single-path descent (no backtracking, like the reference: tools/mad_tree.cpp:144-152) over
+// the heap-ordered shadows.  Returns the breadth-first pool index of the leaf reached and its planarity
+// weight.  Decisions are bit-identical to the reference's FP64 expression by construction.
 __device__ __forceinline__ int descend(const ModelView& M, int root, double qx, double qy, double qz, double& ww) {
   const QueryF q = make_query(qx, qy, qz);
-  int idx = root;
+  const FastRec* base = M.heap + root;
+  unsigned h = 0;
   while (true) {
-    const int link = load_link(M.links + idx);
-    const FastRec p = load_fast(M.fast + idx);  // independent of `link`: both requests are in flight together
-    if (link < 0) {
+    const FastRec p = load_fast(base + h);
+    // the eight nodes three levels below (one of them will be visited) -- 128 B, at most two lines
+    prefetch_line(base + (8u * h + 7u));
+    prefetch_line(base + (8u * h + 14u));
+    if (is_leaf(p)) {
       ww = leaf_weight(p);
-      return idx;
+      return leaf_index(p);
     }
     int side = side_filtered(q, p);
-    if (side < 0) side = side_exact(M.recs + idx, qx, qy, qz) ? 1 : 0;
-    idx = link + side;
+    if (side < 0) side = side_exact(M.recs + M.bfs_of[root + h], qx, qy, qz) ? 1 : 0;
+    h = 2u * h + 1u + unsigned(side);
   }
 }
 

@@ -170,6 +170,12 @@ int madicp_comm_world(const madicp_ctx_t* ctx);
  * [0] item phase of CTA 0, [1] round start -> last CTA arrived, [2] fold of the per-CTA partials,
  * [3] peer exchange + matched count, [4] solve + publish (cycles).  Returns rows written. */
 int madicp_debug_timing(madicp_ctx_t* ctx, int enable, int64_t* out, int max_rounds);
+/* Item-phase cycles of every CTA for the rounds of the last launch (rounds x grid int64, debug timing
+ * must be on).  Returns the grid size. */
+int madicp_debug_cta_cycles(madicp_ctx_t* ctx, int64_t* out, int cap);
+/* Tree-walk variant: 0 breadth-first shadows + link loads (default), 1 implicit-heap shadows,
+ * 2 / 3 heap + 2- / 3-level look-ahead L1 prefetch.  All variants take identical decisions. */
+int madicp_set_walk_mode(madicp_ctx_t* ctx, int mode);
 /* Shape of the persistent kernel: threads per CTA and resident CTAs per SM; supported pairs are
  * (1024,1) default, (768,1), (512,1), (512,2), (256,2), (256,3), (256,4); env MADICP_GN_SHAPE="t,c"
  * selects one at create time.  By default the library picks among the one-CTA-per-SM shapes per

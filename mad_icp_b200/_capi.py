@@ -54,6 +54,8 @@ SYMBOLS = {
     "madicp_comm_connect": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "madicp_comm_world": (C.c_int, [vp]),
     "madicp_debug_timing": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int64), C.c_int]),
+    "madicp_debug_cta_cycles": (C.c_int, [vp, C.POINTER(C.c_int64), C.c_int]),
+    "madicp_set_walk_mode": (C.c_int, [vp, C.c_int]),
     "madicp_set_gn_grid": (C.c_int, [vp, C.c_int, C.c_int]),
 }
 

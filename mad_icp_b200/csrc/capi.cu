@@ -54,6 +54,9 @@ struct madicp_ctx {
   size_t heap_cap = 0;  // heap positions per slot: 2^(depth+1) + skew
   FastRec* d_heap = nullptr;
   int* d_bfs_of = nullptr;
+  FastRec* d_pool_fast = nullptr;  // breadth-first copy of the shadows (walk_mode 0)
+  int walk_mode = 0;
+  long long* d_dbg_cta = nullptr;  // MADICP_MAX_ITERS x grid item-phase cycles when debug timing is on
   int* d_heap_pos = nullptr;  // upload scratch, pool_cap ints
   IcpParams P{0.2, 0.31622776601683794, 0.02};
   double* d_moving = nullptr;               // raw L x 3 means as uploaded
@@ -103,10 +106,16 @@ static ModelView make_view(const madicp_ctx* c) {
   v.links = c->d_pool_links;
   v.heap = c->d_heap;
   v.bfs_of = c->d_bfs_of;
+  v.fast = c->d_pool_fast;
+  v.walk_mode = c->walk_mode;
   v.K = 0;
   for (int s = 0; s < c->max_keyframes; ++s)
-    if (c->slots[s].n_nodes > 0) v.root[v.K++] = int(size_t(s) * c->heap_cap);
-  for (int i = v.K; i < kMaxSlots; ++i) v.root[i] = 0;
+    if (c->slots[s].n_nodes > 0) {
+      v.root[v.K] = int(size_t(s) * c->heap_cap);
+      v.broot[v.K] = int(size_t(s) * c->pool_cap);
+      ++v.K;
+    }
+  for (int i = v.K; i < kMaxSlots; ++i) v.root[i] = v.broot[i] = 0;
   return v;
 }
 
@@ -119,7 +128,7 @@ static int prepare_slot(madicp_ctx* c, int s) {
                      c->stream));
   k_prepare_slot<<<(n + kStepBlock - 1) / kStepBlock, kStepBlock, 0, c->stream>>>(
       c->d_pool_recs + off, c->d_heap_pos, n, int(off), int(hoff), c->P.min_ball, c->d_pool_links + off, c->d_heap,
-      c->d_bfs_of);
+      c->d_bfs_of, c->d_pool_fast + off);
   c->launches++;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));  // heap_pos scratch is reused by the next slot
@@ -146,9 +155,11 @@ static int ensure_pool(madicp_ctx* c, size_t need, size_t need_heap) {
     madtree_rec_t* recs = nullptr;
     int* links = nullptr;
     int* hp = nullptr;
+    FastRec* fast = nullptr;
     const size_t total = cap * size_t(c->max_keyframes);
     CK(cudaMalloc(&recs, total * sizeof(madtree_rec_t)));
     CK(cudaMalloc(&links, total * sizeof(int)));
+    CK(cudaMalloc(&fast, total * sizeof(FastRec)));
     CK(cudaMalloc(&hp, cap * sizeof(int)));
     for (int s = 0; s < c->max_keyframes; ++s)
       if (c->slots[s].n_nodes > 0)
@@ -158,6 +169,8 @@ static int ensure_pool(madicp_ctx* c, size_t need, size_t need_heap) {
     cudaFree(c->d_pool_recs);
     cudaFree(c->d_pool_links);
     cudaFree(c->d_heap_pos);
+    cudaFree(c->d_pool_fast);
+    c->d_pool_fast = fast;
     c->d_pool_recs = recs;
     c->d_pool_links = links;
     c->d_heap_pos = hp;
@@ -187,6 +200,13 @@ static int ensure_pool(madicp_ctx* c, size_t need, size_t need_heap) {
       if (rc) return rc;
     }
   return MADICP_OK;
+}
+
+// index of `slot` among the active slots (the k of ModelView::root[k])
+static int slot_rank(const madicp_ctx* c, int slot) {
+  int k = 0;
+  for (int s = 0; s < slot; ++s) k += (c->slots[s].n_nodes > 0);
+  return k;
 }
 
 static int ensure_items(madicp_ctx* c, size_t items) {
@@ -337,6 +357,8 @@ void madicp_destroy(madicp_ctx_t* c) {
   cudaFree(c->d_heap);
   cudaFree(c->d_bfs_of);
   cudaFree(c->d_heap_pos);
+  cudaFree(c->d_pool_fast);
+  cudaFree(c->d_dbg_cta);
   cudaFree(c->d_moving);
   cudaFree(c->d_mov4);
   cudaFree(c->d_step_matched);
@@ -628,6 +650,7 @@ int madicp_register_async(madicp_ctx_t* c, int iters, const double X0[12]) {
   A.partial = c->d_partial;
   A.st = c->d_state;
   A.dbg = c->d_dbg;
+  A.dbg_cta = c->d_dbg ? c->d_dbg_cta : nullptr;
   c->epoch += uint32_t(iters);
   // control words + initial pose in one small pinned H2D copy
   GnState* hs = c->h_state;
@@ -705,7 +728,7 @@ int madicp_search_cloud(madicp_ctx_t* c, int slot, const double* q, int64_t n, i
   double* d_p = d_out;
   double* d_n = d_out + size_t(n) * 3;
   double* d_d = d_out + size_t(n) * 6;
-  k_search_cloud<<<grid_for(c, n), kStepBlock, 0, c->stream>>>(make_view(c), int(size_t(slot) * c->heap_cap), d_q, n, d_o,
+  k_search_cloud<<<grid_for(c, n), kStepBlock, 0, c->stream>>>(make_view(c), slot_rank(c, slot), d_q, n, d_o,
                                                               points ? d_p : nullptr, normals ? d_n : nullptr,
                                                               dists ? d_d : nullptr);
   c->launches++;
@@ -779,11 +802,29 @@ int madicp_debug_timing(madicp_ctx_t* c, int enable, int64_t* out, int max_round
   if (enable && !c->d_dbg) {
     CK(cudaMalloc(&c->d_dbg, MADICP_MAX_ITERS * 8 * sizeof(long long)));
     CK(cudaMemset(c->d_dbg, 0, MADICP_MAX_ITERS * 8 * sizeof(long long)));
+    CK(cudaMalloc(&c->d_dbg_cta, size_t(MADICP_MAX_ITERS) * c->sm_count * 8 * sizeof(long long)));
   } else if (!enable && c->d_dbg) {
     cudaFree(c->d_dbg);
+    cudaFree(c->d_dbg_cta);
     c->d_dbg = nullptr;
+    c->d_dbg_cta = nullptr;
   }
   return rows;
+}
+
+int madicp_debug_cta_cycles(madicp_ctx_t* c, int64_t* out, int cap) {
+  if (!c || !out || !c->d_dbg_cta) return MADICP_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  const int n = std::min(cap, c->last_iters * c->gn_grid);
+  CK(cudaMemcpy(out, c->d_dbg_cta, size_t(n) * sizeof(long long), cudaMemcpyDeviceToHost));
+  return c->gn_grid;
+}
+
+int madicp_set_walk_mode(madicp_ctx_t* c, int mode) {
+  if (!c || mode < 0 || mode > 3) return MADICP_ERR_INVALID;
+  c->walk_mode = mode;
+  return MADICP_OK;
 }
 
 int madicp_set_gn_grid(madicp_ctx_t* c, int threads_per_cta, int ctas_per_sm) {

@@ -13,7 +13,8 @@ namespace madicp {
 // on the host from the links), `hoff` the slot's offset in the heap array.
 __global__ void __launch_bounds__(kStepBlock)
 k_prepare_slot(const madtree_rec_t* __restrict__ recs, const int* __restrict__ heap_pos, int n, int off, int hoff,
-               double min_ball, int* __restrict__ links, FastRec* __restrict__ heap, int* __restrict__ bfs_of) {
+               double min_ball, int* __restrict__ links, FastRec* __restrict__ heap, int* __restrict__ bfs_of,
+               FastRec* __restrict__ fast) {
   const int i = blockIdx.x * kStepBlock + threadIdx.x;
   if (i >= n) return;
   const Rec r = load_rec(recs + i);
@@ -34,6 +35,11 @@ k_prepare_slot(const madtree_rec_t* __restrict__ recs, const int* __restrict__ h
   const int h = heap_pos[i];
   heap[hoff + h] = f;
   bfs_of[hoff + h] = off + i;
+  if (r.link < 0) {  // breadth-first copy of a leaf shadow: weight in the first 8 bytes
+    f.dx = f.dz;
+    f.dy = f.c;
+  }
+  fast[i] = f;
   links[i] = (r.link >= 0) ? (r.link + off) : r.link;
 }
 
@@ -69,7 +75,7 @@ k_search(const __grid_constant__ ModelView model, const Moving4* __restrict__ mo
     const Moving4 m = load_moving(moving + q);
     double mx, my, mz, ww;
     iso_apply(X, m.px, m.py, m.pz, mx, my, mz);
-    const int leaf = descend(model, model.root[k], mx, my, mz, ww);
+    const int leaf = descend(model, int(k), mx, my, mz, ww);
     if (hit) hit[w] = leaf;
     if (ordinals) ordinals[w] = -1 - model.links[leaf];
   }
@@ -204,6 +210,7 @@ struct GnArgs {
   double* partial;                         // gridDim.x * kAcc
   GnState* st;
   long long* dbg;                          // nullable: per-round SM-clock stamps (madicp_debug_timing)
+  long long* dbg_cta;                      // nullable: [round][CTA] item-phase cycles
 };
 
 // Persistent cooperative grid (all CTAs co-resident), one software grid barrier per round: CTAs
@@ -276,7 +283,7 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
         const Moving4 m = load_moving(A.moving + q);
         double mx, my, mz, ww;
         iso_apply(s_X, m.px, m.py, m.pz, mx, my, mz);
-        const Rec f = load_rec(A.model.recs + descend(A.model, A.model.root[k], mx, my, mz, ww));
+        const Rec f = load_rec(A.model.recs + descend(A.model, int(k), mx, my, mz, ww));
         if (linearize_one(s_X, A.P.rho_ker_sqrt, m, mx, my, mz, f, ww, v) && last_round) {
           if (multi) {
             for (int r = 0; r < A.peers.world; ++r) A.peer_matched[r][q] = 1;
@@ -288,6 +295,10 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
       warp_accumulate(stage, v, c0, c1);
     }
     if (A.dbg && threadIdx.x == 0 && blockIdx.x == 0) A.dbg[it * 8 + 0] = clock64() - t_begin;  // item phase, CTA 0
+    if (A.dbg_cta) {  // per-CTA item phase (slowest warp) + this warp's own time
+      __syncthreads();
+      if (threadIdx.x == 0) A.dbg_cta[size_t(it) * gridDim.x + blockIdx.x] = clock64() - t_begin;
+    }
     block_reduce_store<WARPS>(c0, c1, s_red, A.partial + size_t(blockIdx.x) * kAcc);
     if (multi && last_round) __threadfence_system();  // matched flags stored to peers precede our LL cells
     __syncthreads();

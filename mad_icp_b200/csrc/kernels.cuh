@@ -76,8 +76,11 @@ struct ModelView {  // passed by value (constant bank)
   const int* links;           // breadth-first: pool index of the left child, or -1 - getLeafs ordinal (leaf)
   const FastRec* heap;        // FP32 plane shadows in implicit heap order
   const int* bfs_of;          // heap position -> breadth-first pool index (read only by the FP64 fallback)
+  const FastRec* fast;        // the same shadows in breadth-first order (walk_mode 0)
   int root[kMaxSlots];        // heap position of the root of the k-th active keyframe (= slot * heap_cap)
+  int broot[kMaxSlots];       // breadth-first pool index of that root (= slot * cap)
   int K;
+  int walk_mode;              // 0: breadth-first arrays + link loads; 1: heap; 2/3: heap + 2/3-level look-ahead prefetch
 };
 constexpr unsigned kLeafMarker = 0x7fc0beefu;  // a NaN payload no arithmetic produces, in FastRec::dy of a leaf
 
@@ -185,18 +188,37 @@ __device__ __forceinline__ double leaf_weight(const FastRec& p) {
 }
 __device__ __forceinline__ void prefetch_line(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-// Greedy single-path descent (no backtracking, like the reference: tools/mad_tree.cpp:144-152) over
-// the heap-ordered shadows.  Returns the breadth-first pool index of the leaf reached and its planarity
-// weight.  Decisions are bit-identical to the reference's FP64 expression by construction.
-__device__ __forceinline__ int descend(const ModelView& M, int root, double qx, double qy, double qz, double& ww) {
+// Greedy single-path descent (no backtracking, like the reference: tools/mad_tree.cpp:144-152).
+// Returns the breadth-first pool index of the leaf reached and its planarity weight.  Decisions are
+// bit-identical to the reference's FP64 expression by construction.  `k` = index of the active keyframe.
+__device__ __forceinline__ int descend(const ModelView& M, int k, double qx, double qy, double qz, double& ww) {
   const QueryF q = make_query(qx, qy, qz);
+  if (M.walk_mode == 0) {  // breadth-first shadows + one link load per level
+    int idx = M.broot[k];
+    while (true) {
+      const int link = load_link(M.links + idx);
+      const FastRec p = load_fast(M.fast + idx);  // independent of `link`: both requests are in flight together
+      if (link < 0) {
+        ww = __hiloint2double(__float_as_int(p.dy), __float_as_int(p.dx));
+        return idx;
+      }
+      int side = side_filtered(q, p);
+      if (side < 0) side = side_exact(M.recs + idx, qx, qy, qz) ? 1 : 0;
+      idx = link + side;
+    }
+  }
+  const int root = M.root[k];
   const FastRec* base = M.heap + root;
   unsigned h = 0;
   while (true) {
     const FastRec p = load_fast(base + h);
-    // the eight nodes three levels below (one of them will be visited) -- 128 B, at most two lines
-    prefetch_line(base + (8u * h + 7u));
-    prefetch_line(base + (8u * h + 14u));
+    if (M.walk_mode == 2) {  // the four nodes two levels below: 64 contiguous bytes
+      prefetch_line(base + (4u * h + 3u));
+      prefetch_line(base + (4u * h + 6u));
+    } else if (M.walk_mode == 3) {  // the eight nodes three levels below: 128 contiguous bytes
+      prefetch_line(base + (8u * h + 7u));
+      prefetch_line(base + (8u * h + 14u));
+    }
     if (is_leaf(p)) {
       ww = leaf_weight(p);
       return leaf_index(p);

@@ -212,6 +212,14 @@ class Registrar:
                                                     if fetch else None, 64))
         return buf[:rows]
 
+    def debug_cta_cycles(self, rounds):
+        buf = np.zeros(rounds * 148 * 8, np.int64)
+        grid = check(capi.lib().madicp_debug_cta_cycles(self._h, buf.ctypes.data_as(C.POINTER(C.c_int64)), buf.size))
+        return buf[:rounds * grid].reshape(rounds, grid)
+
+    def set_walk_mode(self, mode):
+        check(capi.lib().madicp_set_walk_mode(self._h, mode))
+
     def set_gn_grid(self, threads_per_cta=1024, ctas_per_sm=1):
         return check(capi.lib().madicp_set_gn_grid(self._h, threads_per_cta, ctas_per_sm))
 

@@ -34,14 +34,21 @@ for iters in (1, 2, 5, 10, 15, 20):
     c = timed(lambda: reg.register_async(X0, iters), cold=True)
     print(f"gn_loop iters={iters:2d}: warm median {w[0]:8.1f} us (min {w[1]:8.1f})   cold median {c[0]:8.1f} us (min {c[1]:8.1f})")
 
-# per-round phase breakdown (SM cycles @ ~1.965 GHz) for the persistent-kernel shapes
+# per-round phase breakdown (SM cycles @ ~1.965 GHz) per walk mode and shape
 reg.debug_timing(True, fetch=False)
-shapes = [(1024, 1), (768, 1), (512, 1), (512, 2), (256, 3), (256, 4)]
-for thr, cps in shapes:
-    reg.set_gn_grid(thr, cps)
-    w = timed(lambda: reg.register_async(X0, 10))
-    c = timed(lambda: reg.register_async(X0, 10), cold=True)
-    reg.register_async(X0, 10); torch.cuda.synchronize()
-    d = reg.debug_timing(True)
-    print(f"shape=({thr},{cps}): 10-iter warm {w[0]:.1f} us cold {c[0]:.1f} us; cycles/round (median): items(cta0)={np.median(d[:,0]):.0f} "
-          f"start->all_arrived={np.median(d[:,1]):.0f} fold={np.median(d[:,2]):.0f} xchg+count={np.median(d[:,3]):.0f} solve={np.median(d[:,4]):.0f}")
+for mode in (0, 1, 2, 3):
+    reg.set_walk_mode(mode)
+    for thr, cps in ((1024, 1), (768, 1)):
+        reg.set_gn_grid(thr, cps)
+        w = timed(lambda: reg.register_async(X0, 10))
+        reg.register_async(X0, 10); torch.cuda.synchronize()
+        d = reg.debug_timing(True)
+        cta = reg.debug_cta_cycles(10)[1:]          # skip the cold first round
+        med = np.median(cta, axis=0)                # per-CTA median over rounds
+        order = np.argsort(med)
+        rho = np.corrcoef(cta[0], cta[-1])[0, 1]    # are the same CTAs slow in every round?
+        print(f"mode={mode} shape=({thr},{cps}): 10-iter warm {w[0]:.1f} us | round cycles: all_arrived={np.median(d[:,1]):.0f} "
+              f"fold={np.median(d[:,2]):.0f} solve={np.median(d[:,4]):.0f} | per-CTA item phase: min={med.min():.0f} "
+              f"p50={np.median(med):.0f} p90={np.percentile(med,90):.0f} max={med.max():.0f} slowest CTAs={order[-4:].tolist()} "
+              f"fastest={order[:4].tolist()} round-to-round corr={rho:.2f}")
+reg.set_walk_mode(0)

@@ -291,3 +291,21 @@ def test_iters_one_clears_and_sets_matched(lidar_small, oracle):
     assert (out["matched"] == ref["matched"]).all()
     ang, dt = pose_error(out["X"], ref["X"])
     assert ang < 1e-9 and dt < 1e-9
+
+
+def test_walk_variants_take_identical_decisions(lidar_small, full16):
+    """Breadth-first + links, implicit heap, heap + look-ahead prefetch: same indices, same result bits."""
+    for g, c, (reg, _, _) in (lidar_small[:3], (None,) + full16):
+        X = c["T_guess"]
+        base_idx, base = None, None
+        for mode in (0, 1, 2, 3):
+            reg.set_walk_mode(mode)
+            idx = reg.search(X)
+            out = reg.register(X, iters=4)
+            if base_idx is None:
+                base_idx, base = idx, out
+            else:
+                assert (idx == base_idx).all(), mode
+                assert bits_equal(out["X"], base["X"]) and bits_equal(out["H"], base["H"]), mode
+                assert (out["matched"] == base["matched"]).all()
+        reg.set_walk_mode(0)

@@ -55,7 +55,7 @@ struct madicp_ctx {
   FastRec* d_heap = nullptr;
   int* d_bfs_of = nullptr;
   FastRec* d_pool_fast = nullptr;  // breadth-first copy of the shadows (walk_mode 0)
-  int walk_mode = 0;
+  int walk_mode = 1;
   long long* d_dbg_cta = nullptr;  // MADICP_MAX_ITERS x grid item-phase cycles when debug timing is on
   int* d_heap_pos = nullptr;  // upload scratch, pool_cap ints
   IcpParams P{0.2, 0.31622776601683794, 0.02};

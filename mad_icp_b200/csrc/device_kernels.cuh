@@ -250,10 +250,21 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
   const unsigned lane = threadIdx.x & 31;
   const unsigned warp = threadIdx.x >> 5;
   double* stage = s_stage_all + warp * kStageTile;
-  const unsigned q_lo = unsigned((uint64_t(L) * blockIdx.x) / gridDim.x);
-  const unsigned q_hi = unsigned((uint64_t(L) * (blockIdx.x + 1)) / gridDim.x);
-  const unsigned n_b = q_hi - q_lo;                      // moving leaves of this CTA
-  const unsigned t_total = unsigned(A.model.K) * n_b;   // CTA-local items
+  // kPieces contiguous stretches per CTA, dealt serpentine-wise (piece p of CTA b is stretch p*G + b for
+  // even p, p*G + G-1-b for odd p): the cost of a stretch varies smoothly along the DFS order of the scan
+  // (tree depth, gate pass rate; measured 18k..32k cycles per CTA with one stretch each), pairing opposite
+  // ends evens it out while every stretch stays one compact spatial region.
+  constexpr unsigned kPieces = 4;
+  unsigned p_lo[kPieces], p_n[kPieces];
+  unsigned n_b = 0;  // moving leaves of this CTA
+#pragma unroll
+  for (unsigned p = 0; p < kPieces; ++p) {
+    const unsigned r = p * gridDim.x + ((p & 1u) ? (gridDim.x - 1u - blockIdx.x) : blockIdx.x);
+    p_lo[p] = unsigned((uint64_t(L) * r) / (uint64_t(kPieces) * gridDim.x));
+    p_n[p] = unsigned((uint64_t(L) * (r + 1)) / (uint64_t(kPieces) * gridDim.x)) - p_lo[p];
+    n_b += p_n[p];
+  }
+  const unsigned t_total = unsigned(A.model.K) * n_b;  // CTA-local items
   (void) total;
 
   for (int it = 0; it < A.iters; ++it) {
@@ -275,7 +286,16 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
         q -= n_b;
         ++k;
       }
-      q += q_lo;
+      {  // CTA-local leaf number -> moving leaf
+        unsigned j = q;
+        q = p_lo[kPieces - 1] + (j - (n_b - p_n[kPieces - 1]));
+        unsigned acc = 0;
+#pragma unroll
+        for (unsigned p = 0; p + 1 < kPieces; ++p) {
+          if (j >= acc && j < acc + p_n[p]) q = p_lo[p] + (j - acc);
+          acc += p_n[p];
+        }
+      }
       double v[kStage];
 #pragma unroll
       for (int i = 0; i < kStage; ++i) v[i] = 0.0;

@@ -55,6 +55,8 @@ struct madicp_ctx {
   FastRec* d_heap = nullptr;
   int* d_bfs_of = nullptr;
   FastRec* d_pool_fast = nullptr;  // breadth-first copy of the shadows (walk_mode 0)
+  size_t quad_cap = 0;             // 4-ary heap positions per slot
+  QuadRec* d_quad = nullptr;
   int walk_mode = 1;
   long long* d_dbg_cta = nullptr;  // MADICP_MAX_ITERS x grid item-phase cycles when debug timing is on
   int* d_heap_pos = nullptr;  // upload scratch, pool_cap ints
@@ -107,15 +109,17 @@ static ModelView make_view(const madicp_ctx* c) {
   v.heap = c->d_heap;
   v.bfs_of = c->d_bfs_of;
   v.fast = c->d_pool_fast;
+  v.quad = c->d_quad;
   v.walk_mode = c->walk_mode;
   v.K = 0;
   for (int s = 0; s < c->max_keyframes; ++s)
     if (c->slots[s].n_nodes > 0) {
       v.root[v.K] = int(size_t(s) * c->heap_cap);
       v.broot[v.K] = int(size_t(s) * c->pool_cap);
+      v.qroot[v.K] = int(size_t(s) * c->quad_cap);
       ++v.K;
     }
-  for (int i = v.K; i < kMaxSlots; ++i) v.root[i] = v.broot[i] = 0;
+  for (int i = v.K; i < kMaxSlots; ++i) v.root[i] = v.broot[i] = v.qroot[i] = 0;
   return v;
 }
 
@@ -128,7 +132,7 @@ static int prepare_slot(madicp_ctx* c, int s) {
                      c->stream));
   k_prepare_slot<<<(n + kStepBlock - 1) / kStepBlock, kStepBlock, 0, c->stream>>>(
       c->d_pool_recs + off, c->d_heap_pos, n, int(off), int(hoff), c->P.min_ball, c->d_pool_links + off, c->d_heap,
-      c->d_bfs_of, c->d_pool_fast + off);
+      c->d_bfs_of, c->d_pool_fast + off, c->d_quad, int(size_t(s) * c->quad_cap));
   c->launches++;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));  // heap_pos scratch is reused by the next slot
@@ -193,6 +197,16 @@ static int ensure_pool(madicp_ctx* c, size_t need, size_t need_heap) {
     CK(cudaMalloc(&c->d_bfs_of, total * sizeof(int)));
     CK(cudaMemsetAsync(c->d_heap, 0, total * sizeof(FastRec), c->stream));  // never-visited positions are prefetched only
     c->heap_cap = cap;
+    // 4-ary heap: a binary tree of depth D has D/2 + 1 four-ary levels; positions < (4^(levels) - 1) / 3
+    int depth = 0;
+    while ((size_t(1) << (depth + 1)) < need_heap / 8) ++depth;  // need_heap = 8 * max binary position + 16
+    size_t qcap = 1;
+    for (int l = 0; l < depth / 2 + 1; ++l) qcap = 4 * qcap + 1;
+    qcap += 40;
+    cudaFree(c->d_quad);
+    c->d_quad = nullptr;
+    CK(cudaMalloc(&c->d_quad, qcap * size_t(c->max_keyframes) * sizeof(QuadRec)));
+    c->quad_cap = qcap;
   }
   for (int s = 0; s < c->max_keyframes; ++s)
     if (c->slots[s].n_nodes > 0) {
@@ -358,6 +372,7 @@ void madicp_destroy(madicp_ctx_t* c) {
   cudaFree(c->d_bfs_of);
   cudaFree(c->d_heap_pos);
   cudaFree(c->d_pool_fast);
+  cudaFree(c->d_quad);
   cudaFree(c->d_dbg_cta);
   cudaFree(c->d_moving);
   cudaFree(c->d_mov4);
@@ -822,7 +837,7 @@ int madicp_debug_cta_cycles(madicp_ctx_t* c, int64_t* out, int cap) {
 }
 
 int madicp_set_walk_mode(madicp_ctx_t* c, int mode) {
-  if (!c || mode < 0 || mode > 3) return MADICP_ERR_INVALID;
+  if (!c || mode < 0 || mode > 4) return MADICP_ERR_INVALID;
   c->walk_mode = mode;
   return MADICP_OK;
 }

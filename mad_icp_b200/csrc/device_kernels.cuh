@@ -14,7 +14,7 @@ namespace madicp {
 __global__ void __launch_bounds__(kStepBlock)
 k_prepare_slot(const madtree_rec_t* __restrict__ recs, const int* __restrict__ heap_pos, int n, int off, int hoff,
                double min_ball, int* __restrict__ links, FastRec* __restrict__ heap, int* __restrict__ bfs_of,
-               FastRec* __restrict__ fast) {
+               FastRec* __restrict__ fast, QuadRec* __restrict__ quad, int qoff) {
   const int i = blockIdx.x * kStepBlock + threadIdx.x;
   if (i >= n) return;
   const Rec r = load_rec(recs + i);
@@ -35,6 +35,19 @@ k_prepare_slot(const madtree_rec_t* __restrict__ recs, const int* __restrict__ h
   const int h = heap_pos[i];
   heap[hoff + h] = f;
   bfs_of[hoff + h] = off + i;
+  {  // 4-ary position: the path from the root (bits of h+1 below its leading one), two bits per 4-ary level
+    const unsigned hp1 = unsigned(h) + 1u;
+    const int depth = 31 - __clz(hp1);
+    unsigned g = 0;
+    for (int j = 0; j < depth / 2; ++j) g = 4u * g + 1u + ((hp1 >> (depth - 2 * j - 2)) & 3u);
+    QuadRec* qr = quad + qoff + g;
+    if (depth & 1) {  // odd depth: child slot of its parent's record, selected by the last path bit
+      if (hp1 & 1u) qr->p2 = f; else qr->p1 = f;
+    } else {
+      qr->p0 = f;
+      qr->bfs0 = off + i;
+    }
+  }
   if (r.link < 0) {  // breadth-first copy of a leaf shadow: weight in the first 8 bytes
     f.dx = f.dz;
     f.dy = f.c;

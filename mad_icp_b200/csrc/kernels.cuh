@@ -59,6 +59,18 @@ static_assert(sizeof(FastRec) == 16, "FastRec must be one 128-bit load");
 // 1e-6 = 16.8 * 2^-24 leaves a 3x margin.  E = kBoundC * (|q|_1 + |c|), rounded up.
 constexpr float kBoundC = 1.0e-6f;
 
+// Two binary levels in one 64-byte record: the node at an even depth (p0) and its two children (p1 left,
+// p2 right); the four grandchildren are the 4-ary children 4g+1 .. 4g+4 of position g.  One dependent
+// memory round trip then resolves two levels of the reference's binary descent (each of the two
+// decisions is still the filtered/exact binary predicate, so indices stay bit-exact).  A slot whose
+// binary node is a leaf holds the leaf code; slots below a leaf are never read.
+struct __align__(32) QuadRec {
+  FastRec p0, p1, p2;
+  int bfs0;      // breadth-first pool index of p0's node (the FP64 fallback needs the exact records)
+  int pad[3];
+};
+static_assert(sizeof(QuadRec) == 64, "QuadRec must be two 256-bit loads");
+
 // All keyframes of a device live in ONE pool; slot s owns the index range [s*cap, (s+1)*cap) of the
 // breadth-first arrays and [s*heap_cap, (s+1)*heap_cap) of the heap-ordered shadow array.
 //
@@ -77,10 +89,12 @@ struct ModelView {  // passed by value (constant bank)
   const FastRec* heap;        // FP32 plane shadows in implicit heap order
   const int* bfs_of;          // heap position -> breadth-first pool index (read only by the FP64 fallback)
   const FastRec* fast;        // the same shadows in breadth-first order (walk_mode 0)
+  const QuadRec* quad;        // two binary levels per 64-byte record, implicit 4-ary heap order (walk_mode 4)
   int root[kMaxSlots];        // heap position of the root of the k-th active keyframe (= slot * heap_cap)
   int broot[kMaxSlots];       // breadth-first pool index of that root (= slot * cap)
+  int qroot[kMaxSlots];       // 4-ary heap position of that root (= slot * quad_cap)
   int K;
-  int walk_mode;              // 0: breadth-first arrays + link loads; 1: heap; 2/3: heap + 2/3-level look-ahead prefetch
+  int walk_mode;              // 0: breadth-first + link loads; 1: binary heap; 2/3: + look-ahead prefetch; 4: 4-ary heap
 };
 constexpr unsigned kLeafMarker = 0x7fc0beefu;  // a NaN payload no arithmetic produces, in FastRec::dy of a leaf
 
@@ -205,6 +219,34 @@ __device__ __forceinline__ int descend(const ModelView& M, int k, double qx, dou
       int side = side_filtered(q, p);
       if (side < 0) side = side_exact(M.recs + idx, qx, qy, qz) ? 1 : 0;
       idx = link + side;
+    }
+  }
+  if (M.walk_mode == 4) {  // 4-ary heap: two binary decisions per memory round trip
+    const QuadRec* qbase = M.quad + M.qroot[k];
+    unsigned g = 0;
+    while (true) {
+      FastRec p0, p1, p2;
+      int bfs0, pad0, pad1, pad2;
+      asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=f"(p0.dx), "=f"(p0.dy), "=f"(p0.dz), "=f"(p0.c), "=f"(p1.dx), "=f"(p1.dy), "=f"(p1.dz), "=f"(p1.c)
+                   : "l"(qbase + g));
+      asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=f"(p2.dx), "=f"(p2.dy), "=f"(p2.dz), "=f"(p2.c), "=r"(bfs0), "=r"(pad0), "=r"(pad1), "=r"(pad2)
+                   : "l"(reinterpret_cast<const char*>(qbase + g) + 32));
+      if (is_leaf(p0)) {
+        ww = leaf_weight(p0);
+        return leaf_index(p0);
+      }
+      int s0 = side_filtered(q, p0);
+      if (s0 < 0) s0 = side_exact(M.recs + bfs0, qx, qy, qz) ? 1 : 0;
+      const FastRec c = s0 ? p2 : p1;
+      if (is_leaf(c)) {
+        ww = leaf_weight(c);
+        return leaf_index(c);
+      }
+      int s1 = side_filtered(q, c);
+      if (s1 < 0) s1 = side_exact(M.recs + (load_link(M.links + bfs0) + s0), qx, qy, qz) ? 1 : 0;
+      g = 4u * g + 1u + 2u * unsigned(s0) + unsigned(s1);
     }
   }
   const int root = M.root[k];

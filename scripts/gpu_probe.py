@@ -36,7 +36,7 @@ for iters in (1, 2, 5, 10, 15, 20):
 
 # per-round phase breakdown (SM cycles @ ~1.965 GHz) per walk mode and shape
 reg.debug_timing(True, fetch=False)
-for mode in (1, 0):
+for mode in (4, 1):
     reg.set_walk_mode(mode)
     for thr, cps in ((1024, 1), (768, 1)):
         reg.set_gn_grid(thr, cps)

@@ -298,7 +298,7 @@ def test_walk_variants_take_identical_decisions(lidar_small, full16):
     for g, c, (reg, _, _) in (lidar_small[:3], (None,) + full16):
         X = c["T_guess"]
         base_idx, base = None, None
-        for mode in (0, 1, 2, 3):
+        for mode in (0, 1, 2, 3, 4):
             reg.set_walk_mode(mode)
             idx = reg.search(X)
             out = reg.register(X, iters=4)

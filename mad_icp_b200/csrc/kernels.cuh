@@ -170,7 +170,10 @@ __device__ __forceinline__ Moving4 load_moving(const Moving4* p) {
 }
 
 // Exact (reference) side test on the 64-byte record: true = right child.
-__device__ __forceinline__ bool side_exact(const madtree_rec_t* rec, double qx, double qy, double qz) {
+// Deliberately NOT inlined: inlined, ptxas if-converts the rare branch and issues its ~10 predicated-off
+// FP64 instructions at every level of every walk (160 of the ~200 FP64-class issue slots per item, and
+// the FP64/XU issue port is what the item phase saturates: profiles/r01p, xu_realtime 66% of elapsed).
+__device__ __noinline__ bool side_exact(const madtree_rec_t* rec, double qx, double qy, double qz) {
   const Rec r = load_rec(rec);
   return !(plane_side(qx, qy, qz, r.mx, r.my, r.mz, r.dx, r.dy, r.dz) < 0.0);
 }

@@ -173,9 +173,9 @@ int madicp_debug_timing(madicp_ctx_t* ctx, int enable, int64_t* out, int max_rou
 /* Item-phase cycles of every CTA for the rounds of the last launch (rounds x grid int64, debug timing
  * must be on).  Returns the grid size. */
 int madicp_debug_cta_cycles(madicp_ctx_t* ctx, int64_t* out, int cap);
-/* Tree-walk variant: 0 breadth-first shadows + link loads, 1 implicit-heap shadows (default),
- * 2 / 3 heap + 2- / 3-level look-ahead L1 prefetch, 4 four-ary heap (two binary levels per 64-byte
- * record).  All variants take identical decisions. */
+/* Tree-walk variant: 0 breadth-first shadows + link loads, 1 implicit-heap shadows,
+ * 2 / 3 heap + 2- / 3-level look-ahead L1 prefetch, 4 (default) four-ary heap (two binary levels per
+ * 64-byte record).  All variants take identical decisions. */
 int madicp_set_walk_mode(madicp_ctx_t* ctx, int mode);
 /* Shape of the persistent kernel: threads per CTA and resident CTAs per SM; supported pairs are
  * (1024,1) default, (768,1), (512,1), (512,2), (256,2), (256,3), (256,4); env MADICP_GN_SHAPE="t,c"

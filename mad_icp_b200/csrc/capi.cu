@@ -57,7 +57,7 @@ struct madicp_ctx {
   FastRec* d_pool_fast = nullptr;  // breadth-first copy of the shadows (walk_mode 0)
   size_t quad_cap = 0;             // 4-ary heap positions per slot
   QuadRec* d_quad = nullptr;
-  int walk_mode = 1;
+  int walk_mode = 4;
   long long* d_dbg_cta = nullptr;  // MADICP_MAX_ITERS x grid item-phase cycles when debug timing is on
   int* d_heap_pos = nullptr;  // upload scratch, pool_cap ints
   IcpParams P{0.2, 0.31622776601683794, 0.02};

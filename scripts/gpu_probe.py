@@ -51,4 +51,4 @@ for mode in (4, 1):
               f"fold={np.median(d[:,2]):.0f} solve={np.median(d[:,4]):.0f} | per-CTA item phase: min={med.min():.0f} "
               f"p50={np.median(med):.0f} p90={np.percentile(med,90):.0f} max={med.max():.0f} slowest CTAs={order[-4:].tolist()} "
               f"fastest={order[:4].tolist()} round-to-round corr={rho:.2f}")
-reg.set_walk_mode(1)
+reg.set_walk_mode(4)

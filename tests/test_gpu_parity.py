@@ -308,4 +308,4 @@ def test_walk_variants_take_identical_decisions(lidar_small, full16):
                 assert (idx == base_idx).all(), mode
                 assert bits_equal(out["X"], base["X"]) and bits_equal(out["H"], base["H"]), mode
                 assert (out["matched"] == base["matched"]).all()
-        reg.set_walk_mode(1)
+        reg.set_walk_mode(4)

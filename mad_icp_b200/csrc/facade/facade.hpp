@@ -56,7 +56,8 @@ inline Matrix4d from12(const double X[12]) {
 class MADtree {
  public:
   // MADtree(vec, begin, end, b_max, b_min, 0, max_parallel_level, nullptr, nullptr) (mad_tree.cpp:33-45)
-  MADtree(const ContainerType& cloud, double b_max, double b_min, int max_parallel_level = 0) : b_max_(b_max) {
+  MADtree(const ContainerType& cloud, double b_max, double b_min, int max_parallel_level = 0)
+      : b_max_(b_max), uid_(next_uid()) {
     check(madtree_build(cloud.empty() ? nullptr : cloud[0].data(), int64_t(cloud.size()), b_max, b_min,
                         1 << (max_parallel_level > 0 ? max_parallel_level : 0), &t_), "madtree_build");
   }
@@ -81,11 +82,18 @@ class MADtree {
   }
   const madtree_t* handle() const { return t_; }
   double bMax() const { return b_max_; }
-  uint64_t version() const { return version_; }
+  // identity of the tree CONTENT for residency caches: unique per object (addresses get reused) and bumped
+  // by every applyTransform
+  uint64_t version() const { return (uid_ << 20) | version_; }
 
  private:
+  static uint64_t next_uid() {
+    static uint64_t counter = 0;
+    return ++counter;
+  }
   madtree_t* t_ = nullptr;
   double b_max_;
+  uint64_t uid_;
   uint64_t version_ = 0;
 };
 
@@ -156,7 +164,7 @@ class MADicp {
     for (const MADtree* t : trees) {
       bool found = false;
       for (size_t s = 0; s < resident_.size(); ++s)
-        if (resident_[s].first == t && resident_[s].second == t->version() && !keep[s]) {
+        if (resident_[s].first && resident_[s].second == t->version() && !keep[s]) {
           keep[s] = 1;
           found = true;
           break;

@@ -1,0 +1,314 @@
+// pipeline.hpp -- the per-scan odometry driver with the reference's interface (odometry/pipeline.h:45-103),
+// host C++, calling the GPU registration through the facade.  What it does per scan is the reference's
+// Pipeline::compute (odometry/pipeline.cpp:125-265): optional deskew, MAD-tree of the scan, constant-
+// velocity prediction, the ICP loop (one persistent-kernel launch instead of 15 OpenMP rounds), inlier
+// ratio, velocity smoothing (odometry/vel_estimator.cpp), frame weight det(H^-1), keyframe promotion.
+// How it is organised differs: trees are flat handles, keyframes are device-resident pool slots that are
+// uploaded once at promotion, and the small dense algebra uses plain row-major arrays.
+#pragma once
+#include <algorithm>
+#include <deque>
+#include <limits>
+
+#include "facade.hpp"
+
+namespace madicp_b200 {
+namespace detail {
+
+struct Pose {  // 3x4 row-major [R|t]
+  double m[12];
+};
+inline Pose poseIdentity() { return Pose{{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0}}; }
+inline Pose poseMul(const Pose& A, const Pose& B) {
+  Pose C;
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c)
+      C.m[r * 4 + c] = (A.m[r * 4] * B.m[c] + A.m[r * 4 + 1] * B.m[4 + c]) + A.m[r * 4 + 2] * B.m[8 + c];
+    C.m[r * 4 + 3] = ((A.m[r * 4] * B.m[3] + A.m[r * 4 + 1] * B.m[7]) + A.m[r * 4 + 2] * B.m[11]) + A.m[r * 4 + 3];
+  }
+  return C;
+}
+inline Pose poseInverse(const Pose& T) {
+  Pose I;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) I.m[r * 4 + c] = T.m[c * 4 + r];
+  for (int r = 0; r < 3; ++r)
+    I.m[r * 4 + 3] = -((I.m[r * 4] * T.m[3] + I.m[r * 4 + 1] * T.m[7]) + I.m[r * 4 + 2] * T.m[11]);
+  return I;
+}
+inline Vector3d poseApply(const Pose& T, const Vector3d& p) {
+  Vector3d o;
+  for (int r = 0; r < 3; ++r) o[r] = ((T.m[r * 4] * p[0] + T.m[r * 4 + 1] * p[1]) + T.m[r * 4 + 2] * p[2]) + T.m[r * 4 + 3];
+  return o;
+}
+// tools/lie_algebra.h:39-52 (small-angle branch theta^2 < 1e-8 -> I + [w]x)
+inline Pose poseFromTwist(const double t[3], const double w[3]) {
+  Pose P = poseIdentity();
+  const double th2 = (w[0] * w[0] + w[1] * w[1]) + w[2] * w[2];
+  const double W[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+  double R[9];
+  if (th2 < 1e-8) {
+    for (int i = 0; i < 9; ++i) R[i] = ((i % 4) == 0 ? 1.0 : 0.0) + W[i];
+  } else {
+    const double th = std::sqrt(th2);
+    double K[9], oK[9];
+    for (int i = 0; i < 9; ++i) K[i] = W[i] / th;
+    const double omc = 2.0 * std::sin(th / 2.0) * std::sin(th / 2.0), s = std::sin(th);
+    for (int i = 0; i < 9; ++i) oK[i] = omc * K[i];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c)
+        R[r * 3 + c] = (((r == c) ? 1.0 : 0.0) + s * K[r * 3 + c]) +
+                       ((oK[r * 3] * K[c] + oK[r * 3 + 1] * K[3 + c]) + oK[r * 3 + 2] * K[6 + c]);
+  }
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) P.m[r * 4 + c] = R[r * 3 + c];
+    P.m[r * 4 + 3] = t[r];
+  }
+  return P;
+}
+// tools/lie_algebra.h:54-89
+inline void logSO3(const Pose& T, double w[3]) {
+  const double R11 = T.m[0], R12 = T.m[1], R13 = T.m[2], R21 = T.m[4], R22 = T.m[5], R23 = T.m[6], R31 = T.m[8],
+               R32 = T.m[9], R33 = T.m[10];
+  const double tr = R11 + R22 + R33;
+  if (tr + 1.0 < 1e-10) {
+    if (std::fabs(R33 + 1.0) > 1e-5) {
+      const double f = M_PI / std::sqrt(2.0 + 2.0 * R33);
+      w[0] = f * R13; w[1] = f * R23; w[2] = f * (1.0 + R33);
+    } else if (std::fabs(R22 + 1.0) > 1e-5) {
+      const double f = M_PI / std::sqrt(2.0 + 2.0 * R22);
+      w[0] = f * R12; w[1] = f * (1.0 + R22); w[2] = f * R32;
+    } else {
+      const double f = M_PI / std::sqrt(2.0 + 2.0 * R11);
+      w[0] = f * (1.0 + R11); w[1] = f * R21; w[2] = f * R31;
+    }
+    return;
+  }
+  double mag;
+  const double tr_3 = tr - 3.0;
+  if (tr_3 < -1e-7) {
+    const double theta = std::acos((tr - 1.0) / 2.0);
+    mag = theta / (2.0 * std::sin(theta));
+  } else {
+    mag = 0.5 - tr_3 * tr_3 / 12.0;
+  }
+  w[0] = mag * (R32 - R23); w[1] = mag * (R13 - R31); w[2] = mag * (R21 - R12);
+}
+// 1 / det(H) by partial-pivot LU (odometry/pipeline.cpp:223: H.inverse().determinant())
+inline double inverseDeterminant(const double H[36]) {
+  double A[36];
+  std::memcpy(A, H, sizeof(A));
+  double det = 1.0;
+  for (int k = 0; k < 6; ++k) {
+    int p = k;
+    for (int i = k + 1; i < 6; ++i)
+      if (std::fabs(A[i * 6 + k]) > std::fabs(A[p * 6 + k])) p = i;
+    if (p != k) {
+      for (int c = 0; c < 6; ++c) std::swap(A[k * 6 + c], A[p * 6 + c]);
+      det = -det;
+    }
+    det *= A[k * 6 + k];
+    for (int i = k + 1; i < 6; ++i) {
+      const double f = A[i * 6 + k] / A[k * 6 + k];
+      for (int c = k; c < 6; ++c) A[i * 6 + c] -= f * A[k * 6 + c];
+    }
+  }
+  return 1.0 / det;
+}
+
+// odometry/vel_estimator.cpp:45-97.  J = I*dt makes H diagonal, so the 6x6 LDLT of the reference reduces to
+// six independent divisions (with the same zero-pivot rule: a zero diagonal gives a zero update).
+struct VelocityEstimator {
+  double X[6] = {0, 0, 0, 0, 0, 0};
+  double ts;
+  explicit VelocityEstimator(double hz) : ts(1. / hz) {}
+  void oneRound(const std::vector<Pose>& odom) {
+    double Hd[6] = {0, 0, 0, 0, 0, 0}, b[6] = {0, 0, 0, 0, 0, 0};
+    const Pose& now = odom.back();
+    for (size_t i = 0; i + 1 < odom.size(); ++i) {
+      const double dt = (odom.size() - 1 - i) * ts;
+      const double weight = 1.f - double(odom.size() - 2 - i) / double(odom.size() - 1);
+      const Pose T = poseMul(poseInverse(odom[i]), now);
+      double e[6];
+      for (int a = 0; a < 3; ++a) e[a] = dt * X[a] - T.m[a * 4 + 3];
+      e[3] = dt * X[3] - std::atan2(-T.m[6], T.m[10]);
+      e[4] = dt * X[4] - std::asin(T.m[2]);
+      e[5] = dt * X[5] - std::atan2(-T.m[1], T.m[0]);
+      double chi2 = 0;
+      for (int a = 0; a < 6; ++a) chi2 += e[a] * e[a];
+      const double chi = std::sqrt(chi2);
+      const double sw = ((chi > 0.3162) ? 0.3162 / chi : 1.) * weight;
+      for (int a = 0; a < 6; ++a) {
+        Hd[a] += (sw * dt) * dt;
+        b[a] += (sw * dt) * e[a];
+      }
+    }
+    for (int a = 0; a < 6; ++a)
+      if (std::fabs(Hd[a]) > std::numeric_limits<double>::min()) X[a] += -b[a] / Hd[a];
+  }
+};
+}  // namespace detail
+
+class Pipeline {
+ public:
+  static constexpr int kMaxIcpIts = 15, kSmoothingT = 10, kFrameWindow = 10, kChunks = 1024;  // tools/constants.h
+
+  Pipeline(double sensor_hz, bool deskew, double b_max, double rho_ker, double p_th, double b_min, double b_ratio,
+           int num_keyframes, int num_threads, bool realtime, int device = 0)
+      : sensor_hz_(sensor_hz), deskew_(deskew), b_max_(b_max), p_th_(p_th), b_min_(b_min), num_keyframes_(num_keyframes),
+        realtime_(realtime), icp_(b_max, rho_ker, b_ratio, num_threads, device, std::max(num_keyframes, 1)),
+        vel_(sensor_hz) {
+    // `realtime` bounds the ICP rounds by the sensor period in the reference (pipeline.cpp:167-169); here
+    // all 15 rounds run in one launch of a few hundred microseconds, so the budget is never the limit.
+    frame_to_map_ = keyframe_to_map_ = detail::poseIdentity();
+    int lvl = 0;
+    while ((1 << (lvl + 1)) <= std::max(num_threads, 1)) ++lvl;
+    max_parallel_levels_ = lvl;  // pipeline.cpp:64
+  }
+
+  Matrix4d currentPose() const { return toM(frame_to_map_); }
+  std::vector<Matrix4d> trajectory() const {
+    std::vector<Matrix4d> out;
+    for (const auto& p : trajectory_) out.push_back(toM(p));
+    return out;
+  }
+  Matrix4d keyframePose() const { return toM(keyframe_to_map_); }
+  bool isInitialized() const { return is_initialized_; }
+  bool isMapUpdated() const { return is_map_updated_; }
+  size_t currentID() const { return seq_; }
+  size_t keyframeID() const { return seq_keyframe_; }
+  double inliersRatio() const { return inliers_ratio_; }
+  size_t numKeyframes() const { return keyframes_.size(); }
+  ContainerType currentLeaves() const { return current_ ? current_->tree->leafMeans() : ContainerType(); }
+  ContainerType modelLeaves() const {
+    ContainerType all;
+    for (const auto& f : keyframes_) {
+      ContainerType l = f->tree->leafMeans();
+      all.insert(all.end(), l.begin(), l.end());
+    }
+    return all;
+  }
+
+  // pipeline.cpp:125-265 (cloud by value, as the reference)
+  void compute(double stamp, ContainerType cloud) {
+    is_map_updated_ = false;
+    if (cloud.empty()) throw Error("Pipeline.compute: empty cloud");
+    if (!is_initialized_) {  // pipeline.cpp:267-284
+      auto f = std::make_shared<FrameB>();
+      f->frame = int(seq_);
+      f->to_map = frame_to_map_;
+      f->stamp = stamp;
+      f->tree.reset(new MADtree(cloud, b_max_, b_min_, max_parallel_levels_));
+      keyframes_.push_back(f);
+      current_ = f;
+      trajectory_.push_back(detail::poseIdentity());
+      is_initialized_ = is_map_updated_ = true;
+      ++seq_;
+      return;
+    }
+    if (deskew_ && trajectory_.size() > 1)
+      deskew(cloud, trajectory_[trajectory_.size() - 2], trajectory_[trajectory_.size() - 1]);
+    auto cur = std::make_shared<FrameB>();
+    cur->tree.reset(new MADtree(cloud, b_max_, b_min_, max_parallel_levels_));
+    double t[3], w[3];
+    for (int a = 0; a < 3; ++a) {
+      t[a] = vel_.X[a] * 1. / sensor_hz_;
+      w[a] = vel_.X[3 + a] * 1. / sensor_hz_;
+    }
+    const detail::Pose prediction = detail::poseMul(frame_to_map_, detail::poseFromTwist(t, w));
+    icp_.setMoving(*cur->tree);
+    icp_.init(toM(prediction));
+    std::vector<const MADtree*> kfs;
+    for (const auto& f : keyframes_) kfs.push_back(f->tree.get());
+    const int matched = icp_.compute(kfs, kMaxIcpIts);  // the whole loop of pipeline.cpp:166-193
+    std::memcpy(frame_to_map_.m, icp_.X_.m, sizeof(frame_to_map_.m));
+    inliers_ratio_ = double(matched) / double(cur->tree->numLeaves());  // :197-204
+    trajectory_.push_back(frame_to_map_);
+    std::vector<detail::Pose> window;
+    for (int i = std::max(0, int(trajectory_.size()) - kSmoothingT); i < int(trajectory_.size()); ++i)
+      window.push_back(trajectory_[size_t(i)]);
+    vel_.oneRound(window);  // :208-217
+    cur->frame = int(seq_);
+    cur->to_map = frame_to_map_;
+    cur->stamp = stamp;
+    cur->weight = detail::inverseDeterminant(icp_.H_adder_);  // :223
+    cur->tree->applyTransform(toM(frame_to_map_));             // :224
+    current_ = cur;
+    frames_.push_back(cur);
+    if (frames_.size() > size_t(kFrameWindow)) frames_.pop_front();
+    if (inliers_ratio_ < p_th_) {  // :234-262
+      double best_w = std::numeric_limits<double>::max();
+      std::shared_ptr<FrameB> best;
+      for (const auto& f : frames_)
+        if (f->weight < best_w) {
+          best_w = f->weight;
+          best = f;
+        }
+      while (!frames_.empty() && frames_.front()->frame <= best->frame) frames_.pop_front();
+      keyframes_.push_back(best);
+      if (keyframes_.size() > size_t(num_keyframes_)) keyframes_.pop_front();
+      is_map_updated_ = true;
+      seq_keyframe_ = size_t(best->frame);
+      keyframe_to_map_ = best->to_map;
+    }
+    ++seq_;
+  }
+
+ private:
+  struct FrameB {  // tools/frame.h:37-51
+    detail::Pose to_map;
+    std::unique_ptr<MADtree> tree;
+    double stamp = 0, weight = 0;
+    int frame = 0;
+  };
+  static Matrix4d toM(const detail::Pose& p) {
+    Matrix4d M = Matrix4d::Identity();
+    std::memcpy(M.m, p.m, sizeof(p.m));
+    return M;
+  }
+  // pipeline.cpp:79-123
+  void deskew(ContainerType& cloud, const detail::Pose& T_prev, const detail::Pose& T_now) const {
+    const double ts = 1. / sensor_hz_;
+    const detail::Pose rel = detail::poseMul(detail::poseInverse(T_prev), T_now);
+    double w[3];
+    detail::logSO3(rel, w);
+    const double v[6] = {rel.m[3] / ts, rel.m[7] / ts, rel.m[11] / ts, w[0] / ts, w[1] / ts, w[2] / ts};
+    std::vector<std::pair<double, Vector3d>> sorted(cloud.size());
+    for (size_t i = 0; i < cloud.size(); ++i) sorted[i] = {std::atan2(cloud[i][1], cloud[i][0]), cloud[i]};
+    std::sort(sorted.begin(), sorted.end(),
+              [](const std::pair<double, Vector3d>& a, const std::pair<double, Vector3d>& b) { return a.first < b.first; });
+    const double resolution = 2 * M_PI / double(kChunks), delta = ts / double(kChunks - 1);
+    double t = -ts;
+    auto at = [&](double tt) {
+      const double tr[3] = {v[0] * tt, v[1] * tt, v[2] * tt}, ro[3] = {v[3] * tt, v[4] * tt, v[5] * tt};
+      return detail::poseFromTwist(tr, ro);
+    };
+    detail::Pose meas = at(t);
+    double angle = M_PI - resolution;
+    for (int i = int(sorted.size()) - 1; i >= 0; --i) {
+      if (sorted[size_t(i)].first < angle) {
+        angle -= resolution;
+        t += delta;
+        meas = at(t);
+      }
+      cloud[size_t(i)] = detail::poseApply(meas, sorted[size_t(i)].second);
+    }
+  }
+
+  double sensor_hz_;
+  bool deskew_;
+  double b_max_, p_th_, b_min_;
+  int num_keyframes_, max_parallel_levels_ = 0;
+  bool realtime_;
+  MADicp icp_;
+  detail::VelocityEstimator vel_;
+  detail::Pose frame_to_map_, keyframe_to_map_;
+  std::deque<std::shared_ptr<FrameB>> keyframes_, frames_;
+  std::shared_ptr<FrameB> current_;
+  std::vector<detail::Pose> trajectory_;
+  size_t seq_ = 0, seq_keyframe_ = 0;
+  bool is_initialized_ = false, is_map_updated_ = false;
+  double inliers_ratio_ = 0;
+};
+
+}  // namespace madicp_b200

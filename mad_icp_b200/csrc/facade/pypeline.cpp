@@ -1,0 +1,30 @@
+// pypeline -- reference: mad_icp/src/pybind/pypeline.cpp:52-75 (Pipeline + VectorEigen3d), same ctor
+// arguments and method names; registration runs on the GPU.
+#include "pipeline.hpp"
+#include "py_common.hpp"
+PYBIND11_MODULE(pypeline, m) {
+  bind_vector_eigen3d(m);
+  py::class_<mb::Pipeline>(m, "Pipeline")
+      .def(py::init<double, bool, double, double, double, double, double, int, int, bool>(), py::arg("sensor_hz"),
+           py::arg("deskew"), py::arg("b_max"), py::arg("rho_ker"), py::arg("p_th"), py::arg("b_min"), py::arg("b_ratio"),
+           py::arg("num_keyframes"), py::arg("num_threads"), py::arg("realtime"))
+      .def("currentPose", [](const mb::Pipeline& p) { return pose_to_numpy(p.currentPose()); })
+      .def("trajectory",
+           [](const mb::Pipeline& p) {
+             py::list out;
+             for (const auto& T : p.trajectory()) out.append(pose_to_numpy(T));
+             return out;
+           })
+      .def("keyframePose", [](const mb::Pipeline& p) { return pose_to_numpy(p.keyframePose()); })
+      .def("isInitialized", &mb::Pipeline::isInitialized)
+      .def("isMapUpdated", &mb::Pipeline::isMapUpdated)
+      .def("currentID", &mb::Pipeline::currentID)
+      .def("keyframeID", &mb::Pipeline::keyframeID)
+      .def("modelLeaves", &mb::Pipeline::modelLeaves)
+      .def("currentLeaves", &mb::Pipeline::currentLeaves)
+      .def("compute", [](mb::Pipeline& p, double stamp, const py::object& cloud) { p.compute(stamp, cloud_arg(cloud)); })
+      // additions (not in the reference): diagnostics
+      .def("inliersRatio", &mb::Pipeline::inliersRatio)
+      .def("numKeyframes", &mb::Pipeline::numKeyframes);
+  py::register_exception<mb::Error>(m, "MadIcpError", PyExc_RuntimeError);
+}

@@ -215,3 +215,31 @@ void orc_expmap(const double* w3, double* R9_rowmajor) {
 int orc_max_threads() { return omp_get_max_threads(); }
 
 }  // extern "C"
+
+// -----------------------------------------------------------------------------
+// Pipeline (the caller of the hot path): odometry/pipeline.{h,cpp}
+// -----------------------------------------------------------------------------
+#include "pipeline_oracle.hpp"
+extern "C" {
+void* orc_pipeline_create(double sensor_hz, int deskew, double b_max, double rho_ker, double p_th, double b_min,
+                          double b_ratio, int num_keyframes, int num_threads, int realtime) {
+  return new orc::Pipeline(sensor_hz, deskew != 0, b_max, rho_ker, p_th, b_min, b_ratio, num_keyframes, num_threads,
+                           realtime != 0);
+}
+void orc_pipeline_free(void* p) { delete static_cast<orc::Pipeline*>(p); }
+void orc_pipeline_compute(void* p, double stamp, const double* pts, int n) {
+  static_cast<orc::Pipeline*>(p)->compute(stamp, pts, n);
+}
+// out: pose 3x4 row-major (12), then [is_map_updated, current_id, keyframe_id, num_keyframes, inliers_ratio,
+// velocity(6)] (11 doubles)
+void orc_pipeline_state(void* p, double* out) {
+  orc::Pipeline* P = static_cast<orc::Pipeline*>(p);
+  iso_to_rowmajor12(P->frame_to_map_, out);
+  out[12] = P->is_map_updated_ ? 1 : 0;
+  out[13] = double(P->seq_);
+  out[14] = double(P->seq_keyframe_);
+  out[15] = double(P->keyframes_.size());
+  out[16] = P->last_inliers_ratio_;
+  for (int i = 0; i < 6; ++i) out[17 + i] = P->current_velocity_.v[i];
+}
+}

@@ -109,3 +109,59 @@ def test_nn_search_demo(oracle):
     for (p, n, d), i, q in zip(d3, oi, cloud[:10] + 0.01):
         assert (p == means[i]).all() and (n == normals[i]).all()
         assert abs(d - np.linalg.norm(q - means[i])) <= 4e-16 * d
+
+
+def _sequence(n, beams=16, azimuths=512):
+    scene = synth.StreetScene(seed=7)
+    for i in range(n):
+        base = synth.pose_xyyaw(0.8 * i, 1.0 + 0.02 * i, 0.004 * i)
+        yield 0.1 * i, np.ascontiguousarray(synth.lidar_scan(scene, base, beams=beams, azimuths=azimuths, seed=100 + i))
+
+
+def test_pipeline_surface(built):
+    """pypeline.cpp:57-74: constructor arguments and methods."""
+    from mad_icp_b200.pybind.pypeline import Pipeline, VectorEigen3d
+    from mad_icp_b200.pybind.pyvector import VectorEigen3d as V2
+    assert VectorEigen3d is V2
+    d = Pipeline.__init__.__doc__
+    for a in ("sensor_hz", "deskew", "b_max", "rho_ker", "p_th", "b_min", "b_ratio", "num_keyframes", "num_threads", "realtime"):
+        assert a in d
+    for mname in ("currentPose", "trajectory", "keyframePose", "isInitialized", "isMapUpdated", "currentID", "keyframeID",
+                  "modelLeaves", "currentLeaves", "compute"):
+        assert hasattr(Pipeline, mname)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("deskew", [False, True])
+def test_pipeline_tracks_like_the_oracle(oracle, deskew):
+    """Streaming odometry (BASELINE cfg5 shape, shortened): the GPU Pipeline and the CPU restatement of
+    odometry/pipeline.cpp follow the same trajectory, promote the same keyframes."""
+    import ctypes as C
+    from mad_icp_b200.pybind.pypeline import Pipeline, VectorEigen3d
+    L = oracle.lib()
+    L.orc_pipeline_create.restype = C.c_void_p
+    L.orc_pipeline_create.argtypes = [C.c_double, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                      C.c_int, C.c_int, C.c_int]
+    L.orc_pipeline_compute.argtypes = [C.c_void_p, C.c_double, oracle._dp, C.c_int]
+    L.orc_pipeline_state.argtypes = [C.c_void_p, oracle._dp]
+    L.orc_pipeline_free.argtypes = [C.c_void_p]
+    ref = C.c_void_p(L.orc_pipeline_create(10.0, int(deskew), 0.2, 0.1, 0.8, 0.1, 0.02, 4, 4, 0))
+    pipe = Pipeline(sensor_hz=10.0, deskew=deskew, b_max=0.2, rho_ker=0.1, p_th=0.8, b_min=0.1, b_ratio=0.02,
+                    num_keyframes=4, num_threads=4, realtime=False)
+    st = np.zeros(23)
+    n = 25
+    for i, (stamp, pts) in enumerate(_sequence(n)):
+        L.orc_pipeline_compute(ref, stamp, oracle._d(pts), pts.shape[0])
+        L.orc_pipeline_state(ref, oracle._d(st))
+        pipe.compute(stamp, VectorEigen3d(pts))
+        T = pipe.currentPose()
+        ang, dt = pose_error(T, st[:12].reshape(3, 4))
+        assert ang < POSE_RAD and dt < POSE_M, (i, ang, dt)
+        assert pipe.isMapUpdated() == bool(st[12]) and pipe.currentID() == int(st[13]), i
+        assert pipe.keyframeID() == int(st[14]) and pipe.numKeyframes() == int(st[15]), i
+        assert abs(pipe.inliersRatio() - st[16]) < 2e-3, i
+    assert pipe.isInitialized() and len(pipe.trajectory()) == n
+    if not deskew:  # the simulated vehicle moves 0.8 m per scan along x
+        assert abs(pipe.currentPose()[0, 3] - 0.8 * (n - 1)) < 0.05
+    assert len(pipe.currentLeaves()) > 100 and len(pipe.modelLeaves()) > len(pipe.currentLeaves())
+    L.orc_pipeline_free(ref)

@@ -189,6 +189,15 @@ class Pipeline {
     return all;
   }
 
+  // test hook: the deskew step alone (poses 4x4 row-major)
+  static ContainerType deskewOnly(ContainerType cloud, const Matrix4d& T_prev, const Matrix4d& T_now, double sensor_hz) {
+    detail::Pose a, b;
+    std::memcpy(a.m, T_prev.m, sizeof(a.m));
+    std::memcpy(b.m, T_now.m, sizeof(b.m));
+    deskew(cloud, a, b, sensor_hz);
+    return cloud;
+  }
+
   // pipeline.cpp:125-265 (cloud by value, as the reference)
   void compute(double stamp, ContainerType cloud) {
     is_map_updated_ = false;
@@ -207,7 +216,7 @@ class Pipeline {
       return;
     }
     if (deskew_ && trajectory_.size() > 1)
-      deskew(cloud, trajectory_[trajectory_.size() - 2], trajectory_[trajectory_.size() - 1]);
+      deskew(cloud, trajectory_[trajectory_.size() - 2], trajectory_[trajectory_.size() - 1], sensor_hz_);
     auto cur = std::make_shared<FrameB>();
     cur->tree.reset(new MADtree(cloud, b_max_, b_min_, max_parallel_levels_));
     double t[3], w[3];
@@ -267,8 +276,8 @@ class Pipeline {
     return M;
   }
   // pipeline.cpp:79-123
-  void deskew(ContainerType& cloud, const detail::Pose& T_prev, const detail::Pose& T_now) const {
-    const double ts = 1. / sensor_hz_;
+  static void deskew(ContainerType& cloud, const detail::Pose& T_prev, const detail::Pose& T_now, double sensor_hz) {
+    const double ts = 1. / sensor_hz;
     const detail::Pose rel = detail::poseMul(detail::poseInverse(T_prev), T_now);
     double w[3];
     detail::logSO3(rel, w);

@@ -24,6 +24,9 @@ PYBIND11_MODULE(pypeline, m) {
       .def("currentLeaves", &mb::Pipeline::currentLeaves)
       .def("compute", [](mb::Pipeline& p, double stamp, const py::object& cloud) { p.compute(stamp, cloud_arg(cloud)); })
       // additions (not in the reference): diagnostics
+      .def_static("_deskewOnly", [](const py::object& cloud, const NpArr& a, const NpArr& b, double sensor_hz) {
+        return mb::Pipeline::deskewOnly(cloud_arg(cloud), pose_from_numpy(a), pose_from_numpy(b), sensor_hz);
+      })
       .def("inliersRatio", &mb::Pipeline::inliersRatio)
       .def("numKeyframes", &mb::Pipeline::numKeyframes);
   py::register_exception<mb::Error>(m, "MadIcpError", PyExc_RuntimeError);

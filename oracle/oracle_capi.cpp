@@ -243,3 +243,10 @@ void orc_pipeline_state(void* p, double* out) {
   for (int i = 0; i < 6; ++i) out[17 + i] = P->current_velocity_.v[i];
 }
 }
+extern "C" void orc_pipeline_deskew(void* p, double* pts, int n, const double* Tprev12, const double* Tnow12) {
+  orc::Cloud c(n);
+  for (int i = 0; i < n; ++i) c[i] = V3{{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]}};
+  static_cast<orc::Pipeline*>(p)->deskew(&c, iso_from_rowmajor12(Tprev12), iso_from_rowmajor12(Tnow12));
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < 3; ++j) pts[3 * i + j] = c[i][j];
+}

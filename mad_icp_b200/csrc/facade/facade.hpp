@@ -197,11 +197,11 @@ class MADicpWrapper {
  public:
   explicit MADicpWrapper(int num_threads, int device = 0) : num_threads_(num_threads), device_(device) {}
   void setQueryCloud(const ContainerType& query, double b_max, double b_min) {  // :40-45
-    query_tree_.reset(new MADtree(query, b_max, b_min, 0));  // (the reference never clears query_leaves_; here
+    query_tree_.reset(new MADtree(query, b_max, b_min, levels()));  // (the reference never clears query_leaves_; here
   }                                                          //  a new cloud replaces the old one)
   void setReferenceCloud(const ContainerType& reference, double b_max, double b_min) {  // :47-52
     ref_b_max_ = b_max;
-    ref_tree_.reset(new MADtree(reference, b_max, b_min, 0));
+    ref_tree_.reset(new MADtree(reference, b_max, b_min, levels()));
   }
   Matrix4d compute(const Matrix4d& T, size_t max_icp_iterations, double rho_ker, double b_ratio, bool print_stats) {
     if (!ref_tree_ || !query_tree_) throw Error("MADicp.compute: set the reference and the query cloud first");
@@ -223,6 +223,11 @@ class MADicpWrapper {
   }
 
  private:
+  int levels() const {  // max_parallel_levels_ = log2(num_threads) (mad_icp_wrapper.h:36)
+    int l = 0;
+    while ((2 << l) <= num_threads_) ++l;
+    return l;
+  }
   std::unique_ptr<MADicp> icp_;
   std::unique_ptr<MADtree> ref_tree_, query_tree_;
   double ref_b_max_ = 0.2, icp_b_max_ = -1, rho_ker_ = -1, b_ratio_ = -1;

@@ -9,6 +9,10 @@
 // adjacent and emits the device records.  Subtrees below the top levels are independent index
 // ranges of the point array, so they are expanded by separate threads and spliced back in pre-order.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -33,15 +37,21 @@ struct Node {
   double ev[9];  // column-major eigenvectors: col0 normal, col2 split direction
   double bbox[3];
   int32_t npts;
-  int32_t left, right, parent;  // node ids (pre-order), -1 when absent
-  int32_t leaf_ordinal;         // getLeafs position, -1 for internal nodes
+  int32_t left, right;   // node ids (pre-order), -1 when absent; <= -2 while building: frontier reference
+  int32_t leaf_ordinal;  // getLeafs position, -1 for internal nodes
 };
 
-struct Job {  // pending range [begin,end) of the point array
+// Pending range [begin,end) of the point array plus what the reference reaches through pointers
+// (plane_predecessor, the parent chain) carried by value, so subtrees can be expanded independently:
+//   pp_col0  : eigenvectors.col(0) of the plane predecessor, if one was set above (mad_tree.cpp:65-67,90-93)
+//   anc_col0 : col(0) of the nearest ancestor with >= 3 points, or of the root (the walk of mad_tree.cpp:68-73)
+struct Job {
   int64_t begin, end;
-  int32_t parent;      // node id of the parent (within the same arena) or -1
-  int32_t plane_pred;  // node id of the plane predecessor or -1
+  int32_t parent;  // node id of the parent within the same arena, -1 for the arena's root
   bool is_right;
+  bool has_pp, is_root;
+  double pp_col0[3], anc_col0[3];
+  int depth;
 };
 
 struct Builder {
@@ -102,26 +112,18 @@ struct Builder {
     return hi;
   }
 
-  // Leaf finalisation (tools/mad_tree.cpp:64-88).  `chain` resolves a node id to a Node for the
-  // ancestor walk (ids < 0 index the caller-supplied ancestors above this arena's root).
-  template <class Resolve>
-  void make_leaf(Node& nd, int32_t self, int32_t plane_pred, int64_t begin, int64_t end, Resolve&& at) const {
-    if (plane_pred != INT32_MIN) {
-      const Node& pp = at(plane_pred);
-      nd.ev[0] = pp.ev[0]; nd.ev[1] = pp.ev[1]; nd.ev[2] = pp.ev[2];
-    } else if (nd.npts < 3) {
-      (void) self;
-      const Node* n = &nd;
-      while (n->parent != INT32_MIN && n->npts < 3) n = &at(n->parent);
-      if (n != &nd) {
-        nd.ev[0] = n->ev[0]; nd.ev[1] = n->ev[1]; nd.ev[2] = n->ev[2];
-      }
+  // Leaf finalisation (tools/mad_tree.cpp:64-88).
+  void make_leaf(Node& nd, const Job& j) const {
+    if (j.has_pp) {
+      nd.ev[0] = j.pp_col0[0]; nd.ev[1] = j.pp_col0[1]; nd.ev[2] = j.pp_col0[2];
+    } else if (nd.npts < 3 && !j.is_root) {
+      nd.ev[0] = j.anc_col0[0]; nd.ev[1] = j.anc_col0[1]; nd.ev[2] = j.anc_col0[2];
     }
     // nearest cloud point to the centroid; first minimum wins.  The reference writes each new
     // minimum through a reference to *begin, i.e. into the first slot of the range.
     double best = std::numeric_limits<double>::max();
-    double* first = pts + 3 * begin;
-    for (int64_t i = begin; i != end; ++i) {
+    double* first = pts + 3 * j.begin;
+    for (int64_t i = j.begin; i != j.end; ++i) {
       const double vx = pts[3 * i], vy = pts[3 * i + 1], vz = pts[3 * i + 2];
       const double d = norm3(vx - nd.mean[0], vy - nd.mean[1], vz - nd.mean[2]);
       if (d < best) {
@@ -131,12 +133,83 @@ struct Builder {
     }
     nd.mean[0] = first[0]; nd.mean[1] = first[1]; nd.mean[2] = first[2];
   }
+
+  // Expand `root` depth first, appending nodes to `nodes` in pre-order (ids local to `nodes`).  Ranges
+  // that would start at depth `frontier_depth` are not expanded: they are appended to `frontier` and the
+  // parent's child id is the reference -2 - (index in frontier).  frontier_depth < 0: expand everything.
+  void expand(std::vector<Node>& nodes, const Job& root, int frontier_depth, std::vector<Job>* frontier) const {
+    std::vector<Job> stack;
+    stack.push_back(root);
+    while (!stack.empty()) {
+      const Job j = stack.back();
+      stack.pop_back();
+      if (frontier_depth >= 0 && j.depth == frontier_depth && j.parent >= 0) {
+        const int32_t ref = -2 - int32_t(frontier->size());
+        frontier->push_back(j);
+        (j.is_right ? nodes[size_t(j.parent)].right : nodes[size_t(j.parent)].left) = ref;
+        continue;
+      }
+      const int32_t id = int32_t(nodes.size());
+      nodes.emplace_back();
+      Node& nd = nodes.back();
+      nd.left = nd.right = -1;
+      nd.leaf_ordinal = -1;
+      if (j.parent >= 0) (j.is_right ? nodes[size_t(j.parent)].right : nodes[size_t(j.parent)].left) = id;
+      stats(nd, j.begin, j.end);
+      if (nd.bbox[2] < b_max) {
+        make_leaf(nd, j);
+        continue;
+      }
+      Job c = j;  // children inherit the by-value context
+      c.parent = id;
+      c.is_root = false;
+      c.depth = j.depth + 1;
+      if (!j.has_pp && nd.bbox[0] < b_min) {  // this node becomes the plane predecessor of its subtree
+        c.has_pp = true;
+        c.pp_col0[0] = nd.ev[0]; c.pp_col0[1] = nd.ev[1]; c.pp_col0[2] = nd.ev[2];
+      }
+      if (nd.npts >= 3 || j.is_root) {  // where the "fewer than 3 points" walk of a descendant leaf stops
+        c.anc_col0[0] = nd.ev[0]; c.anc_col0[1] = nd.ev[1]; c.anc_col0[2] = nd.ev[2];
+      }
+      const int64_t mid = partition(j.begin, j.end, nd);
+      // right first so the left child is popped (and numbered) next: pre-order, left before right
+      Job r = c, l = c;
+      r.begin = mid; r.end = j.end; r.is_right = true;
+      l.begin = j.begin; l.end = mid; l.is_right = false;
+      stack.push_back(r);
+      stack.push_back(l);
+    }
+  }
 };
+
+// Copies arena `src` behind `dst` (pre-order is preserved inside an arena); returns the offset.
+int32_t splice(std::vector<Node>& dst, const std::vector<Node>& src) {
+  const int32_t off = int32_t(dst.size());
+  for (const Node& n : src) {
+    dst.push_back(n);
+    Node& m = dst.back();
+    if (m.left >= 0) m.left += off;
+    if (m.right >= 0) m.right += off;
+  }
+  return off;
+}
+
+// Emits the top skeleton in pre-order, replacing frontier references by the spliced subtrees.
+int32_t emit(std::vector<Node>& out, const std::vector<Node>& top, int32_t id, const std::vector<std::vector<Node>>& sub) {
+  const int32_t me = int32_t(out.size());
+  out.push_back(top[size_t(id)]);
+  const int32_t l = top[size_t(id)].left, r = top[size_t(id)].right;
+  if (l == -1) return me;  // leaf
+  const int32_t nl = (l <= -2) ? splice(out, sub[size_t(-2 - l)]) : emit(out, top, l, sub);
+  const int32_t nr = (r <= -2) ? splice(out, sub[size_t(-2 - r)]) : emit(out, top, r, sub);
+  out[size_t(me)].left = nl;
+  out[size_t(me)].right = nr;
+  return me;
+}
 
 }  // namespace
 
-// Parent / plane-predecessor ids use INT32_MIN for "none"; ids >= 0 are positions in the tree's
-// final node array.
+// Node ids are positions in the tree's final pre-order node array.
 struct madtree {
   std::vector<double> pts;
   std::vector<Node> nodes;          // DFS pre-order
@@ -165,43 +238,6 @@ struct madtree {
   }
 };
 
-namespace {
-
-// Expand the point range [begin,end) depth first, appending nodes to `nodes` in pre-order.
-void expand(const Builder& B, std::vector<Node>& nodes, int64_t begin, int64_t end) {
-  std::vector<Job> stack;
-  stack.push_back(Job{begin, end, INT32_MIN, INT32_MIN, false});
-  while (!stack.empty()) {
-    const Job j = stack.back();
-    stack.pop_back();
-    const int32_t id = int32_t(nodes.size());
-    nodes.emplace_back();
-    Node& nd = nodes.back();
-    nd.left = nd.right = -1;
-    nd.parent = j.parent;
-    nd.leaf_ordinal = -1;
-    if (j.parent != INT32_MIN) {
-      if (j.is_right)
-        nodes[j.parent].right = id;
-      else
-        nodes[j.parent].left = id;
-    }
-    B.stats(nd, j.begin, j.end);
-    if (nd.bbox[2] < B.b_max) {
-      B.make_leaf(nd, id, j.plane_pred, j.begin, j.end, [&](int32_t k) -> const Node& { return nodes[k]; });
-      continue;
-    }
-    int32_t pp = j.plane_pred;
-    if (pp == INT32_MIN && nd.bbox[0] < B.b_min) pp = id;
-    const int64_t mid = B.partition(j.begin, j.end, nd);
-    // right first so the left child is popped (and numbered) next: pre-order, left before right
-    stack.push_back(Job{mid, j.end, id, pp, true});
-    stack.push_back(Job{j.begin, mid, id, pp, false});
-  }
-}
-
-}  // namespace
-
 extern "C" {
 
 int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_min, int num_threads, madtree_t** out) {
@@ -209,15 +245,61 @@ int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_mi
     madicp::set_error("madtree_build: null pointer or empty cloud (the reference dereferences *begin on an empty range)");
     return MADICP_ERR_INVALID;
   }
-  (void) num_threads;
+  const bool timing = getenv("MADTREE_TIMING") != nullptr;
+  auto now = []() { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count();
+  };
+  const auto t0 = now();
   madtree* t = new (std::nothrow) madtree;
   if (!t) return MADICP_ERR_NOMEM;
   t->pts.assign(points_xyz, points_xyz + 3 * n);
   t->b_max = b_max;
   t->b_min = b_min;
   Builder B{t->pts.data(), b_max, b_min};
-  t->nodes.reserve(size_t(n / 2 + 16));
-  expand(B, t->nodes, 0, n);
+  Job root{};
+  root.begin = 0;
+  root.end = n;
+  root.parent = -1;
+  root.is_root = true;
+  int threads = num_threads;
+  if (threads > 64) threads = 64;
+  if (threads <= 1 || n < 20000) {
+    t->nodes.reserve(size_t(n / 2 + 16));
+    B.expand(t->nodes, root, -1, nullptr);
+  } else {
+    // The sums of a node are accumulated in array order (that order defines the result), so a single
+    // node cannot be split across threads -- but disjoint ranges are independent (the reference uses
+    // std::async on the top log2(num_threads) levels, mad_tree.cpp:99-129).  Top levels on this thread
+    // down to ~4 ranges per worker, the subtrees below on a pool, then one splice in pre-order.
+    int depth = 0;
+    while ((1 << depth) < 4 * threads) ++depth;
+    std::vector<Node> top;
+    std::vector<Job> frontier;
+    B.expand(top, root, depth, &frontier);
+    const auto ta = now();
+    std::vector<std::vector<Node>> sub(frontier.size());
+    std::atomic<size_t> next{0};
+    auto worker = [&]() {
+      for (size_t k = next.fetch_add(1); k < frontier.size(); k = next.fetch_add(1)) {
+        Job j = frontier[k];
+        j.parent = -1;
+        sub[k].reserve(size_t((j.end - j.begin) / 2 + 16));
+        B.expand(sub[k], j, -1, nullptr);
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int i = 1; i < threads; ++i) pool.emplace_back(worker);
+    worker();
+    for (std::thread& th : pool) th.join();
+    const auto tb = now();
+    if (timing) std::fprintf(stderr, "  top %.2f ms (%zu ranges), pool %.2f ms\n", ms(t0, ta), frontier.size(), ms(ta, tb));
+    size_t total = top.size();
+    for (const auto& v : sub) total += v.size();
+    t->nodes.reserve(total);
+    emit(t->nodes, top, 0, sub);
+  }
+  const auto t1 = now();
   // leaves in pre-order == getLeafs order (left subtree fully before right subtree)
   for (size_t i = 0; i < t->nodes.size(); ++i)
     if (t->nodes[i].left < 0) {
@@ -240,6 +322,9 @@ int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_mi
     }
   }
   t->refresh_records();
+  if (timing)
+    std::fprintf(stderr, "madtree_build: n=%lld threads=%d expand %.2f ms, order+records %.2f ms\n", (long long) n, threads,
+                 ms(t0, t1), ms(t1, now()));
   *out = t;
   return MADICP_OK;
 }

@@ -25,6 +25,13 @@ def test_four_walls_tree_identical(oracle, built, b_max, ppw):
     _same_tree(FlatTree(cloud, b_max=b_max), oracle.OracleTree(cloud, b_max=b_max))
 
 
+@pytest.mark.parametrize("threads", [2, 5, 16])
+def test_threaded_build_is_bit_identical(oracle, built, threads):
+    """Subtrees expanded on a thread pool and spliced back: same nodes, same order, same bits."""
+    c = synth.registration_case(K=1, beams=32, azimuths=1024, seed=12)
+    _same_tree(FlatTree(c["scans"][0], num_threads=threads), oracle.OracleTree(c["scans"][0]))
+
+
 def test_lidar_tree_identical_after_transform(oracle, built):
     c = synth.registration_case(K=1, beams=32, azimuths=1024, seed=11)
     ft, ot = FlatTree(c["scans"][0]), oracle.OracleTree(c["scans"][0])

@@ -134,44 +134,44 @@ struct Builder {
     nd.mean[0] = first[0]; nd.mean[1] = first[1]; nd.mean[2] = first[2];
   }
 
-  // Expand `root` depth first, appending nodes to `nodes` in pre-order (ids local to `nodes`).  Ranges
-  // that would start at depth `frontier_depth` are not expanded: they are appended to `frontier` and the
-  // parent's child id is the reference -2 - (index in frontier).  frontier_depth < 0: expand everything.
-  void expand(std::vector<Node>& nodes, const Job& root, int frontier_depth, std::vector<Job>* frontier) const {
+  // One node: statistics, leaf test, leaf finalisation or split.  Returns true for an internal node and
+  // then fills the context its children inherit (`child`, ranges not set) and the split position.
+  bool process(Node& nd, const Job& j, Job& child, int64_t& mid) const {
+    nd.left = nd.right = -1;
+    nd.leaf_ordinal = -1;
+    stats(nd, j.begin, j.end);
+    if (nd.bbox[2] < b_max) {
+      make_leaf(nd, j);
+      return false;
+    }
+    child = j;
+    child.is_root = false;
+    child.depth = j.depth + 1;
+    if (!j.has_pp && nd.bbox[0] < b_min) {  // this node becomes the plane predecessor of its subtree
+      child.has_pp = true;
+      child.pp_col0[0] = nd.ev[0]; child.pp_col0[1] = nd.ev[1]; child.pp_col0[2] = nd.ev[2];
+    }
+    if (nd.npts >= 3 || j.is_root) {  // where the "fewer than 3 points" walk of a descendant leaf stops
+      child.anc_col0[0] = nd.ev[0]; child.anc_col0[1] = nd.ev[1]; child.anc_col0[2] = nd.ev[2];
+    }
+    mid = partition(j.begin, j.end, nd);
+    return true;
+  }
+
+  // Expand `root` depth first, appending nodes to `nodes` in pre-order (ids local to `nodes`).
+  void expand(std::vector<Node>& nodes, const Job& root) const {
     std::vector<Job> stack;
     stack.push_back(root);
     while (!stack.empty()) {
       const Job j = stack.back();
       stack.pop_back();
-      if (frontier_depth >= 0 && j.depth == frontier_depth && j.parent >= 0) {
-        const int32_t ref = -2 - int32_t(frontier->size());
-        frontier->push_back(j);
-        (j.is_right ? nodes[size_t(j.parent)].right : nodes[size_t(j.parent)].left) = ref;
-        continue;
-      }
       const int32_t id = int32_t(nodes.size());
       nodes.emplace_back();
-      Node& nd = nodes.back();
-      nd.left = nd.right = -1;
-      nd.leaf_ordinal = -1;
       if (j.parent >= 0) (j.is_right ? nodes[size_t(j.parent)].right : nodes[size_t(j.parent)].left) = id;
-      stats(nd, j.begin, j.end);
-      if (nd.bbox[2] < b_max) {
-        make_leaf(nd, j);
-        continue;
-      }
-      Job c = j;  // children inherit the by-value context
+      Job c;
+      int64_t mid = 0;
+      if (!process(nodes.back(), j, c, mid)) continue;
       c.parent = id;
-      c.is_root = false;
-      c.depth = j.depth + 1;
-      if (!j.has_pp && nd.bbox[0] < b_min) {  // this node becomes the plane predecessor of its subtree
-        c.has_pp = true;
-        c.pp_col0[0] = nd.ev[0]; c.pp_col0[1] = nd.ev[1]; c.pp_col0[2] = nd.ev[2];
-      }
-      if (nd.npts >= 3 || j.is_root) {  // where the "fewer than 3 points" walk of a descendant leaf stops
-        c.anc_col0[0] = nd.ev[0]; c.anc_col0[1] = nd.ev[1]; c.anc_col0[2] = nd.ev[2];
-      }
-      const int64_t mid = partition(j.begin, j.end, nd);
       // right first so the left child is popped (and numbered) next: pre-order, left before right
       Job r = c, l = c;
       r.begin = mid; r.end = j.end; r.is_right = true;
@@ -181,6 +181,21 @@ struct Builder {
     }
   }
 };
+
+// Runs fn(i) for i in [0,n) on up to `threads` threads (the calling thread included).
+template <class F>
+void parallel_for(size_t n, int threads, F&& fn) {
+  if (n == 0) return;
+  std::atomic<size_t> next{0};
+  auto worker = [&]() {
+    for (size_t i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i);
+  };
+  std::vector<std::thread> pool;
+  const size_t extra = std::min(size_t(threads > 1 ? threads - 1 : 0), n - 1);
+  for (size_t i = 0; i < extra; ++i) pool.emplace_back(worker);
+  worker();
+  for (std::thread& th : pool) th.join();
+}
 
 // Copies arena `src` behind `dst` (pre-order is preserved inside an arena); returns the offset.
 int32_t splice(std::vector<Node>& dst, const std::vector<Node>& src) {
@@ -266,32 +281,57 @@ int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_mi
   if (threads > 64) threads = 64;
   if (threads <= 1 || n < 20000) {
     t->nodes.reserve(size_t(n / 2 + 16));
-    B.expand(t->nodes, root, -1, nullptr);
+    B.expand(t->nodes, root);
   } else {
     // The sums of a node are accumulated in array order (that order defines the result), so a single
     // node cannot be split across threads -- but disjoint ranges are independent (the reference uses
-    // std::async on the top log2(num_threads) levels, mad_tree.cpp:99-129).  Top levels on this thread
-    // down to ~4 ranges per worker, the subtrees below on a pool, then one splice in pre-order.
+    // std::async on the top log2(num_threads) levels, mad_tree.cpp:99-129).  The top levels are done
+    // level by level (all nodes of a level in parallel) down to ~4 ranges per worker, the subtrees
+    // below on the same pool, then one splice in pre-order.
     int depth = 0;
     while ((1 << depth) < 4 * threads) ++depth;
-    std::vector<Node> top;
+    std::vector<Node> top(1);
+    std::vector<Job> level{root};    // jobs of the current level; job.parent = id of ITS node in `top`
+    level[0].parent = 0;
     std::vector<Job> frontier;
-    B.expand(top, root, depth, &frontier);
+    std::vector<int32_t> frontier_parent;  // (parent id << 1) | is_right
+    for (int d = 0; d < depth && !level.empty(); ++d) {
+      std::vector<Job> ctx(level.size());
+      std::vector<int64_t> mids(level.size(), 0);
+      std::vector<char> internal(level.size(), 0);
+      parallel_for(level.size(), threads, [&](size_t i) {
+        internal[i] = B.process(top[size_t(level[i].parent)], level[i], ctx[i], mids[i]) ? 1 : 0;
+      });
+      std::vector<Job> next;
+      for (size_t i = 0; i < level.size(); ++i) {
+        if (!internal[i]) continue;
+        const int32_t me = level[i].parent;
+        for (int side = 0; side < 2; ++side) {
+          Job c = ctx[i];
+          c.begin = side ? mids[i] : level[i].begin;
+          c.end = side ? level[i].end : mids[i];
+          c.is_right = side != 0;
+          if (d + 1 == depth) {  // stop here: this range becomes an independent subtree job
+            (side ? top[size_t(me)].right : top[size_t(me)].left) = -2 - int32_t(frontier.size());
+            c.parent = -1;
+            frontier.push_back(c);
+          } else {
+            const int32_t id = int32_t(top.size());
+            top.emplace_back();
+            (side ? top[size_t(me)].right : top[size_t(me)].left) = id;
+            c.parent = id;
+            next.push_back(c);
+          }
+        }
+      }
+      level.swap(next);
+    }
     const auto ta = now();
     std::vector<std::vector<Node>> sub(frontier.size());
-    std::atomic<size_t> next{0};
-    auto worker = [&]() {
-      for (size_t k = next.fetch_add(1); k < frontier.size(); k = next.fetch_add(1)) {
-        Job j = frontier[k];
-        j.parent = -1;
-        sub[k].reserve(size_t((j.end - j.begin) / 2 + 16));
-        B.expand(sub[k], j, -1, nullptr);
-      }
-    };
-    std::vector<std::thread> pool;
-    for (int i = 1; i < threads; ++i) pool.emplace_back(worker);
-    worker();
-    for (std::thread& th : pool) th.join();
+    parallel_for(frontier.size(), threads, [&](size_t k) {
+      sub[k].reserve(size_t((frontier[k].end - frontier[k].begin) / 2 + 16));
+      B.expand(sub[k], frontier[k]);
+    });
     const auto tb = now();
     if (timing) std::fprintf(stderr, "  top %.2f ms (%zu ranges), pool %.2f ms\n", ms(t0, ta), frontier.size(), ms(ta, tb));
     size_t total = top.size();

@@ -9,22 +9,21 @@
 //                       (reference loop: odometry/pipeline.cpp:166-193), optional in-kernel
 //                       all-reduce of H/b across GPUs through peer mailboxes (NVLink stores)
 //
-// The walk is a latency chain (one dependent memory round trip per tree level), not a bandwidth or
-// FLOP problem, so the design shortens the chain instead of widening it:
-//   * FILTERED PREDICATE.  Each node has a 32-byte FP32 shadow record (mean, split direction, link,
-//     error bound).  The side test is evaluated in FP32 (4-cycle pipe, FMA allowed); it is accepted
-//     only when |s32| exceeds a rigorous bound on |s32 - s64| (arith below), otherwise the lane
-//     re-evaluates the reference's FP64 expression on the exact 64-byte record.  The decision is
-//     therefore always the FP64 one -- indices stay bit-exact -- while >99.9% of visits never touch
-//     the FP64 pipe or the exact record.
-//   * SPECULATIVE SIBLING FETCH.  Children are adjacent, so both 32-byte shadows (one aligned
-//     64-byte pair, two LDG.E.256) are requested as soon as the node's link is known, before its
-//     own predicate is evaluated; the predicate then only selects registers.  The chain per level
-//     is one load latency plus a select.
-//   * Moving leaves are in getLeafs (DFS) order and each CTA owns a contiguous item range, so the
-//     lanes of a warp and the warps of an SM share the upper levels: L1 hits there, and the
-//     inter-round barrier uses release-only atomics / L2-coherent loads so L1 is never invalidated
-//     between rounds.
+// What bounds the path was measured step by step (profiles/): not HBM (the model is
+// L2-resident), not FLOPs, but a chain of dependent L1/L2 round trips per walk, the L1->register
+// write-back width, FP64 issue slots and the serial tail of every Gauss-Newton round.  Hence:
+//   * FILTERED PREDICATE.  Every node has a 16-byte FP32 shadow: the split plane in offset form.  The
+//     side test is evaluated in FP32 (FMA allowed) and accepted only when |s32| exceeds a rigorous bound
+//     on |s32 - s64|; otherwise the lane calls the out-of-line exact test, which re-evaluates the
+//     reference's FP64 expression on the 64-byte record.  The decision is therefore always the FP64 one
+//     (indices stay bit-exact) while >99.9% of visits never touch the FP64 pipe or the exact record.
+//   * TWO LEVELS PER ROUND TRIP.  The shadows are stored as 64-byte records in implicit 4-ary heap order
+//     (a node at an even depth + its two children; grandchildren = records 4g+1..4g+4): no child link is
+//     loaded and one memory round trip resolves two binary decisions.
+//   * Each CTA owns a few contiguous stretches of the scan's leaves (DFS order = spatially compact) and
+//     registers them against every keyframe: balanced across SMs, and the lanes of a warp / the warps of
+//     an SM share the upper levels in L1.  The inter-round barrier uses release-only atomics and
+//     L2-coherent loads, so L1 is never invalidated between rounds.
 // No tcgen05: there is no dense contraction.  The only tensor-pipe use is the FP64 DMMA fold of the
 // per-correspondence outer products (warp_accumulate), which exists to save registers.
 // Compiled with -fmad=false; exact predicates use __d*_rn intrinsics (arith.h).

@@ -28,7 +28,9 @@ using namespace madicp;
 namespace {
 struct Slot {  // slot s owns pool indices [s*pool_cap, (s+1)*pool_cap) and heap positions [s*heap_cap, ...)
   int n_nodes = 0, n_leaves = 0;
-  std::vector<int> heap_pos;  // node -> position in the implicit heap (kept to re-home the slot on growth)
+  std::vector<int> heap_pos;    // node -> position in the implicit heap (kept to re-home the slot on growth)
+  std::vector<int> quad_pos;    // node -> 4-ary record * 4 + slot
+  std::vector<int> quad_child;  // even-depth node -> first record of its grandchildren
 };
 constexpr size_t kMatchedCap = size_t(1) << 20;  // bytes reserved for matched flags (max moving leaves)
 
@@ -55,7 +57,7 @@ struct madicp_ctx {
   FastRec* d_heap = nullptr;
   int* d_bfs_of = nullptr;
   FastRec* d_pool_fast = nullptr;  // breadth-first copy of the shadows (walk_mode 0)
-  size_t quad_cap = 0;             // 4-ary heap positions per slot
+  size_t quad_cap = 0;             // 4-ary records per slot (= 2 * pool_cap)
   QuadRec* d_quad = nullptr;
   int walk_mode = 4;
   long long* d_dbg_cta = nullptr;  // MADICP_MAX_ITERS x grid item-phase cycles when debug timing is on
@@ -130,8 +132,13 @@ static int prepare_slot(madicp_ctx* c, int s) {
   const size_t off = size_t(s) * c->pool_cap, hoff = size_t(s) * c->heap_cap;
   CK(cudaMemcpyAsync(c->d_heap_pos, c->slots[s].heap_pos.data(), size_t(n) * sizeof(int), cudaMemcpyHostToDevice,
                      c->stream));
+  CK(cudaMemcpyAsync(c->d_heap_pos + c->pool_cap, c->slots[s].quad_pos.data(), size_t(n) * sizeof(int),
+                     cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_heap_pos + 2 * c->pool_cap, c->slots[s].quad_child.data(), size_t(n) * sizeof(int),
+                     cudaMemcpyHostToDevice, c->stream));
   k_prepare_slot<<<(n + kStepBlock - 1) / kStepBlock, kStepBlock, 0, c->stream>>>(
-      c->d_pool_recs + off, c->d_heap_pos, n, int(off), int(hoff), c->P.min_ball, c->d_pool_links + off, c->d_heap,
+      c->d_pool_recs + off, c->d_heap_pos, c->d_heap_pos + c->pool_cap, c->d_heap_pos + 2 * c->pool_cap, n, int(off),
+      int(hoff), c->P.min_ball, c->d_pool_links + off, c->d_heap,
       c->d_bfs_of, c->d_pool_fast + off, c->d_quad, int(size_t(s) * c->quad_cap));
   c->launches++;
   CK(cudaGetLastError());
@@ -164,7 +171,7 @@ static int ensure_pool(madicp_ctx* c, size_t need, size_t need_heap) {
     CK(cudaMalloc(&recs, total * sizeof(madtree_rec_t)));
     CK(cudaMalloc(&links, total * sizeof(int)));
     CK(cudaMalloc(&fast, total * sizeof(FastRec)));
-    CK(cudaMalloc(&hp, cap * sizeof(int)));
+    CK(cudaMalloc(&hp, 3 * cap * sizeof(int)));
     for (int s = 0; s < c->max_keyframes; ++s)
       if (c->slots[s].n_nodes > 0)
         CK(cudaMemcpyAsync(recs + size_t(s) * cap, c->d_pool_recs + size_t(s) * c->pool_cap,
@@ -174,6 +181,10 @@ static int ensure_pool(madicp_ctx* c, size_t need, size_t need_heap) {
     cudaFree(c->d_pool_links);
     cudaFree(c->d_heap_pos);
     cudaFree(c->d_pool_fast);
+    cudaFree(c->d_quad);
+    c->d_quad = nullptr;
+    CK(cudaMalloc(&c->d_quad, 2 * cap * size_t(c->max_keyframes) * sizeof(QuadRec)));
+    c->quad_cap = 2 * cap;
     c->d_pool_fast = fast;
     c->d_pool_recs = recs;
     c->d_pool_links = links;
@@ -197,16 +208,6 @@ static int ensure_pool(madicp_ctx* c, size_t need, size_t need_heap) {
     CK(cudaMalloc(&c->d_bfs_of, total * sizeof(int)));
     CK(cudaMemsetAsync(c->d_heap, 0, total * sizeof(FastRec), c->stream));  // never-visited positions are prefetched only
     c->heap_cap = cap;
-    // 4-ary heap: a binary tree of depth D has D/2 + 1 four-ary levels; positions < (4^(levels) - 1) / 3
-    int depth = 0;
-    while ((size_t(1) << (depth + 1)) < need_heap / 8) ++depth;  // need_heap = 8 * max binary position + 16
-    size_t qcap = 1;
-    for (int l = 0; l < depth / 2 + 1; ++l) qcap = 4 * qcap + 1;
-    qcap += 40;
-    cudaFree(c->d_quad);
-    c->d_quad = nullptr;
-    CK(cudaMalloc(&c->d_quad, qcap * size_t(c->max_keyframes) * sizeof(QuadRec)));
-    c->quad_cap = qcap;
   }
   for (int s = 0; s < c->max_keyframes; ++s)
     if (c->slots[s].n_nodes > 0) {
@@ -261,6 +262,9 @@ static int configure_gn(madicp_ctx* c, int threads, int ctas) {
   for (int i = 0; i < n; ++i)
     if (t[i].threads == threads && t[i].ctas == ctas) {
       CK(cudaFuncSetAttribute(t[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(t[i].smem)));
+      // ask for the smallest shared-memory carve-out that fits: the rest of the 228 KB is L1 for the tree
+      CK(cudaFuncSetAttribute(t[i].fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                              int((t[i].smem * size_t(ctas) + 2048) * 100 / (228 * 1024)) + 1));
       int per_sm = 0;
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, t[i].fn, threads, t[i].smem));
       if (per_sm < ctas) {
@@ -444,6 +448,37 @@ int madicp_put_keyframe_records(madicp_ctx_t* c, int slot, const madtree_rec_t* 
     heap_pos[size_t(link) + 1] = int(h + 1);
     if (h + 1 > max_pos) max_pos = h + 1;
   }
+  // dense 4-ary records: breadth-first over the even-depth nodes; the (up to four) grandchildren of a node
+  // get four contiguous records.  depth parity from the heap position (depth = floor(log2(pos + 1))).
+  std::vector<int> quad_pos(size_t(n_nodes), 0), quad_child(size_t(n_nodes), 0);
+  {
+    int next_rec = 1;  // record 0 = the root
+    std::vector<int> order{0};  // even-depth nodes in breadth-first order; their record = quad_pos >> 2
+    for (size_t h = 0; h < order.size(); ++h) {
+      const int i = order[h];
+      const int rec = quad_pos[size_t(i)] >> 2;
+      const int l0 = recs[i].link;
+      if (l0 < 0) continue;  // a leaf at an even depth: p0 holds the leaf code
+      bool any = false;
+      for (int s0 = 0; s0 < 2; ++s0) {
+        const int ch = l0 + s0;
+        quad_pos[size_t(ch)] = rec * 4 + 1 + s0;
+        const int l1 = recs[ch].link;
+        if (l1 < 0) continue;
+        for (int s1 = 0; s1 < 2; ++s1) {
+          quad_pos[size_t(l1 + s1)] = (next_rec + 2 * s0 + s1) * 4;
+          order.push_back(l1 + s1);
+          any = true;
+        }
+      }
+      quad_child[size_t(i)] = next_rec;
+      if (any) next_rec += 4;
+    }
+    if (size_t(next_rec) > 2 * (size_t(n_nodes) + 64)) {
+      set_error("madicp_put_keyframe: internal error (4-ary record count)");
+      return MADICP_ERR_INVALID;
+    }
+  }
   int rc = ensure_pool(c, size_t(n_nodes), size_t(8 * max_pos + 16));  // room for the 3-level look-ahead prefetch
   if (rc) return rc;
   Slot& s = c->slots[slot];
@@ -452,6 +487,8 @@ int madicp_put_keyframe_records(madicp_ctx_t* c, int slot, const madtree_rec_t* 
   s.n_nodes = n_nodes;
   s.n_leaves = n_leaves;
   s.heap_pos.swap(heap_pos);
+  s.quad_pos.swap(quad_pos);
+  s.quad_child.swap(quad_child);
   rc = prepare_slot(c, slot);
   if (rc) return rc;
   CK(cudaStreamSynchronize(c->stream));  // caller may free/modify the host tree right after

@@ -12,7 +12,8 @@ namespace madicp {
 // breadth-first) at pool offset `off`; heap_pos[i] is node i's position in the implicit heap (computed
 // on the host from the links), `hoff` the slot's offset in the heap array.
 __global__ void __launch_bounds__(kStepBlock)
-k_prepare_slot(const madtree_rec_t* __restrict__ recs, const int* __restrict__ heap_pos, int n, int off, int hoff,
+k_prepare_slot(const madtree_rec_t* __restrict__ recs, const int* __restrict__ heap_pos,
+               const int* __restrict__ quad_pos, const int* __restrict__ quad_child, int n, int off, int hoff,
                double min_ball, int* __restrict__ links, FastRec* __restrict__ heap, int* __restrict__ bfs_of,
                FastRec* __restrict__ fast, QuadRec* __restrict__ quad, int qoff) {
   const int i = blockIdx.x * kStepBlock + threadIdx.x;
@@ -35,17 +36,16 @@ k_prepare_slot(const madtree_rec_t* __restrict__ recs, const int* __restrict__ h
   const int h = heap_pos[i];
   heap[hoff + h] = f;
   bfs_of[hoff + h] = off + i;
-  {  // 4-ary position: the path from the root (bits of h+1 below its leading one), two bits per 4-ary level
-    const unsigned hp1 = unsigned(h) + 1u;
-    const int depth = 31 - __clz(hp1);
-    unsigned g = 0;
-    for (int j = 0; j < depth / 2; ++j) g = 4u * g + 1u + ((hp1 >> (depth - 2 * j - 2)) & 3u);
-    QuadRec* qr = quad + qoff + g;
-    if (depth & 1) {  // odd depth: child slot of its parent's record, selected by the last path bit
-      if (hp1 & 1u) qr->p2 = f; else qr->p1 = f;
-    } else {
+  {  // dense 4-ary record: quad_pos = record * 4 + slot (0: even-depth node, 1/2: its left/right child)
+    const int qp = quad_pos[i];
+    QuadRec* qr = quad + qoff + (qp >> 2);
+    const int slot = qp & 3;
+    if (slot == 1) qr->p1 = f;
+    else if (slot == 2) qr->p2 = f;
+    else {
       qr->p0 = f;
       qr->bfs0 = off + i;
+      qr->child0 = quad_child[i];  // first of the four contiguous records of the grandchildren (slot-relative)
     }
   }
   if (r.link < 0) {  // breadth-first copy of a leaf shadow: weight in the first 8 bytes
@@ -247,10 +247,12 @@ __global__ void __launch_bounds__(THREADS, CTAS)
 k_gn_loop(const __grid_constant__ GnArgs A) {
   constexpr int WARPS = THREADS / 32;
   extern __shared__ __align__(16) double s_dyn[];
-  // layout: [WARPS][kStageTile] staging tiles | [WARPS][64] reduction scratch | peers
+  // [WARPS][kStageTile] staging tiles; the reduction scratch and the peer staging alias them (the tiles
+  // are dead once the item loop is over) so that the shared-memory carve-out stays small and L1 large
   double* s_stage_all = s_dyn;
-  double(*s_red)[64] = reinterpret_cast<double(*)[64]>(s_dyn + WARPS * kStageTile);
-  double(*s_peer)[kAcc] = reinterpret_cast<double(*)[kAcc]>(s_dyn + WARPS * kStageTile + WARPS * 64);
+  double(*s_red)[64] = reinterpret_cast<double(*)[64]>(s_dyn);
+  double(*s_peer)[kAcc] = reinterpret_cast<double(*)[kAcc]>(s_dyn + WARPS * 64);
+  static_assert(WARPS * 64 + kMaxPeers * kAcc <= WARPS * kStageTile, "scratch must fit in the staging tiles");
   __shared__ double s_tot[kAcc];
   __shared__ double s_b[6];
   __shared__ double s_X[12];
@@ -332,6 +334,7 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
       __syncthreads();
       if (threadIdx.x == 0) A.dbg_cta[size_t(it) * gridDim.x + blockIdx.x] = clock64() - t_begin;
     }
+    __syncthreads();  // every warp is done with its staging tile: s_red aliases them
     block_reduce_store<WARPS>(c0, c1, s_red, A.partial + size_t(blockIdx.x) * kAcc);
     if (multi && last_round) __threadfence_system();  // matched flags stored to peers precede our LL cells
     __syncthreads();
@@ -383,7 +386,7 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
 
 template <int THREADS>
 constexpr size_t gn_dynamic_smem() {
-  return sizeof(double) * (size_t(THREADS / 32) * kStageTile + size_t(THREADS / 32) * 64 + size_t(kMaxPeers) * kAcc);
+  return sizeof(double) * size_t(THREADS / 32) * kStageTile;
 }
 
 }  // namespace madicp

@@ -59,14 +59,16 @@ static_assert(sizeof(FastRec) == 16, "FastRec must be one 128-bit load");
 constexpr float kBoundC = 1.0e-6f;
 
 // Two binary levels in one 64-byte record: the node at an even depth (p0) and its two children (p1 left,
-// p2 right); the four grandchildren are the 4-ary children 4g+1 .. 4g+4 of position g.  One dependent
+// p2 right); the records of the four grandchildren are contiguous and start at `child0` (allocated in
+// breadth-first order, so the array is dense and same-level neighbours are adjacent).  One dependent
 // memory round trip then resolves two levels of the reference's binary descent (each of the two
-// decisions is still the filtered/exact binary predicate, so indices stay bit-exact).  A slot whose
-// binary node is a leaf holds the leaf code; slots below a leaf are never read.
+// decisions is still the filtered/exact binary predicate, so indices stay bit-exact), and the address
+// of the next record comes with the same load.  A slot whose binary node is a leaf holds the leaf code.
 struct __align__(32) QuadRec {
   FastRec p0, p1, p2;
   int bfs0;      // breadth-first pool index of p0's node (the FP64 fallback needs the exact records)
-  int pad[3];
+  int child0;    // slot-relative index of the first grandchild record (grandchild 2*s0+s1 is child0 + that)
+  int pad[2];
 };
 static_assert(sizeof(QuadRec) == 64, "QuadRec must be two 256-bit loads");
 
@@ -88,10 +90,10 @@ struct ModelView {  // passed by value (constant bank)
   const FastRec* heap;        // FP32 plane shadows in implicit heap order
   const int* bfs_of;          // heap position -> breadth-first pool index (read only by the FP64 fallback)
   const FastRec* fast;        // the same shadows in breadth-first order (walk_mode 0)
-  const QuadRec* quad;        // two binary levels per 64-byte record, implicit 4-ary heap order (walk_mode 4)
+  const QuadRec* quad;        // two binary levels per 64-byte record, dense, explicit child groups (walk_mode 4)
   int root[kMaxSlots];        // heap position of the root of the k-th active keyframe (= slot * heap_cap)
   int broot[kMaxSlots];       // breadth-first pool index of that root (= slot * cap)
-  int qroot[kMaxSlots];       // 4-ary heap position of that root (= slot * quad_cap)
+  int qroot[kMaxSlots];       // index of that root's record (= slot * quad_cap)
   int K;
   int walk_mode;              // 0: breadth-first + link loads; 1: binary heap; 2/3: + look-ahead prefetch; 4: 4-ary heap
 };
@@ -223,17 +225,17 @@ __device__ __forceinline__ int descend(const ModelView& M, int k, double qx, dou
       idx = link + side;
     }
   }
-  if (M.walk_mode == 4) {  // 4-ary heap: two binary decisions per memory round trip
+  if (M.walk_mode == 4) {  // 4-ary records: two binary decisions per memory round trip
     const QuadRec* qbase = M.quad + M.qroot[k];
     unsigned g = 0;
     while (true) {
       FastRec p0, p1, p2;
-      int bfs0, pad0, pad1, pad2;
+      int bfs0, child0, pad1, pad2;
       asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                    : "=f"(p0.dx), "=f"(p0.dy), "=f"(p0.dz), "=f"(p0.c), "=f"(p1.dx), "=f"(p1.dy), "=f"(p1.dz), "=f"(p1.c)
                    : "l"(qbase + g));
       asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                   : "=f"(p2.dx), "=f"(p2.dy), "=f"(p2.dz), "=f"(p2.c), "=r"(bfs0), "=r"(pad0), "=r"(pad1), "=r"(pad2)
+                   : "=f"(p2.dx), "=f"(p2.dy), "=f"(p2.dz), "=f"(p2.c), "=r"(bfs0), "=r"(child0), "=r"(pad1), "=r"(pad2)
                    : "l"(reinterpret_cast<const char*>(qbase + g) + 32));
       if (is_leaf(p0)) {
         ww = leaf_weight(p0);
@@ -248,7 +250,7 @@ __device__ __forceinline__ int descend(const ModelView& M, int k, double qx, dou
       }
       int s1 = side_filtered(q, c);
       if (s1 < 0) s1 = side_exact(M.recs + (load_link(M.links + bfs0) + s0), qx, qy, qz) ? 1 : 0;
-      g = 4u * g + 1u + 2u * unsigned(s0) + unsigned(s1);
+      g = unsigned(child0) + 2u * unsigned(s0) + unsigned(s1);
     }
   }
   const int root = M.root[k];

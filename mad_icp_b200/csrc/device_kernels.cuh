@@ -246,20 +246,13 @@ template <int THREADS, int CTAS>
 __global__ void __launch_bounds__(THREADS, CTAS)
 k_gn_loop(const __grid_constant__ GnArgs A) {
   constexpr int WARPS = THREADS / 32;
-  extern __shared__ __align__(32) double s_dyn[];
+  extern __shared__ __align__(16) double s_dyn[];
   // [WARPS][kStageTile] staging tiles; the reduction scratch and the peer staging alias them (the tiles
   // are dead once the item loop is over) so that the shared-memory carve-out stays small and L1 large
   double* s_stage_all = s_dyn;
   double(*s_red)[64] = reinterpret_cast<double(*)[64]>(s_dyn);
   double(*s_peer)[kAcc] = reinterpret_cast<double(*)[kAcc]>(s_dyn + WARPS * 64);
   static_assert(WARPS * 64 + kMaxPeers * kAcc <= WARPS * kStageTile, "scratch must fit in the staging tiles");
-  // per-round cache of this CTA's moving leaves: the transformed point X*m and its FP32 query do not
-  // depend on the keyframe, so they are computed once per round instead of once per (leaf, keyframe);
-  // it also takes the moving-leaf load (an L2 round trip) off the head of every walk
-  Moving4* s_m = reinterpret_cast<Moving4*>(s_dyn + WARPS * kStageTile);
-  double(*s_ml)[3] = reinterpret_cast<double(*)[3]>(s_m + kLeafCache);
-  QueryF* s_qf = reinterpret_cast<QueryF*>(s_ml + kLeafCache);
-  int* s_q = reinterpret_cast<int*>(s_qf + kLeafCache);
   __shared__ double s_tot[kAcc];
   __shared__ double s_b[6];
   __shared__ double s_X[12];
@@ -288,17 +281,6 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
   }
   const unsigned t_total = unsigned(A.model.K) * n_b;  // CTA-local items
   (void) total;
-  const bool cached = n_b <= unsigned(kLeafCache);
-  auto leaf_of = [&](unsigned j) -> unsigned {  // CTA-local leaf number -> moving leaf
-    unsigned q = p_lo[kPieces - 1] + (j - (n_b - p_n[kPieces - 1]));
-    unsigned acc = 0;
-#pragma unroll
-    for (unsigned p = 0; p + 1 < kPieces; ++p) {
-      if (j >= acc && j < acc + p_n[p]) q = p_lo[p] + (j - acc);
-      acc += p_n[p];
-    }
-    return q;
-  };
 
   for (int it = 0; it < A.iters; ++it) {
     if (threadIdx.x == 0 && it > 0)
@@ -310,19 +292,6 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
     double c0 = 0.0, c1 = 0.0;
     long long t_begin = 0;
     if (A.dbg && threadIdx.x == 0) t_begin = clock64();
-    if (cached) {
-      for (unsigned j = threadIdx.x; j < n_b; j += THREADS) {
-        const unsigned q = leaf_of(j);
-        const Moving4 m = load_moving(A.moving + q);
-        double mx, my, mz;
-        iso_apply(s_X, m.px, m.py, m.pz, mx, my, mz);
-        s_m[j] = m;
-        s_ml[j][0] = mx; s_ml[j][1] = my; s_ml[j][2] = mz;
-        s_qf[j] = make_query(mx, my, mz);
-        s_q[j] = int(q);
-      }
-      __syncthreads();
-    }
 
     for (unsigned t0 = warp * 32; t0 < t_total; t0 += THREADS) {
       // (keyframe, leaf) of this lane: one 32-bit division per warp-item, then a carry
@@ -332,31 +301,29 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
         q -= n_b;
         ++k;
       }
+      {  // CTA-local leaf number -> moving leaf
+        unsigned j = q;
+        q = p_lo[kPieces - 1] + (j - (n_b - p_n[kPieces - 1]));
+        unsigned acc = 0;
+#pragma unroll
+        for (unsigned p = 0; p + 1 < kPieces; ++p) {
+          if (j >= acc && j < acc + p_n[p]) q = p_lo[p] + (j - acc);
+          acc += p_n[p];
+        }
+      }
       double v[kStage];
 #pragma unroll
       for (int i = 0; i < kStage; ++i) v[i] = 0.0;
       if (t0 + lane < t_total) {
-        Moving4 m;
+        const Moving4 m = load_moving(A.moving + q);
         double mx, my, mz, ww;
-        int leaf;
-        unsigned qm;
-        if (cached) {
-          m = s_m[q];
-          mx = s_ml[q][0]; my = s_ml[q][1]; mz = s_ml[q][2];
-          qm = unsigned(s_q[q]);
-          leaf = descend(A.model, int(k), s_qf[q], mx, my, mz, ww);
-        } else {
-          qm = leaf_of(q);
-          m = load_moving(A.moving + qm);
-          iso_apply(s_X, m.px, m.py, m.pz, mx, my, mz);
-          leaf = descend(A.model, int(k), mx, my, mz, ww);
-        }
-        const Rec f = load_rec(A.model.recs + leaf);
+        iso_apply(s_X, m.px, m.py, m.pz, mx, my, mz);
+        const Rec f = load_rec(A.model.recs + descend(A.model, int(k), mx, my, mz, ww));
         if (linearize_one(s_X, A.P.rho_ker_sqrt, m, mx, my, mz, f, ww, v) && last_round) {
           if (multi) {
-            for (int r = 0; r < A.peers.world; ++r) A.peer_matched[r][qm] = 1;
+            for (int r = 0; r < A.peers.world; ++r) A.peer_matched[r][q] = 1;
           } else {
-            A.matched[qm] = 1;
+            A.matched[q] = 1;
           }
         }
       }
@@ -419,8 +386,7 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
 
 template <int THREADS>
 constexpr size_t gn_dynamic_smem() {
-  return sizeof(double) * size_t(THREADS / 32) * kStageTile +
-         size_t(kLeafCache) * (sizeof(Moving4) + 3 * sizeof(double) + sizeof(QueryF) + sizeof(int));
+  return sizeof(double) * size_t(THREADS / 32) * kStageTile;
 }
 
 }  // namespace madicp

@@ -44,7 +44,6 @@ constexpr int kStage = 13;        // doubles staged per correspondence: sJ[6], J
 constexpr int kStageItems = 16;   // correspondences staged per DMMA pass (half a warp)
 constexpr int kStagePitch = 20;   // doubles per staged value row (16 items + 4 padding: conflict-free)
 constexpr int kStageTile = kStage * kStagePitch;  // doubles of shared memory per warp
-constexpr int kLeafCache = 512;   // moving leaves of a CTA cached in shared memory per round (76 B each)
 constexpr int kMaxPeers = 16;
 constexpr int kMailboxSlots = 2;  // double-buffered by round parity
 
@@ -210,8 +209,8 @@ __device__ __forceinline__ void prefetch_line(const void* p) { asm volatile("pre
 // Greedy single-path descent (no backtracking, like the reference: tools/mad_tree.cpp:144-152).
 // Returns the breadth-first pool index of the leaf reached and its planarity weight.  Decisions are
 // bit-identical to the reference's FP64 expression by construction.  `k` = index of the active keyframe.
-__device__ __forceinline__ int descend(const ModelView& M, int k, const QueryF& q, double qx, double qy, double qz,
-                                       double& ww) {
+__device__ __forceinline__ int descend(const ModelView& M, int k, double qx, double qy, double qz, double& ww) {
+  const QueryF q = make_query(qx, qy, qz);
   if (M.walk_mode == 0) {  // breadth-first shadows + one link load per level
     int idx = M.broot[k];
     while (true) {
@@ -274,10 +273,6 @@ __device__ __forceinline__ int descend(const ModelView& M, int k, const QueryF& 
     if (side < 0) side = side_exact(M.recs + M.bfs_of[root + h], qx, qy, qz) ? 1 : 0;
     h = 2u * h + 1u + unsigned(side);
   }
-}
-
-__device__ __forceinline__ int descend(const ModelView& M, int k, double qx, double qy, double qz, double& ww) {
-  return descend(M, k, make_query(qx, qy, qz), qx, qy, qz, ww);
 }
 
 // One correspondence (reference: odometry/mad_icp.cpp:81-101): gate, error, Jacobian, Huber scale,

@@ -79,7 +79,12 @@ struct madicp_ctx {
   double* d_X = nullptr;  // 12 (step API pose) + 36 + 6 scratch
   CommBlock* d_comm = nullptr;
   double* h_pinned = nullptr;  // 12 + 36 + 6 + ... staging
-  GnState* h_state = nullptr;  // pinned mirror
+  GnState* h_state = nullptr;  // pinned mirror (results)
+  // pinned ring of launch headers (control words + initial pose): a header may only be rewritten once the
+  // copy that reads it has executed, so back-to-back asynchronous registrations stay correct
+  static constexpr int kInRing = 16;
+  unsigned char* h_in = nullptr;
+  cudaEvent_t in_done[kInRing] = {};
   unsigned char* h_matched = nullptr;
   int gn_grid = 0;
   bool gn_auto = true;  // pick the shape per launch from the item count (see pick_shape)
@@ -351,6 +356,8 @@ int madicp_create(madicp_ctx_t** out, int device, int max_keyframes) {
   CK(cudaMemset(c->d_comm, 0, sizeof(CommBlock)));
   CK(cudaMallocHost(&c->h_pinned, sizeof(double) * 64));
   CK(cudaMallocHost(&c->h_state, sizeof(GnState)));
+  CK(cudaMallocHost(&c->h_in, size_t(madicp_ctx::kInRing) * 128));
+  for (int i = 0; i < madicp_ctx::kInRing; ++i) CK(cudaEventCreateWithFlags(&c->in_done[i], cudaEventDisableTiming));
   CK(cudaMallocHost(&c->h_matched, kMatchedCap));
   int threads = 1024, ctas = 1;
   if (const char* e = getenv("MADICP_GN_SHAPE"))
@@ -390,6 +397,9 @@ void madicp_destroy(madicp_ctx_t* c) {
   cudaFree(c->d_dbg);
   cudaFreeHost(c->h_pinned);
   cudaFreeHost(c->h_state);
+  cudaFreeHost(c->h_in);
+  for (int i = 0; i < madicp_ctx::kInRing; ++i)
+    if (c->in_done[i]) cudaEventDestroy(c->in_done[i]);
   cudaFreeHost(c->h_matched);
   cudaStreamDestroy(c->own_stream);
   delete c;
@@ -704,15 +714,18 @@ int madicp_register_async(madicp_ctx_t* c, int iters, const double X0[12]) {
   A.dbg = c->d_dbg;
   A.dbg_cta = c->d_dbg ? c->d_dbg_cta : nullptr;
   c->epoch += uint32_t(iters);
-  // control words + initial pose in one small pinned H2D copy
-  GnState* hs = c->h_state;
+  // control words + initial pose: one small pinned H2D copy from the next header of the ring
+  static_assert(offsetof(GnState, X_out) <= 128, "launch header must fit a ring entry");
+  const int ring = int(c->call_seq % madicp_ctx::kInRing);
+  if (c->call_seq >= madicp_ctx::kInRing) CK(cudaEventSynchronize(c->in_done[ring]));
+  GnState* hs = reinterpret_cast<GnState*>(c->h_in + size_t(ring) * 128);
   hs->ticket = 0;
   hs->round = 0;
   hs->n_matched = 0;
   hs->pad = 0;
-  CK(cudaMemcpyAsync(c->d_state, hs, 16, cudaMemcpyHostToDevice, c->stream));
-  memcpy(c->h_pinned, X0, 12 * sizeof(double));
-  CK(cudaMemcpyAsync(c->d_state->X_trace, c->h_pinned, 12 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  memcpy(hs->X_in, X0, 12 * sizeof(double));
+  CK(cudaMemcpyAsync(c->d_state, hs, offsetof(GnState, X_out), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaEventRecord(c->in_done[ring], c->stream));
   // zero the flags buffer of the NEXT call (nobody can be writing it yet; see CommBlock)
   CK(cudaMemsetAsync(c->d_comm->matched[mb ^ 1], 0, std::min(kMatchedCap, c->cap_moving), c->stream));
   void* args[] = {&A};
@@ -729,15 +742,12 @@ int madicp_register_fetch(madicp_ctx_t* c, double X[12], double H[36], double b[
     return MADICP_ERR_STATE;
   }
   CK(cudaSetDevice(c->device));
-  const int it = c->last_iters;
   CK(cudaMemcpyAsync(c->h_state, c->d_state, offsetof(GnState, X_trace), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(c->h_state->X_trace + it * 12, c->d_state->X_trace + it * 12, 12 * sizeof(double),
-                     cudaMemcpyDeviceToHost, c->stream));
   if (matched)
     CK(cudaMemcpyAsync(c->h_matched, c->d_comm->matched[(c->call_seq - 1u) & 1u], size_t(c->L), cudaMemcpyDeviceToHost,
                        c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  if (X) memcpy(X, c->h_state->X_trace + it * 12, 12 * sizeof(double));
+  if (X) memcpy(X, c->h_state->X_out, 12 * sizeof(double));
   if (H) memcpy(H, c->h_state->H, 36 * sizeof(double));
   if (b) memcpy(b, c->h_state->b, 6 * sizeof(double));
   if (matched) memcpy(matched, c->h_matched, size_t(c->L));

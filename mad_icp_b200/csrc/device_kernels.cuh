@@ -286,7 +286,11 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
     if (threadIdx.x == 0 && it > 0)
       while (ld_relaxed_s32(&st->round) < it) {}
     __syncthreads();
-    if (threadIdx.x < 12) s_X[threadIdx.x] = ld_relaxed_f64(&st->X_trace[it * 12 + threadIdx.x]);
+    if (threadIdx.x < 12) {
+      const double x = ld_relaxed_f64(it == 0 ? &st->X_in[threadIdx.x] : &st->X_trace[it * 12 + threadIdx.x]);
+      s_X[threadIdx.x] = x;
+      if (it == 0 && blockIdx.x == 0) st->X_trace[threadIdx.x] = x;
+    }
     __syncthreads();
     const bool last_round = (it == A.iters - 1);
     double c0 = 0.0, c1 = 0.0;
@@ -368,6 +372,8 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
 #pragma unroll
         for (int i = 0; i < 12; ++i) st->X_trace[(it + 1) * 12 + i] = Xn[i];
         if (last_round) {
+#pragma unroll
+          for (int i = 0; i < 12; ++i) st->X_out[i] = Xn[i];
           unpack_Hb(s_tot, st->H, st->b);
           int c = 0;
           for (int w2 = 0; w2 < WARPS; ++w2) c += s_count[w2];

@@ -115,9 +115,11 @@ struct GnState {
   int round;      // number of completed rounds (flag the CTAs spin on)
   int n_matched;  // matched moving leaves in the last round
   int pad;
-  double H[36];   // last round; H[r*6+c] = sum (scale*J_r)*J_c, both triangles accumulated independently
+  double X_in[12];  // initial pose: [ticket .. X_in] is ONE host-to-device copy per registration
+  double X_out[12]; // final pose:   [ticket .. b] is ONE device-to-host copy per registration
+  double H[36];     // last round; H[r*6+c] = sum (scale*J_r)*J_c, both triangles accumulated independently
   double b[6];
-  double X_trace[(MADICP_MAX_ITERS + 1) * 12];  // pose before round i; [iters] = final pose
+  double X_trace[(MADICP_MAX_ITERS + 1) * 12];  // pose before round i; [iters] = final pose (debug / parity aid)
 };
 
 // LL-style mailbox cell: a double split into two 32-bit halves, each paired with a 32-bit epoch

@@ -309,3 +309,40 @@ def test_walk_variants_take_identical_decisions(lidar_small, full16):
                 assert bits_equal(out["X"], base["X"]) and bits_equal(out["H"], base["H"]), mode
                 assert (out["matched"] == base["matched"]).all()
         reg.set_walk_mode(4)
+
+
+def test_pool_growth_and_few_moving_leaves(oracle):
+    """A keyframe larger than the initial pool slot (65 576 nodes) arrives after a small one: the pool is
+    re-homed and both stay correct.  Also fewer moving leaves than CTAs (most CTAs own no work)."""
+    rs = np.random.RandomState(3)
+    small = synth.registration_case(K=1, beams=8, azimuths=256, seed=21)
+    big_cloud = np.concatenate([synth.four_walls(points_per_wall=60000, rng=rs) * [10, 10, 3],
+                                rs.uniform(-1, 41, (60000, 3)) * [1, 1, 0.1]])
+    reg = Registrar(device=0, max_keyframes=3)
+    f_small = FlatTree(small["scans"][0])
+    f_small.apply_transform(small["kf_poses"][0])
+    reg.put_keyframe(0, f_small)
+    f_big = FlatTree(big_cloud, b_max=0.05)
+    assert f_big.num_nodes > 70000
+    reg.put_keyframe(2, f_big)                     # forces the pool (and the shadow arrays) to grow
+    o_small = oracle.OracleTree(small["scans"][0])
+    o_small.apply_transform(small["kf_poses"][0])
+    o_big = oracle.OracleTree(big_cloud, b_max=0.05)
+    q = FlatTree(small["query"])
+    oq = oracle.OracleTree(small["query"])
+    reg.set_moving(q.leaf_means())
+    X = small["T_guess"]
+    idx = reg.search(X)
+    assert (idx[0] == o_small.search((X[:3, :3] @ q.leaf_means().T).T + X[:3, 3])).all()
+    assert (idx[1] == o_big.search((X[:3, :3] @ q.leaf_means().T).T + X[:3, 3])).all()
+    ref = oracle.icp_run([o_small, o_big], oq, X, iters=5, min_ball=0.2)
+    out = reg.register(X, iters=5)
+    ang, dt = pose_error(out["X"], ref["X"])
+    assert ang < POSE_RAD and dt < POSE_M and (out["matched"] == ref["matched"]).all()
+    # three moving leaves only
+    few = q.leaf_means()[:3].copy()
+    reg.set_moving(few)
+    out = reg.register(X, iters=3)
+    H, b, m = reg.linearize(X)
+    assert np.isfinite(out["X"]).all() and out["matched"].shape == (3,) and m.shape == (3,)
+    assert (reg.search(X)[:, :3] == idx[:, :3]).all()

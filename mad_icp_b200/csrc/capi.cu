@@ -60,6 +60,7 @@ struct madicp_ctx {
   size_t quad_cap = 0;             // 4-ary records per slot (= 2 * pool_cap)
   QuadRec* d_quad = nullptr;
   int walk_mode = 4;
+  bool heap_ok = true;  // false once a keyframe deeper than the implicit-heap limit has been seen
   long long* d_dbg_cta = nullptr;  // MADICP_MAX_ITERS x grid item-phase cycles when debug timing is on
   int* d_heap_pos = nullptr;  // upload scratch, pool_cap ints
   IcpParams P{0.2, 0.31622776601683794, 0.02};
@@ -449,10 +450,14 @@ int madicp_put_keyframe_records(madicp_ctx_t* c, int slot, const madtree_rec_t* 
       set_error("madicp_put_keyframe: records are not a breadth-first tree with adjacent siblings");
       return MADICP_ERR_INVALID;
     }
-    const int64_t h = 2 * int64_t(heap_pos[size_t(i)]) + 1;
-    if (h + 1 >= (int64_t(1) << 26)) {
-      set_error("madicp_put_keyframe: tree deeper than 25 levels is not supported by the implicit-heap layout");
-      return MADICP_ERR_INVALID;
+    // the implicit binary heap (walk modes 1-3, kept for measurements) is limited to 20 levels; deeper nodes
+    // get no heap position and those modes are switched off -- the default 4-ary records have no depth limit
+    const int64_t h = (heap_pos[size_t(i)] < 0) ? -1 : 2 * int64_t(heap_pos[size_t(i)]) + 1;
+    if (h < 0 || h + 1 >= (int64_t(1) << 21)) {
+      heap_pos[size_t(link)] = heap_pos[size_t(link) + 1] = -1;
+      c->heap_ok = false;
+      if (c->walk_mode >= 1 && c->walk_mode <= 3) c->walk_mode = 4;
+      continue;
     }
     heap_pos[size_t(link)] = int(h);
     heap_pos[size_t(link) + 1] = int(h + 1);
@@ -885,6 +890,10 @@ int madicp_debug_cta_cycles(madicp_ctx_t* c, int64_t* out, int cap) {
 
 int madicp_set_walk_mode(madicp_ctx_t* c, int mode) {
   if (!c || mode < 0 || mode > 4) return MADICP_ERR_INVALID;
+  if (mode >= 1 && mode <= 3 && !c->heap_ok) {
+    set_error("madicp_set_walk_mode: a resident keyframe is deeper than the implicit-heap limit (20 levels)");
+    return MADICP_ERR_STATE;
+  }
   c->walk_mode = mode;
   return MADICP_OK;
 }

@@ -34,8 +34,10 @@ k_prepare_slot(const madtree_rec_t* __restrict__ recs, const int* __restrict__ h
     f.c = __int_as_float(__double2hiint(ww));
   }
   const int h = heap_pos[i];
-  heap[hoff + h] = f;
-  bfs_of[hoff + h] = off + i;
+  if (h >= 0) {  // (deeper than the implicit-heap limit: no heap position, walk modes 1-3 are off)
+    heap[hoff + h] = f;
+    bfs_of[hoff + h] = off + i;
+  }
   {  // dense 4-ary record: quad_pos = record * 4 + slot (0: even-depth node, 1/2: its left/right child)
     const int qp = quad_pos[i];
     QuadRec* qr = quad + qoff + (qp >> 2);

@@ -346,3 +346,19 @@ def test_pool_growth_and_few_moving_leaves(oracle):
     H, b, m = reg.linearize(X)
     assert np.isfinite(out["X"]).all() and out["matched"].shape == (3,) and m.shape == (3,)
     assert (reg.search(X)[:, :3] == idx[:, :3]).all()
+
+
+def test_very_deep_tree(oracle):
+    """A degenerate cloud (points on a geometric progression) gives a tree far deeper than the implicit-heap
+    experiments support; the default 4-ary walk has no depth limit."""
+    t = np.arange(60)
+    cloud = np.stack([1.5 ** t * 1e-3, np.zeros(60), np.zeros(60)], axis=1)
+    ft, ot = FlatTree(cloud, b_max=1e-6), oracle.OracleTree(cloud, b_max=1e-6)
+    depth = ot.search(cloud, want_depth=True)[1].max()
+    assert depth > 25
+    reg = Registrar(device=0, max_keyframes=1)
+    reg.put_keyframe(0, ft)
+    out = reg.search_cloud(0, cloud * 1.0001)
+    assert (out["ordinals"] == ot.search(cloud * 1.0001)).all()
+    with pytest.raises(MadIcpError):
+        reg.set_walk_mode(1)

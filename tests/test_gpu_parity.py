@@ -348,17 +348,33 @@ def test_pool_growth_and_few_moving_leaves(oracle):
     assert (reg.search(X)[:, :3] == idx[:, :3]).all()
 
 
-def test_very_deep_tree(oracle):
-    """A degenerate cloud (points on a geometric progression) gives a tree far deeper than the implicit-heap
-    experiments support; the default 4-ary walk has no depth limit."""
-    t = np.arange(60)
-    cloud = np.stack([1.5 ** t * 1e-3, np.zeros(60), np.zeros(60)], axis=1)
-    ft, ot = FlatTree(cloud, b_max=1e-6), oracle.OracleTree(cloud, b_max=1e-6)
-    depth = ot.search(cloud, want_depth=True)[1].max()
-    assert depth > 25
+def test_very_deep_tree():
+    """A hand-made caterpillar tree 40 levels deep (every internal node: a leaf on the left, the rest on the
+    right; split planes x = d + 0.5).  Far deeper than the implicit-heap experiments support; the default
+    4-ary walk has no depth limit.  The answer is analytic: the leaf reached is min(floor(x + 0.5), D)."""
+    from mad_icp_b200 import _capi
+    D = 40
+    recs = np.zeros(2 * D + 1, dtype=_capi.REC_DTYPE)
+    for d in range(D):            # internal node of depth d at index 2d, children at 2d+1 (leaf), 2d+2
+        recs[2 * d]["mean"] = [d + 0.5, 0, 0]
+        recs[2 * d]["dir"] = [1, 0, 0]
+        recs[2 * d]["link"] = 2 * d + 1
+        recs[2 * d + 1]["mean"] = [d, 0, 0]
+        recs[2 * d + 1]["dir"] = [0, 0, 1]
+        recs[2 * d + 1]["link"] = -1 - d
+    recs[2 * D]["mean"] = [D, 0, 0]
+    recs[2 * D]["dir"] = [0, 0, 1]
+    recs[2 * D]["link"] = -1 - D
     reg = Registrar(device=0, max_keyframes=1)
-    reg.put_keyframe(0, ft)
-    out = reg.search_cloud(0, cloud * 1.0001)
-    assert (out["ordinals"] == ot.search(cloud * 1.0001)).all()
+    reg.put_keyframe_records(0, recs, D + 1)
+    x = np.random.RandomState(0).uniform(-2, D + 3, 5000)
+    q = np.stack([x, np.zeros_like(x), np.zeros_like(x)], axis=1)
+    out = reg.search_cloud(0, q)
+    want = np.clip(np.floor(x + 0.5), 0, D).astype(np.int32)
+    assert (out["ordinals"] == want).all()
+    assert (out["points"][:, 0] == want).all()
+    exact = np.arange(D + 1) + 0.5          # queries exactly ON the planes: s == 0 is "not < 0" -> right
+    out = reg.search_cloud(0, np.stack([exact[:-1], np.zeros(D), np.zeros(D)], axis=1))
+    assert (out["ordinals"] == np.arange(1, D + 1)).all()
     with pytest.raises(MadIcpError):
         reg.set_walk_mode(1)

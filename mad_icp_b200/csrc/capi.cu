@@ -99,6 +99,7 @@ struct madicp_ctx {
   int rank = 0, world = 1;
   CommBlock* peer_comm[kMaxPeers] = {};
   uint32_t epoch = 0;
+  uint32_t pose_epoch = 1;  // GnState::X_ll epochs (never reset: the cells are zeroed once)
 };
 
 #define CK(call)                                                                                   \
@@ -719,6 +720,8 @@ int madicp_register_async(madicp_ctx_t* c, int iters, const double X0[12]) {
   A.dbg = c->d_dbg;
   A.dbg_cta = c->d_dbg ? c->d_dbg_cta : nullptr;
   c->epoch += uint32_t(iters);
+  A.pose_epoch = c->pose_epoch;
+  c->pose_epoch += uint32_t(iters);
   // control words + initial pose: one small pinned H2D copy from the next header of the ring
   static_assert(offsetof(GnState, X_out) <= 128, "launch header must fit a ring entry");
   const int ring = int(c->call_seq % madicp_ctx::kInRing);

@@ -224,6 +224,7 @@ struct GnArgs {
   unsigned char* peer_matched[kMaxPeers];  // world > 1: every rank's matched array (peer mapped)
   double* partial;                         // gridDim.x * kAcc
   GnState* st;
+  uint32_t pose_epoch;                     // epoch of round 0's pose; monotonic across launches, never reused
   long long* dbg;                          // nullable: per-round SM-clock stamps (madicp_debug_timing)
   long long* dbg_cta;                      // nullable: [round][CTA] item-phase cycles
 };
@@ -285,11 +286,19 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
   (void) total;
 
   for (int it = 0; it < A.iters; ++it) {
-    if (threadIdx.x == 0 && it > 0)
-      while (ld_relaxed_s32(&st->round) < it) {}
-    __syncthreads();
     if (threadIdx.x < 12) {
-      const double x = ld_relaxed_f64(it == 0 ? &st->X_in[threadIdx.x] : &st->X_trace[it * 12 + threadIdx.x]);
+      double x;
+      if (it == 0) {
+        x = ld_relaxed_f64(&st->X_in[threadIdx.x]);
+      } else {  // round barrier: spin until the pose of THIS round (epoch-tagged) has been published
+        const uint32_t ep = A.pose_epoch + uint32_t(it);
+        uint32_t lo, hi, f0, f1;
+        do {
+          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1)
+                       : "l"(&st->X_ll[threadIdx.x]) : "memory");
+        } while (f0 != ep || f1 != ep);
+        x = __hiloint2double(int(hi), int(lo));
+      }
       s_X[threadIdx.x] = x;
       if (it == 0 && blockIdx.x == 0) st->X_trace[threadIdx.x] = x;
     }
@@ -381,7 +390,14 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
           for (int w2 = 0; w2 < WARPS; ++w2) c += s_count[w2];
           st->n_matched = c;
         }
-        st_release_s32(&st->round, it + 1);
+        if (!last_round) {
+          const uint32_t ep = A.pose_epoch + uint32_t(it) + 1u;
+#pragma unroll
+          for (int i = 0; i < 12; ++i)
+            asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(&st->X_ll[i]),
+                         "r"(uint32_t(__double2loint(Xn[i]))), "r"(ep), "r"(uint32_t(__double2hiint(Xn[i]))), "r"(ep)
+                         : "memory");
+        }
         if (A.dbg) {
           A.dbg[it * 8 + 2] = t1 - t0;         // fold of the per-CTA partials
           A.dbg[it * 8 + 3] = t2 - t1;         // peer exchange + matched count

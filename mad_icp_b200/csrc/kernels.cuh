@@ -110,6 +110,12 @@ struct __align__(32) Moving4 {
 };
 
 // Control block + results of one registration, in device global memory.
+// LL-style mailbox cell: a double split into two 32-bit halves, each paired with a 32-bit epoch
+// flag, written with ONE 16-byte store so data and flags arrive together (no fence on the wire).
+struct __align__(16) LLCell {
+  uint32_t lo, flag_lo, hi, flag_hi;
+};
+
 struct GnState {
   int ticket;     // monotonically increasing arrival counter (reset by the host before a launch)
   int round;      // number of completed rounds (flag the CTAs spin on)
@@ -120,13 +126,9 @@ struct GnState {
   double H[36];     // last round; H[r*6+c] = sum (scale*J_r)*J_c, both triangles accumulated independently
   double b[6];
   double X_trace[(MADICP_MAX_ITERS + 1) * 12];  // pose before round i; [iters] = final pose (debug / parity aid)
+  LLCell X_ll[12];  // pose of the next round, published with its epoch: waiting CTAs get value and flag in one load
 };
 
-// LL-style mailbox cell: a double split into two 32-bit halves, each paired with a 32-bit epoch
-// flag, written with ONE 16-byte store so data and flags arrive together (no fence on the wire).
-struct __align__(16) LLCell {
-  uint32_t lo, flag_lo, hi, flag_hi;
-};
 struct Mailbox {  // lives on every rank; cell [slot][src_rank][i] is written by src_rank
   LLCell cell[kMailboxSlots][kMaxPeers][kAcc];
 };

@@ -6,14 +6,20 @@
 // cpu_baseline / `--impl reference` legs of bench.py may use it.  The product
 // (mad_icp_b200/) never includes, links or calls anything in this directory.
 //
-// PARITY UNPINNED: the reference ships no tests/golden vectors and cannot be
-// compiled in this image (every TU includes Eigen, which is absent; there is no
-// network).  This file follows the reference statement by statement and restates
-// the three Eigen 3.4.0 routines the reference calls (SelfAdjointEigenSolver<
-// Matrix3d>::computeDirect, LDLT<Matrix6d>, fixed-size coefficient products)
-// from their published algorithm.  Where Eigen's floating-point evaluation order
-// is not recoverable from the reference tree, the order is DEFINED here
-// (see dot3) and the product mirrors it.
+// PARITY STATUS: the reference ships no tests/golden vectors, and Eigen is absent
+// from this image (no network).  Two anchors exist:
+//  (1) tests/test_reference_pin.py compiles the reference's OWN sources (from
+//      /root/reference, unmodified) against oracle/eigen_standin and requires this
+//      restatement to equal them BIT FOR BIT (trees, searches, every GN round,
+//      the streamed Pipeline).  Control flow, statement order and data handling
+//      are therefore the reference's, verified.
+//  (2) UNPINNED: the evaluation order inside Eigen's own operators.  This file
+//      restates the three Eigen 3.4.0 routines the reference calls
+//      (SelfAdjointEigenSolver<Matrix3d>::computeDirect, LDLT<Matrix6d>, fixed-size
+//      coefficient products) from their published algorithm, the stand-in reuses
+//      them, and where Eigen's floating-point evaluation order is not recoverable
+//      from the reference tree the order is DEFINED here (see dot3) and the
+//      product mirrors it.
 //
 // Each function cites the reference file:line it follows (paths relative to
 // /root/reference/mad_icp/src).

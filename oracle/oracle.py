@@ -1,8 +1,9 @@
 """ctypes driver for the CPU oracle (oracle/_build/libmadicp_oracle.so).
 
 TEST INFRASTRUCTURE -- only tests/, __graft_entry__.smoke() and bench.py's
-cpu_baseline / --impl reference legs import this.  PARITY UNPINNED: the reference
-has no golden vectors and cannot be compiled here (Eigen absent); see
+cpu_baseline / --impl reference legs import this.  Parity status: pinned bit for bit to the
+reference's own sources compiled against oracle/eigen_standin (oracle/reference.py,
+tests/test_reference_pin.py); Eigen's internal evaluation order is unpinned.  See
 oracle/madicp_oracle.hpp for the statement-by-statement citations.
 """
 import ctypes as C

@@ -1,7 +1,7 @@
 // =============================================================================
 // oracle/oracle_capi.cpp -- TEST INFRASTRUCTURE (see madicp_oracle.hpp header).
 // C entry points over the CPU restatement so tests/ and bench.py's cpu_baseline
-// leg can drive it through ctypes.  PARITY UNPINNED (no reference goldens exist).
+// leg can drive it through ctypes.  Parity status: see madicp_oracle.hpp.
 // =============================================================================
 #include "madicp_oracle.hpp"
 

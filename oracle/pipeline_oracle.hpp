@@ -5,7 +5,8 @@
 //                               velocity smoothing, keyframe selection by det(H^-1))
 //   odometry/vel_estimator.{h,cpp}
 //   tools/lie_algebra.h:54-89  logMapSO3
-// PARITY UNPINNED (no reference goldens; see madicp_oracle.hpp).
+// Pinned bit for bit to the reference's sources built against oracle/eigen_standin
+// (tests/test_reference_pin.py); Eigen's internal evaluation order stays unpinned (madicp_oracle.hpp).
 // =============================================================================
 #pragma once
 #include <algorithm>

@@ -191,6 +191,42 @@ def test_full_size_cfg3_indices_and_pose(full16, oracle):
     assert ang < 2e-3 and dt < 3e-2
 
 
+def test_full_size_cfg3_against_the_compiled_reference(full16):
+    """The same check with the reference's OWN sources on the CPU side (oracle/_ref: mad_tree.cpp and
+    mad_icp.cpp compiled against oracle/eigen_standin, shipped prebuilt; tests/test_reference_pin.py):
+    GPU correspondences at the reference's poses, H/b at those poses, final pose."""
+    from oracle import reference as R
+    if not os.path.exists(R._SO):
+        pytest.skip("oracle/_ref not shipped (it is built where /root/reference exists)")
+    c, (reg, _, _) = full16
+    rtrees = []
+    for scan, P in zip(c["scans"], c["kf_poses"]):
+        t = R.ReferenceTree(scan, max_parallel_level=2)
+        t.apply_transform(P)
+        rtrees.append(t)
+    rq = R.ReferenceTree(c["query"])
+    ref = R.icp_run(rtrees, rq, c["T_guess"], iters=10, num_threads=min(16, R.max_threads()))
+    for it in (0, 5, 9):
+        idx = reg.search(ref["X_hist"][it])
+        # the reference does not record correspondences; its leaves do: compare the leaf each query got
+        for k in (0, 7, 15):
+            q = (ref["X_hist"][it][:, :3] @ _moving_means(rq).T).T + ref["X_hist"][it][:, 3]
+            assert (idx[k] == rtrees[k].search(q)).mean() > 0.999  # q is recomputed in numpy: last-bit ties
+        H, b, _ = reg.linearize(ref["X_hist"][it])
+        _check_Hb(H, b, ref["H_hist"][it], ref["b_hist"][it], tol=10 * HB_REL)
+    out = reg.register(c["T_guess"], iters=10)
+    ang, dt = pose_error(out["X"], ref["X"])
+    assert ang < POSE_RAD and dt < POSE_M, (ang, dt)
+    assert (out["matched"] == ref["matched"]).mean() > 0.9999
+
+
+def _moving_means(rtree):
+    e = rtree.export()
+    leaf = e["leaf_ordinal"] >= 0
+    order = np.argsort(e["leaf_ordinal"][leaf])
+    return e["mean"][leaf][order]
+
+
 def test_full_size_cfg2_single_keyframe(full16, oracle):
     c, (reg16, otrees, oq) = full16
     reg = Registrar(device=0, max_keyframes=1)

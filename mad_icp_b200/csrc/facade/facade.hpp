@@ -65,22 +65,29 @@ class MADtree {
   MADtree(const MADtree&) = delete;
   MADtree& operator=(const MADtree&) = delete;
 
-  // reference: applyTransform(r, t) (mad_tree.cpp:165-172); T row-major 4x4
+  // reference: applyTransform(r, t) (mad_tree.cpp:165-172); T row-major 4x4.  The reference transforms
+  // every scan's tree (pipeline.cpp:224) although only promoted frames are ever read again; here the
+  // pass over the nodes runs when something first looks at the tree (upload, leaves), with the same
+  // arithmetic, so frames that are dropped unread never pay for it.
   void applyTransform(const Matrix4d& T) {
-    double X[12];
-    pose12(T, X);
-    check(madtree_apply_transform(t_, X), "madtree_apply_transform");
+    flush();  // an earlier pending transform is applied first: composing poses would round differently
+    pose12(T, pending_);
+    has_pending_ = true;
     ++version_;
   }
   int numLeaves() const { return madtree_num_leaves(t_); }
   int numNodes() const { return madtree_num_nodes(t_); }
   // reference: getLeafs(back_inserter) (mad_tree.cpp:154-163) -> leaf->mean_
   ContainerType leafMeans() const {
+    flush();
     ContainerType out(static_cast<size_t>(numLeaves()));
     if (!out.empty()) check(madtree_leaves(t_, out[0].data(), nullptr, nullptr, nullptr), "madtree_leaves");
     return out;
   }
-  const madtree_t* handle() const { return t_; }
+  const madtree_t* handle() const {
+    flush();
+    return t_;
+  }
   double bMax() const { return b_max_; }
   // identity of the tree CONTENT for residency caches: unique per object (addresses get reused) and bumped
   // by every applyTransform
@@ -91,10 +98,17 @@ class MADtree {
     static uint64_t counter = 0;
     return ++counter;
   }
+  void flush() const {
+    if (!has_pending_) return;
+    has_pending_ = false;
+    check(madtree_apply_transform(t_, pending_), "madtree_apply_transform");
+  }
   madtree_t* t_ = nullptr;
   double b_max_;
   uint64_t uid_;
   uint64_t version_ = 0;
+  mutable bool has_pending_ = false;
+  double pending_[12];
 };
 
 // reference: class MADicp (odometry/mad_icp.h:41-79).  `update(tree)` under the reference's OpenMP loop

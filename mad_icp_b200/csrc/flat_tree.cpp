@@ -8,14 +8,20 @@
 // getLeafs order for free), followed by one breadth-first renumbering pass that makes siblings
 // adjacent and emits the device records.  Subtrees below the top levels are independent index
 // ranges of the point array, so they are expanded by separate threads and spliced back in pre-order.
+#include <emmintrin.h>
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -39,6 +45,7 @@ struct Node {
   int32_t npts;
   int32_t left, right;   // node ids (pre-order), -1 when absent; <= -2 while building: frontier reference
   int32_t leaf_ordinal;  // getLeafs position, -1 for internal nodes
+  int32_t depth;         // root = 0
 };
 
 // Pending range [begin,end) of the point array plus what the reference reaches through pointers
@@ -54,22 +61,40 @@ struct Job {
   int depth;
 };
 
+// Raw sums of one range, in array order (tools/utils.h:55-73): S = {sx,sy,sz, cxx,cyx,czx, cyy,czy,czz}.
+// The nine chains are independent of each other, so a group of three may run on its own thread; the
+// order WITHIN a chain is the result and is never changed.
+inline void sums_group(const double* pts, int64_t begin, int64_t end, int group, double* S) {
+  double a = 0, b = 0, c = 0;
+  if (group == 0) {
+    for (int64_t i = begin; i != end; ++i) { a += pts[3 * i]; b += pts[3 * i + 1]; c += pts[3 * i + 2]; }
+  } else if (group == 1) {
+    for (int64_t i = begin; i != end; ++i) {
+      const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+      a += x * x; b += y * x; c += z * x;
+    }
+  } else {
+    for (int64_t i = begin; i != end; ++i) {
+      const double y = pts[3 * i + 1], z = pts[3 * i + 2];
+      a += y * y; b += z * y; c += z * z;
+    }
+  }
+  S[3 * group] = a; S[3 * group + 1] = b; S[3 * group + 2] = c;
+}
+
 struct Builder {
   double* pts;  // n x 3, reordered in place
   double b_max, b_min;
+  // scratch, indexed like the point array (a node only touches its own [begin,end) slice)
+  double* tmp;          // n x 3
+  unsigned char* flag;  // 1 = the point is on the negative side of the node's split plane
+  int32_t* xf;          // split(): positions (relative to begin) of the misplaced points of the lower part
+  int32_t* bp;          // split(): positions of the misplaced points of the upper part, ascending
 
-  // statistics of one range -> fills mean/ev/bbox/npts of `nd`
-  void stats(Node& nd, int64_t begin, int64_t end) const {
-    double sx = 0, sy = 0, sz = 0;
-    double cxx = 0, cyx = 0, czx = 0, cyy = 0, czy = 0, czz = 0;
-    int k = 0;
-    for (int64_t i = begin; i != end; ++i) {
-      const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
-      sx += x; sy += y; sz += z;
-      cxx += x * x; cyx += y * x; czx += z * x;
-      cyy += y * y; czy += z * y; czz += z * z;
-      ++k;
-    }
+  // mean / covariance / eigenvectors from the raw sums (tools/utils.h:66-70, mad_tree.cpp:59-61)
+  static void finish_stats(Node& nd, const double* S, int64_t k) {
+    double sx = S[0], sy = S[1], sz = S[2];
+    double cxx = S[3], cyx = S[4], czx = S[5], cyy = S[6], czy = S[7], czz = S[8];
     const double inv = 1. / k;
     sx *= inv; sy *= inv; sz *= inv;
     cxx *= inv; cyx *= inv; czx *= inv; cyy *= inv; czy *= inv; czz *= inv;
@@ -79,37 +104,117 @@ struct Builder {
     madicp::Sym3 c{cxx * f, cyx * f, czx * f, cyy * f, czy * f, czz * f};
     nd.mean[0] = sx; nd.mean[1] = sy; nd.mean[2] = sz;
     madicp::eig3_symmetric(c, nd.ev);
-    double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
-    for (int64_t i = begin; i != end; ++i) {
-      const double dx = pts[3 * i] - sx, dy = pts[3 * i + 1] - sy, dz = pts[3 * i + 2] - sz;
-      for (int a = 0; a < 3; ++a) {
-        const double v = dot3(nd.ev[3 * a], nd.ev[3 * a + 1], nd.ev[3 * a + 2], dx, dy, dz);
-        lo[a] = (v < lo[a]) ? v : lo[a];  // NaN never replaces (one-point ranges give NaN axes)
-        hi[a] = (hi[a] < v) ? v : hi[a];
-      }
-    }
-    for (int a = 0; a < 3; ++a) nd.bbox[a] = hi[a] - lo[a];
-    nd.npts = k;
+    nd.npts = int32_t(k);
   }
 
-  // Hoare-style unstable partition of the reference (tools/utils.h:38-52): order of the two halves
-  // matters because child sums are accumulated in array order.
-  int64_t partition(int64_t begin, int64_t end, const Node& nd) const {
-    int64_t lo = begin, hi = end;
-    const double nx = nd.ev[6], ny = nd.ev[7], nz = nd.ev[8];
-    while (lo != hi) {
-      double* p = pts + 3 * lo;
-      if (madicp::plane_side(p[0], p[1], p[2], nd.mean[0], nd.mean[1], nd.mean[2], nx, ny, nz) < 0.0) {
-        ++lo;
-      } else {
-        double* q = pts + 3 * (hi - 1);
-        std::swap(p[0], q[0]);
-        std::swap(p[1], q[1]);
-        std::swap(p[2], q[2]);
-        --hi;
-      }
+  // Extents of [begin,end) along the three axes (tools/utils.h:76-97; extents start from 0, a NaN never
+  // replaces) AND, from the same products, the side of every point with respect to the split plane:
+  // v(2) = col(2).(p - mean) is the very expression split() tests (mad_tree.cpp:95-97), so the flags
+  // cost nothing.  min/max are exact, so chunks of a range may be done by different threads and merged.
+  // Returns the number of points on the negative side.
+  int64_t box_flags(const Node& nd, int64_t begin, int64_t end, double* lo, double* hi) const {
+    const __m128d mx = _mm_set1_pd(nd.mean[0]), my = _mm_set1_pd(nd.mean[1]), mz = _mm_set1_pd(nd.mean[2]);
+    __m128d e[9];
+    for (int a = 0; a < 9; ++a) e[a] = _mm_set1_pd(nd.ev[a]);
+    __m128d l0 = _mm_setzero_pd(), l1 = l0, l2 = l0, h0 = l0, h1 = l0, h2 = l0;
+    const __m128d zero = _mm_setzero_pd();
+    int64_t npass = 0;
+    int64_t i = begin;
+    for (; i + 2 <= end; i += 2) {
+      const double* p = pts + 3 * i;
+      const __m128d A = _mm_loadu_pd(p), B = _mm_loadu_pd(p + 2), C = _mm_loadu_pd(p + 4);
+      const __m128d dx = _mm_sub_pd(_mm_shuffle_pd(A, B, 2), mx);
+      const __m128d dy = _mm_sub_pd(_mm_shuffle_pd(A, C, 1), my);
+      const __m128d dz = _mm_sub_pd(_mm_shuffle_pd(B, C, 2), mz);
+      // dot3: (e0*dx + e1*dy) + e2*dz, no contraction
+      const __m128d v0 = _mm_add_pd(_mm_add_pd(_mm_mul_pd(e[0], dx), _mm_mul_pd(e[1], dy)), _mm_mul_pd(e[2], dz));
+      const __m128d v1 = _mm_add_pd(_mm_add_pd(_mm_mul_pd(e[3], dx), _mm_mul_pd(e[4], dy)), _mm_mul_pd(e[5], dz));
+      const __m128d v2 = _mm_add_pd(_mm_add_pd(_mm_mul_pd(e[6], dx), _mm_mul_pd(e[7], dy)), _mm_mul_pd(e[8], dz));
+      l0 = _mm_min_pd(v0, l0); h0 = _mm_max_pd(v0, h0);  // minpd(a,b) = a < b ? a : b: a NaN in v keeps l
+      l1 = _mm_min_pd(v1, l1); h1 = _mm_max_pd(v1, h1);
+      l2 = _mm_min_pd(v2, l2); h2 = _mm_max_pd(v2, h2);
+      const int mk = _mm_movemask_pd(_mm_cmplt_pd(v2, zero));
+      flag[i] = (unsigned char) (mk & 1);
+      flag[i + 1] = (unsigned char) (mk >> 1);
+      npass += (mk & 1) + (mk >> 1);
     }
-    return hi;
+    double t[2];
+    _mm_storeu_pd(t, l0); lo[0] = t[1] < t[0] ? t[1] : t[0];
+    _mm_storeu_pd(t, l1); lo[1] = t[1] < t[0] ? t[1] : t[0];
+    _mm_storeu_pd(t, l2); lo[2] = t[1] < t[0] ? t[1] : t[0];
+    _mm_storeu_pd(t, h0); hi[0] = t[0] < t[1] ? t[1] : t[0];
+    _mm_storeu_pd(t, h1); hi[1] = t[0] < t[1] ? t[1] : t[0];
+    _mm_storeu_pd(t, h2); hi[2] = t[0] < t[1] ? t[1] : t[0];
+    for (; i != end; ++i) {
+      const double dx = pts[3 * i] - nd.mean[0], dy = pts[3 * i + 1] - nd.mean[1], dz = pts[3 * i + 2] - nd.mean[2];
+      double v[3];
+      for (int a = 0; a < 3; ++a) {
+        v[a] = dot3(nd.ev[3 * a], nd.ev[3 * a + 1], nd.ev[3 * a + 2], dx, dy, dz);
+        lo[a] = (v[a] < lo[a]) ? v[a] : lo[a];
+        hi[a] = (hi[a] < v[a]) ? v[a] : hi[a];
+      }
+      flag[i] = (v[2] < 0.0) ? 1 : 0;
+      npass += flag[i];
+    }
+    return npass;
+  }
+
+  // statistics of one range -> fills mean/ev/bbox/npts of `nd`, the side flags, returns #negative
+  int64_t stats(Node& nd, int64_t begin, int64_t end) const {
+    double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t i = begin; i != end; ++i) {  // the nine chains of sums_group in one pass
+      const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+      S[0] += x; S[1] += y; S[2] += z;
+      S[3] += x * x; S[4] += y * x; S[5] += z * x;
+      S[6] += y * y; S[7] += z * y; S[8] += z * z;
+    }
+    finish_stats(nd, S, end - begin);
+    double lo[3], hi[3];
+    const int64_t npass = box_flags(nd, begin, end, lo, hi);
+    for (int a = 0; a < 3; ++a) nd.bbox[a] = hi[a] - lo[a];
+    return npass;
+  }
+
+  // split() of the reference (tools/utils.h:38-52) in closed form.  The reference walks `lower` up and
+  // `upper` down, swapping a failing *lower with *upper; the ORDER it leaves inside the two halves
+  // matters (child sums run in array order).  Its outcome, with m = number of points that pass:
+  //   * a passing point of [0,m) stays;
+  //   * the a-th failing point of [0,m) (ascending, a = 1..A) is replaced by the a-th passing point of
+  //     [m,n) counted from the top, and itself goes to n-1 (a = 1) or just below where the (a-1)-th of
+  //     those passing points was;
+  //   * every failing point of (m,n) moves down by one; a failing point AT m goes just below the lowest
+  //     passing point of [m,n) (to n-1 if there is none).
+  // (tests/test_host_tree.py compares the trees this produces with those of the sequential loop, bit for bit.)
+  // Positions here are relative to `begin`; `m` comes from box_flags.
+  void split_lists(int64_t begin, int64_t end, int64_t m, int64_t& A) const {
+    const unsigned char* f = flag + begin;
+    int32_t* XF = xf + begin;
+    int32_t* BP = bp + begin;
+    const int64_t n = end - begin;
+    int64_t a = 0, r = 0;
+    for (int64_t i = 0; i < m; ++i) { XF[a] = int32_t(i); a += 1 - f[i]; }
+    for (int64_t i = m; i < n; ++i) { BP[r] = int32_t(i); r += f[i]; }
+    A = a;  // == r
+  }
+  void split(int64_t begin, int64_t end, int64_t m) const {
+    const int64_t n = end - begin;
+    if (m == n) return;  // every point passes: `lower` runs to the end, nothing is swapped
+    int64_t A = 0;
+    split_lists(begin, end, m, A);
+    const unsigned char* f = flag + begin;
+    const int32_t* XF = xf + begin;
+    const int32_t* BP = bp + begin;
+    double* P = pts + 3 * begin;
+    double* T = tmp + 3 * begin;
+    auto cp = [](double* d, const double* s2) { d[0] = s2[0]; d[1] = s2[1]; d[2] = s2[2]; };
+    for (int64_t a = 0; a < A; ++a) cp(T + 3 * a, P + 3 * XF[a]);
+    const bool m_fails = f[m] == 0;
+    if (m_fails) cp(T + 3 * A, P + 3 * m);
+    for (int64_t a = 0; a < A; ++a) cp(P + 3 * XF[a], P + 3 * BP[A - 1 - a]);
+    for (int64_t p = m + 1; p < n; ++p)
+      if (!f[p]) cp(P + 3 * (p - 1), P + 3 * p);
+    for (int64_t a = 0; a < A; ++a) cp(P + 3 * (a == 0 ? n - 1 : BP[A - a] - 1), T + 3 * a);
+    if (m_fails) cp(P + 3 * ((A > 0 ? BP[0] : n) - 1), T + 3 * A);
   }
 
   // Leaf finalisation (tools/mad_tree.cpp:64-88).
@@ -139,7 +244,13 @@ struct Builder {
   bool process(Node& nd, const Job& j, Job& child, int64_t& mid) const {
     nd.left = nd.right = -1;
     nd.leaf_ordinal = -1;
-    stats(nd, j.begin, j.end);
+    nd.depth = j.depth;
+    const int64_t npass = stats(nd, j.begin, j.end);
+    return decide(nd, j, child, mid, npass, true);
+  }
+  // Leaf test and what follows it, once the statistics are known.  `do_split` = false leaves the
+  // reordering to the caller (top levels: done by several threads).
+  bool decide(Node& nd, const Job& j, Job& child, int64_t& mid, int64_t npass, bool do_split) const {
     if (nd.bbox[2] < b_max) {
       make_leaf(nd, j);
       return false;
@@ -154,7 +265,8 @@ struct Builder {
     if (nd.npts >= 3 || j.is_root) {  // where the "fewer than 3 points" walk of a descendant leaf stops
       child.anc_col0[0] = nd.ev[0]; child.anc_col0[1] = nd.ev[1]; child.anc_col0[2] = nd.ev[2];
     }
-    mid = partition(j.begin, j.end, nd);
+    if (do_split) split(j.begin, j.end, npass);
+    mid = j.begin + npass;
     return true;
   }
 
@@ -182,19 +294,224 @@ struct Builder {
   }
 };
 
-// Runs fn(i) for i in [0,n) on up to `threads` threads (the calling thread included).
+// Worker pool: run(n, fn) executes fn(i) for i in [0,n) on the workers plus the calling thread and
+// returns when all are done.  A build issues a few dozen short parallel sections back to back, so the
+// workers spin briefly between sections before they go to sleep.
+class Pool {
+public:
+  explicit Pool(int threads) {
+    const int extra = threads > 1 ? threads - 1 : 0;
+    for (int i = 0; i < extra; ++i) workers_.emplace_back([this]() { loop(); });
+  }
+  ~Pool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+      gen_.fetch_add(1, std::memory_order_release);
+    }
+    cv_.notify_all();
+    for (std::thread& t : workers_) t.join();
+  }
+  int threads() const { return int(workers_.size()) + 1; }
+
+  template <class F>
+  void run(size_t n, F&& fn) {
+    if (n == 0) return;
+    if (workers_.empty() || n == 1) {
+      for (size_t i = 0; i < n; ++i) fn(i);
+      return;
+    }
+    task_ = [&fn](size_t i) { fn(i); };
+    n_ = n;
+    next_.store(0, std::memory_order_relaxed);
+    done_.store(0, std::memory_order_relaxed);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      gen_.fetch_add(1, std::memory_order_release);
+    }
+    cv_.notify_all();
+    drain();
+    const int w = int(workers_.size());
+    for (int spin = 0; done_.load(std::memory_order_acquire) != w; ++spin)
+      if (spin > 1500) std::this_thread::yield(); else _mm_pause();
+  }
+
+private:
+  void drain() {
+    for (size_t i = next_.fetch_add(1, std::memory_order_relaxed); i < n_; i = next_.fetch_add(1, std::memory_order_relaxed))
+      task_(i);
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      int spin = 0;
+      while (gen_.load(std::memory_order_acquire) == seen) {
+        if (++spin < 1500) {
+          _mm_pause();
+        } else {
+          std::unique_lock<std::mutex> lk(mu_);
+          cv_.wait(lk, [&]() { return gen_.load(std::memory_order_acquire) != seen; });
+        }
+      }
+      seen = gen_.load(std::memory_order_acquire);
+      if (stop_) return;
+      drain();
+      done_.fetch_add(1, std::memory_order_release);
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::function<void(size_t)> task_;
+  size_t n_ = 0;
+  std::atomic<size_t> next_{0};
+  std::atomic<int> done_{0};
+  std::atomic<uint64_t> gen_{0};
+  bool stop_ = false;
+};
+
+// One pool per process, re-created when a build asks for a different width; a build that finds it busy
+// (another host thread is building) uses a private one.
+std::mutex g_pool_mu;
+std::unique_ptr<Pool> g_pool;
+
+// fn(chunk_begin, chunk_end) over [0,n) on the process pool when it is free, else on this thread.
 template <class F>
-void parallel_for(size_t n, int threads, F&& fn) {
-  if (n == 0) return;
-  std::atomic<size_t> next{0};
-  auto worker = [&]() {
-    for (size_t i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i);
+void for_chunks(int threads, size_t n, size_t chunk, F&& fn) {
+  const size_t nc = (n + chunk - 1) / chunk;
+  auto one = [&](size_t c) { fn(c * chunk, std::min(n, (c + 1) * chunk)); };
+  std::unique_lock<std::mutex> lk(g_pool_mu, std::try_to_lock);
+  if (threads > 1 && nc > 1 && lk.owns_lock()) {
+    if (!g_pool || g_pool->threads() != threads) g_pool.reset(new Pool(threads));
+    g_pool->run(nc, one);
+  } else {
+    for (size_t c = 0; c < nc; ++c) one(c);
+  }
+}
+
+// One level of the top of the tree when it has fewer nodes than there are threads: every pass over a
+// node's range is cut into chunks that any thread may take.  What may be reordered is only what is
+// exact: the three groups of sum chains run side by side (each chain still in array order), extents
+// are min/max, and the split is applied from its closed form (Builder::split) with per-chunk counts.
+void process_level_shared(const Builder& B, Pool& pool, std::vector<Node>& top, const std::vector<Job>& level,
+                          std::vector<Job>& ctx, std::vector<int64_t>& mids, std::vector<char>& internal) {
+  constexpr int64_t kChunk = 4096;
+  struct Chunk {
+    int job;
+    int64_t b, e;  // absolute positions
+    double lo[3], hi[3];
+    int64_t npass, nxf, nbp, off_xf, off_bp;
   };
-  std::vector<std::thread> pool;
-  const size_t extra = std::min(size_t(threads > 1 ? threads - 1 : 0), n - 1);
-  for (size_t i = 0; i < extra; ++i) pool.emplace_back(worker);
-  worker();
-  for (std::thread& th : pool) th.join();
+  const size_t J = level.size();
+  std::vector<Chunk> chunks;
+  std::vector<size_t> first(J + 1, 0);
+  for (size_t j = 0; j < J; ++j) {
+    first[j] = chunks.size();
+    for (int64_t b = level[j].begin; b < level[j].end; b += kChunk)
+      chunks.push_back(Chunk{int(j), b, std::min(b + kChunk, level[j].end), {0, 0, 0}, {0, 0, 0}, 0, 0, 0, 0, 0});
+  }
+  first[J] = chunks.size();
+  // A: raw sums, three chain groups per node
+  std::vector<double> S(9 * J);
+  pool.run(3 * J, [&](size_t t) { sums_group(B.pts, level[t / 3].begin, level[t / 3].end, int(t % 3), &S[9 * (t / 3)]); });
+  for (size_t j = 0; j < J; ++j) {
+    Node& nd = top[size_t(level[j].parent)];
+    nd.left = nd.right = -1;
+    nd.leaf_ordinal = -1;
+    nd.depth = level[j].depth;
+    Builder::finish_stats(nd, &S[9 * j], level[j].end - level[j].begin);
+  }
+  // B: extents + side flags per chunk
+  pool.run(chunks.size(), [&](size_t c) {
+    Chunk& ch = chunks[c];
+    ch.npass = B.box_flags(top[size_t(level[size_t(ch.job)].parent)], ch.b, ch.e, ch.lo, ch.hi);
+  });
+  std::vector<int64_t> m(J, 0), A(J, 0);
+  for (size_t j = 0; j < J; ++j) {
+    Node& nd = top[size_t(level[j].parent)];
+    double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    for (size_t c = first[j]; c < first[j + 1]; ++c) {
+      for (int a = 0; a < 3; ++a) {
+        lo[a] = (chunks[c].lo[a] < lo[a]) ? chunks[c].lo[a] : lo[a];
+        hi[a] = (hi[a] < chunks[c].hi[a]) ? chunks[c].hi[a] : hi[a];
+      }
+      m[j] += chunks[c].npass;
+    }
+    for (int a = 0; a < 3; ++a) nd.bbox[a] = hi[a] - lo[a];
+    internal[j] = B.decide(nd, level[j], ctx[j], mids[j], m[j], false) ? 1 : 0;
+  }
+  // C1: misplaced points per chunk
+  pool.run(chunks.size(), [&](size_t c) {
+    Chunk& ch = chunks[c];
+    const size_t j = size_t(ch.job);
+    if (!internal[j]) return;
+    const int64_t split = level[j].begin + m[j];
+    int64_t nxf = 0, nbp = 0;
+    for (int64_t i = ch.b; i < ch.e; ++i) {
+      nxf += (i < split) & (B.flag[i] == 0);
+      nbp += (i >= split) & (B.flag[i] != 0);
+    }
+    ch.nxf = nxf;
+    ch.nbp = nbp;
+  });
+  for (size_t j = 0; j < J; ++j) {
+    int64_t ox = 0, ob = 0;
+    for (size_t c = first[j]; c < first[j + 1]; ++c) {
+      chunks[c].off_xf = ox;
+      chunks[c].off_bp = ob;
+      ox += chunks[c].nxf;
+      ob += chunks[c].nbp;
+    }
+    A[j] = ox;  // == ob
+  }
+  // C2: the two position lists (relative to the node's begin) and a copy of the points
+  pool.run(chunks.size(), [&](size_t c) {
+    const Chunk& ch = chunks[c];
+    const size_t j = size_t(ch.job);
+    if (!internal[j] || m[j] == level[j].end - level[j].begin) return;
+    const int64_t b0 = level[j].begin, split = b0 + m[j];
+    int32_t* XF = B.xf + b0 + ch.off_xf;
+    int32_t* BP = B.bp + b0 + ch.off_bp;
+    int64_t a = 0, r = 0;
+    for (int64_t i = ch.b; i < ch.e; ++i) {
+      // (no speculative stores here: the slot after this chunk's last entry belongs to the next chunk)
+      if (i < split) {
+        if (!B.flag[i]) XF[a++] = int32_t(i - b0);
+      } else if (B.flag[i]) {
+        BP[r++] = int32_t(i - b0);
+      }
+    }
+    std::memcpy(B.tmp + 3 * ch.b, B.pts + 3 * ch.b, sizeof(double) * 3 * size_t(ch.e - ch.b));
+  });
+  // C3: every point that moves is written to its final place (all destinations are distinct)
+  pool.run(chunks.size(), [&](size_t c) {
+    const Chunk& ch = chunks[c];
+    const size_t j = size_t(ch.job);
+    const int64_t b0 = level[j].begin, n = level[j].end - b0, mm = m[j], AA = A[j];
+    if (!internal[j] || mm == n) return;
+    const int32_t* XF = B.xf + b0;
+    const int32_t* BP = B.bp + b0;
+    int64_t a = ch.off_xf, r = ch.off_bp;
+    for (int64_t i = ch.b; i < ch.e; ++i) {
+      const int64_t rel = i - b0;
+      int64_t dest;
+      if (rel < mm) {
+        if (B.flag[i]) continue;
+        dest = (a == 0) ? n - 1 : BP[AA - a] - 1;
+        ++a;
+      } else if (B.flag[i]) {
+        dest = XF[AA - 1 - r];
+        ++r;
+      } else if (rel == mm) {
+        dest = (AA > 0 ? BP[0] : n) - 1;
+      } else {
+        dest = rel - 1;
+      }
+      double* d = B.pts + 3 * (b0 + dest);
+      const double* s2 = B.tmp + 3 * i;
+      d[0] = s2[0]; d[1] = s2[1]; d[2] = s2[2];
+    }
+  });
 }
 
 // Copies arena `src` behind `dst` (pre-order is preserved inside an arena); returns the offset.
@@ -232,10 +549,14 @@ struct madtree {
   std::vector<int32_t> bfs_index;   // node id -> breadth-first position
   std::vector<madtree_rec_t> recs;  // breadth-first records
   double b_max = 0, b_min = 0;
+  int threads = 1;  // width the tree was built with; later whole-tree passes use the same
 
   void refresh_records() {
     recs.resize(nodes.size());
-    for (size_t i = 0; i < nodes.size(); ++i) {
+    for_chunks(threads, nodes.size(), 4096, [&](size_t c0, size_t c1) { fill_records(c0, c1); });
+  }
+  void fill_records(size_t c0, size_t c1) {
+    for (size_t i = c0; i < c1; ++i) {
       const Node& n = nodes[i];
       madtree_rec_t& r = recs[bfs_index[i]];
       for (int a = 0; a < 3; ++a) r.mean[a] = n.mean[a];
@@ -271,7 +592,11 @@ int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_mi
   t->pts.assign(points_xyz, points_xyz + 3 * n);
   t->b_max = b_max;
   t->b_min = b_min;
-  Builder B{t->pts.data(), b_max, b_min};
+  const size_t un = static_cast<size_t>(n);
+  std::vector<double> tmp(3 * un);
+  std::vector<unsigned char> flag(un);
+  std::vector<int32_t> xf(un), bp(un);  // the split's misplaced-point lists
+  Builder B{t->pts.data(), b_max, b_min, tmp.data(), flag.data(), xf.data(), bp.data()};
   Job root{};
   root.begin = 0;
   root.end = n;
@@ -279,6 +604,8 @@ int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_mi
   root.is_root = true;
   int threads = num_threads;
   if (threads > 64) threads = 64;
+  if (threads < 1) threads = 1;
+  t->threads = (n < 20000) ? 1 : threads;
   if (threads <= 1 || n < 20000) {
     t->nodes.reserve(size_t(n / 2 + 16));
     B.expand(t->nodes, root);
@@ -288,20 +615,34 @@ int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_mi
     // std::async on the top log2(num_threads) levels, mad_tree.cpp:99-129).  The top levels are done
     // level by level (all nodes of a level in parallel) down to ~4 ranges per worker, the subtrees
     // below on the same pool, then one splice in pre-order.
+    std::unique_lock<std::mutex> pool_lock(g_pool_mu, std::try_to_lock);
+    std::unique_ptr<Pool> private_pool;
+    Pool* pool;
+    if (pool_lock.owns_lock()) {
+      if (!g_pool || g_pool->threads() != threads) g_pool.reset(new Pool(threads));
+      pool = g_pool.get();
+    } else {
+      private_pool.reset(new Pool(threads));
+      pool = private_pool.get();
+    }
     int depth = 0;
-    while ((1 << depth) < 4 * threads) ++depth;
+    while ((1 << depth) < 8 * threads) ++depth;
     std::vector<Node> top(1);
     std::vector<Job> level{root};    // jobs of the current level; job.parent = id of ITS node in `top`
     level[0].parent = 0;
     std::vector<Job> frontier;
-    std::vector<int32_t> frontier_parent;  // (parent id << 1) | is_right
     for (int d = 0; d < depth && !level.empty(); ++d) {
       std::vector<Job> ctx(level.size());
       std::vector<int64_t> mids(level.size(), 0);
       std::vector<char> internal(level.size(), 0);
-      parallel_for(level.size(), threads, [&](size_t i) {
-        internal[i] = B.process(top[size_t(level[i].parent)], level[i], ctx[i], mids[i]) ? 1 : 0;
-      });
+      if (level.size() < size_t(threads)) {
+        // fewer nodes than threads: the passes over each node's range are shared between the threads
+        process_level_shared(B, *pool, top, level, ctx, mids, internal);
+      } else {
+        pool->run(level.size(), [&](size_t i) {
+          internal[i] = B.process(top[size_t(level[i].parent)], level[i], ctx[i], mids[i]) ? 1 : 0;
+        });
+      }
       std::vector<Job> next;
       for (size_t i = 0; i < level.size(); ++i) {
         if (!internal[i]) continue;
@@ -328,7 +669,14 @@ int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_mi
     }
     const auto ta = now();
     std::vector<std::vector<Node>> sub(frontier.size());
-    parallel_for(frontier.size(), threads, [&](size_t k) {
+    // largest ranges first, so the tail of the section is made of small ones
+    std::vector<size_t> by_size(frontier.size());
+    for (size_t k = 0; k < by_size.size(); ++k) by_size[k] = k;
+    std::sort(by_size.begin(), by_size.end(), [&](size_t a, size_t b2) {
+      return (frontier[a].end - frontier[a].begin) > (frontier[b2].end - frontier[b2].begin);
+    });
+    pool->run(frontier.size(), [&](size_t q) {
+      const size_t k = by_size[q];
       sub[k].reserve(size_t((frontier[k].end - frontier[k].begin) / 2 + 16));
       B.expand(sub[k], frontier[k]);
     });
@@ -340,28 +688,64 @@ int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_mi
     emit(t->nodes, top, 0, sub);
   }
   const auto t1 = now();
-  // leaves in pre-order == getLeafs order (left subtree fully before right subtree)
-  for (size_t i = 0; i < t->nodes.size(); ++i)
-    if (t->nodes[i].left < 0) {
-      t->nodes[i].leaf_ordinal = int32_t(t->leaf_nodes.size());
-      t->leaf_nodes.push_back(int32_t(i));
+  // Leaves in pre-order == getLeafs order (left subtree fully before right subtree).  Breadth-first
+  // position = (nodes on shallower levels) + (pre-order rank among the nodes of the same depth): the
+  // same numbering a queue traversal gives (siblings adjacent), computed from per-chunk histograms so
+  // the chunks of the pre-order array can be numbered independently.
+  {
+    const size_t N = t->nodes.size();
+    constexpr size_t kChunk = 4096;
+    const size_t nc = (N + kChunk - 1) / kChunk;
+    std::vector<std::vector<int32_t>> hist(nc);
+    std::vector<int32_t> leaves_in(nc, 0);
+    for_chunks(t->threads, N, kChunk, [&](size_t c0, size_t c1) {
+      std::vector<int32_t>& h = hist[c0 / kChunk];
+      int32_t nl = 0;
+      for (size_t i = c0; i < c1; ++i) {
+        const Node& nd = t->nodes[i];
+        if (size_t(nd.depth) >= h.size()) h.resize(size_t(nd.depth) + 1, 0);
+        ++h[size_t(nd.depth)];
+        nl += nd.left < 0;
+      }
+      leaves_in[c0 / kChunk] = nl;
+    });
+    size_t levels = 0;
+    for (const auto& h : hist) levels = std::max(levels, h.size());
+    std::vector<int32_t> level_start(levels + 1, 0);
+    for (const auto& h : hist)
+      for (size_t d = 0; d < h.size(); ++d) level_start[d + 1] += h[d];
+    for (size_t d = 0; d < levels; ++d) level_start[d + 1] += level_start[d];
+    // hist[c][d] <- first breadth-first position of chunk c on level d ; leaves_in[c] <- first ordinal
+    std::vector<int32_t> run(level_start.begin(), level_start.end() - 1);
+    int32_t leaf_run = 0;
+    for (size_t c = 0; c < nc; ++c) {
+      for (size_t d = 0; d < hist[c].size(); ++d) {
+        const int32_t cnt = hist[c][d];
+        hist[c][d] = run[d];
+        run[d] += cnt;
+      }
+      const int32_t nl = leaves_in[c];
+      leaves_in[c] = leaf_run;
+      leaf_run += nl;
     }
-  // breadth-first numbering with adjacent siblings
-  t->bfs_index.assign(t->nodes.size(), -1);
-  std::vector<int32_t> order;
-  order.reserve(t->nodes.size());
-  order.push_back(0);
-  t->bfs_index[0] = 0;
-  for (size_t h = 0; h < order.size(); ++h) {
-    const Node& nd = t->nodes[order[h]];
-    if (nd.left >= 0) {
-      t->bfs_index[nd.left] = int32_t(order.size());
-      order.push_back(nd.left);
-      t->bfs_index[nd.right] = int32_t(order.size());
-      order.push_back(nd.right);
-    }
+    t->bfs_index.resize(N);
+    t->leaf_nodes.resize(size_t(leaf_run));
+    for_chunks(t->threads, N, kChunk, [&](size_t c0, size_t c1) {
+      std::vector<int32_t>& h = hist[c0 / kChunk];
+      int32_t ord = leaves_in[c0 / kChunk];
+      for (size_t i = c0; i < c1; ++i) {
+        Node& nd = t->nodes[i];
+        t->bfs_index[i] = h[size_t(nd.depth)]++;
+        if (nd.left < 0) {
+          nd.leaf_ordinal = ord;
+          t->leaf_nodes[size_t(ord++)] = int32_t(i);
+        }
+      }
+    });
   }
+  const auto t2 = now();
   t->refresh_records();
+  if (timing) std::fprintf(stderr, "  leaves+bfs %.2f ms, records %.2f ms\n", ms(t1, t2), ms(t2, now()));
   if (timing)
     std::fprintf(stderr, "madtree_build: n=%lld threads=%d expand %.2f ms, order+records %.2f ms\n", (long long) n, threads,
                  ms(t0, t1), ms(t1, now()));
@@ -375,16 +759,19 @@ int madtree_num_leaves(const madtree_t* t) { return t ? int(t->leaf_nodes.size()
 
 int madtree_apply_transform(madtree_t* t, const double X[12]) {
   if (!t || !X) return MADICP_ERR_INVALID;
-  for (Node& n : t->nodes) {
-    double o[3];
-    madicp::iso_apply(X, n.mean[0], n.mean[1], n.mean[2], o[0], o[1], o[2]);
-    n.mean[0] = o[0]; n.mean[1] = o[1]; n.mean[2] = o[2];
-    double e[9];
-    for (int c = 0; c < 3; ++c)
-      for (int r = 0; r < 3; ++r)
-        e[c * 3 + r] = dot3(X[r * 4], X[r * 4 + 1], X[r * 4 + 2], n.ev[c * 3], n.ev[c * 3 + 1], n.ev[c * 3 + 2]);
-    std::memcpy(n.ev, e, sizeof(e));
-  }
+  for_chunks(t->threads, t->nodes.size(), 4096, [&](size_t c0, size_t c1) {
+    for (size_t i = c0; i < c1; ++i) {
+      Node& n = t->nodes[i];
+      double o[3];
+      madicp::iso_apply(X, n.mean[0], n.mean[1], n.mean[2], o[0], o[1], o[2]);
+      n.mean[0] = o[0]; n.mean[1] = o[1]; n.mean[2] = o[2];
+      double e[9];
+      for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 3; ++r)
+          e[c * 3 + r] = dot3(X[r * 4], X[r * 4 + 1], X[r * 4 + 2], n.ev[c * 3], n.ev[c * 3 + 1], n.ev[c * 3 + 2]);
+      std::memcpy(n.ev, e, sizeof(e));
+    }
+  });
   t->refresh_records();
   return MADICP_OK;
 }

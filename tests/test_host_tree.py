@@ -32,6 +32,44 @@ def test_threaded_build_is_bit_identical(oracle, built, threads):
     _same_tree(FlatTree(c["scans"][0], num_threads=threads), oracle.OracleTree(c["scans"][0]))
 
 
+@pytest.mark.parametrize("threads", [3, 16, 64])
+def test_threaded_build_full_size_scan(oracle, built, threads):
+    """131 072 points: the top levels are processed with the passes over one node shared between threads
+    (chunked extents, closed-form split applied in parallel), the subtrees below on the pool."""
+    c = synth.registration_case(K=1, seed=5)
+    _same_tree(FlatTree(c["scans"][0], num_threads=threads), oracle.OracleTree(c["scans"][0]))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_threaded_build_unstructured_clouds(oracle, built, seed):
+    """Blobs, a line and heavy duplicates: split sizes far from n/2, leaves high up in the tree."""
+    rs = np.random.RandomState(seed)
+    cloud = np.concatenate([rs.normal(0, s, (n, 3)) + rs.uniform(-20, 20, 3)
+                            for s, n in ((0.01, 9000), (1.0, 12000), (5.0, 7000), (0.2, 3000))]
+                           + [np.c_[np.linspace(0, 30, 4000), np.zeros((4000, 2))]]
+                           + [np.repeat(rs.uniform(-5, 5, (10, 3)), 300, axis=0)])
+    cloud = cloud[rs.permutation(cloud.shape[0])]
+    for b_max in (0.2, 1e-5):
+        _same_tree(FlatTree(cloud, b_max=b_max, num_threads=7), oracle.OracleTree(cloud, b_max=b_max))
+
+
+def test_concurrent_builds_from_two_host_threads(oracle, built):
+    """The process-wide pool serves one build; a second one running at the same time gets its own."""
+    import threading
+    c = synth.registration_case(K=2, beams=32, azimuths=1024, seed=21)
+    out = [None, None]
+
+    def work(i):
+        for _ in range(3):
+            out[i] = FlatTree(c["scans"][i], num_threads=4)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for i in range(2):
+        _same_tree(out[i], oracle.OracleTree(c["scans"][i]))
+
+
 def test_lidar_tree_identical_after_transform(oracle, built):
     c = synth.registration_case(K=1, beams=32, azimuths=1024, seed=11)
     ft, ot = FlatTree(c["scans"][0]), oracle.OracleTree(c["scans"][0])

@@ -7,6 +7,8 @@
 // uploaded once at promotion, and the small dense algebra uses plain row-major arrays.
 #pragma once
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <deque>
 #include <limits>
 
@@ -164,6 +166,13 @@ class Pipeline {
     int lvl = 0;
     while ((1 << (lvl + 1)) <= std::max(num_threads, 1)) ++lvl;
     max_parallel_levels_ = lvl;  // pipeline.cpp:64
+    timing_ = std::getenv("MADICP_PIPELINE_TIMING") != nullptr;
+  }
+  ~Pipeline() {
+    if (timing_ && timed_scans_ > 0)
+      std::fprintf(stderr, "Pipeline phases, mean over %d scans [ms]: deskew %.3f  tree build %.3f  set moving %.3f  "
+                   "register (incl. keyframe upload) %.3f  rest %.3f\n", timed_scans_, t_ph_[0] / timed_scans_,
+                   t_ph_[1] / timed_scans_, t_ph_[2] / timed_scans_, t_ph_[3] / timed_scans_, t_ph_[4] / timed_scans_);
   }
 
   Matrix4d currentPose() const { return toM(frame_to_map_); }
@@ -215,10 +224,13 @@ class Pipeline {
       ++seq_;
       return;
     }
+    const auto c0 = clk();
     if (deskew_ && trajectory_.size() > 1)
       deskew(cloud, trajectory_[trajectory_.size() - 2], trajectory_[trajectory_.size() - 1], sensor_hz_);
+    const auto c1 = clk();
     auto cur = std::make_shared<FrameB>();
     cur->tree.reset(new MADtree(cloud, b_max_, b_min_, max_parallel_levels_));
+    const auto c2 = clk();
     double t[3], w[3];
     for (int a = 0; a < 3; ++a) {
       t[a] = vel_.X[a] * 1. / sensor_hz_;
@@ -226,10 +238,12 @@ class Pipeline {
     }
     const detail::Pose prediction = detail::poseMul(frame_to_map_, detail::poseFromTwist(t, w));
     icp_.setMoving(*cur->tree);
+    const auto c3 = clk();
     icp_.init(toM(prediction));
     std::vector<const MADtree*> kfs;
     for (const auto& f : keyframes_) kfs.push_back(f->tree.get());
     const int matched = icp_.compute(kfs, kMaxIcpIts);  // the whole loop of pipeline.cpp:166-193
+    const auto c4 = clk();
     std::memcpy(frame_to_map_.m, icp_.X_.m, sizeof(frame_to_map_.m));
     inliers_ratio_ = double(matched) / double(cur->tree->numLeaves());  // :197-204
     trajectory_.push_back(frame_to_map_);
@@ -261,6 +275,11 @@ class Pipeline {
       keyframe_to_map_ = best->to_map;
     }
     ++seq_;
+    if (timing_) {
+      const auto c5 = clk();
+      t_ph_[0] += ms(c0, c1); t_ph_[1] += ms(c1, c2); t_ph_[2] += ms(c2, c3); t_ph_[3] += ms(c3, c4); t_ph_[4] += ms(c4, c5);
+      ++timed_scans_;
+    }
   }
 
  private:
@@ -304,6 +323,13 @@ class Pipeline {
     }
   }
 
+  static std::chrono::steady_clock::time_point clk() { return std::chrono::steady_clock::now(); }
+  static double ms(std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count();
+  }
+  bool timing_ = false;  // MADICP_PIPELINE_TIMING: per-phase host wall clock, printed by the destructor
+  int timed_scans_ = 0;
+  double t_ph_[5] = {0, 0, 0, 0, 0};
   double sensor_hz_;
   bool deskew_;
   double b_max_, p_th_, b_min_;

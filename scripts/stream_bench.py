@@ -14,10 +14,19 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 beams = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 az = int(sys.argv[3]) if len(sys.argv) > 3 else 2048
 scene = synth.StreetScene(seed=7, x_min=-45.0, x_max=60.0 + 0.8 * n)
-scans = []
-for i in range(n):
+
+
+def make_scan(i):
     base = synth.pose_xyyaw(0.8 * i, 1.0 + 0.3 * np.sin(0.05 * i), 0.02 * np.sin(0.03 * i))
-    scans.append(np.ascontiguousarray(synth.lidar_scan(scene, base, beams=beams, azimuths=az, seed=100 + i)))
+    return np.ascontiguousarray(synth.lidar_scan(scene, base, beams=beams, azimuths=az, seed=100 + i))
+
+
+if n > 64:  # ray-casting the sequence is the slow part of a long run: spread it over the host cores (before CUDA starts)
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(min(32, os.cpu_count() or 1)) as pool:
+        scans = pool.map(make_scan, range(n), chunksize=4)
+else:
+    scans = [make_scan(i) for i in range(n)]
 threads = min(16, os.cpu_count() or 1)
 L = O.lib()
 L.orc_pipeline_create.restype = C.c_void_p

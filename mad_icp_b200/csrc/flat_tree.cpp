@@ -375,6 +375,35 @@ private:
 std::mutex g_pool_mu;
 std::unique_ptr<Pool> g_pool;
 
+// Working memory of a build (the point array that is reordered, and what Builder::split needs).  It is
+// never read after the build, so the process keeps one set alive next to the pool instead of faulting
+// in ~8 MB of fresh pages per scan; left uninitialised on purpose.
+struct Scratch {
+  size_t cap = 0;
+  std::unique_ptr<double[]> pts, tmp;
+  std::unique_ptr<unsigned char[]> flag;
+  std::unique_ptr<int32_t[]> xf, bp;
+  void ensure(size_t n) {
+    if (n <= cap) return;
+    cap = n + n / 8;
+    pts.reset(new double[3 * cap]);
+    tmp.reset(new double[3 * cap]);
+    flag.reset(new unsigned char[cap]);
+    xf.reset(new int32_t[cap]);
+    bp.reset(new int32_t[cap]);
+  }
+};
+Scratch g_scratch;  // guarded by g_pool_mu, like the pool
+
+// std::vector that leaves trivially-constructible elements uninitialised on resize()
+template <class T>
+struct default_init_allocator : std::allocator<T> {
+  template <class U> struct rebind { using other = default_init_allocator<U>; };
+  using std::allocator<T>::allocator;
+  template <class U> void construct(U* p) noexcept { ::new (static_cast<void*>(p)) U; }
+  template <class U, class... Args> void construct(U* p, Args&&... args) { ::new (static_cast<void*>(p)) U(std::forward<Args>(args)...); }
+};
+
 // fn(chunk_begin, chunk_end) over [0,n) on the process pool when it is free, else on this thread.
 template <class F>
 void for_chunks(int threads, size_t n, size_t chunk, F&& fn) {
@@ -514,37 +543,11 @@ void process_level_shared(const Builder& B, Pool& pool, std::vector<Node>& top, 
   });
 }
 
-// Copies arena `src` behind `dst` (pre-order is preserved inside an arena); returns the offset.
-int32_t splice(std::vector<Node>& dst, const std::vector<Node>& src) {
-  const int32_t off = int32_t(dst.size());
-  for (const Node& n : src) {
-    dst.push_back(n);
-    Node& m = dst.back();
-    if (m.left >= 0) m.left += off;
-    if (m.right >= 0) m.right += off;
-  }
-  return off;
-}
-
-// Emits the top skeleton in pre-order, replacing frontier references by the spliced subtrees.
-int32_t emit(std::vector<Node>& out, const std::vector<Node>& top, int32_t id, const std::vector<std::vector<Node>>& sub) {
-  const int32_t me = int32_t(out.size());
-  out.push_back(top[size_t(id)]);
-  const int32_t l = top[size_t(id)].left, r = top[size_t(id)].right;
-  if (l == -1) return me;  // leaf
-  const int32_t nl = (l <= -2) ? splice(out, sub[size_t(-2 - l)]) : emit(out, top, l, sub);
-  const int32_t nr = (r <= -2) ? splice(out, sub[size_t(-2 - r)]) : emit(out, top, r, sub);
-  out[size_t(me)].left = nl;
-  out[size_t(me)].right = nr;
-  return me;
-}
-
 }  // namespace
 
 // Node ids are positions in the tree's final pre-order node array.
 struct madtree {
-  std::vector<double> pts;
-  std::vector<Node> nodes;          // DFS pre-order
+  std::vector<Node, default_init_allocator<Node>> nodes;  // DFS pre-order
   std::vector<int32_t> leaf_nodes;  // getLeafs order -> node id
   std::vector<int32_t> bfs_index;   // node id -> breadth-first position
   std::vector<madtree_rec_t> recs;  // breadth-first records
@@ -589,14 +592,9 @@ int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_mi
   const auto t0 = now();
   madtree* t = new (std::nothrow) madtree;
   if (!t) return MADICP_ERR_NOMEM;
-  t->pts.assign(points_xyz, points_xyz + 3 * n);
   t->b_max = b_max;
   t->b_min = b_min;
   const size_t un = static_cast<size_t>(n);
-  std::vector<double> tmp(3 * un);
-  std::vector<unsigned char> flag(un);
-  std::vector<int32_t> xf(un), bp(un);  // the split's misplaced-point lists
-  Builder B{t->pts.data(), b_max, b_min, tmp.data(), flag.data(), xf.data(), bp.data()};
   Job root{};
   root.begin = 0;
   root.end = n;
@@ -605,19 +603,16 @@ int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_mi
   int threads = num_threads;
   if (threads > 64) threads = 64;
   if (threads < 1) threads = 1;
-  t->threads = (n < 20000) ? 1 : threads;
-  if (threads <= 1 || n < 20000) {
-    t->nodes.reserve(size_t(n / 2 + 16));
-    B.expand(t->nodes, root);
-  } else {
-    // The sums of a node are accumulated in array order (that order defines the result), so a single
-    // node cannot be split across threads -- but disjoint ranges are independent (the reference uses
-    // std::async on the top log2(num_threads) levels, mad_tree.cpp:99-129).  The top levels are done
-    // level by level (all nodes of a level in parallel) down to ~4 ranges per worker, the subtrees
-    // below on the same pool, then one splice in pre-order.
-    std::unique_lock<std::mutex> pool_lock(g_pool_mu, std::try_to_lock);
-    std::unique_ptr<Pool> private_pool;
-    Pool* pool;
+  if (n < 20000) threads = 1;
+  t->threads = threads;
+  // pool + working memory: the process-wide set if no other build is using it, else private
+  std::unique_lock<std::mutex> pool_lock(g_pool_mu, std::try_to_lock);
+  std::unique_ptr<Pool> private_pool;
+  Scratch private_scratch;
+  Scratch* sc = pool_lock.owns_lock() ? &g_scratch : &private_scratch;
+  sc->ensure(un);
+  Pool* pool = nullptr;
+  if (threads > 1) {
     if (pool_lock.owns_lock()) {
       if (!g_pool || g_pool->threads() != threads) g_pool.reset(new Pool(threads));
       pool = g_pool.get();
@@ -625,24 +620,40 @@ int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_mi
       private_pool.reset(new Pool(threads));
       pool = private_pool.get();
     }
+  }
+  Builder B{sc->pts.get(), b_max, b_min, sc->tmp.get(), sc->flag.get(), sc->xf.get(), sc->bp.get()};
+  if (!pool) {
+    std::memcpy(B.pts, points_xyz, sizeof(double) * 3 * un);
+    std::vector<Node> nodes;
+    nodes.reserve(size_t(n / 2 + 16));
+    B.expand(nodes, root);
+    t->nodes.assign(nodes.begin(), nodes.end());
+  } else {
+    // The sums of a node are accumulated in array order (that order defines the result), so the chains of
+    // one node cannot be cut -- but everything else can (process_level_shared), and disjoint ranges are
+    // independent (the reference uses std::async on the top log2(num_threads) levels,
+    // mad_tree.cpp:99-129).  The top levels are done level by level with every pass chunked over the
+    // pool, down to ~8 ranges per worker; the subtrees below are expanded on the same pool and copied
+    // to their pre-order position in parallel.
+    constexpr size_t kCopy = 16384;
+    pool->run((un + kCopy - 1) / kCopy, [&](size_t c) {
+      const size_t b = c * kCopy, e = std::min(un, b + kCopy);
+      std::memcpy(B.pts + 3 * b, points_xyz + 3 * b, sizeof(double) * 3 * (e - b));
+    });
+    const auto ts = now();
     int depth = 0;
     while ((1 << depth) < 8 * threads) ++depth;
     std::vector<Node> top(1);
     std::vector<Job> level{root};    // jobs of the current level; job.parent = id of ITS node in `top`
     level[0].parent = 0;
     std::vector<Job> frontier;
+    std::string level_ms;
     for (int d = 0; d < depth && !level.empty(); ++d) {
+      const auto tl = now();
       std::vector<Job> ctx(level.size());
       std::vector<int64_t> mids(level.size(), 0);
       std::vector<char> internal(level.size(), 0);
-      if (level.size() < size_t(threads)) {
-        // fewer nodes than threads: the passes over each node's range are shared between the threads
-        process_level_shared(B, *pool, top, level, ctx, mids, internal);
-      } else {
-        pool->run(level.size(), [&](size_t i) {
-          internal[i] = B.process(top[size_t(level[i].parent)], level[i], ctx[i], mids[i]) ? 1 : 0;
-        });
-      }
+      process_level_shared(B, *pool, top, level, ctx, mids, internal);
       std::vector<Job> next;
       for (size_t i = 0; i < level.size(); ++i) {
         if (!internal[i]) continue;
@@ -666,6 +677,11 @@ int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_mi
         }
       }
       level.swap(next);
+      if (timing) {
+        char buf[32];
+        std::snprintf(buf, sizeof buf, " %.2f", ms(tl, now()));
+        level_ms += buf;
+      }
     }
     const auto ta = now();
     std::vector<std::vector<Node>> sub(frontier.size());
@@ -681,11 +697,50 @@ int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_mi
       B.expand(sub[k], frontier[k]);
     });
     const auto tb = now();
-    if (timing) std::fprintf(stderr, "  top %.2f ms (%zu ranges), pool %.2f ms\n", ms(t0, ta), frontier.size(), ms(ta, tb));
-    size_t total = top.size();
-    for (const auto& v : sub) total += v.size();
-    t->nodes.reserve(total);
-    emit(t->nodes, top, 0, sub);
+    // pre-order positions: walk the top skeleton once, then every arena is copied to its place
+    std::vector<int32_t> top_pos(top.size(), -1), sub_pos(sub.size(), -1);
+    {
+      int32_t cursor = 0;
+      std::vector<int32_t> stack{0};  // top ids >= 0, frontier references <= -2
+      while (!stack.empty()) {
+        const int32_t id = stack.back();
+        stack.pop_back();
+        if (id <= -2) {
+          sub_pos[size_t(-2 - id)] = cursor;
+          cursor += int32_t(sub[size_t(-2 - id)].size());
+          continue;
+        }
+        top_pos[size_t(id)] = cursor++;
+        if (top[size_t(id)].left != -1) {  // right first: the left subtree is numbered next
+          stack.push_back(top[size_t(id)].right);
+          stack.push_back(top[size_t(id)].left);
+        }
+      }
+      t->nodes.resize(size_t(cursor));
+    }
+    auto place = [&](int32_t ref) { return ref <= -2 ? sub_pos[size_t(-2 - ref)] : top_pos[size_t(ref)]; };
+    for (size_t i = 0; i < top.size(); ++i) {
+      Node nd = top[i];
+      if (nd.left != -1) {
+        nd.left = place(nd.left);
+        nd.right = place(nd.right);
+      }
+      t->nodes[size_t(top_pos[i])] = nd;
+    }
+    pool->run(sub.size(), [&](size_t q) {
+      const size_t k = by_size[q];
+      const int32_t off = sub_pos[k];
+      Node* dst = t->nodes.data() + off;
+      for (size_t i = 0; i < sub[k].size(); ++i) {
+        Node nd = sub[k][i];
+        if (nd.left >= 0) nd.left += off;
+        if (nd.right >= 0) nd.right += off;
+        dst[i] = nd;
+      }
+    });
+    if (timing)
+      std::fprintf(stderr, "  copy-in %.2f ms, top %.2f ms (levels:%s; %zu ranges), subtrees %.2f ms, placement %.2f ms\n",
+                   ms(t0, ts), ms(ts, ta), level_ms.c_str(), frontier.size(), ms(ta, tb), ms(tb, now()));
   }
   const auto t1 = now();
   // Leaves in pre-order == getLeafs order (left subtree fully before right subtree).  Breadth-first

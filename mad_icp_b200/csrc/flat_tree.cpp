@@ -344,13 +344,20 @@ private:
   void loop() {
     uint64_t seen = 0;
     for (;;) {
+      // Sections of one build follow each other within microseconds, but a section with few tasks (the
+      // sum chains of the root: three) leaves most workers idle for its whole length: keep spinning for
+      // a while (kSpinNs) before paying a futex sleep + wake-up.
       int spin = 0;
+      std::chrono::steady_clock::time_point idle_since;
       while (gen_.load(std::memory_order_acquire) == seen) {
-        if (++spin < 1500) {
-          _mm_pause();
-        } else {
-          std::unique_lock<std::mutex> lk(mu_);
-          cv_.wait(lk, [&]() { return gen_.load(std::memory_order_acquire) != seen; });
+        _mm_pause();
+        if ((++spin & 255) == 0) {
+          const auto nowt = std::chrono::steady_clock::now();
+          if (spin == 256) idle_since = nowt;
+          if (nowt - idle_since > std::chrono::nanoseconds(kSpinNs)) {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&]() { return gen_.load(std::memory_order_acquire) != seen; });
+          }
         }
       }
       seen = gen_.load(std::memory_order_acquire);
@@ -359,6 +366,7 @@ private:
       done_.fetch_add(1, std::memory_order_release);
     }
   }
+  static constexpr long kSpinNs = 500000;
   std::vector<std::thread> workers_;
   std::mutex mu_;
   std::condition_variable cv_;
@@ -469,20 +477,24 @@ void process_level_shared(const Builder& B, Pool& pool, std::vector<Node>& top, 
     for (int a = 0; a < 3; ++a) nd.bbox[a] = hi[a] - lo[a];
     internal[j] = B.decide(nd, level[j], ctx[j], mids[j], m[j], false) ? 1 : 0;
   }
-  // C1: misplaced points per chunk
-  pool.run(chunks.size(), [&](size_t c) {
-    Chunk& ch = chunks[c];
+  // C1: misplaced points per chunk -- known from the chunk's pass count unless it straddles the split
+  for (Chunk& ch : chunks) {
     const size_t j = size_t(ch.job);
-    if (!internal[j]) return;
+    if (!internal[j]) continue;
     const int64_t split = level[j].begin + m[j];
-    int64_t nxf = 0, nbp = 0;
-    for (int64_t i = ch.b; i < ch.e; ++i) {
-      nxf += (i < split) & (B.flag[i] == 0);
-      nbp += (i >= split) & (B.flag[i] != 0);
+    if (ch.e <= split) {
+      ch.nxf = (ch.e - ch.b) - ch.npass;
+      ch.nbp = 0;
+    } else if (ch.b >= split) {
+      ch.nxf = 0;
+      ch.nbp = ch.npass;
+    } else {
+      int64_t nxf = 0;
+      for (int64_t i = ch.b; i < split; ++i) nxf += B.flag[i] == 0;
+      ch.nxf = nxf;
+      ch.nbp = ch.npass - ((split - ch.b) - nxf);
     }
-    ch.nxf = nxf;
-    ch.nbp = nbp;
-  });
+  }
   for (size_t j = 0; j < J; ++j) {
     int64_t ox = 0, ob = 0;
     for (size_t c = first[j]; c < first[j + 1]; ++c) {
@@ -742,6 +754,7 @@ int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_mi
       std::fprintf(stderr, "  copy-in %.2f ms, top %.2f ms (levels:%s; %zu ranges), subtrees %.2f ms, placement %.2f ms\n",
                    ms(t0, ts), ms(ts, ta), level_ms.c_str(), frontier.size(), ms(ta, tb), ms(tb, now()));
   }
+  if (pool_lock.owns_lock()) pool_lock.unlock();  // the numbering passes below take the pool themselves
   const auto t1 = now();
   // Leaves in pre-order == getLeafs order (left subtree fully before right subtree).  Breadth-first
   // position = (nodes on shallower levels) + (pre-order rank among the nodes of the same depth): the

@@ -301,7 +301,7 @@ class Pool {
 public:
   explicit Pool(int threads) {
     const int extra = threads > 1 ? threads - 1 : 0;
-    for (int i = 0; i < extra; ++i) workers_.emplace_back([this]() { loop(); });
+    for (int i = 0; i < extra; ++i) workers_.emplace_back([this, i]() { loop(i + 1); });
   }
   ~Pool() {
     {
@@ -314,6 +314,15 @@ public:
   }
   int threads() const { return int(workers_.size()) + 1; }
 
+  // run(): indices handed out one at a time.  run_blocked(): worker w takes the w-th contiguous share, so
+  // a thread meets the same part of an array in consecutive sections (and levels) and finds it in its
+  // own cache; use it when the per-index cost is uniform.
+  template <class F>
+  void run_blocked(size_t n, F&& fn) {
+    blocked_ = true;
+    run(n, fn);
+    blocked_ = false;
+  }
   template <class F>
   void run(size_t n, F&& fn) {
     if (n == 0) return;
@@ -330,18 +339,23 @@ public:
       gen_.fetch_add(1, std::memory_order_release);
     }
     cv_.notify_all();
-    drain();
+    drain(0);
     const int w = int(workers_.size());
     for (int spin = 0; done_.load(std::memory_order_acquire) != w; ++spin)
       if (spin > 1500) std::this_thread::yield(); else _mm_pause();
   }
 
 private:
-  void drain() {
+  void drain(int me) {
+    if (blocked_) {
+      const size_t W = workers_.size() + 1;
+      for (size_t i = n_ * size_t(me) / W, e = n_ * size_t(me + 1) / W; i < e; ++i) task_(i);
+      return;
+    }
     for (size_t i = next_.fetch_add(1, std::memory_order_relaxed); i < n_; i = next_.fetch_add(1, std::memory_order_relaxed))
       task_(i);
   }
-  void loop() {
+  void loop(int me) {
     uint64_t seen = 0;
     for (;;) {
       // Sections of one build follow each other within microseconds, but a section with few tasks (the
@@ -362,7 +376,7 @@ private:
       }
       seen = gen_.load(std::memory_order_acquire);
       if (stop_) return;
-      drain();
+      drain(me);
       done_.fetch_add(1, std::memory_order_release);
     }
   }
@@ -372,6 +386,7 @@ private:
   std::condition_variable cv_;
   std::function<void(size_t)> task_;
   size_t n_ = 0;
+  bool blocked_ = false;
   std::atomic<size_t> next_{0};
   std::atomic<int> done_{0};
   std::atomic<uint64_t> gen_{0};
@@ -426,7 +441,9 @@ void for_chunks(int threads, size_t n, size_t chunk, F&& fn) {
   }
 }
 
-// One level of the top of the tree when it has fewer nodes than there are threads: every pass over a
+double g_phase_us[5];  // MADTREE_TIMING: sums, extents+flags, decisions, lists+copy, placement (guarded by g_pool_mu)
+
+// One level of the top of the tree: every pass over a
 // node's range is cut into chunks that any thread may take.  What may be reordered is only what is
 // exact: the three groups of sum chains run side by side (each chain still in array order), extents
 // are min/max, and the split is applied from its closed form (Builder::split) with per-chunk counts.
@@ -450,7 +467,24 @@ void process_level_shared(const Builder& B, Pool& pool, std::vector<Node>& top, 
   first[J] = chunks.size();
   // A: raw sums, three chain groups per node
   std::vector<double> S(9 * J);
-  pool.run(3 * J, [&](size_t t) { sums_group(B.pts, level[t / 3].begin, level[t / 3].end, int(t % 3), &S[9 * (t / 3)]); });
+  const auto tA = std::chrono::steady_clock::now();
+  if (2 * J >= size_t(pool.threads())) {  // enough nodes: one pass per node feeds all nine chains
+    pool.run(J, [&](size_t j) {
+      double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0, s7 = 0, s8 = 0;  // locals: no aliasing with S
+      const double* P = B.pts;
+      for (int64_t i = level[j].begin; i != level[j].end; ++i) {
+        const double x = P[3 * i], y = P[3 * i + 1], z = P[3 * i + 2];
+        s0 += x; s1 += y; s2 += z;
+        s3 += x * x; s4 += y * x; s5 += z * x;
+        s6 += y * y; s7 += z * y; s8 += z * z;
+      }
+      double* Sj = &S[9 * j];
+      Sj[0] = s0; Sj[1] = s1; Sj[2] = s2; Sj[3] = s3; Sj[4] = s4; Sj[5] = s5; Sj[6] = s6; Sj[7] = s7; Sj[8] = s8;
+    });
+  } else {
+    pool.run(3 * J, [&](size_t t) { sums_group(B.pts, level[t / 3].begin, level[t / 3].end, int(t % 3), &S[9 * (t / 3)]); });
+  }
+  const auto tB = std::chrono::steady_clock::now();
   for (size_t j = 0; j < J; ++j) {
     Node& nd = top[size_t(level[j].parent)];
     nd.left = nd.right = -1;
@@ -459,10 +493,11 @@ void process_level_shared(const Builder& B, Pool& pool, std::vector<Node>& top, 
     Builder::finish_stats(nd, &S[9 * j], level[j].end - level[j].begin);
   }
   // B: extents + side flags per chunk
-  pool.run(chunks.size(), [&](size_t c) {
+  pool.run_blocked(chunks.size(), [&](size_t c) {
     Chunk& ch = chunks[c];
     ch.npass = B.box_flags(top[size_t(level[size_t(ch.job)].parent)], ch.b, ch.e, ch.lo, ch.hi);
   });
+  const auto tC = std::chrono::steady_clock::now();
   std::vector<int64_t> m(J, 0), A(J, 0);
   for (size_t j = 0; j < J; ++j) {
     Node& nd = top[size_t(level[j].parent)];
@@ -506,7 +541,8 @@ void process_level_shared(const Builder& B, Pool& pool, std::vector<Node>& top, 
     A[j] = ox;  // == ob
   }
   // C2: the two position lists (relative to the node's begin) and a copy of the points
-  pool.run(chunks.size(), [&](size_t c) {
+  const auto tD = std::chrono::steady_clock::now();
+  pool.run_blocked(chunks.size(), [&](size_t c) {
     const Chunk& ch = chunks[c];
     const size_t j = size_t(ch.job);
     if (!internal[j] || m[j] == level[j].end - level[j].begin) return;
@@ -525,7 +561,8 @@ void process_level_shared(const Builder& B, Pool& pool, std::vector<Node>& top, 
     std::memcpy(B.tmp + 3 * ch.b, B.pts + 3 * ch.b, sizeof(double) * 3 * size_t(ch.e - ch.b));
   });
   // C3: every point that moves is written to its final place (all destinations are distinct)
-  pool.run(chunks.size(), [&](size_t c) {
+  const auto tE = std::chrono::steady_clock::now();
+  pool.run_blocked(chunks.size(), [&](size_t c) {
     const Chunk& ch = chunks[c];
     const size_t j = size_t(ch.job);
     const int64_t b0 = level[j].begin, n = level[j].end - b0, mm = m[j], AA = A[j];
@@ -553,6 +590,12 @@ void process_level_shared(const Builder& B, Pool& pool, std::vector<Node>& top, 
       d[0] = s2[0]; d[1] = s2[1]; d[2] = s2[2];
     }
   });
+  const auto tF = std::chrono::steady_clock::now();
+  auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b2) {
+    return std::chrono::duration<double, std::micro>(b2 - a).count();
+  };
+  g_phase_us[0] += us(tA, tB); g_phase_us[1] += us(tB, tC); g_phase_us[2] += us(tC, tD);
+  g_phase_us[3] += us(tD, tE); g_phase_us[4] += us(tE, tF);
 }
 
 }  // namespace
@@ -750,6 +793,11 @@ int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_mi
         dst[i] = nd;
       }
     });
+    if (timing) {
+      std::fprintf(stderr, "  top phases [us]: sums %.0f, extents+flags %.0f, decide %.0f, lists+copy %.0f, place %.0f\n",
+                   g_phase_us[0], g_phase_us[1], g_phase_us[2], g_phase_us[3], g_phase_us[4]);
+      for (double& v : g_phase_us) v = 0;
+    }
     if (timing)
       std::fprintf(stderr, "  copy-in %.2f ms, top %.2f ms (levels:%s; %zu ranges), subtrees %.2f ms, placement %.2f ms\n",
                    ms(t0, ts), ms(ts, ta), level_ms.c_str(), frontier.size(), ms(ta, tb), ms(tb, now()));

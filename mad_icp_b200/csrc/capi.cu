@@ -75,9 +75,6 @@ struct madicp_ctx {
   int* d_ord = nullptr;
   size_t cap_items = 0;
   double* d_partial = nullptr;
-  PathMemo* d_memo = nullptr;               // persistent kernel: path of every (keyframe, moving leaf) pair
-  size_t cap_memo = 0;
-  int use_memo = 1;                         // MADICP_PATH_MEMO=0 switches the path reuse off (measurements)
   size_t cap_partial = 0;
   GnState* d_state = nullptr;
   double* d_X = nullptr;  // 12 (step API pose) + 36 + 6 scratch
@@ -365,7 +362,6 @@ int madicp_create(madicp_ctx_t** out, int device, int max_keyframes) {
   for (int i = 0; i < madicp_ctx::kInRing; ++i) CK(cudaEventCreateWithFlags(&c->in_done[i], cudaEventDisableTiming));
   CK(cudaMallocHost(&c->h_matched, kMatchedCap));
   int threads = 1024, ctas = 1;
-  if (const char* e = getenv("MADICP_PATH_MEMO")) c->use_memo = atoi(e) != 0;
   if (const char* e = getenv("MADICP_GN_SHAPE"))
     if (sscanf(e, "%d,%d", &threads, &ctas) == 2) c->gn_auto = false;
   int rc = configure_gn(c, threads, ctas);
@@ -397,7 +393,6 @@ void madicp_destroy(madicp_ctx_t* c) {
   cudaFree(c->d_hit);
   cudaFree(c->d_ord);
   cudaFree(c->d_partial);
-  cudaFree(c->d_memo);
   cudaFree(c->d_state);
   cudaFree(c->d_X);
   cudaFree(c->d_comm);
@@ -721,18 +716,6 @@ int madicp_register_async(madicp_ctx_t* c, int iters, const double X0[12]) {
   A.iters = iters;
   A.matched = c->d_comm->matched[mb];
   A.partial = c->d_partial;
-  A.memo = nullptr;
-  if (c->use_memo && c->walk_mode == 4) {
-    const size_t pairs = size_t(madicp_num_keyframes(c)) * size_t(c->L);
-    if (pairs > c->cap_memo) {
-      if (c->d_memo) cudaFree(c->d_memo);
-      c->d_memo = nullptr;
-      c->cap_memo = 0;
-      CK(cudaMalloc(&c->d_memo, pairs * sizeof(PathMemo)));
-      c->cap_memo = pairs;
-    }
-    A.memo = c->d_memo;
-  }
   A.st = c->d_state;
   A.dbg = c->d_dbg;
   A.dbg_cta = c->d_dbg ? c->d_dbg_cta : nullptr;

@@ -224,7 +224,6 @@ struct GnArgs {
   unsigned char* peer_matched[kMaxPeers];  // world > 1: every rank's matched array (peer mapped)
   double* partial;                         // gridDim.x * kAcc
   GnState* st;
-  PathMemo* memo;                          // [K][L] paths of the previous round (walk mode 4), or null
   uint32_t pose_epoch;                     // epoch of round 0's pose; monotonic across launches, never reused
   long long* dbg;                          // nullable: per-round SM-clock stamps (madicp_debug_timing)
   long long* dbg_cta;                      // nullable: [round][CTA] item-phase cycles
@@ -334,9 +333,7 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
         const Moving4 m = load_moving(A.moving + q);
         double mx, my, mz, ww;
         iso_apply(s_X, m.px, m.py, m.pz, mx, my, mz);
-        const int leaf = A.memo ? descend_memo(A.model, int(k), mx, my, mz, ww, A.memo + (size_t(k) * unsigned(A.L) + q), it > 0)
-                                : descend(A.model, int(k), mx, my, mz, ww);
-        const Rec f = load_rec(A.model.recs + leaf);
+        const Rec f = load_rec(A.model.recs + descend(A.model, int(k), mx, my, mz, ww));
         if (linearize_one(s_X, A.P.rho_ker_sqrt, m, mx, my, mz, f, ww, v) && last_round) {
           if (multi) {
             for (int r = 0; r < A.peers.world; ++r) A.peer_matched[r][q] = 1;

@@ -72,22 +72,6 @@ struct __align__(32) QuadRec {
 };
 static_assert(sizeof(QuadRec) == 64, "QuadRec must be two 256-bit loads");
 
-// The path a (moving leaf, keyframe) pair took in the previous Gauss-Newton round: the quad records it
-// visited below the root and the two binary decisions taken in each.  Between rounds the pose moves by
-// less and less, so the greedy descent almost always repeats itself; with the path known, the planes on
-// it can be fetched with INDEPENDENT loads and the decisions re-checked in order, instead of one
-// dependent memory round trip per record.  The check evaluates the same predicates at the same nodes as
-// a fresh descent would, so the result is the fresh descent's by construction; the first decision that
-// differs (or cannot be settled in FP32) hands over to the ordinary loop at that record.
-//   bits: [2j], [2j+1] = decisions in record j (j = 0 is the root record); [16..19] = records on the
-//   path (1..8); [20] = the leaf was found in the child slot of the last record (else in its first slot);
-//   [21] = the path continues below the 8th record (not stored).
-struct __align__(16) PathMemo {
-  int rec[7];
-  unsigned bits;
-};
-static_assert(sizeof(PathMemo) == 32, "PathMemo must be two 128-bit accesses");
-
 // All keyframes of a device live in ONE pool; slot s owns the index range [s*cap, (s+1)*cap) of the
 // breadth-first arrays and [s*heap_cap, (s+1)*heap_cap) of the heap-ordered shadow array.
 //
@@ -292,108 +276,6 @@ __device__ __forceinline__ int descend(const ModelView& M, int k, double qx, dou
     int side = side_filtered(q, p);
     if (side < 0) side = side_exact(M.recs + M.bfs_of[root + h], qx, qy, qz) ? 1 : 0;
     h = 2u * h + 1u + unsigned(side);
-  }
-}
-
-// The 4-ary walk of descend() with the path memo: `reuse` = the memo holds this pair's path of the
-// previous round.  Always leaves the memo describing the path taken now.
-__device__ __forceinline__ int descend_memo(const ModelView& M, int k, double qx, double qy, double qz, double& ww,
-                                            PathMemo* memo, bool reuse) {
-  const QueryF q = make_query(qx, qy, qz);
-  const QuadRec* qbase = M.quad + M.qroot[k];
-  unsigned g = 0, bits = 0;
-  int j = 0;  // record counter along the path
-  if (reuse) {
-    int r[8];
-    unsigned old;
-    r[0] = 0;
-    asm volatile("ld.global.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]) : "l"(memo) : "memory");
-    asm volatile("ld.global.v4.s32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(old)
-                 : "l"(reinterpret_cast<const char*>(memo) + 16)
-                 : "memory");
-    const int n = int((old >> 16) & 15u);
-    const bool end_in_child = (old >> 20) & 1u;
-    const bool truncated = (old >> 21) & 1u;  // the leaf lies below the 8th record: nothing ends here
-    bool ok = true;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      FastRec P[4], C[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {  // all loads of this half are in flight together
-        const int jj = half * 4 + i;
-        if (ok && jj < n) {
-          const FastRec* base = reinterpret_cast<const FastRec*>(qbase + r[jj]);
-          P[i] = load_fast(base);
-          C[i] = load_fast(base + 1 + ((old >> (2 * jj)) & 1u));
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int jj = half * 4 + i;
-        if (ok && jj < n) {
-          g = unsigned(r[jj]);  // where the loop takes over if this record disagrees, or after the last one
-          j = jj;
-          const bool last = (jj == n - 1) && !truncated;
-          if (last && !end_in_child) {  // the path ended in the first slot of this record
-            ww = leaf_weight(P[i]);
-            return leaf_index(P[i]);
-          }
-          const unsigned o0 = (old >> (2 * jj)) & 1u, o1 = (old >> (2 * jj + 1)) & 1u;
-          const int s0 = side_filtered(q, P[i]);
-          if (s0 != int(o0)) {  // different (or undecided): take over from this record
-            ok = false;
-          } else if (last) {  // leaf in the child slot that was taken
-            ww = leaf_weight(C[i]);
-            return leaf_index(C[i]);
-          } else {
-            const int s1 = side_filtered(q, C[i]);
-            if (s1 != int(o1)) ok = false;
-          }
-        }
-      }
-    }
-    // (all stored records agree and the path went on below them: g, j = the last one, re-walked by the loop)
-    bits = old & ((1u << (2 * j)) - 1u);
-  }
-  while (true) {
-    FastRec p0, p1, p2;
-    int bfs0, child0, pad1, pad2;
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(p0.dx), "=f"(p0.dy), "=f"(p0.dz), "=f"(p0.c), "=f"(p1.dx), "=f"(p1.dy), "=f"(p1.dz), "=f"(p1.c)
-                 : "l"(qbase + g));
-    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(p2.dx), "=f"(p2.dy), "=f"(p2.dz), "=f"(p2.c), "=r"(bfs0), "=r"(child0), "=r"(pad1), "=r"(pad2)
-                 : "l"(reinterpret_cast<const char*>(qbase + g) + 32));
-    if (j >= 1 && j < 8) memo->rec[j - 1] = int(g);
-    int leaf = -1;
-    unsigned in_child = 0;
-    if (is_leaf(p0)) {
-      ww = leaf_weight(p0);
-      leaf = leaf_index(p0);
-    } else {
-      int s0 = side_filtered(q, p0);
-      if (s0 < 0) s0 = side_exact(M.recs + bfs0, qx, qy, qz) ? 1 : 0;
-      const FastRec c = s0 ? p2 : p1;
-      if (j < 8) bits |= unsigned(s0) << (2 * j);
-      if (is_leaf(c)) {
-        ww = leaf_weight(c);
-        leaf = leaf_index(c);
-        in_child = 1;
-      } else {
-        int s1 = side_filtered(q, c);
-        if (s1 < 0) s1 = side_exact(M.recs + (load_link(M.links + bfs0) + s0), qx, qy, qz) ? 1 : 0;
-        if (j < 8) bits |= unsigned(s1) << (2 * j + 1);
-        g = unsigned(child0) + 2u * unsigned(s0) + unsigned(s1);
-      }
-    }
-    if (leaf >= 0) {
-      const unsigned n = unsigned(j < 8 ? j + 1 : 8);
-      // a path longer than 8 records is stored up to the 8th; the check then resumes the loop there
-      memo->bits = (bits & 0xffffu) | (n << 16) | ((j < 8 ? in_child : 0u) << 20) | ((j >= 8 ? 1u : 0u) << 21);
-      return leaf;
-    }
-    ++j;
   }
 }
 

@@ -268,7 +268,7 @@ static int configure_gn(madicp_ctx* c, int threads, int ctas) {
   const GnShape* t = gn_shapes(&n);
   for (int i = 0; i < n; ++i)
     if (t[i].threads == threads && t[i].ctas == ctas) {
-      CK(cudaFuncSetAttribute(t[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(t[i].smem)));
+      CK(cudaFuncSetAttribute(t[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(t[i].smem + kGnMapMaxBytes)));
       // ask for the smallest shared-memory carve-out that fits: the rest of the 228 KB is L1 for the tree
       CK(cudaFuncSetAttribute(t[i].fn, cudaFuncAttributePreferredSharedMemoryCarveout,
                               int((t[i].smem * size_t(ctas) + 2048) * 100 / (228 * 1024)) + 1));
@@ -716,6 +716,22 @@ int madicp_register_async(madicp_ctx_t* c, int iters, const double X0[12]) {
   A.iters = iters;
   A.matched = c->d_comm->matched[mb];
   A.partial = c->d_partial;
+  // Item map in shared memory: 4 bytes per CTA-local item, taken only if it neither exceeds the reserve
+  // nor pushes the CTA into the next shared-memory carve-out (that would shrink L1, which holds the tree).
+  size_t map_bytes = 0;
+  {
+    const size_t per_cta = size_t(madicp_num_keyframes(c)) * (size_t(c->L) / size_t(c->gn_grid) + 8) * 4 + 128;
+    auto bucket = [](size_t bytes) {
+      const size_t kb[] = {8, 16, 32, 64, 100, 132, 164, 196, 228};
+      for (size_t b : kb)
+        if (bytes + 1024 <= b * 1024) return b;  // 1 KB of static shared memory + system reserve
+      return size_t(1 << 20);
+    };
+    const size_t ctas = size_t(c->gn_grid / c->sm_count);
+    if (per_cta <= kGnMapMaxBytes && c->L < (1 << 26) && bucket((c->gn_smem + per_cta) * ctas) == bucket(c->gn_smem * ctas))
+      map_bytes = per_cta;
+  }
+  A.map_in_smem = map_bytes ? 1 : 0;
   A.st = c->d_state;
   A.dbg = c->d_dbg;
   A.dbg_cta = c->d_dbg ? c->d_dbg_cta : nullptr;
@@ -737,7 +753,7 @@ int madicp_register_async(madicp_ctx_t* c, int iters, const double X0[12]) {
   // zero the flags buffer of the NEXT call (nobody can be writing it yet; see CommBlock)
   CK(cudaMemsetAsync(c->d_comm->matched[mb ^ 1], 0, std::min(kMatchedCap, c->cap_moving), c->stream));
   void* args[] = {&A};
-  CK(cudaLaunchCooperativeKernel(c->gn_kernel, dim3(c->gn_grid), dim3(c->gn_threads), args, c->gn_smem, c->stream));
+  CK(cudaLaunchCooperativeKernel(c->gn_kernel, dim3(c->gn_grid), dim3(c->gn_threads), args, c->gn_smem + map_bytes, c->stream));
   c->launches++;
   c->last_iters = iters;
   c->call_seq++;

@@ -224,6 +224,7 @@ struct GnArgs {
   unsigned char* peer_matched[kMaxPeers];  // world > 1: every rank's matched array (peer mapped)
   double* partial;                         // gridDim.x * kAcc
   GnState* st;
+  int map_in_smem;                         // 1: the launch reserved 4 bytes per CTA-local item behind the staging tiles
   uint32_t pose_epoch;                     // epoch of round 0's pose; monotonic across launches, never reused
   long long* dbg;                          // nullable: per-round SM-clock stamps (madicp_debug_timing)
   long long* dbg_cta;                      // nullable: [round][CTA] item-phase cycles
@@ -284,6 +285,34 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
   }
   const unsigned t_total = unsigned(A.model.K) * n_b;  // CTA-local items
   (void) total;
+  // (keyframe, moving leaf) of CTA-local item t: one 32-bit division per warp-item, a carry, and the
+  // stretch lookup.  The assignment is the same in every round, so when the launch could spare the
+  // shared memory each warp works it out once and keeps it packed (k << 26 | q) next to the tiles.
+  auto item_of = [&](unsigned t0, unsigned& k, unsigned& q) {
+    k = t0 / n_b;
+    q = t0 - k * n_b + lane;
+    while (q >= n_b) {
+      q -= n_b;
+      ++k;
+    }
+    const unsigned j = q;
+    q = p_lo[kPieces - 1] + (j - (n_b - p_n[kPieces - 1]));
+    unsigned acc = 0;
+#pragma unroll
+    for (unsigned p = 0; p + 1 < kPieces; ++p) {
+      if (j >= acc && j < acc + p_n[p]) q = p_lo[p] + (j - acc);
+      acc += p_n[p];
+    }
+  };
+  unsigned* s_map = A.map_in_smem ? reinterpret_cast<unsigned*>(s_dyn + WARPS * kStageTile) : nullptr;
+  if (s_map) {
+    for (unsigned t0 = warp * 32; t0 < t_total; t0 += THREADS) {
+      unsigned k, q;
+      item_of(t0, k, q);
+      s_map[t0 + lane] = (k << 26) | q;  // entries past t_total are never used
+    }
+    __syncwarp();  // a warp only ever reads what it wrote itself
+  }
 
   for (int it = 0; it < A.iters; ++it) {
     if (threadIdx.x < 12) {
@@ -309,22 +338,13 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
     if (A.dbg && threadIdx.x == 0) t_begin = clock64();
 
     for (unsigned t0 = warp * 32; t0 < t_total; t0 += THREADS) {
-      // (keyframe, leaf) of this lane: one 32-bit division per warp-item, then a carry
-      unsigned k = t0 / n_b;
-      unsigned q = t0 - k * n_b + lane;
-      while (q >= n_b) {
-        q -= n_b;
-        ++k;
-      }
-      {  // CTA-local leaf number -> moving leaf
-        unsigned j = q;
-        q = p_lo[kPieces - 1] + (j - (n_b - p_n[kPieces - 1]));
-        unsigned acc = 0;
-#pragma unroll
-        for (unsigned p = 0; p + 1 < kPieces; ++p) {
-          if (j >= acc && j < acc + p_n[p]) q = p_lo[p] + (j - acc);
-          acc += p_n[p];
-        }
+      unsigned k, q;
+      if (s_map) {
+        const unsigned pk = s_map[t0 + lane];
+        k = pk >> 26;
+        q = pk & 0x3ffffffu;
+      } else {
+        item_of(t0, k, q);
       }
       double v[kStage];
 #pragma unroll
@@ -412,5 +432,6 @@ template <int THREADS>
 constexpr size_t gn_dynamic_smem() {
   return sizeof(double) * size_t(THREADS / 32) * kStageTile;
 }
+constexpr size_t kGnMapMaxBytes = 16 * 1024;  // optional item map behind the tiles (GnArgs::map_in_smem)
 
 }  // namespace madicp

@@ -195,12 +195,24 @@ __device__ __forceinline__ QueryF make_query(double qx, double qy, double qz) {
   q.eq = __fmul_ru(kBoundC, __fadd_ru(__fadd_ru(fabsf(q.x), fabsf(q.y)), fabsf(q.z)));
   return q;
 }
-// Filtered side test at one node: +1 right, 0 left, -1 undecided (|s32| within the error bound
-// E = kBoundC*(|q|_1 + |c|): the caller must evaluate the exact FP64 predicate).
-__device__ __forceinline__ int side_filtered(const QueryF& q, const FastRec& p) {
+// Filtered side test at one node.  E = kBoundC*(|q|_1 + |c|) bounds |s32 - s_exact|: when |s32| > E the
+// sign of s32 is the sign of the exact FP64 expression; otherwise (or on a NaN) the caller must evaluate
+// the exact predicate.  Two compares, no selects: `right` is only meaningful when `decided`.
+struct SideF {
+  bool decided, right;
+};
+__device__ __forceinline__ SideF side_filtered2(const QueryF& q, const FastRec& p) {
   const float s = fmaf(q.z, p.dz, fmaf(q.y, p.dy, q.x * p.dx)) - p.c;
   const float E = __fmaf_ru(kBoundC, fabsf(p.c), q.eq);
-  return (s > E) ? 1 : ((s < -E) ? 0 : -1);
+  SideF r;
+  r.decided = fabsf(s) > E;
+  r.right = s > 0.0f;
+  return r;
+}
+// the same as +1 right, 0 left, -1 undecided
+__device__ __forceinline__ int side_filtered(const QueryF& q, const FastRec& p) {
+  const SideF r = side_filtered2(q, p);
+  return r.decided ? (r.right ? 1 : 0) : -1;
 }
 __device__ __forceinline__ bool is_leaf(const FastRec& p) { return __float_as_uint(p.dy) == kLeafMarker; }
 __device__ __forceinline__ int leaf_index(const FastRec& p) { return __float_as_int(p.dx); }
@@ -230,8 +242,9 @@ __device__ __forceinline__ int descend(const ModelView& M, int k, double qx, dou
     }
   }
   if (M.walk_mode == 4) {  // 4-ary records: two binary decisions per memory round trip
-    const QuadRec* qbase = M.quad + M.qroot[k];
-    unsigned g = 0;
+    const unsigned qroot = unsigned(M.qroot[k]);
+    const QuadRec* qbase = M.quad;  // uniform base + 32-bit pool index: one IMAD.WIDE per record address
+    unsigned g = qroot;
     while (true) {
       FastRec p0, p1, p2;
       int bfs0, child0, pad1, pad2;
@@ -245,16 +258,18 @@ __device__ __forceinline__ int descend(const ModelView& M, int k, double qx, dou
         ww = leaf_weight(p0);
         return leaf_index(p0);
       }
-      int s0 = side_filtered(q, p0);
-      if (s0 < 0) s0 = side_exact(M.recs + bfs0, qx, qy, qz) ? 1 : 0;
+      const SideF f0 = side_filtered2(q, p0);
+      bool s0 = f0.right;
+      if (!f0.decided) s0 = side_exact(M.recs + bfs0, qx, qy, qz);
       const FastRec c = s0 ? p2 : p1;
       if (is_leaf(c)) {
         ww = leaf_weight(c);
         return leaf_index(c);
       }
-      int s1 = side_filtered(q, c);
-      if (s1 < 0) s1 = side_exact(M.recs + (load_link(M.links + bfs0) + s0), qx, qy, qz) ? 1 : 0;
-      g = unsigned(child0) + 2u * unsigned(s0) + unsigned(s1);
+      const SideF f1 = side_filtered2(q, c);
+      bool s1 = f1.right;
+      if (!f1.decided) s1 = side_exact(M.recs + (load_link(M.links + bfs0) + (s0 ? 1 : 0)), qx, qy, qz);
+      g = qroot + unsigned(child0) + (s0 ? 2u : 0u) + (s1 ? 1u : 0u);
     }
   }
   const int root = M.root[k];

@@ -257,7 +257,8 @@ static GnShape gn_shape() {
 }
 static const GnShape* gn_shapes(int* n) {
   static const GnShape table[] = {
-      gn_shape<1024, 1>(), gn_shape<768, 1>(), gn_shape<512, 1>(), gn_shape<512, 2>(),
+      gn_shape<1024, 1>(), gn_shape<896, 1>(), gn_shape<768, 1>(), gn_shape<704, 1>(), gn_shape<640, 1>(),
+      gn_shape<512, 1>(),  gn_shape<512, 2>(),
       gn_shape<256, 2>(),  gn_shape<256, 3>(), gn_shape<256, 4>(),
   };
   *n = int(sizeof(table) / sizeof(table[0]));
@@ -297,7 +298,7 @@ static int pick_shape(madicp_ctx* c, int64_t items) {
   const double per_sm = double((items + 31) / 32) / double(c->sm_count);
   int best = 1024;
   double best_cost = 1e300;
-  for (int threads : {1024, 768, 512}) {
+  for (int threads : {1024, 896, 768, 704, 640, 512}) {
     const int warps = threads / 32;
     const double passes = ceil(per_sm / warps);
     const double cost = passes * (6500.0 + 150.0 * warps);

@@ -8,7 +8,7 @@ for s in range(16):
     ft = FlatTree(case["scans"][s]); ft.apply_transform(case["kf_poses"][s]); reg.put_keyframe(s, ft)
 reg.set_moving(FlatTree(case["query"]).leaf_means())
 st = torch.cuda.Stream(); reg.set_stream(st.cuda_stream)
-for shape in ((768, 1), (512, 1), (256, 2), (512, 2), (1024, 1)):
+for shape in ((768, 1), (704, 1), (896, 1), (640, 1), (1024, 1)):
     reg.set_gn_grid(*shape)
     reg.debug_timing(False, fetch=False)
     ts = []
@@ -20,5 +20,5 @@ for shape in ((768, 1), (512, 1), (256, 2), (512, 2), (1024, 1)):
     for _ in range(2):
         reg.register_async(case["T_guess"], 10); torch.cuda.synchronize()
     d = reg.debug_timing(True)
-    print("memo", os.environ.get("MADICP_PATH_MEMO", "1"), "shape", shape, f"10-iter warm median {np.median(ts):.1f} us",
+    print("shape", shape, f"10-iter warm median {np.median(ts):.1f} us",
           "per-round all_arrived cycles:", d[:, 1].astype(int).tolist())

@@ -290,21 +290,24 @@ static int configure_gn(madicp_ctx* c, int threads, int ctas) {
 }
 
 // The item phase of a round costs (passes) x (time of one pass); a pass walks one warp-item per
-// resident warp and its time grows mildly with the number of resident warps (L1 contention).  Measured
-// on B200 (profiles/r01h_probe_v6.txt): ~6.5k + 150/warp cycles.  With W warps per SM and n warp-items
-// per SM the passes are ceil(n / W): pick the one-CTA-per-SM shape that minimises the product.
+// resident warp and its time grows with the number of resident warps (L1 contention, and fewer
+// registers per thread).  Measured on B200 at cfg3 (profiles/r01zg_probe_shapes.txt), cycles per
+// full pass: 512 threads 7.6k, 640: 8.4k, 704: 9.5k, 768: 9.5k, 896: 10.4k, 1024: 11.5k.  With W warps
+// per SM and n warp-items per SM the passes are ceil(n / W): pick the one-CTA-per-SM shape that minimises
+// the product (ties go to the earlier entry).
 static int pick_shape(madicp_ctx* c, int64_t items) {
   if (!c->gn_auto) return MADICP_OK;
   const double per_sm = double((items + 31) / 32) / double(c->sm_count);
   int best = 1024;
   double best_cost = 1e300;
-  for (int threads : {1024, 896, 768, 704, 640, 512}) {
-    const int warps = threads / 32;
-    const double passes = ceil(per_sm / warps);
-    const double cost = passes * (6500.0 + 150.0 * warps);
+  static const struct { int threads; double pass_cycles; } kShapes[] = {
+      {768, 9500.0}, {1024, 11500.0}, {896, 10400.0}, {704, 9500.0}, {640, 8400.0}, {512, 7600.0}};
+  for (const auto& sh : kShapes) {
+    const double passes = ceil(per_sm / double(sh.threads / 32));
+    const double cost = passes * sh.pass_cycles;
     if (cost < best_cost) {
       best_cost = cost;
-      best = threads;
+      best = sh.threads;
     }
   }
   if (best == c->gn_threads && c->gn_grid == c->sm_count) return MADICP_OK;

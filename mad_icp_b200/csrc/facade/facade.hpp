@@ -57,9 +57,12 @@ class MADtree {
  public:
   // MADtree(vec, begin, end, b_max, b_min, 0, max_parallel_level, nullptr, nullptr) (mad_tree.cpp:33-45)
   MADtree(const ContainerType& cloud, double b_max, double b_min, int max_parallel_level = 0)
+      : MADtree(cloud.empty() ? nullptr : cloud[0].data(), cloud.size(), b_max, b_min, max_parallel_level) {}
+  // the same from a bare N x 3 buffer (the build copies the points into its own working memory)
+  MADtree(const double* xyz, size_t n, double b_max, double b_min, int max_parallel_level = 0)
       : b_max_(b_max), uid_(next_uid()) {
-    check(madtree_build(cloud.empty() ? nullptr : cloud[0].data(), int64_t(cloud.size()), b_max, b_min,
-                        1 << (max_parallel_level > 0 ? max_parallel_level : 0), &t_), "madtree_build");
+    check(madtree_build(xyz, int64_t(n), b_max, b_min, 1 << (max_parallel_level > 0 ? max_parallel_level : 0), &t_),
+          "madtree_build");
   }
   ~MADtree() { madtree_free(t_); }
   MADtree(const MADtree&) = delete;

@@ -208,15 +208,34 @@ class Pipeline {
   }
 
   // pipeline.cpp:125-265 (cloud by value, as the reference)
+  // reference signature (pipeline.h:71): the cloud by value
   void compute(double stamp, ContainerType cloud) {
-    is_map_updated_ = false;
     if (cloud.empty()) throw Error("Pipeline.compute: empty cloud");
+    if (deskew_ && is_initialized_ && trajectory_.size() > 1)
+      deskew(cloud, trajectory_[trajectory_.size() - 2], trajectory_[trajectory_.size() - 1], sensor_hz_);
+    computeDeskewed(stamp, cloud[0].data(), cloud.size());
+  }
+  // the same without taking ownership: N x 3 doubles read in place (copied only if the scan is deskewed)
+  void compute(double stamp, const double* xyz, size_t n) {
+    if (!xyz || n == 0) throw Error("Pipeline.compute: empty cloud");
+    if (deskew_ && is_initialized_ && trajectory_.size() > 1) {
+      ContainerType cloud(n);
+      std::memcpy(cloud[0].data(), xyz, sizeof(double) * 3 * n);
+      compute(stamp, std::move(cloud));
+    } else {
+      computeDeskewed(stamp, xyz, n);
+    }
+  }
+
+ private:
+  void computeDeskewed(double stamp, const double* xyz, size_t n) {
+    is_map_updated_ = false;
     if (!is_initialized_) {  // pipeline.cpp:267-284
       auto f = std::make_shared<FrameB>();
       f->frame = int(seq_);
       f->to_map = frame_to_map_;
       f->stamp = stamp;
-      f->tree.reset(new MADtree(cloud, b_max_, b_min_, max_parallel_levels_));
+      f->tree.reset(new MADtree(xyz, n, b_max_, b_min_, max_parallel_levels_));
       keyframes_.push_back(f);
       current_ = f;
       trajectory_.push_back(detail::poseIdentity());
@@ -225,11 +244,9 @@ class Pipeline {
       return;
     }
     const auto c0 = clk();
-    if (deskew_ && trajectory_.size() > 1)
-      deskew(cloud, trajectory_[trajectory_.size() - 2], trajectory_[trajectory_.size() - 1], sensor_hz_);
-    const auto c1 = clk();
+    const auto c1 = c0;  // (deskewing happens in compute(), before this point)
     auto cur = std::make_shared<FrameB>();
-    cur->tree.reset(new MADtree(cloud, b_max_, b_min_, max_parallel_levels_));
+    cur->tree.reset(new MADtree(xyz, n, b_max_, b_min_, max_parallel_levels_));
     const auto c2 = clk();
     double t[3], w[3];
     for (int a = 0; a < 3; ++a) {
@@ -282,7 +299,6 @@ class Pipeline {
     }
   }
 
- private:
   struct FrameB {  // tools/frame.h:37-51
     detail::Pose to_map;
     std::unique_ptr<MADtree> tree;

@@ -22,7 +22,16 @@ PYBIND11_MODULE(pypeline, m) {
       .def("keyframeID", &mb::Pipeline::keyframeID)
       .def("modelLeaves", &mb::Pipeline::modelLeaves)
       .def("currentLeaves", &mb::Pipeline::currentLeaves)
-      .def("compute", [](mb::Pipeline& p, double stamp, const py::object& cloud) { p.compute(stamp, cloud_arg(cloud)); })
+      .def("compute", [](mb::Pipeline& p, double stamp, const py::object& cloud) {
+        // read the points where they are: a bound VectorEigen3d by reference, a numpy array through its buffer
+        if (py::isinstance<mb::ContainerType>(cloud)) {
+          const mb::ContainerType& v = cloud.cast<const mb::ContainerType&>();
+          p.compute(stamp, v.empty() ? nullptr : v[0].data(), v.size());
+        } else {
+          const mb::ContainerType v = cloud_arg(cloud);
+          p.compute(stamp, v.empty() ? nullptr : v[0].data(), v.size());
+        }
+      })
       // additions (not in the reference): diagnostics
       .def_static("_deskewOnly", [](const py::object& cloud, const NpArr& a, const NpArr& b, double sensor_hz) {
         return mb::Pipeline::deskewOnly(cloud_arg(cloud), pose_from_numpy(a), pose_from_numpy(b), sensor_hz);

@@ -9,6 +9,7 @@
 // adjacent and emits the device records.  Subtrees below the top levels are independent index
 // ranges of the point array, so they are expanded by separate threads and spliced back in pre-order.
 #include <emmintrin.h>
+#include <immintrin.h>
 
 #include <algorithm>
 #include <atomic>
@@ -113,6 +114,68 @@ struct Builder {
   // cost nothing.  min/max are exact, so chunks of a range may be done by different threads and merged.
   // Returns the number of points on the negative side.
   int64_t box_flags(const Node& nd, int64_t begin, int64_t end, double* lo, double* hi) const {
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    return have_avx2 ? box_flags_avx2(nd, begin, end, lo, hi) : box_flags_sse2(nd, begin, end, lo, hi);
+  }
+  // four points at a time; the same operations in the same order per point as the SSE2 and scalar forms
+  __attribute__((target("avx2"))) int64_t box_flags_avx2(const Node& nd, int64_t begin, int64_t end, double* lo,
+                                                          double* hi) const {
+    const __m256d mx = _mm256_set1_pd(nd.mean[0]), my = _mm256_set1_pd(nd.mean[1]), mz = _mm256_set1_pd(nd.mean[2]);
+    __m256d e[9];
+    for (int a = 0; a < 9; ++a) e[a] = _mm256_set1_pd(nd.ev[a]);
+    __m256d l0 = _mm256_setzero_pd(), l1 = l0, l2 = l0, h0 = l0, h1 = l0, h2 = l0;
+    const __m256d zero = _mm256_setzero_pd();
+    int64_t npass = 0;
+    int64_t i = begin;
+    for (; i + 4 <= end; i += 4) {
+      const double* p = pts + 3 * i;
+      // A = x0 y0 z0 x1, B = y1 z1 x2 y2, C = z2 x3 y3 z3  ->  X = x0 x1 x2 x3, Y, Z
+      const __m256d A = _mm256_loadu_pd(p), B = _mm256_loadu_pd(p + 4), C = _mm256_loadu_pd(p + 8);
+      const __m256d P = _mm256_permute2f128_pd(A, B, 0x30);  // x0 y0 | x2 y2
+      const __m256d Q = _mm256_permute2f128_pd(A, C, 0x21);  // z0 x1 | z2 x3
+      const __m256d R = _mm256_permute2f128_pd(B, C, 0x30);  // y1 z1 | y3 z3
+      const __m256d dx = _mm256_sub_pd(_mm256_shuffle_pd(P, Q, 0xA), mx);
+      const __m256d dy = _mm256_sub_pd(_mm256_shuffle_pd(P, R, 0x5), my);
+      const __m256d dz = _mm256_sub_pd(_mm256_shuffle_pd(Q, R, 0xA), mz);
+      const __m256d v0 = _mm256_add_pd(_mm256_add_pd(_mm256_mul_pd(e[0], dx), _mm256_mul_pd(e[1], dy)), _mm256_mul_pd(e[2], dz));
+      const __m256d v1 = _mm256_add_pd(_mm256_add_pd(_mm256_mul_pd(e[3], dx), _mm256_mul_pd(e[4], dy)), _mm256_mul_pd(e[5], dz));
+      const __m256d v2 = _mm256_add_pd(_mm256_add_pd(_mm256_mul_pd(e[6], dx), _mm256_mul_pd(e[7], dy)), _mm256_mul_pd(e[8], dz));
+      l0 = _mm256_min_pd(v0, l0); h0 = _mm256_max_pd(v0, h0);
+      l1 = _mm256_min_pd(v1, l1); h1 = _mm256_max_pd(v1, h1);
+      l2 = _mm256_min_pd(v2, l2); h2 = _mm256_max_pd(v2, h2);
+      const int mk = _mm256_movemask_pd(_mm256_cmp_pd(v2, zero, _CMP_LT_OQ));
+      flag[i] = (unsigned char) (mk & 1);
+      flag[i + 1] = (unsigned char) ((mk >> 1) & 1);
+      flag[i + 2] = (unsigned char) ((mk >> 2) & 1);
+      flag[i + 3] = (unsigned char) ((mk >> 3) & 1);
+      npass += __builtin_popcount(unsigned(mk));
+    }
+    double t[6][4];  // (lambdas would not inherit the target attribute)
+    _mm256_storeu_pd(t[0], l0); _mm256_storeu_pd(t[1], l1); _mm256_storeu_pd(t[2], l2);
+    _mm256_storeu_pd(t[3], h0); _mm256_storeu_pd(t[4], h1); _mm256_storeu_pd(t[5], h2);
+    for (int a = 0; a < 3; ++a) {
+      double l = 0, h = 0;
+      for (int k = 0; k < 4; ++k) {
+        l = (t[a][k] < l) ? t[a][k] : l;
+        h = (h < t[3 + a][k]) ? t[3 + a][k] : h;
+      }
+      lo[a] = l;
+      hi[a] = h;
+    }
+    for (; i != end; ++i) {
+      const double dx = pts[3 * i] - nd.mean[0], dy = pts[3 * i + 1] - nd.mean[1], dz = pts[3 * i + 2] - nd.mean[2];
+      double v[3];
+      for (int a = 0; a < 3; ++a) {
+        v[a] = dot3(nd.ev[3 * a], nd.ev[3 * a + 1], nd.ev[3 * a + 2], dx, dy, dz);
+        lo[a] = (v[a] < lo[a]) ? v[a] : lo[a];
+        hi[a] = (hi[a] < v[a]) ? v[a] : hi[a];
+      }
+      flag[i] = (v[2] < 0.0) ? 1 : 0;
+      npass += flag[i];
+    }
+    return npass;
+  }
+  int64_t box_flags_sse2(const Node& nd, int64_t begin, int64_t end, double* lo, double* hi) const {
     const __m128d mx = _mm_set1_pd(nd.mean[0]), my = _mm_set1_pd(nd.mean[1]), mz = _mm_set1_pd(nd.mean[2]);
     __m128d e[9];
     for (int a = 0; a < 9; ++a) e[a] = _mm_set1_pd(nd.ev[a]);
@@ -211,8 +274,17 @@ struct Builder {
     const bool m_fails = f[m] == 0;
     if (m_fails) cp(T + 3 * A, P + 3 * m);
     for (int64_t a = 0; a < A; ++a) cp(P + 3 * XF[a], P + 3 * BP[A - 1 - a]);
-    for (int64_t p = m + 1; p < n; ++p)
-      if (!f[p]) cp(P + 3 * (p - 1), P + 3 * p);
+    // every failing point of (m,n) moves down by one: the stretches between consecutive passing points
+    // of [m,n) are moved as blocks (no per-point test, nothing for the branch predictor to miss)
+    {
+      int64_t start = m + 1;
+      for (int64_t r = 0; r < A; ++r) {
+        const int64_t bpos = BP[r];
+        if (bpos > start) std::memmove(P + 3 * (start - 1), P + 3 * start, sizeof(double) * 3 * size_t(bpos - start));
+        start = bpos + 1;
+      }
+      if (n > start) std::memmove(P + 3 * (start - 1), P + 3 * start, sizeof(double) * 3 * size_t(n - start));
+    }
     for (int64_t a = 0; a < A; ++a) cp(P + 3 * (a == 0 ? n - 1 : BP[A - a] - 1), T + 3 * a);
     if (m_fails) cp(P + 3 * ((A > 0 ? BP[0] : n) - 1), T + 3 * A);
   }
@@ -569,25 +641,25 @@ void process_level_shared(const Builder& B, Pool& pool, std::vector<Node>& top, 
     if (!internal[j] || mm == n) return;
     const int32_t* XF = B.xf + b0;
     const int32_t* BP = B.bp + b0;
-    int64_t a = ch.off_xf, r = ch.off_bp;
-    for (int64_t i = ch.b; i < ch.e; ++i) {
-      const int64_t rel = i - b0;
-      int64_t dest;
-      if (rel < mm) {
-        if (B.flag[i]) continue;
-        dest = (a == 0) ? n - 1 : BP[AA - a] - 1;
-        ++a;
-      } else if (B.flag[i]) {
-        dest = XF[AA - 1 - r];
-        ++r;
-      } else if (rel == mm) {
-        dest = (AA > 0 ? BP[0] : n) - 1;
-      } else {
-        dest = rel - 1;
+    const double* src = B.tmp + 3 * b0;
+    double* dst = B.pts + 3 * b0;
+    auto cp = [&](int64_t to, int64_t from) {
+      dst[3 * to] = src[3 * from]; dst[3 * to + 1] = src[3 * from + 1]; dst[3 * to + 2] = src[3 * from + 2];
+    };
+    // driven by the two lists instead of a test per point: this chunk's misplaced points of the lower
+    // part, its passing points of the upper part, and the stretches of failing points between those
+    for (int64_t a = ch.off_xf; a < ch.off_xf + ch.nxf; ++a) cp(a == 0 ? n - 1 : BP[AA - a] - 1, XF[a]);
+    for (int64_t r = ch.off_bp; r < ch.off_bp + ch.nbp; ++r) cp(XF[AA - 1 - r], BP[r]);
+    const int64_t cb = ch.b - b0, ce = ch.e - b0;
+    if (ce > mm) {
+      if (cb <= mm && B.flag[b0 + mm] == 0) cp((AA > 0 ? BP[0] : n) - 1, mm);
+      int64_t start = std::max(cb, mm + 1);
+      for (int64_t r = ch.off_bp; r < ch.off_bp + ch.nbp; ++r) {
+        const int64_t bpos = BP[r];
+        if (bpos > start) std::memcpy(dst + 3 * (start - 1), src + 3 * start, sizeof(double) * 3 * size_t(bpos - start));
+        start = std::max(start, bpos + 1);
       }
-      double* d = B.pts + 3 * (b0 + dest);
-      const double* s2 = B.tmp + 3 * i;
-      d[0] = s2[0]; d[1] = s2[1]; d[2] = s2[2];
+      if (ce > start) std::memcpy(dst + 3 * (start - 1), src + 3 * start, sizeof(double) * 3 * size_t(ce - start));
     }
   });
   const auto tF = std::chrono::steady_clock::now();

@@ -646,20 +646,31 @@ void process_level_shared(const Builder& B, Pool& pool, std::vector<Node>& top, 
     auto cp = [&](int64_t to, int64_t from) {
       dst[3 * to] = src[3 * from]; dst[3 * to + 1] = src[3 * from + 1]; dst[3 * to + 2] = src[3 * from + 2];
     };
-    // driven by the two lists instead of a test per point: this chunk's misplaced points of the lower
-    // part, its passing points of the upper part, and the stretches of failing points between those
-    for (int64_t a = ch.off_xf; a < ch.off_xf + ch.nxf; ++a) cp(a == 0 ? n - 1 : BP[AA - a] - 1, XF[a]);
-    for (int64_t r = ch.off_bp; r < ch.off_bp + ch.nbp; ++r) cp(XF[AA - 1 - r], BP[r]);
+    // Written per DESTINATION: a thread fills its own chunk of the array (each cache line has one
+    // writer) and reads the points from wherever they were.  Writing per source instead makes the lines
+    // near the top of a large node bounce between the cores whose misplaced points land side by side.
+    //   lower part: a passing point stays; the slot of the a-th failing point takes the a-th passing point
+    //               of the upper part counted from the top;
+    //   upper part: position p takes the failing point at p+1 if there is one; if p+1 is the j-th passing
+    //               point of the upper part (ascending, j >= 1) it takes the (A-j)-th failing point of the
+    //               lower part, for j = 0 the point at m; the top position takes failing point 0 (or m).
     const int64_t cb = ch.b - b0, ce = ch.e - b0;
-    if (ce > mm) {
-      if (cb <= mm && B.flag[b0 + mm] == 0) cp((AA > 0 ? BP[0] : n) - 1, mm);
-      int64_t start = std::max(cb, mm + 1);
-      for (int64_t r = ch.off_bp; r < ch.off_bp + ch.nbp; ++r) {
-        const int64_t bpos = BP[r];
-        if (bpos > start) std::memcpy(dst + 3 * (start - 1), src + 3 * start, sizeof(double) * 3 * size_t(bpos - start));
-        start = std::max(start, bpos + 1);
+    const unsigned char* f = B.flag + b0;
+    int64_t a0 = ch.off_xf;  // rank of the next failing point of the lower part met in this chunk
+    int64_t cntp = ch.off_bp;  // passing points of the upper part at positions <= p
+    for (int64_t p = cb; p < ce; ++p) {
+      int64_t from;
+      if (p < mm) {
+        if (f[p]) continue;
+        from = BP[AA - 1 - a0];
+        ++a0;
+      } else {
+        cntp += f[p];
+        if (p + 1 == n) from = (AA > 0) ? XF[0] : mm;
+        else if (!f[p + 1]) from = p + 1;
+        else from = (cntp >= 1) ? XF[AA - cntp] : mm;
       }
-      if (ce > start) std::memcpy(dst + 3 * (start - 1), src + 3 * start, sizeof(double) * 3 * size_t(ce - start));
+      cp(p, from);
     }
   });
   const auto tF = std::chrono::steady_clock::now();

@@ -520,7 +520,8 @@ double g_phase_us[5];  // MADTREE_TIMING: sums, extents+flags, decisions, lists+
 // exact: the three groups of sum chains run side by side (each chain still in array order), extents
 // are min/max, and the split is applied from its closed form (Builder::split) with per-chunk counts.
 void process_level_shared(const Builder& B, Pool& pool, std::vector<Node>& top, const std::vector<Job>& level,
-                          std::vector<Job>& ctx, std::vector<int64_t>& mids, std::vector<char>& internal) {
+                          std::vector<Job>& ctx, std::vector<int64_t>& mids, std::vector<char>& internal,
+                          const double* root_sums = nullptr) {
   constexpr int64_t kChunk = 4096;
   struct Chunk {
     int job;
@@ -540,7 +541,9 @@ void process_level_shared(const Builder& B, Pool& pool, std::vector<Node>& top, 
   // A: raw sums, three chain groups per node
   std::vector<double> S(9 * J);
   const auto tA = std::chrono::steady_clock::now();
-  if (2 * J >= size_t(pool.threads())) {  // enough nodes: one pass per node feeds all nine chains
+  if (root_sums && J == 1) {  // the root's chains were run over the caller's buffer while it was being copied in
+    for (int a = 0; a < 9; ++a) S[a] = root_sums[a];
+  } else if (2 * J >= size_t(pool.threads())) {  // enough nodes: one pass per node feeds all nine chains
     pool.run(J, [&](size_t j) {
       double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0, s7 = 0, s8 = 0;  // locals: no aliasing with S
       const double* P = B.pts;
@@ -773,9 +776,18 @@ int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_mi
     // mad_tree.cpp:99-129).  The top levels are done level by level with every pass chunked over the
     // pool, down to ~8 ranges per worker; the subtrees below are expanded on the same pool and copied
     // to their pre-order position in parallel.
+    // Copy-in, and at the same time the root's nine sum chains straight from the caller's buffer: its
+    // lines are clean, whereas the working copy sits modified in sixteen different caches by the time
+    // the chains could start on it (three threads streaming 3 MB each: the longest step of the build).
     constexpr size_t kCopy = 16384;
-    pool->run((un + kCopy - 1) / kCopy, [&](size_t c) {
-      const size_t b = c * kCopy, e = std::min(un, b + kCopy);
+    const size_t ncopy = (un + kCopy - 1) / kCopy;
+    double root_sums[9];
+    pool->run(3 + ncopy, [&](size_t t) {
+      if (t < 3) {
+        sums_group(points_xyz, 0, n, int(t), root_sums);
+        return;
+      }
+      const size_t b = (t - 3) * kCopy, e = std::min(un, b + kCopy);
       std::memcpy(B.pts + 3 * b, points_xyz + 3 * b, sizeof(double) * 3 * (e - b));
     });
     const auto ts = now();
@@ -791,7 +803,7 @@ int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_mi
       std::vector<Job> ctx(level.size());
       std::vector<int64_t> mids(level.size(), 0);
       std::vector<char> internal(level.size(), 0);
-      process_level_shared(B, *pool, top, level, ctx, mids, internal);
+      process_level_shared(B, *pool, top, level, ctx, mids, internal, d == 0 ? root_sums : nullptr);
       std::vector<Job> next;
       for (size_t i = 0; i < level.size(); ++i) {
         if (!internal[i]) continue;

@@ -9,6 +9,7 @@
 // adjacent and emits the device records.  Subtrees below the top levels are independent index
 // ranges of the point array, so they are expanded by separate threads and spliced back in pre-order.
 #include <emmintrin.h>
+#include <pthread.h>
 #include <immintrin.h>
 
 #include <algorithm>
@@ -489,6 +490,17 @@ struct Scratch {
   }
 };
 Scratch g_scratch;  // guarded by g_pool_mu, like the pool
+
+// fork(): the child inherits the pool object but none of its threads.  Forget it there (the object is
+// leaked on purpose: its destructor would join threads that do not exist) and start from a fresh lock.
+struct ForkGuard {
+  ForkGuard() {
+    pthread_atfork(nullptr, nullptr, []() {
+      (void) g_pool.release();
+      new (&g_pool_mu) std::mutex;
+    });
+  }
+} g_fork_guard;
 
 // std::vector that leaves trivially-constructible elements uninitialised on resize()
 template <class T>

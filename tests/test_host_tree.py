@@ -120,3 +120,24 @@ def test_record_layout(built):
     import sys
     sys.setrecursionlimit(10000)
     walk(0, 0)
+
+
+@pytest.mark.filterwarnings("ignore::DeprecationWarning")  # Python's generic fork-with-threads warning
+def test_build_in_a_forked_child(oracle, built):
+    """A forked child (e.g. a data-loader worker) inherits the worker pool object without its threads;
+    it must notice and start its own."""
+    import multiprocessing as mp
+    c = synth.registration_case(K=1, beams=32, azimuths=1024, seed=31)
+    parent = FlatTree(c["scans"][0], num_threads=4)  # the pool exists in the parent now
+    ctx = mp.get_context("fork")
+    q = ctx.Queue()
+
+    def child():
+        ft = FlatTree(c["scans"][0], num_threads=4)
+        q.put((ft.num_nodes, ft.num_leaves))
+
+    p = ctx.Process(target=child)
+    p.start()
+    p.join(60)
+    assert p.exitcode == 0, "child hung or crashed"
+    assert q.get(timeout=5) == (parent.num_nodes, parent.num_leaves)

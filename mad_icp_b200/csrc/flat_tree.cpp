@@ -737,6 +737,10 @@ int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_mi
     madicp::set_error("madtree_build: null pointer or empty cloud (the reference dereferences *begin on an empty range)");
     return MADICP_ERR_INVALID;
   }
+  if (n > (int64_t(1) << 30)) {  // positions, node ids and counts are 32-bit (the reference's num_points_ is an int too)
+    madicp::set_error("madtree_build: more than 2^30 points");
+    return MADICP_ERR_INVALID;
+  }
   const bool timing = getenv("MADTREE_TIMING") != nullptr;
   auto now = []() { return std::chrono::steady_clock::now(); };
   auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {

@@ -28,8 +28,9 @@ PYBIND11_MODULE(pypeline, m) {
           const mb::ContainerType& v = cloud.cast<const mb::ContainerType&>();
           p.compute(stamp, v.empty() ? nullptr : v[0].data(), v.size());
         } else {
-          const mb::ContainerType v = cloud_arg(cloud);
-          p.compute(stamp, v.empty() ? nullptr : v[0].data(), v.size());
+          const NpArr a = cloud.cast<NpArr>();  // a view when the array already is C-contiguous float64
+          if (a.ndim() != 2 || a.shape(1) != 3) throw py::cast_error();
+          p.compute(stamp, a.shape(0) ? a.data() : nullptr, size_t(a.shape(0)));
         }
       })
       // additions (not in the reference): diagnostics

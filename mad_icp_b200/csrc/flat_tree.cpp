@@ -701,9 +701,9 @@ void process_level_shared(const Builder& B, Pool& pool, std::vector<Node>& top, 
 // Node ids are positions in the tree's final pre-order node array.
 struct madtree {
   std::vector<Node, default_init_allocator<Node>> nodes;  // DFS pre-order
-  std::vector<int32_t> leaf_nodes;  // getLeafs order -> node id
-  std::vector<int32_t> bfs_index;   // node id -> breadth-first position
-  std::vector<madtree_rec_t> recs;  // breadth-first records
+  std::vector<int32_t, default_init_allocator<int32_t>> leaf_nodes;  // getLeafs order -> node id
+  std::vector<int32_t, default_init_allocator<int32_t>> bfs_index;   // node id -> breadth-first position
+  std::vector<madtree_rec_t, default_init_allocator<madtree_rec_t>> recs;  // breadth-first records
   double b_max = 0, b_min = 0;
   int threads = 1;  // width the tree was built with; later whole-tree passes use the same
 
@@ -730,6 +730,22 @@ struct madtree {
   }
 };
 
+// A streamed sequence builds one tree per scan and frees one per scan.  The arrays of a tree are
+// several MB each, i.e. mmap'ed and unmapped by malloc every time, and faulting ~2000 fresh pages costs
+// more than filling them.  Freed trees therefore keep their arrays in a small cache for the next build.
+namespace {
+std::mutex g_tree_cache_mu;
+std::vector<madtree*> g_tree_cache;
+constexpr size_t kTreeCacheMax = 4;
+madtree* tree_from_cache() {
+  std::lock_guard<std::mutex> lk(g_tree_cache_mu);
+  if (g_tree_cache.empty()) return nullptr;
+  madtree* t = g_tree_cache.back();
+  g_tree_cache.pop_back();
+  return t;
+}
+}  // namespace
+
 extern "C" {
 
 int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_min, int num_threads, madtree_t** out) {
@@ -747,7 +763,8 @@ int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_mi
     return std::chrono::duration<double, std::milli>(b - a).count();
   };
   const auto t0 = now();
-  madtree* t = new (std::nothrow) madtree;
+  madtree* t = tree_from_cache();
+  if (!t) t = new (std::nothrow) madtree;
   if (!t) return MADICP_ERR_NOMEM;
   t->b_max = b_max;
   t->b_min = b_min;
@@ -980,7 +997,17 @@ int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_mi
   return MADICP_OK;
 }
 
-void madtree_free(madtree_t* t) { delete t; }
+void madtree_free(madtree_t* t) {
+  if (!t) return;
+  {
+    std::lock_guard<std::mutex> lk(g_tree_cache_mu);
+    if (g_tree_cache.size() < kTreeCacheMax) {
+      g_tree_cache.push_back(t);  // contents are overwritten by the next build (every array is resized and filled)
+      return;
+    }
+  }
+  delete t;
+}
 int madtree_num_nodes(const madtree_t* t) { return t ? int(t->nodes.size()) : MADICP_ERR_INVALID; }
 int madtree_num_leaves(const madtree_t* t) { return t ? int(t->leaf_nodes.size()) : MADICP_ERR_INVALID; }
 

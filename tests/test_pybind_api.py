@@ -153,7 +153,7 @@ def test_pipeline_tracks_like_the_oracle(oracle, deskew):
     for i, (stamp, pts) in enumerate(_sequence(n)):
         L.orc_pipeline_compute(ref, stamp, oracle._d(pts), pts.shape[0])
         L.orc_pipeline_state(ref, oracle._d(st))
-        pipe.compute(stamp, VectorEigen3d(pts))
+        pipe.compute(stamp, VectorEigen3d(pts) if i % 2 == 0 else pts)  # a bound vector or a plain N x 3 array
         T = pipe.currentPose()
         ang, dt = pose_error(T, st[:12].reshape(3, 4))
         assert pipe.currentID() == int(st[13]), i

@@ -141,6 +141,14 @@ int madicp_register_fetch(madicp_ctx_t* ctx, double X[12], double H_last[36], do
  * last row is the final pose).  Debug/parity aid. */
 int madicp_register_trace(madicp_ctx_t* ctx, double* X_trace, int max_rounds);
 
+/* Pipeline::deskew (odometry/pipeline.cpp:79-123), host side: sorts the n points by azimuth, cuts the
+ * sweep into 1024 chunks, applies to every chunk the pose interpolated from the relative motion of the
+ * last two estimates (T_prev, T_now: 3x4 row-major), and rewrites points_xyz in sorted order -- the
+ * reference's permutation exactly, ties of its unstable sort included.  Runs on num_threads host
+ * threads; no device work. */
+int madicp_deskew(double* points_xyz, int64_t n, const double T_prev[12], const double T_now[12], double sensor_hz,
+                  int num_threads);
+
 /* MADtreeWrapper::searchCloud / searchCloudDist (pybind/tools/mad_tree_wrapper.h:48-67): nearest-leaf
  * search of n host query points in slot `slot`.  Any output may be NULL: ordinals n, points n x 3
  * (leaf mean), normals n x 3, dists n. */

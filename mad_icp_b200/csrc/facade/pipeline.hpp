@@ -12,89 +12,22 @@
 #include <deque>
 #include <limits>
 
+#include "../pose_math.h"
 #include "facade.hpp"
 
 namespace madicp_b200 {
 namespace detail {
 
-struct Pose {  // 3x4 row-major [R|t]
-  double m[12];
-};
-inline Pose poseIdentity() { return Pose{{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0}}; }
-inline Pose poseMul(const Pose& A, const Pose& B) {
-  Pose C;
-  for (int r = 0; r < 3; ++r) {
-    for (int c = 0; c < 3; ++c)
-      C.m[r * 4 + c] = (A.m[r * 4] * B.m[c] + A.m[r * 4 + 1] * B.m[4 + c]) + A.m[r * 4 + 2] * B.m[8 + c];
-    C.m[r * 4 + 3] = ((A.m[r * 4] * B.m[3] + A.m[r * 4 + 1] * B.m[7]) + A.m[r * 4 + 2] * B.m[11]) + A.m[r * 4 + 3];
-  }
-  return C;
-}
-inline Pose poseInverse(const Pose& T) {
-  Pose I;
-  for (int r = 0; r < 3; ++r)
-    for (int c = 0; c < 3; ++c) I.m[r * 4 + c] = T.m[c * 4 + r];
-  for (int r = 0; r < 3; ++r)
-    I.m[r * 4 + 3] = -((I.m[r * 4] * T.m[3] + I.m[r * 4 + 1] * T.m[7]) + I.m[r * 4 + 2] * T.m[11]);
-  return I;
-}
+using madicp_pose::Pose;
+using madicp_pose::poseIdentity;
+using madicp_pose::poseMul;
+using madicp_pose::poseInverse;
+using madicp_pose::poseFromTwist;
+using madicp_pose::logSO3;
 inline Vector3d poseApply(const Pose& T, const Vector3d& p) {
   Vector3d o;
-  for (int r = 0; r < 3; ++r) o[r] = ((T.m[r * 4] * p[0] + T.m[r * 4 + 1] * p[1]) + T.m[r * 4 + 2] * p[2]) + T.m[r * 4 + 3];
+  madicp_pose::poseApply(T, p.data(), o.data());
   return o;
-}
-// tools/lie_algebra.h:39-52 (small-angle branch theta^2 < 1e-8 -> I + [w]x)
-inline Pose poseFromTwist(const double t[3], const double w[3]) {
-  Pose P = poseIdentity();
-  const double th2 = (w[0] * w[0] + w[1] * w[1]) + w[2] * w[2];
-  const double W[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
-  double R[9];
-  if (th2 < 1e-8) {
-    for (int i = 0; i < 9; ++i) R[i] = ((i % 4) == 0 ? 1.0 : 0.0) + W[i];
-  } else {
-    const double th = std::sqrt(th2);
-    double K[9], oK[9];
-    for (int i = 0; i < 9; ++i) K[i] = W[i] / th;
-    const double omc = 2.0 * std::sin(th / 2.0) * std::sin(th / 2.0), s = std::sin(th);
-    for (int i = 0; i < 9; ++i) oK[i] = omc * K[i];
-    for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c)
-        R[r * 3 + c] = (((r == c) ? 1.0 : 0.0) + s * K[r * 3 + c]) +
-                       ((oK[r * 3] * K[c] + oK[r * 3 + 1] * K[3 + c]) + oK[r * 3 + 2] * K[6 + c]);
-  }
-  for (int r = 0; r < 3; ++r) {
-    for (int c = 0; c < 3; ++c) P.m[r * 4 + c] = R[r * 3 + c];
-    P.m[r * 4 + 3] = t[r];
-  }
-  return P;
-}
-// tools/lie_algebra.h:54-89
-inline void logSO3(const Pose& T, double w[3]) {
-  const double R11 = T.m[0], R12 = T.m[1], R13 = T.m[2], R21 = T.m[4], R22 = T.m[5], R23 = T.m[6], R31 = T.m[8],
-               R32 = T.m[9], R33 = T.m[10];
-  const double tr = R11 + R22 + R33;
-  if (tr + 1.0 < 1e-10) {
-    if (std::fabs(R33 + 1.0) > 1e-5) {
-      const double f = M_PI / std::sqrt(2.0 + 2.0 * R33);
-      w[0] = f * R13; w[1] = f * R23; w[2] = f * (1.0 + R33);
-    } else if (std::fabs(R22 + 1.0) > 1e-5) {
-      const double f = M_PI / std::sqrt(2.0 + 2.0 * R22);
-      w[0] = f * R12; w[1] = f * (1.0 + R22); w[2] = f * R32;
-    } else {
-      const double f = M_PI / std::sqrt(2.0 + 2.0 * R11);
-      w[0] = f * (1.0 + R11); w[1] = f * R21; w[2] = f * R31;
-    }
-    return;
-  }
-  double mag;
-  const double tr_3 = tr - 3.0;
-  if (tr_3 < -1e-7) {
-    const double theta = std::acos((tr - 1.0) / 2.0);
-    mag = theta / (2.0 * std::sin(theta));
-  } else {
-    mag = 0.5 - tr_3 * tr_3 / 12.0;
-  }
-  w[0] = mag * (R32 - R23); w[1] = mag * (R13 - R31); w[2] = mag * (R21 - R12);
 }
 // 1 / det(H) by partial-pivot LU (odometry/pipeline.cpp:223: H.inverse().determinant())
 inline double inverseDeterminant(const double H[36]) {
@@ -199,11 +132,12 @@ class Pipeline {
   }
 
   // test hook: the deskew step alone (poses 4x4 row-major)
-  static ContainerType deskewOnly(ContainerType cloud, const Matrix4d& T_prev, const Matrix4d& T_now, double sensor_hz) {
+  static ContainerType deskewOnly(ContainerType cloud, const Matrix4d& T_prev, const Matrix4d& T_now, double sensor_hz,
+                                  int num_threads = 1) {
     detail::Pose a, b;
     std::memcpy(a.m, T_prev.m, sizeof(a.m));
     std::memcpy(b.m, T_now.m, sizeof(b.m));
-    deskew(cloud, a, b, sensor_hz);
+    deskew(cloud, a, b, sensor_hz, num_threads);
     return cloud;
   }
 
@@ -212,7 +146,8 @@ class Pipeline {
   void compute(double stamp, ContainerType cloud) {
     if (cloud.empty()) throw Error("Pipeline.compute: empty cloud");
     if (deskew_ && is_initialized_ && trajectory_.size() > 1)
-      deskew(cloud, trajectory_[trajectory_.size() - 2], trajectory_[trajectory_.size() - 1], sensor_hz_);
+      deskew(cloud, trajectory_[trajectory_.size() - 2], trajectory_[trajectory_.size() - 1], sensor_hz_,
+             1 << max_parallel_levels_);
     computeDeskewed(stamp, cloud[0].data(), cloud.size());
   }
   // the same without taking ownership: N x 3 doubles read in place (copied only if the scan is deskewed)
@@ -310,33 +245,11 @@ class Pipeline {
     std::memcpy(M.m, p.m, sizeof(p.m));
     return M;
   }
-  // pipeline.cpp:79-123
-  static void deskew(ContainerType& cloud, const detail::Pose& T_prev, const detail::Pose& T_now, double sensor_hz) {
-    const double ts = 1. / sensor_hz;
-    const detail::Pose rel = detail::poseMul(detail::poseInverse(T_prev), T_now);
-    double w[3];
-    detail::logSO3(rel, w);
-    const double v[6] = {rel.m[3] / ts, rel.m[7] / ts, rel.m[11] / ts, w[0] / ts, w[1] / ts, w[2] / ts};
-    std::vector<std::pair<double, Vector3d>> sorted(cloud.size());
-    for (size_t i = 0; i < cloud.size(); ++i) sorted[i] = {std::atan2(cloud[i][1], cloud[i][0]), cloud[i]};
-    std::sort(sorted.begin(), sorted.end(),
-              [](const std::pair<double, Vector3d>& a, const std::pair<double, Vector3d>& b) { return a.first < b.first; });
-    const double resolution = 2 * M_PI / double(kChunks), delta = ts / double(kChunks - 1);
-    double t = -ts;
-    auto at = [&](double tt) {
-      const double tr[3] = {v[0] * tt, v[1] * tt, v[2] * tt}, ro[3] = {v[3] * tt, v[4] * tt, v[5] * tt};
-      return detail::poseFromTwist(tr, ro);
-    };
-    detail::Pose meas = at(t);
-    double angle = M_PI - resolution;
-    for (int i = int(sorted.size()) - 1; i >= 0; --i) {
-      if (sorted[size_t(i)].first < angle) {
-        angle -= resolution;
-        t += delta;
-        meas = at(t);
-      }
-      cloud[size_t(i)] = detail::poseApply(meas, sorted[size_t(i)].second);
-    }
+  // pipeline.cpp:79-123: done by the library (madicp_deskew: threaded, same permutation and poses)
+  static void deskew(ContainerType& cloud, const detail::Pose& T_prev, const detail::Pose& T_now, double sensor_hz,
+                     int num_threads) {
+    if (cloud.empty()) return;
+    check(madicp_deskew(cloud[0].data(), int64_t(cloud.size()), T_prev.m, T_now.m, sensor_hz, num_threads), "madicp_deskew");
   }
 
   static std::chrono::steady_clock::time_point clk() { return std::chrono::steady_clock::now(); }

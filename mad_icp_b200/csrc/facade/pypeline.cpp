@@ -34,9 +34,9 @@ PYBIND11_MODULE(pypeline, m) {
         }
       })
       // additions (not in the reference): diagnostics
-      .def_static("_deskewOnly", [](const py::object& cloud, const NpArr& a, const NpArr& b, double sensor_hz) {
-        return mb::Pipeline::deskewOnly(cloud_arg(cloud), pose_from_numpy(a), pose_from_numpy(b), sensor_hz);
-      })
+      .def_static("_deskewOnly", [](const py::object& cloud, const NpArr& a, const NpArr& b, double sensor_hz, int num_threads) {
+        return mb::Pipeline::deskewOnly(cloud_arg(cloud), pose_from_numpy(a), pose_from_numpy(b), sensor_hz, num_threads);
+      }, py::arg("cloud"), py::arg("T_prev"), py::arg("T_now"), py::arg("sensor_hz"), py::arg("num_threads") = 1)
       .def("inliersRatio", &mb::Pipeline::inliersRatio)
       .def("numKeyframes", &mb::Pipeline::numKeyframes);
   py::register_exception<mb::Error>(m, "MadIcpError", PyExc_RuntimeError);

@@ -31,6 +31,7 @@
 #include "../../include/madicp_b200.h"
 #include "arith.h"
 #include "eig3.h"
+#include "host_pool.hpp"
 
 namespace madicp {
 void set_error(const std::string& msg);
@@ -38,6 +39,11 @@ void set_error(const std::string& msg);
 
 namespace {
 using madicp::dot3;
+using madicp_host::Pool;
+using madicp_host::default_init_allocator;
+using madicp_host::for_chunks;
+using madicp_host::g_pool;
+using madicp_host::g_pool_mu;
 using madicp::norm3;
 
 struct Node {
@@ -367,110 +373,6 @@ struct Builder {
   }
 };
 
-// Worker pool: run(n, fn) executes fn(i) for i in [0,n) on the workers plus the calling thread and
-// returns when all are done.  A build issues a few dozen short parallel sections back to back, so the
-// workers spin briefly between sections before they go to sleep.
-class Pool {
-public:
-  explicit Pool(int threads) {
-    const int extra = threads > 1 ? threads - 1 : 0;
-    for (int i = 0; i < extra; ++i) workers_.emplace_back([this, i]() { loop(i + 1); });
-  }
-  ~Pool() {
-    {
-      std::lock_guard<std::mutex> lk(mu_);
-      stop_ = true;
-      gen_.fetch_add(1, std::memory_order_release);
-    }
-    cv_.notify_all();
-    for (std::thread& t : workers_) t.join();
-  }
-  int threads() const { return int(workers_.size()) + 1; }
-
-  // run(): indices handed out one at a time.  run_blocked(): worker w takes the w-th contiguous share, so
-  // a thread meets the same part of an array in consecutive sections (and levels) and finds it in its
-  // own cache; use it when the per-index cost is uniform.
-  template <class F>
-  void run_blocked(size_t n, F&& fn) {
-    blocked_ = true;
-    run(n, fn);
-    blocked_ = false;
-  }
-  template <class F>
-  void run(size_t n, F&& fn) {
-    if (n == 0) return;
-    if (workers_.empty() || n == 1) {
-      for (size_t i = 0; i < n; ++i) fn(i);
-      return;
-    }
-    task_ = [&fn](size_t i) { fn(i); };
-    n_ = n;
-    next_.store(0, std::memory_order_relaxed);
-    done_.store(0, std::memory_order_relaxed);
-    {
-      std::lock_guard<std::mutex> lk(mu_);
-      gen_.fetch_add(1, std::memory_order_release);
-    }
-    cv_.notify_all();
-    drain(0);
-    const int w = int(workers_.size());
-    for (int spin = 0; done_.load(std::memory_order_acquire) != w; ++spin)
-      if (spin > 1500) std::this_thread::yield(); else _mm_pause();
-  }
-
-private:
-  void drain(int me) {
-    if (blocked_) {
-      const size_t W = workers_.size() + 1;
-      for (size_t i = n_ * size_t(me) / W, e = n_ * size_t(me + 1) / W; i < e; ++i) task_(i);
-      return;
-    }
-    for (size_t i = next_.fetch_add(1, std::memory_order_relaxed); i < n_; i = next_.fetch_add(1, std::memory_order_relaxed))
-      task_(i);
-  }
-  void loop(int me) {
-    uint64_t seen = 0;
-    for (;;) {
-      // Sections of one build follow each other within microseconds, but a section with few tasks (the
-      // sum chains of the root: three) leaves most workers idle for its whole length: keep spinning for
-      // a while (kSpinNs) before paying a futex sleep + wake-up.
-      int spin = 0;
-      std::chrono::steady_clock::time_point idle_since;
-      while (gen_.load(std::memory_order_acquire) == seen) {
-        _mm_pause();
-        if ((++spin & 255) == 0) {
-          const auto nowt = std::chrono::steady_clock::now();
-          if (spin == 256) idle_since = nowt;
-          if (nowt - idle_since > std::chrono::nanoseconds(kSpinNs)) {
-            std::unique_lock<std::mutex> lk(mu_);
-            cv_.wait(lk, [&]() { return gen_.load(std::memory_order_acquire) != seen; });
-          }
-        }
-      }
-      seen = gen_.load(std::memory_order_acquire);
-      if (stop_) return;
-      drain(me);
-      done_.fetch_add(1, std::memory_order_release);
-    }
-  }
-  static constexpr long kSpinNs = 500000;
-  std::vector<std::thread> workers_;
-  std::mutex mu_;
-  std::condition_variable cv_;
-  std::function<void(size_t)> task_;
-  size_t n_ = 0;
-  bool blocked_ = false;
-  std::atomic<size_t> next_{0};
-  std::atomic<int> done_{0};
-  std::atomic<uint64_t> gen_{0};
-  bool stop_ = false;
-};
-
-// One pool per process, re-created when a build asks for a different width; a build that finds it busy
-// (another host thread is building) uses a private one.
-std::mutex g_pool_mu;
-std::unique_ptr<Pool> g_pool;
-
 // Working memory of a build (the point array that is reordered, and what Builder::split needs).  It is
 // never read after the build, so the process keeps one set alive next to the pool instead of faulting
 // in ~8 MB of fresh pages per scan; left uninitialised on purpose.
@@ -490,40 +392,6 @@ struct Scratch {
   }
 };
 Scratch g_scratch;  // guarded by g_pool_mu, like the pool
-
-// fork(): the child inherits the pool object but none of its threads.  Forget it there (the object is
-// leaked on purpose: its destructor would join threads that do not exist) and start from a fresh lock.
-struct ForkGuard {
-  ForkGuard() {
-    pthread_atfork(nullptr, nullptr, []() {
-      (void) g_pool.release();
-      new (&g_pool_mu) std::mutex;
-    });
-  }
-} g_fork_guard;
-
-// std::vector that leaves trivially-constructible elements uninitialised on resize()
-template <class T>
-struct default_init_allocator : std::allocator<T> {
-  template <class U> struct rebind { using other = default_init_allocator<U>; };
-  using std::allocator<T>::allocator;
-  template <class U> void construct(U* p) noexcept { ::new (static_cast<void*>(p)) U; }
-  template <class U, class... Args> void construct(U* p, Args&&... args) { ::new (static_cast<void*>(p)) U(std::forward<Args>(args)...); }
-};
-
-// fn(chunk_begin, chunk_end) over [0,n) on the process pool when it is free, else on this thread.
-template <class F>
-void for_chunks(int threads, size_t n, size_t chunk, F&& fn) {
-  const size_t nc = (n + chunk - 1) / chunk;
-  auto one = [&](size_t c) { fn(c * chunk, std::min(n, (c + 1) * chunk)); };
-  std::unique_lock<std::mutex> lk(g_pool_mu, std::try_to_lock);
-  if (threads > 1 && nc > 1 && lk.owns_lock()) {
-    if (!g_pool || g_pool->threads() != threads) g_pool.reset(new Pool(threads));
-    g_pool->run(nc, one);
-  } else {
-    for (size_t c = 0; c < nc; ++c) one(c);
-  }
-}
 
 double g_phase_us[5];  // MADTREE_TIMING: sums, extents+flags, decisions, lists+copy, placement (guarded by g_pool_mu)
 

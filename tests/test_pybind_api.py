@@ -176,3 +176,40 @@ def test_pipeline_tracks_like_the_oracle(oracle, deskew):
         assert abs(pipe.currentPose()[0, 3] - 0.8 * (n - 1)) < 0.05
     assert len(pipe.currentLeaves()) > 100 and len(pipe.modelLeaves()) > len(pipe.currentLeaves())
     L.orc_pipeline_free(ref)
+
+
+def test_deskew_is_bit_identical_to_the_cpu_pipeline(oracle):
+    """Pipeline::deskew (pipeline.cpp:79-123) is host code on both sides: same sorted order (ties
+    included), same chunk poses, same points."""
+    import ctypes as C
+    from mad_icp_b200.pybind.pypeline import Pipeline
+    L = oracle.lib()
+    L.orc_pipeline_create.restype = C.c_void_p
+    L.orc_pipeline_create.argtypes = [C.c_double, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                      C.c_int, C.c_int, C.c_int]
+    L.orc_pipeline_deskew.argtypes = [C.c_void_p, oracle._dp, C.c_int, oracle._dp, oracle._dp]
+    L.orc_pipeline_free.argtypes = [C.c_void_p]
+    po = C.c_void_p(L.orc_pipeline_create(10.0, 1, 0.2, 0.1, 0.8, 0.1, 0.02, 4, 1, 0))
+    Ta, Tb = synth.pose_xyyaw(0.0, 1.0, 0.0), synth.pose_xyyaw(0.8, 1.05, 0.03)
+    Tb[2, 3] = 0.02
+    _, pts = next(_sequence(1, beams=32, azimuths=1024))
+    rs = np.random.RandomState(5)
+    dup = pts[rs.randint(0, pts.shape[0], 500)] * np.array([1.0, 1.0, 0.5])  # same azimuth as another point: ties
+    clouds = [pts, np.concatenate([pts, dup])[rs.permutation(pts.shape[0] + 500)], pts[:1], pts[:2]]
+    for cloud in clouds:
+        cloud = np.ascontiguousarray(cloud)
+        want = cloud.copy()
+        L.orc_pipeline_deskew(po, oracle._d(want), want.shape[0], oracle._d(np.ascontiguousarray(Ta[:3])),
+                              oracle._d(np.ascontiguousarray(Tb[:3])))
+        for threads in (1, 4):
+            got = np.asarray(Pipeline._deskewOnly(cloud, Ta, Tb, 10.0, threads))
+            assert got.shape == want.shape and (got == want).all(), threads
+    # full-size scan: the threaded merge sort path (no ties), and with a few exact duplicates (fallback path)
+    full = np.ascontiguousarray(synth.registration_case(K=1)["scans"][0])
+    for cloud in (full, np.concatenate([full, full[:7]])):
+        want = cloud.copy()
+        L.orc_pipeline_deskew(po, oracle._d(want), want.shape[0], oracle._d(np.ascontiguousarray(Ta[:3])),
+                              oracle._d(np.ascontiguousarray(Tb[:3])))
+        got = np.asarray(Pipeline._deskewOnly(cloud, Ta, Tb, 10.0, 8))
+        assert (got == want).all()
+    L.orc_pipeline_free(po)

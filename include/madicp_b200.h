@@ -149,6 +149,10 @@ int madicp_register_trace(madicp_ctx_t* ctx, double* X_trace, int max_rounds);
 int madicp_deskew(double* points_xyz, int64_t n, const double T_prev[12], const double T_now[12], double sensor_hz,
                   int num_threads);
 
+/* Diagnostic for madicp_deskew's sort: n pseudo-random keys over `distinct` values, sorted by std::sort
+ * and by the threaded restatement of it; returns how many positions of the two permutations differ (0). */
+int64_t madicp_debug_sort_check(int64_t n, uint32_t seed, int64_t distinct, int num_threads);
+
 /* MADtreeWrapper::searchCloud / searchCloudDist (pybind/tools/mad_tree_wrapper.h:48-67): nearest-leaf
  * search of n host query points in slot `slot`.  Any output may be NULL: ordinals n, points n x 3
  * (leaf mean), normals n x 3, dists n. */

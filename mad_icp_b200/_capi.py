@@ -49,6 +49,7 @@ SYMBOLS = {
     "madicp_register_trace": (C.c_int, [vp, dp, C.c_int]),
     "madicp_search_cloud": (C.c_int, [vp, C.c_int, dp, C.c_int64, ip, dp, dp, dp]),
     "madicp_deskew": (C.c_int, [dp, C.c_int64, dp, dp, C.c_double, C.c_int]),
+    "madicp_debug_sort_check": (C.c_int64, [C.c_int64, C.c_uint32, C.c_int64, C.c_int]),
     "madicp_kernel_launches": (C.c_int64, [vp]),
     "madicp_model_nodes": (C.c_int64, [vp]),
     "madicp_comm_export": (C.c_int, [vp, vp]),

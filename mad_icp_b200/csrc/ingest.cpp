@@ -49,6 +49,105 @@ struct P3 {
 template <class T>
 using RawVec = std::vector<T, default_init_allocator<T>>;
 
+// ---------------------------------------------------------------------------------------------
+// std::sort's outcome, in parallel.  GNU libstdc++ sorts with introsort: quicksort steps (pivot = median
+// of the second, middle and last element, moved to the front; Hoare-style unguarded partition) down to
+// ranges of 16, heapsort when a range has used up 2*floor(log2 n) levels, then one insertion-sort pass
+// over everything.  What it leaves among equal keys is decided by those steps, so they are restated here
+// step for step -- but the two sides of a partition never interact again, so they go to different
+// threads, and the closing insertion sort, being stable, gives the same array whether it runs over
+// everything or over each partition-ordered range separately.  tests/test_pybind_api.py checks the
+// permutation against std::sort itself (madicp_debug_sort_check) on keys with many ties.
+struct KeyLess {
+  bool operator()(const Item& x, const Item& y) const { return x.key < y.key; }
+};
+inline void median_to_first(Item* result, Item* a, Item* b, Item* c) {
+  KeyLess lt;
+  if (lt(*a, *b)) {
+    if (lt(*b, *c)) std::swap(*result, *b);
+    else if (lt(*a, *c)) std::swap(*result, *c);
+    else std::swap(*result, *a);
+  } else if (lt(*a, *c)) std::swap(*result, *a);
+  else if (lt(*b, *c)) std::swap(*result, *c);
+  else std::swap(*result, *b);
+}
+inline Item* partition_step(Item* first, Item* last) {
+  KeyLess lt;
+  Item* mid = first + (last - first) / 2;
+  median_to_first(first, first + 1, mid, last - 1);
+  Item* lo = first + 1;
+  Item* hi = last;
+  for (;;) {
+    while (lt(*lo, *first)) ++lo;
+    --hi;
+    while (lt(*first, *hi)) --hi;
+    if (!(lo < hi)) return lo;
+    std::swap(*lo, *hi);
+    ++lo;
+  }
+}
+void quick_phase(Item* first, Item* last, int depth_limit) {  // the loop that precedes the insertion pass
+  while (last - first > 16) {
+    if (depth_limit == 0) {
+      std::partial_sort(first, last, last, KeyLess());  // make_heap + sort_heap over the range
+      return;
+    }
+    --depth_limit;
+    Item* cut = partition_step(first, last);
+    quick_phase(cut, last, depth_limit);
+    last = cut;
+  }
+}
+void insertion_pass(Item* first, Item* last) {  // stable
+  KeyLess lt;
+  for (Item* i = first + (first != last); i < last; ++i) {
+    const Item v = *i;
+    Item* j = i;
+    while (j > first && lt(v, *(j - 1))) {
+      *j = *(j - 1);
+      --j;
+    }
+    *j = v;
+  }
+}
+struct Range {
+  Item *first, *last;
+  int depth_limit;
+  bool done;  // heap-sorted or at most 16 long: only the insertion pass is left
+};
+void sort_like_std(Item* first, Item* last, int threads) {
+  const ptrdiff_t n = last - first;
+  if (n < 2) return;
+  int lg = 0;
+  for (ptrdiff_t m = n; m > 1; m >>= 1) ++lg;
+  std::vector<Range> ranges{Range{first, last, 2 * lg, false}};
+  // The first splits are done here, one after the other (a pass over the data each), until there are
+  // about two ranges per thread; everything below them is then finished in ONE parallel section.  (Handing
+  // the early rounds to the pool as well would save a fraction of a millisecond on an idle machine and
+  // cost several wake-ups of every worker on a busy or virtualised one.)
+  const ptrdiff_t cutoff = std::max<ptrdiff_t>(4096, n / (2 * std::max(threads, 1)));
+  for (size_t r = 0; r < ranges.size(); ++r) {
+    while (!ranges[r].done && ranges[r].last - ranges[r].first > cutoff) {
+      Range& R = ranges[r];
+      if (R.depth_limit == 0) {
+        std::partial_sort(R.first, R.last, R.last, KeyLess());
+        R.done = true;
+        break;
+      }
+      --R.depth_limit;
+      Item* cut = partition_step(R.first, R.last);
+      const Range right{cut, R.last, R.depth_limit, false};
+      R.last = cut;
+      ranges.push_back(right);  // (invalidates R: it is re-read at the top of the loop)
+    }
+  }
+  for_chunks(threads, ranges.size(), 1, [&](size_t r0, size_t) {
+    Range& R = ranges[r0];
+    if (!R.done) quick_phase(R.first, R.last, R.depth_limit);
+    insertion_pass(R.first, R.last);
+  });
+}
+
 // sorted keys -> chunk number of every position (the reference advances by at most one chunk per point)
 void sweep(const Item* it, int64_t n, double resolution, RawVec<int32_t>& cid, int32_t& last) {
   double angle = M_PI - resolution;
@@ -104,7 +203,8 @@ extern "C" int madicp_deskew(double* points_xyz, int64_t n, const double T_prev[
   const auto t1 = now();
 
   // the reference's sort (pipeline.cpp:97-99), on records that carry an index instead of the point
-  std::sort(items.begin(), items.end(), [](const Item& x, const Item& y) { return x.key < y.key; });
+  if (threads > 1) sort_like_std(items.data(), items.data() + un, threads);
+  else std::sort(items.begin(), items.end(), KeyLess());
 
   const auto t2 = now();
   // which chunk each sorted position falls in, then the chunk poses (t accumulates as in the reference)
@@ -128,4 +228,22 @@ extern "C" int madicp_deskew(double* points_xyz, int64_t n, const double T_prev[
     std::fprintf(stderr, "madicp_deskew: n=%lld threads=%d azimuths %.2f ms, sort %.2f ms%s, sweep+poses+apply %.2f ms\n", (long long) n,
                  threads, ms(t0, t1), ms(t1, t2), "", ms(t2, now()));
   return MADICP_OK;
+}
+
+// Diagnostic: sorts n pseudo-random keys drawn from `distinct` values (many ties when distinct << n) with
+// std::sort and with the parallel restatement; returns the number of positions where the permutations differ.
+extern "C" int64_t madicp_debug_sort_check(int64_t n, uint32_t seed, int64_t distinct, int num_threads) {
+  if (n < 0 || distinct < 1) return -1;
+  std::vector<Item> a(static_cast<size_t>(n)), b2;
+  uint64_t st = seed * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+  for (int64_t i = 0; i < n; ++i) {
+    st = st * 6364136223846793005ull + 1442695040888963407ull;
+    a[size_t(i)] = Item{double((st >> 33) % uint64_t(distinct)) * 0.37 - 1.0, int32_t(i), 0};
+  }
+  b2 = a;
+  std::sort(a.begin(), a.end(), KeyLess());
+  sort_like_std(b2.data(), b2.data() + b2.size(), num_threads < 1 ? 1 : num_threads);
+  int64_t diff = 0;
+  for (int64_t i = 0; i < n; ++i) diff += (a[size_t(i)].idx != b2[size_t(i)].idx);
+  return diff;
 }

@@ -213,3 +213,15 @@ def test_deskew_is_bit_identical_to_the_cpu_pipeline(oracle):
         got = np.asarray(Pipeline._deskewOnly(cloud, Ta, Tb, 10.0, 8))
         assert (got == want).all()
     L.orc_pipeline_free(po)
+
+
+def test_threaded_sort_leaves_std_sorts_permutation(built):
+    """madicp_deskew sorts by azimuth with a threaded restatement of std::sort; equal keys are the rule
+    (one firing column), so the order among them must be std::sort's.  Keys with few distinct values, all
+    equal, all distinct; sizes around the algorithm's thresholds."""
+    from mad_icp_b200 import _capi
+    L = _capi.lib()
+    for n in (0, 1, 2, 15, 16, 17, 33, 1000, 20000, 131072):
+        for distinct in (1, 2, 7, 100, 10 ** 9):
+            for threads in (2, 5, 16):
+                assert L.madicp_debug_sort_check(n, 11, distinct, threads) == 0, (n, distinct, threads)

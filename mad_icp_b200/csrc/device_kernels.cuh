@@ -232,10 +232,10 @@ struct GnArgs {
 
 // Persistent cooperative grid (all CTAs co-resident), one software grid barrier per round: CTAs
 // publish their partial, take a release-ticket, the last one folds / exchanges / solves and
-// publishes the new pose and st->round; the others poll st->round with L2-coherent relaxed loads.
-// No acquire fence is ever executed in the loop, so L1 is not invalidated between rounds; everything
-// that crosses SMs (partials, pose, flags) is read with ld.relaxed.gpu (L2) behind a control
-// dependency on the flag.
+// publishes the new pose as 12 epoch-tagged LL cells (value and flag in one 16-byte store); twelve
+// threads of every other CTA spin on one cell each with a volatile 16-byte load, so the wake-up is a
+// single L2 round trip.  No acquire fence is ever executed in the loop, so L1 is not invalidated between
+// rounds; everything that crosses SMs (partials, pose) is read with L2-coherent loads.
 //
 // Work distribution.  CTA b owns the moving leaves [L*b/G, L*(b+1)/G) -- a contiguous stretch of the
 // scan's own tree in DFS order, i.e. one spatial region -- and registers them against EVERY keyframe:

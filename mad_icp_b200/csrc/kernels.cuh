@@ -118,7 +118,7 @@ struct __align__(16) LLCell {
 
 struct GnState {
   int ticket;     // monotonically increasing arrival counter (reset by the host before a launch)
-  int round;      // number of completed rounds (flag the CTAs spin on)
+  int round;      // unused since the pose carries its own flag (X_ll); kept so the launch header keeps its layout
   int n_matched;  // matched moving leaves in the last round
   int pad;
   double X_in[12];  // initial pose: [ticket .. X_in] is ONE host-to-device copy per registration

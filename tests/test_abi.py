@@ -45,3 +45,23 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle" not in txt.lower(), f"{f} mentions the oracle: product code must not touch it"
+
+
+def test_host_entry_points_reject_bad_arguments(built):
+    """madtree_build / madicp_deskew are host code: their argument checks run without a GPU."""
+    import ctypes as C
+    import numpy as np
+    L = _capi.lib()
+    pts = np.zeros((4, 3))
+    dp = C.POINTER(C.c_double)
+    T = np.eye(4)[:3].copy()
+    ok = lambda a: a.ctypes.data_as(dp)
+    assert L.madicp_deskew(None, 4, ok(T), ok(T), 10.0, 1) < 0
+    assert L.madicp_deskew(ok(pts), 0, ok(T), ok(T), 10.0, 1) < 0
+    assert L.madicp_deskew(ok(pts), 4, ok(T), ok(T), 0.0, 1) < 0
+    assert L.madicp_deskew(ok(pts), 4, None, ok(T), 10.0, 1) < 0
+    assert b"madicp_deskew" in L.madicp_last_error()
+    assert L.madicp_deskew(ok(pts), 4, ok(T), ok(T), 10.0, 1) == 0  # identity motion, four points at the origin
+    out = C.c_void_p()
+    assert L.madtree_build(None, 4, 0.2, 0.1, 1, C.byref(out)) < 0
+    assert L.madtree_build(ok(pts), 0, 0.2, 0.1, 1, C.byref(out)) < 0

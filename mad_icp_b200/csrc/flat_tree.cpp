@@ -630,6 +630,7 @@ int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_mi
   auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
     return std::chrono::duration<double, std::milli>(b - a).count();
   };
+  madicp_host::HotScope hot;  // sections follow each other for the whole build; the numbering passes included
   const auto t0 = now();
   madtree* t = tree_from_cache();
   if (!t) t = new (std::nothrow) madtree;

@@ -16,6 +16,16 @@
 
 namespace madicp_host {
 
+// > 0 while a library call that strings several parallel sections together is running (HotScope):
+// workers then keep spinning through its serial stretches instead of going to sleep between sections.
+inline std::atomic<int> g_hot{0};
+struct HotScope {
+  HotScope() { g_hot.fetch_add(1, std::memory_order_relaxed); }
+  ~HotScope() { g_hot.fetch_sub(1, std::memory_order_relaxed); }
+  HotScope(const HotScope&) = delete;
+  HotScope& operator=(const HotScope&) = delete;
+};
+
 // Worker pool: run(n, fn) executes fn(i) for i in [0,n) on the workers plus the calling thread and
 // returns when all are done.  A build issues a few dozen short parallel sections back to back, so the
 // workers spin briefly between sections before they go to sleep.
@@ -90,7 +100,8 @@ private:
         if ((++spin & 255) == 0) {
           const auto nowt = std::chrono::steady_clock::now();
           if (spin == 256) idle_since = nowt;
-          if (nowt - idle_since > std::chrono::nanoseconds(kSpinNs)) {
+          if (nowt - idle_since > std::chrono::nanoseconds(kSpinNs) &&
+              (g_hot.load(std::memory_order_relaxed) == 0 || nowt - idle_since > std::chrono::nanoseconds(40 * kSpinNs))) {
             std::unique_lock<std::mutex> lk(mu_);
             cv_.wait(lk, [&]() { return gen_.load(std::memory_order_acquire) != seen; });
           }

@@ -184,6 +184,7 @@ extern "C" int madicp_deskew(double* points_xyz, int64_t n, const double T_prev[
   const double vel[6] = {rel.m[3] / ts, rel.m[7] / ts, rel.m[11] / ts, w[0] / ts, w[1] / ts, w[2] / ts};
   const double resolution = 2 * M_PI / double(kChunks), delta = ts / double(kChunks - 1);
 
+  madicp_host::HotScope hot;  // the serial first splits of the sort sit between two parallel sections
   const bool timing = std::getenv("MADTREE_TIMING") != nullptr;
   auto now = []() { return std::chrono::steady_clock::now(); };
   auto ms = [](std::chrono::steady_clock::time_point x, std::chrono::steady_clock::time_point y) {

@@ -150,3 +150,24 @@ def test_deskew_is_the_references(oracle, ref):
     assert np.array_equal(mine, pr.deskew(pts, Ta, Tb))
     assert np.abs(mine - pts).max() > 1e-3  # it did something
     L.orc_pipeline_free(po)
+
+
+@pytest.mark.parametrize("b_max,b_min,rho_ker,b_ratio", [(0.1, 0.05, 0.05, 0.01), (0.4, 0.2, 0.3, 0.05), (0.2, 0.1, 1e-3, 0.0)])
+def test_parameter_sweep_is_the_references(oracle, ref, b_max, b_min, rho_ker, b_ratio):
+    """Other leaf sizes, kernel widths and gate ratios than the defaults: trees and every GN round."""
+    case = synth.registration_case(K=2, beams=16, azimuths=512, seed=9)
+    kfo, kfr = [], []
+    for s, P in zip(case["scans"], case["kf_poses"]):
+        a, b = oracle.OracleTree(s, b_max=b_max, b_min=b_min), ref.ReferenceTree(s, b_max=b_max, b_min=b_min)
+        _same_tree(a, b)
+        a.apply_transform(P)
+        b.apply_transform(P)
+        kfo.append(a)
+        kfr.append(b)
+    mo = oracle.OracleTree(case["query"], b_max=b_max, b_min=b_min)
+    mr = ref.ReferenceTree(case["query"], b_max=b_max, b_min=b_min)
+    ro = oracle.icp_run(kfo, mo, case["T_guess"], iters=6, min_ball=b_max, rho_ker=rho_ker, b_ratio=b_ratio, num_threads=2,
+                        record_matches=False)
+    rr = ref.icp_run(kfr, mr, case["T_guess"], iters=6, min_ball=b_max, rho_ker=rho_ker, b_ratio=b_ratio, num_threads=2)
+    for k in ("X_hist", "H_hist", "b_hist", "X", "matched"):
+        assert np.array_equal(ro[k], rr[k], equal_nan=True) if ro[k].dtype.kind == "f" else np.array_equal(ro[k], rr[k]), k

@@ -163,13 +163,15 @@ def cpu_reference_leg(a, steps, warmup, budget_s=None):
         for _ in range(warmup):
             M.icp_run(trees, q, case["T_guess"], iters=a.iters, num_threads=threads, record=False)
         secs, t0 = [], time.perf_counter()
-        arm_steps = max(1, steps // len(arms))
-        for i in range(arm_steps):
-            secs.append(M.icp_run(trees, q, case["T_guess"], iters=a.iters, num_threads=threads, record=False)["seconds"])
+        for i in range(max(1, steps)):  # every CPU build runs the SAME number of steps (bounded by its budget share)
+            last = M.icp_run(trees, q, case["T_guess"], iters=a.iters, num_threads=threads, record=False)
+            secs.append(last["seconds"])
             if budget_s is not None and time.perf_counter() - t0 > budget_s / len(arms) and i >= 2:
                 break
         total = float(sum(secs))
-        results.append(dict(kind=kind, value=len(secs) / total, seconds=total, steps=len(secs), L=q.num_leaves))
+        results.append(dict(kind=kind, value=len(secs) / total, seconds=total, steps=len(secs), L=q.num_leaves,
+                            X=np.asarray(last["X"], dtype=np.float64)[:3].copy(), n_matched=int(np.count_nonzero(last["matched"])),
+                            matched=np.asarray(last["matched"]).astype(np.uint8).copy()))
         del trees, q
     best = max(results, key=lambda r: r["value"])
     names = {"reference": "reference sources (mad_tree.cpp, mad_icp.cpp) built against oracle/eigen_standin",
@@ -177,25 +179,67 @@ def cpu_reference_leg(a, steps, warmup, budget_s=None):
     others = "; ".join(f"{names[r['kind']]}: {r['value']:.2f} scans/s over {r['steps']} registrations"
                        for r in results if r is not best)
     return dict(value=best["value"], seconds=best["seconds"], steps=best["steps"], cores=threads, kind=best["kind"],
-                host_cores=os.cpu_count(), L=best["L"],
+                host_cores=os.cpu_count(), L=best["L"], X=best["X"], n_matched=best["n_matched"], matched=best["matched"],
                 sample=f"{best['steps']} full registrations ({a.iters} GN iters, {K_MODEL} keyframes, {best['L']} moving "
                        f"leaves), trees pre-built, {threads} OpenMP threads over keyframes; {names[best['kind']]} "
                        f"(the faster of the CPU builds" + (f"; {others})" if others else ")"))
 
 
+def pose_error(Xa, Xb):
+    """(rotation angle [rad], translation distance [m]) between two 3x4 poses."""
+    Xa, Xb = np.asarray(Xa)[:3], np.asarray(Xb)[:3]
+    dR = Xa[:, :3] @ Xb[:, :3].T
+    s = 0.5 * np.linalg.norm([dR[2, 1] - dR[1, 2], dR[0, 2] - dR[2, 0], dR[1, 0] - dR[0, 1]])
+    return float(np.arctan2(s, (np.trace(dR) - 1.0) / 2.0)), float(np.linalg.norm(Xa[:, 3] - Xb[:, 3]))
+
+
 def run_reference(a, rank):
+    """--impl reference.  N = 1: one CPU registration loop (16 OpenMP threads over keyframes).  N > 1: the GPU arm
+    runs N replicas (N scans in flight), so the CPU arm runs N replicas too -- N concurrent processes, each with its
+    own 16 threads pinned to its own cores -- and reports their aggregate: like for like."""
     if rank != 0:
         return
-    r = cpu_reference_leg(a, a.steps, max(a.warmup, 1), budget_s=150.0)
-    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "scans/s", "n_gpus": a.gpus,
-            "steps": r["steps"], "warmup": a.warmup, "ms_per_step": 1e3 * r["seconds"] / r["steps"],
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(a, 1), "impl_note": "the reference's OpenMP registration loop on the "
+    n = max(1, a.gpus)
+    if n == 1:
+        r = cpu_reference_leg(a, a.steps, max(a.warmup, 1), budget_s=150.0)
+        value, steps, seconds, note = r["value"], r["steps"], r["seconds"], ""
+    else:
+        import subprocess
+        threads = min(16, os.cpu_count() or 1)
+        procs = []
+        for i in range(n):
+            env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_PORT",
+                                                                     "MASTER_ADDR", "TORCHELASTIC_RUN_ID")}
+            if (os.cpu_count() or 1) >= threads * n:
+                env["OMP_PLACES"] = "{%d:%d}" % (threads * i, threads)
+                env["OMP_PROC_BIND"] = "close"
+            else:
+                env["OMP_PROC_BIND"] = "false"
+            procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--gpus", "1",
+                                           "--steps", str(a.steps), "--warmup", str(a.warmup), "--iters", str(a.iters),
+                                           "--beams", str(a.beams), "--azimuths", str(a.azimuths)],
+                                          env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True))
+        lines = []
+        for p in procs:
+            out, _ = p.communicate(timeout=1200)
+            lines.append(json.loads([ln for ln in out.splitlines() if ln.startswith("{")][-1]))
+        r = dict(lines[0]["cpu_baseline"], steps=lines[0]["steps"])
+        r["sample"] = f"{n} concurrent CPU replicas, each: " + r["sample"]
+        r["cores"] = threads * n
+        value = float(sum(ln["value"] for ln in lines))  # replicas run concurrently: aggregate scans/s of the box
+        steps = int(sum(ln["steps"] for ln in lines))
+        seconds = max(ln["ms_per_step"] * ln["steps"] for ln in lines) * 1e-3
+        r["value"] = value
+        note = f"; {n} concurrent replicas x {threads} threads (the GPU arm at N={n} is {n} replicas too)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": a.gpus,
+            "steps": steps, "warmup": a.warmup, "ms_per_step": 1e3 * seconds / max(steps, 1) * (n if n > 1 else 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a, n), "impl_note": "the reference's OpenMP registration loop on the "
                        "host cores; kind=reference: its own sources built against an Eigen stand-in (no Eigen in "
-                       "the image), kind=port: the restatement"},
-            "cpu_baseline": {"value": r["value"], "unit": "scans/s", "cores": r["cores"], "kind": r["kind"],
-                             "sample": r["sample"], "host_cores": r["host_cores"]},
-            "e2e": {"value": r["value"], "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                       "the image), kind=port: the restatement" + note},
+            "cpu_baseline": {"value": value, "unit": "scans/s", "cores": r["cores"], "kind": r["kind"],
+                             "sample": r["sample"], "host_cores": r.get("host_cores", os.cpu_count())},
+            "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -203,6 +247,8 @@ def run_reference(a, rank):
 # --------------------------------------------------------------------------------------------
 def main():
     a = parse()
+    if int(os.environ.get("WORLD_SIZE", "1")) == 1 or a.impl == "reference":
+        os.environ.setdefault("OMP_PROC_BIND", "close")  # the CPU arm's thread placement
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -333,10 +379,12 @@ def main():
         sh.comm_connect(rank, world, [bytes(t.cpu().tolist()) for t in allh])
         dist.barrier()
         sh_ms, _ = timed_resident(sh)
-        sh_res = sh.register_fetch()
+        sh_res = sh.register_fetch(want_matched=True)
         dpose = float(np.abs(sh_res["X"] - res["X"]).max())
         sharded = {"value": a.steps / (sh_ms * 1e-3), "unit": "scans/s", "ms_per_scan": sh_ms / a.steps,
                    "scaling": "strong", "max_abs_pose_diff_vs_single_gpu": dpose,
+                   "n_matched_equal_vs_single_gpu": int(sh_res["n_matched"]) == int(res["n_matched"]),
+                   "matched_flags_equal_vs_single_gpu": bool(np.array_equal(sh_res["matched"], res["matched"])),
                    "note": f"one scan, keyframe slot s on rank s%{n}, in-kernel NVLink all-reduce of H/b each GN round"}
         sh.close()
 
@@ -363,11 +411,20 @@ def main():
               "note": "model (record bytes above) is L2-resident after the first round, so DRAM traffic << algorithmic "
                       "bytes and frac can exceed 1; see DESIGN.md section 6"}
 
-    cpu = None
+    cpu, parity = None, None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         r = cpu_reference_leg(a, steps=1000, warmup=1, budget_s=a.cpu_seconds)
         cpu = {"value": r["value"], "unit": "scans/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
                "host_cores": r["host_cores"]}
+        # in-run parity guard: the GPU result of the timed workload against the CPU leg's, same inputs
+        ang, dt = pose_error(res["X"], r["X"])
+        parity = {"against": r["kind"], "pose_rad": ang, "pose_m": dt, "tol_rad": 1e-5, "tol_m": 1e-4,
+                  "n_matched_gpu": int(res["n_matched"]), "n_matched_cpu": int(r["n_matched"]),
+                  "n_matched_equal": int(res["n_matched"]) == int(r["n_matched"]),
+                  "matched_flags_equal": bool(res["matched"] is not None and np.array_equal(res["matched"] != 0, r["matched"] != 0)),
+                  "ok": bool(ang < 1e-5 and dt < 1e-4 and int(res["n_matched"]) == int(r["n_matched"]))}
+        if not parity["ok"]:
+            print(f"bench.py: PARITY FAILURE against the CPU {r['kind']}: {parity}", file=sys.stderr, flush=True)
 
     if rank == 0:
         clocks = sampler.summary()
@@ -387,6 +444,8 @@ def main():
             line["roofline"] = rf
         if cpu:
             line["cpu_baseline"] = cpu
+        if parity:
+            line["parity"] = parity
         if sharded:
             line["sharded"] = sharded
         print(json.dumps(line), flush=True)

@@ -118,7 +118,7 @@ void ref_tree_search(void* t, const double* q, int n, int* ordinal_out) {
 // Outputs as orc_icp_run: X_hist = pose before each iteration, H/b after updateState (H column-major).
 double ref_icp_run(void** keyframes, int K, void* moving, const double* X0, int iters, double min_ball, double rho_ker,
                    double b_ratio, int num_threads, double* X_final, double* X_hist, double* H_hist, double* b_hist,
-                   unsigned char* matched) {
+                   unsigned char* matched, int* idx_hist) {
   std::deque<Frame*> frames;
   for (int k = 0; k < K; ++k) {
     Frame* f = new Frame;
@@ -131,9 +131,22 @@ double ref_icp_run(void** keyframes, int K, void* moving, const double* X0, int 
   MADicp icp(min_ball, rho_ker, b_ratio, num_threads);
   icp.setMoving(mv->leaves);
   icp.init(iso_from_rowmajor12(X0));
-  const auto t0 = std::chrono::steady_clock::now();
+  double seconds = 0.0;
   for (int it = 0; it < iters; ++it) {
     if (X_hist) iso_to_rowmajor12(icp.X_, X_hist + 12 * it);
+    if (idx_hist) {  // the reference's OWN correspondences of this round (mad_icp.cpp:78-79), as getLeafs ordinals;
+                     // outside the timed region
+      const size_t L = mv->leaves.size();
+      for (int k = 0; k < K; ++k) {
+        TreeHandle* kf = static_cast<TreeHandle*>(keyframes[k]);
+#pragma omp parallel for
+        for (size_t q = 0; q < L; ++q) {
+          const Eigen::Vector3d moving_leaf = icp.X_ * mv->leaves[q]->mean_;
+          idx_hist[(size_t(it) * K + k) * L + q] = kf->ordinal.find(kf->root->bestMatchingLeafFast(moving_leaf))->second;
+        }
+      }
+    }
+    const auto t0 = std::chrono::steady_clock::now();
     if (it == iters - 1)
       for (MADtree* l : mv->leaves) l->matched_ = false;
     icp.resetAdders();
@@ -142,15 +155,15 @@ double ref_icp_run(void** keyframes, int K, void* moving, const double* X0, int 
       icp.update(frame->tree_);
     }
     icp.updateState();
+    seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (H_hist) std::memcpy(H_hist + 36 * it, icp.H_adder_.data(), sizeof(double) * 36);
     if (b_hist) std::memcpy(b_hist + 6 * it, icp.b_adder_.data(), sizeof(double) * 6);
   }
-  const auto t1 = std::chrono::steady_clock::now();
   iso_to_rowmajor12(icp.X_, X_final);
   if (matched)
     for (size_t q = 0; q < mv->leaves.size(); ++q) matched[q] = mv->leaves[q]->matched_ ? 1 : 0;
   for (Frame* f : frames) delete f;
-  return std::chrono::duration<double>(t1 - t0).count();
+  return seconds;
 }
 
 void* ref_pipeline_create(double sensor_hz, int deskew, double b_max, double rho_ker, double p_th, double b_min,

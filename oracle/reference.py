@@ -53,7 +53,7 @@ def lib():
         L.ref_tree_search.argtypes = [C.c_void_p, _dp, C.c_int, _ip]
         L.ref_icp_run.restype = C.c_double
         L.ref_icp_run.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, _dp, C.c_int, C.c_double, C.c_double,
-                                  C.c_double, C.c_int, _dp, _dp, _dp, _dp, _bp]
+                                  C.c_double, C.c_int, _dp, _dp, _dp, _dp, _bp, _ip]
         L.ref_pipeline_create.restype = C.c_void_p
         L.ref_pipeline_create.argtypes = [C.c_double, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                                           C.c_double, C.c_int, C.c_int, C.c_int]
@@ -112,8 +112,11 @@ class ReferenceTree:
         return idx
 
 
-def icp_run(keyframes, moving, X0, iters=15, min_ball=0.2, rho_ker=0.1, b_ratio=0.02, num_threads=1, record=True):
-    """The loop of pipeline.cpp:166-193 over the reference's MADicp; same outputs as oracle.icp_run."""
+def icp_run(keyframes, moving, X0, iters=15, min_ball=0.2, rho_ker=0.1, b_ratio=0.02, num_threads=1, record=True,
+            record_idx=False):
+    """The loop of pipeline.cpp:166-193 over the reference's MADicp; same outputs as oracle.icp_run.
+    record_idx: also idx_hist[it, k, q] = getLeafs ordinal of the leaf the reference's bestMatchingLeafFast
+    returns for moving leaf q in keyframe k at the pose of round `it` (computed outside the timed region)."""
     K, L = len(keyframes), moving.num_leaves
     X0 = _pose12(X0)
     Xf = np.empty((3, 4))
@@ -121,10 +124,13 @@ def icp_run(keyframes, moving, X0, iters=15, min_ball=0.2, rho_ker=0.1, b_ratio=
     Hh = np.empty((iters, 36)) if record else None
     bh = np.empty((iters, 6)) if record else None
     m = np.empty(L, np.uint8)
+    ih = np.empty((iters, K, L), np.int32) if record_idx else None
     arr = (C.c_void_p * K)(*[t._h for t in keyframes])
     secs = lib().ref_icp_run(arr, K, moving._h, _d(X0), iters, min_ball, rho_ker, b_ratio, num_threads, _d(Xf), _d(Xh),
-                             _d(Hh), _d(bh), _b(m))
+                             _d(Hh), _d(bh), _b(m), _i(ih))
     out = dict(X=Xf, seconds=secs, matched=m)
+    if record_idx:
+        out["idx_hist"] = ih
     if record:
         out.update(X_hist=Xh, H_hist=Hh.reshape(iters, 6, 6).transpose(0, 2, 1).copy(), b_hist=bh)
     return out

@@ -9,6 +9,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.distributed as dist
 from mad_icp_b200 import FlatTree, Registrar, synth
 
+NO_TIMING = "--no-timing" in sys.argv
+sys.argv = [a for a in sys.argv if a != "--no-timing"]
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 beams = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 az = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
@@ -62,8 +64,12 @@ def timed(r, n=50):
     t = torch.tensor([a.elapsed_time(b) / n * 1e3], device=f"cuda:{lr}")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
-t_shard, t_single = timed(reg), timed(ref)
-if rank == 0:
+if not NO_TIMING:
+  t_shard, t_single = timed(reg), timed(ref)
+  if rank == 0:
     print(f"world={world} K={K} L={means.shape[0]}: sharded {t_shard:.1f} us/scan, single-GPU full model {t_single:.1f} us/scan, speed-up {t_single / t_shard:.2f}x")
-    print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL", flush=True)
+okt = torch.tensor([int(ok)], device=f"cuda:{lr}")
+dist.all_reduce(okt, op=dist.ReduceOp.MIN)  # every rank's own checks must hold
+if rank == 0:
+    print("MULTI_GPU_CHECK", "PASS" if int(okt.item()) else "FAIL", flush=True)
 dist.barrier(); dist.destroy_process_group()

@@ -194,7 +194,7 @@ def test_full_size_cfg3_indices_and_pose(full16, oracle):
 def test_full_size_cfg3_against_the_compiled_reference(full16):
     """The same check with the reference's OWN sources on the CPU side (oracle/_ref: mad_tree.cpp and
     mad_icp.cpp compiled against oracle/eigen_standin, shipped prebuilt; tests/test_reference_pin.py):
-    GPU correspondences at the reference's poses, H/b at those poses, final pose."""
+    GPU correspondences == the reference's own at every round / keyframe / leaf, H/b at its poses, final pose."""
     from oracle import reference as R
     if not os.path.exists(R._SO):
         pytest.skip("oracle/_ref not shipped (it is built where /root/reference exists)")
@@ -205,13 +205,13 @@ def test_full_size_cfg3_against_the_compiled_reference(full16):
         t.apply_transform(P)
         rtrees.append(t)
     rq = R.ReferenceTree(c["query"])
-    ref = R.icp_run(rtrees, rq, c["T_guess"], iters=10, num_threads=min(16, R.max_threads()))
-    for it in (0, 5, 9):
+    ref = R.icp_run(rtrees, rq, c["T_guess"], iters=10, num_threads=min(16, R.max_threads()), record_idx=True)
+    # the reference's OWN correspondences (its bestMatchingLeafFast on its own X_ * mean_, mad_icp.cpp:78-79),
+    # every round, every keyframe, every moving leaf: bit-exact, no sampling
+    for it in range(10):
         idx = reg.search(ref["X_hist"][it])
-        # the reference does not record correspondences; its leaves do: compare the leaf each query got
-        for k in (0, 7, 15):
-            q = (ref["X_hist"][it][:, :3] @ _moving_means(rq).T).T + ref["X_hist"][it][:, 3]
-            assert (idx[k] == rtrees[k].search(q)).mean() > 0.999  # q is recomputed in numpy: last-bit ties
+        assert idx.shape == ref["idx_hist"][it].shape == (16, rq.num_leaves)
+        assert (idx == ref["idx_hist"][it]).all(), f"round {it}: {(idx != ref['idx_hist'][it]).sum()} differ"
         H, b, _ = reg.linearize(ref["X_hist"][it])
         _check_Hb(H, b, ref["H_hist"][it], ref["b_hist"][it], tol=10 * HB_REL)
     out = reg.register(c["T_guess"], iters=10)

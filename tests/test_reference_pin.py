@@ -77,10 +77,12 @@ def test_registration_loop_is_the_references(oracle, ref, K, threads):
         kfo.append(a)
         kfr.append(b)
     mo, mr = oracle.OracleTree(case["query"]), ref.ReferenceTree(case["query"])
-    ro = oracle.icp_run(kfo, mo, case["T_guess"], iters=10, num_threads=threads, record_matches=False)
-    rr = ref.icp_run(kfr, mr, case["T_guess"], iters=10, num_threads=threads)
+    ro = oracle.icp_run(kfo, mo, case["T_guess"], iters=10, num_threads=threads)
+    rr = ref.icp_run(kfr, mr, case["T_guess"], iters=10, num_threads=threads, record_idx=True)
     for k in ("X_hist", "H_hist", "b_hist", "X", "matched"):
         assert np.array_equal(ro[k], rr[k]), k
+    # the correspondences themselves: the reference's bestMatchingLeafFast on its own X_ * mean_, every round
+    assert np.array_equal(np.asarray(ro["idx_hist"]), rr["idx_hist"])
 
 
 def test_four_walls_demo_is_the_references(oracle, ref):

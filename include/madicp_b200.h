@@ -77,6 +77,12 @@ int madtree_apply_transform(madtree_t* t, const double X[12]);
 int madtree_leaves(const madtree_t* t, double* means, double* normals, double* bbox0, int32_t* num_points);
 /* Breadth-first 64-byte records (see madtree_rec_t); valid until the next apply_transform/free. */
 const madtree_rec_t* madtree_records(const madtree_t* t);
+/* Depth of the tree + 1, and the level table: out[d] = breadth-first index of the first node of depth d,
+ * out[levels] = node count (cap >= levels + 1).  Returns the number of levels. */
+int madtree_num_levels(const madtree_t* t);
+int madtree_level_offsets(const madtree_t* t, int32_t* out, int cap);
+/* getLeafs order -> breadth-first record index, L entries.  Returns L. */
+int madtree_leaf_records(const madtree_t* t, int32_t* out);
 /* Full per-node dump in DFS pre-order for audits/tests: mean n x 3, eigenvectors n x 9 (column-major),
  * bbox n x 3, num_points n, left/right pre-order index (-1 on leaves), leaf_ordinal (-1 on internal). */
 int madtree_export(const madtree_t* t, double* mean, double* eigenvectors, double* bbox, int32_t* num_points,
@@ -100,6 +106,12 @@ void* madicp_get_stream(const madicp_ctx_t* ctx);
 /* Upload a (map-frame, i.e. already applyTransform-ed) keyframe tree into model slot `slot`
  * (replaces pushing a Frame onto keyframes_, odometry/pipeline.cpp:250-257). Overwrites the slot. */
 int madicp_put_keyframe(madicp_ctx_t* ctx, int slot, const madtree_t* tree);
+/* The same for a SENSOR-frame tree plus its pose: MADtree::applyTransform(R, t) (tools/mad_tree.cpp:165-172,
+ * called at odometry/pipeline.cpp:224) runs on the device, fused into the upload, with the reference's operand
+ * order and no FMA -- bit-identical to madtree_apply_transform + madicp_put_keyframe.  X = NULL: no transform.
+ * Asynchronous on the context's stream; the host tree may be freed as soon as the call returns. */
+int madicp_put_keyframe_transformed(madicp_ctx_t* ctx, int slot, const madtree_t* tree, const double X[12]);
+/* Caller-supplied records (validated: one breadth-first tree, siblings adjacent, ordinals a permutation). */
 int madicp_put_keyframe_records(madicp_ctx_t* ctx, int slot, const madtree_rec_t* recs, int n_nodes, int n_leaves);
 int madicp_drop_keyframe(madicp_ctx_t* ctx, int slot); /* keyframes_.pop_front(), pipeline.cpp:253-256 */
 int madicp_num_keyframes(const madicp_ctx_t* ctx);     /* active slots on THIS device */
@@ -110,6 +122,50 @@ int madicp_keyframe_leaves(const madicp_ctx_t* ctx, int slot); /* leaves in slot
 /* MADicp::setMoving (mad_icp.cpp:51-53): sensor-frame means of the current scan's leaves, in
  * getLeafs order, L x 3 doubles on the HOST; copied to the device. */
 int madicp_set_moving(madicp_ctx_t* ctx, const double* means_xyz, int L);
+/* Wait for everything enqueued on the context's stream. */
+int madicp_synchronize(madicp_ctx_t* ctx);
+
+/* ---------------- device-resident MAD-trees ----------------------------------
+ * A madtree_gpu_t is a sensor-frame MAD-tree living in device memory of ONE context: breadth-first records,
+ * level table, getLeafs table.  The scan's tree never has to exist on the host: build (or upload) -> the
+ * scan's leaves become the moving leaves -> on promotion the tree is transformed and laid out in a keyframe
+ * slot, all on the device, all asynchronous on the context's stream. */
+typedef struct madtree_gpu madtree_gpu_t;
+/* MADtree::MADtree(...) (tools/mad_tree.cpp:33-130) ON THE DEVICE: points_xyz n x 3 doubles on the host (one
+ * H2D copy), same tree bit for bit as madtree_build / the reference (split order, NaN nodes, normal inheritance).
+ * The three libm calls per node of Eigen's computeDirect (atan2, cos, sin: glibc is not correctly rounded, so no
+ * device implementation can reproduce its bits) are served by the host between two kernels of a level. */
+int madtree_gpu_build(madicp_ctx_t* ctx, const double* points_xyz, int64_t n, double b_max, double b_min,
+                      madtree_gpu_t** out);
+/* The same from a cloud already on the device (madicp_ingest). */
+int madtree_gpu_build_resident(madicp_ctx_t* ctx, double b_max, double b_min, madtree_gpu_t** out);
+/* Upload of a host-built tree (records + tables), asynchronous. */
+int madtree_gpu_upload(madicp_ctx_t* ctx, const madtree_t* tree, madtree_gpu_t** out);
+void madtree_gpu_free(madtree_gpu_t* t);
+int madtree_gpu_num_nodes(const madtree_gpu_t* t);
+int madtree_gpu_num_leaves(const madtree_gpu_t* t);
+int madtree_gpu_num_levels(const madtree_gpu_t* t);
+/* Device -> host (synchronises): the breadth-first records and/or the getLeafs table.  Either may be NULL. */
+int madtree_gpu_download(const madtree_gpu_t* t, madtree_rec_t* recs_out, int32_t* leaf_records_out);
+/* Audit dump of a DEVICE-BUILT tree in breadth-first order: mean n x 3, eigenvectors n x 9 (column-major), bbox
+ * n x 3, num_points n (any may be NULL).  Valid for the most recently built tree of the context.  Synchronises. */
+int madtree_gpu_export(const madtree_gpu_t* t, double* mean, double* eigenvectors, double* bbox, int32_t* num_points);
+/* MADicp::setMoving with the leaves of a device tree (no host copy of the means). */
+int madicp_set_moving_tree(madicp_ctx_t* ctx, const madtree_gpu_t* t);
+/* The current moving-leaf means back on the host (L x 3), e.g. for Pipeline::currentLeaves.  Returns L. */
+int madicp_get_moving(madicp_ctx_t* ctx, double* means_out, int cap_leaves);
+/* Keyframe promotion from a device tree: D2D copy + applyTransform(X) (NULL: none) + layout, no host sync. */
+int madicp_put_keyframe_tree(madicp_ctx_t* ctx, int slot, const madtree_gpu_t* t, const double X[12]);
+
+/* Ingest of a raw scan on the device (odometry/pipeline.cpp:79-123 and the float32 -> float64
+ * conversion of the readers / pybind/eigen_stl_bindings.h:44-60).  xyz: n x 3 float32 (is_f32 != 0) or float64 on
+ * the host, copied as is.  deskew == 0: conversion only.  deskew != 0: Pipeline::deskew -- the azimuth sort (the
+ * reference's std::sort permutation, ties included) and the <= 1024 chunk poses come from the host
+ * (threaded; atan2/sin/cos are glibc's), the gather by that permutation, the conversion and the per-chunk rigid
+ * transform (reference operand order, no FMA) run on the device.  The result is the device-resident cloud that
+ * madtree_gpu_build_resident consumes; points_out (nullable, n x 3 doubles) receives a copy. */
+int madicp_ingest(madicp_ctx_t* ctx, const void* xyz, int64_t n, int is_f32, int deskew, const double T_prev[12],
+                  const double T_now[12], double sensor_hz, int num_threads, double* points_out);
 
 /* K1 only -- MADtree::bestMatchingLeafFast (tools/mad_tree.cpp:144-152) of X*mean for every moving
  * leaf against every active keyframe.  out_ordinals: K_active x L int32 on the host (row k = k-th
@@ -137,6 +193,14 @@ int madicp_register(madicp_ctx_t* ctx, int iters, double X_inout[12], double H_l
 int madicp_register_async(madicp_ctx_t* ctx, int iters, const double X0[12]);
 int madicp_register_fetch(madicp_ctx_t* ctx, double X[12], double H_last[36], double b_last[6], uint8_t* matched_last,
                           int* n_matched);
+/* The same plus Frame::weight_ = det(H^-1) of the last round's H (odometry/pipeline.cpp:223), computed by the
+ * solve thread on the device. */
+int madicp_register_fetch_weight(madicp_ctx_t* ctx, double X[12], double H_last[36], double b_last[6],
+                                 uint8_t* matched_last, int* n_matched, double* weight);
+/* A loop the `realtime` budget cut short (odometry/pipeline.cpp:167-169): `iters` < MAX_ICP_ITS rounds ran, so the
+ * clear of the matched flags that belongs to round MAX_ICP_ITS-1 (pipeline.cpp:172-176) never happened and the
+ * flags are the union over all rounds. */
+int madicp_register_partial_async(madicp_ctx_t* ctx, int iters, const double X0[12]);
 /* Per-round poses of the last madicp_register* call: (iters+1) x 12 doubles (X before round i; the
  * last row is the final pose).  Debug/parity aid. */
 int madicp_register_trace(madicp_ctx_t* ctx, double* X_trace, int max_rounds);
@@ -148,10 +212,6 @@ int madicp_register_trace(madicp_ctx_t* ctx, double* X_trace, int max_rounds);
  * threads; no device work. */
 int madicp_deskew(double* points_xyz, int64_t n, const double T_prev[12], const double T_now[12], double sensor_hz,
                   int num_threads);
-
-/* Diagnostic for madicp_deskew's sort: n pseudo-random keys over `distinct` values, sorted by std::sort
- * and by the threaded restatement of it; returns how many positions of the two permutations differ (0). */
-int64_t madicp_debug_sort_check(int64_t n, uint32_t seed, int64_t distinct, int num_threads);
 
 /* MADtreeWrapper::searchCloud / searchCloudDist (pybind/tools/mad_tree_wrapper.h:48-67): nearest-leaf
  * search of n host query points in slot `slot`.  Any output may be NULL: ordinals n, points n x 3
@@ -176,24 +236,12 @@ int madicp_comm_export(madicp_ctx_t* ctx, void* handle_out /* 64 bytes */);
 int madicp_comm_connect(madicp_ctx_t* ctx, int rank, int world, const void* all_handles /* world x 64 bytes */);
 int madicp_comm_world(const madicp_ctx_t* ctx);
 
-/* ================================ tuning / debug (not part of the drop-in surface) ============ */
-/* Per-round SM-clock stamps of the persistent kernel: enable != 0 switches recording on for the
- * following launches; out (nullable) receives rounds x 8 int64 of the LAST launch:
- * [0] item phase of CTA 0, [1] round start -> last CTA arrived, [2] fold of the per-CTA partials,
- * [3] peer exchange + matched count, [4] solve + publish (cycles).  Returns rows written. */
-int madicp_debug_timing(madicp_ctx_t* ctx, int enable, int64_t* out, int max_rounds);
-/* Item-phase cycles of every CTA for the rounds of the last launch (rounds x grid int64, debug timing
- * must be on).  Returns the grid size. */
-int madicp_debug_cta_cycles(madicp_ctx_t* ctx, int64_t* out, int cap);
-/* Tree-walk variant: 0 breadth-first shadows + link loads, 1 implicit-heap shadows,
- * 2 / 3 heap + 2- / 3-level look-ahead L1 prefetch, 4 (default) four-ary heap (two binary levels per
- * 64-byte record).  All variants take identical decisions. */
-int madicp_set_walk_mode(madicp_ctx_t* ctx, int mode);
-/* Shape of the persistent kernel: threads per CTA and resident CTAs per SM; supported pairs are
- * (1024,1) default, (768,1), (512,1), (512,2), (256,2), (256,3), (256,4); env MADICP_GN_SHAPE="t,c"
- * selects one at create time.  By default the library picks among the one-CTA-per-SM shapes per
- * launch from the item count; threads_per_cta = 0 restores that.  Returns the CTAs per SM in effect. */
-int madicp_set_gn_grid(madicp_ctx_t* ctx, int threads_per_cta, int ctas_per_sm);
+/* Measures, on the resident model and moving leaves, the per-pass cost of each persistent-kernel shape the
+ * automatic choice considers (a few one-round registrations each) and uses it from then on.  Optional: without it
+ * a prior measured on B200 is used.  Returns the number of shapes measured. */
+int madicp_calibrate(madicp_ctx_t* ctx, const double X0[12]);
+
+/* Tuning and debug entry points (clock stamps, kernel shape override) are declared in madicp_b200_debug.h. */
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ ip = C.POINTER(C.c_int32)
 bp = C.POINTER(C.c_uint8)
 vp = C.c_void_p
 
-# every symbol include/madicp_b200.h declares: name -> (restype, argtypes)
+# every symbol include/madicp_b200.h and include/madicp_b200_debug.h declare: name -> (restype, argtypes)
 SYMBOLS = {
     "madicp_last_error": (C.c_char_p, []),
     "madicp_abi_version": (C.c_int, []),
@@ -27,6 +27,9 @@ SYMBOLS = {
     "madtree_apply_transform": (C.c_int, [vp, dp]),
     "madtree_leaves": (C.c_int, [vp, dp, dp, dp, ip]),
     "madtree_records": (vp, [vp]),
+    "madtree_num_levels": (C.c_int, [vp]),
+    "madtree_level_offsets": (C.c_int, [vp, ip, C.c_int]),
+    "madtree_leaf_records": (C.c_int, [vp, ip]),
     "madtree_export": (C.c_int, [vp, dp, dp, dp, ip, ip, ip, ip]),
     "madicp_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int]),
     "madicp_destroy": (None, [vp]),
@@ -34,7 +37,25 @@ SYMBOLS = {
     "madicp_set_stream": (C.c_int, [vp, vp]),
     "madicp_get_stream": (vp, [vp]),
     "madicp_put_keyframe": (C.c_int, [vp, C.c_int, vp]),
+    "madicp_put_keyframe_transformed": (C.c_int, [vp, C.c_int, vp, dp]),
     "madicp_put_keyframe_records": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int]),
+    "madicp_put_keyframe_tree": (C.c_int, [vp, C.c_int, vp, dp]),
+    "madicp_synchronize": (C.c_int, [vp]),
+    "madtree_gpu_build": (C.c_int, [vp, dp, C.c_int64, C.c_double, C.c_double, C.POINTER(vp)]),
+    "madtree_gpu_build_resident": (C.c_int, [vp, C.c_double, C.c_double, C.POINTER(vp)]),
+    "madtree_gpu_upload": (C.c_int, [vp, vp, C.POINTER(vp)]),
+    "madtree_gpu_free": (None, [vp]),
+    "madtree_gpu_num_nodes": (C.c_int, [vp]),
+    "madtree_gpu_num_leaves": (C.c_int, [vp]),
+    "madtree_gpu_num_levels": (C.c_int, [vp]),
+    "madtree_gpu_download": (C.c_int, [vp, vp, ip]),
+    "madtree_gpu_export": (C.c_int, [vp, dp, dp, dp, ip]),
+    "madicp_set_moving_tree": (C.c_int, [vp, vp]),
+    "madicp_get_moving": (C.c_int, [vp, dp, C.c_int]),
+    "madicp_ingest": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.c_int, dp, dp, C.c_double, C.c_int, dp]),
+    "madicp_register_fetch_weight": (C.c_int, [vp, dp, dp, dp, bp, C.POINTER(C.c_int), dp]),
+    "madicp_register_partial_async": (C.c_int, [vp, C.c_int, dp]),
+    "madicp_calibrate": (C.c_int, [vp, dp]),
     "madicp_drop_keyframe": (C.c_int, [vp, C.c_int]),
     "madicp_num_keyframes": (C.c_int, [vp]),
     "madicp_active_slots": (C.c_int, [vp, ip, C.c_int]),
@@ -57,7 +78,6 @@ SYMBOLS = {
     "madicp_comm_world": (C.c_int, [vp]),
     "madicp_debug_timing": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int64), C.c_int]),
     "madicp_debug_cta_cycles": (C.c_int, [vp, C.POINTER(C.c_int64), C.c_int]),
-    "madicp_set_walk_mode": (C.c_int, [vp, C.c_int]),
     "madicp_set_gn_grid": (C.c_int, [vp, C.c_int, C.c_int]),
 }
 

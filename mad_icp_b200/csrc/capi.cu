@@ -8,9 +8,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
+#include "../../include/madicp_b200_debug.h"
+#include "ctx.hpp"
 #include "device_kernels.cuh"
 
 namespace madicp {
@@ -20,211 +24,120 @@ void set_error(const std::string& msg) { g_error = msg; }
 
 }  // namespace madicp
 
-// =============================================================================================
-// Context
-// =============================================================================================
 using namespace madicp;
 
-namespace {
-struct Slot {  // slot s owns pool indices [s*pool_cap, (s+1)*pool_cap) and heap positions [s*heap_cap, ...)
-  int n_nodes = 0, n_leaves = 0;
-  std::vector<int> heap_pos;    // node -> position in the implicit heap (kept to re-home the slot on growth)
-  std::vector<int> quad_pos;    // node -> 4-ary record * 4 + slot
-  std::vector<int> quad_child;  // even-depth node -> first record of its grandchildren
-};
-constexpr size_t kMatchedCap = size_t(1) << 20;  // bytes reserved for matched flags (max moving leaves)
-
-// One cudaMalloc, exported over CUDA IPC: mailbox + matched flags.  The flags are double-buffered by
-// registration-call parity: peers store into buffer (call & 1) during their last round while the
-// owner zeroes buffer ((call + 1) & 1) ahead of the NEXT call, so a zeroing can never race a peer.
-struct CommBlock {
-  Mailbox box;
-  unsigned char matched[2][kMatchedCap];
-};
-}  // namespace
-
-struct madicp_ctx {
-  int device = 0;
-  int max_keyframes = 0;
-  cudaStream_t own_stream = nullptr, stream = nullptr;
-  int sm_count = 0;
-  std::vector<Slot> slots;
-  // keyframe pool: three parallel arrays, pool_cap nodes per slot (kernels.cuh: ModelView)
-  size_t pool_cap = 0;
-  madtree_rec_t* d_pool_recs = nullptr;
-  int* d_pool_links = nullptr;
-  size_t heap_cap = 0;  // heap positions per slot: 2^(depth+1) + skew
-  FastRec* d_heap = nullptr;
-  int* d_bfs_of = nullptr;
-  FastRec* d_pool_fast = nullptr;  // breadth-first copy of the shadows (walk_mode 0)
-  size_t quad_cap = 0;             // 4-ary records per slot (= 2 * pool_cap)
-  QuadRec* d_quad = nullptr;
-  int walk_mode = 4;
-  bool heap_ok = true;  // false once a keyframe deeper than the implicit-heap limit has been seen
-  long long* d_dbg_cta = nullptr;  // MADICP_MAX_ITERS x grid item-phase cycles when debug timing is on
-  int* d_heap_pos = nullptr;  // upload scratch, pool_cap ints
-  IcpParams P{0.2, 0.31622776601683794, 0.02};
-  double* d_moving = nullptr;               // raw L x 3 means as uploaded
-  Moving4* d_mov4 = nullptr;                // prepared (mean, gate radius) records the kernels read
-  bool mov4_stale = true;                   // params changed / new means since the last preparation
-  unsigned char* d_step_matched = nullptr;  // matched flags of the step API (madicp_linearize)
-  int L = 0;
-  size_t cap_moving = 0;
-  uint32_t call_seq = 0;  // registrations enqueued so far (selects the matched buffer)
-  int* d_hit = nullptr;
-  int* d_ord = nullptr;
-  size_t cap_items = 0;
-  double* d_partial = nullptr;
-  size_t cap_partial = 0;
-  GnState* d_state = nullptr;
-  double* d_X = nullptr;  // 12 (step API pose) + 36 + 6 scratch
-  CommBlock* d_comm = nullptr;
-  double* h_pinned = nullptr;  // 12 + 36 + 6 + ... staging
-  GnState* h_state = nullptr;  // pinned mirror (results)
-  // pinned ring of launch headers (control words + initial pose): a header may only be rewritten once the
-  // copy that reads it has executed, so back-to-back asynchronous registrations stay correct
-  static constexpr int kInRing = 16;
-  unsigned char* h_in = nullptr;
-  cudaEvent_t in_done[kInRing] = {};
-  unsigned char* h_matched = nullptr;
-  int gn_grid = 0;
-  bool gn_auto = true;  // pick the shape per launch from the item count (see pick_shape)
-  int gn_threads = 1024;
-  const void* gn_kernel = nullptr;
-  size_t gn_smem = 0;
-  int last_iters = 0;
-  long long* d_dbg = nullptr;  // MADICP_MAX_ITERS x 8 clock stamps when debug timing is on
-  int64_t launches = 0;
-  // peers
-  int rank = 0, world = 1;
-  CommBlock* peer_comm[kMaxPeers] = {};
-  uint32_t epoch = 0;
-  uint32_t pose_epoch = 1;  // GnState::X_ll epochs (never reset: the cells are zeroed once)
-};
-
-#define CK(call)                                                                                   \
-  do {                                                                                             \
-    cudaError_t e_ = (call);                                                                       \
-    if (e_ != cudaSuccess) {                                                                       \
-      set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                               \
-      return MADICP_ERR_CUDA;                                                                      \
-    }                                                                                              \
-  } while (0)
-
-static ModelView make_view(const madicp_ctx* c) {
+// =============================================================================================
+// Keyframe pool
+// =============================================================================================
+ModelView madicp_make_view(const madicp_ctx* c) {
   ModelView v;
   v.recs = c->d_pool_recs;
-  v.links = c->d_pool_links;
-  v.heap = c->d_heap;
-  v.bfs_of = c->d_bfs_of;
-  v.fast = c->d_pool_fast;
   v.quad = c->d_quad;
-  v.walk_mode = c->walk_mode;
   v.K = 0;
   for (int s = 0; s < c->max_keyframes; ++s)
     if (c->slots[s].n_nodes > 0) {
-      v.root[v.K] = int(size_t(s) * c->heap_cap);
       v.broot[v.K] = int(size_t(s) * c->pool_cap);
       v.qroot[v.K] = int(size_t(s) * c->quad_cap);
       ++v.K;
     }
-  for (int i = v.K; i < kMaxSlots; ++i) v.root[i] = v.broot[i] = v.qroot[i] = 0;
+  for (int i = v.K; i < kMaxSlots; ++i) v.broot[i] = v.qroot[i] = 0;
   return v;
 }
+static ModelView make_view(const madicp_ctx* c) { return madicp_make_view(c); }
 
-// (Re)builds the shadows (heap order), the heap->record map and the absolute links of slot `s` from
-// its exact records in the pool.
+static int blocks_for(int64_t n) { return int((n + kStepBlock - 1) / kStepBlock); }
+
+// Quad records of slot `s` from its exact records and its child0 / rec_of tables (all in the pool): re-run
+// alone when min_ball changes (the leaf codes carry the planarity weight).
 static int prepare_slot(madicp_ctx* c, int s) {
   const int n = c->slots[s].n_nodes;
-  const size_t off = size_t(s) * c->pool_cap, hoff = size_t(s) * c->heap_cap;
-  CK(cudaMemcpyAsync(c->d_heap_pos, c->slots[s].heap_pos.data(), size_t(n) * sizeof(int), cudaMemcpyHostToDevice,
-                     c->stream));
-  CK(cudaMemcpyAsync(c->d_heap_pos + c->pool_cap, c->slots[s].quad_pos.data(), size_t(n) * sizeof(int),
-                     cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_heap_pos + 2 * c->pool_cap, c->slots[s].quad_child.data(), size_t(n) * sizeof(int),
-                     cudaMemcpyHostToDevice, c->stream));
-  k_prepare_slot<<<(n + kStepBlock - 1) / kStepBlock, kStepBlock, 0, c->stream>>>(
-      c->d_pool_recs + off, c->d_heap_pos, c->d_heap_pos + c->pool_cap, c->d_heap_pos + 2 * c->pool_cap, n, int(off),
-      int(hoff), c->P.min_ball, c->d_pool_links + off, c->d_heap,
-      c->d_bfs_of, c->d_pool_fast + off, c->d_quad, int(size_t(s) * c->quad_cap));
+  const size_t off = size_t(s) * c->pool_cap;
+  k_prepare_slot<<<blocks_for(n), kStepBlock, 0, c->stream>>>(
+      c->d_pool_recs + off, n, int(off), c->P.min_ball, c->d_pool_lvl + size_t(s) * (kMaxLevels + 1),
+      c->slots[s].n_levels, c->d_pool_child0 + off, c->d_pool_rec_of + off, c->d_quad + size_t(s) * c->quad_cap);
   c->launches++;
   CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(c->stream));  // heap_pos scratch is reused by the next slot
   return MADICP_OK;
 }
 
-// Makes every slot at least `need` nodes large and the heap at least `need_heap` positions per slot.
-// Growing re-homes the resident keyframes (device to device) and rebuilds their shadows; it only
-// happens when a larger or deeper tree than any before shows up.
-static int ensure_pool(madicp_ctx* c, size_t need, size_t need_heap) {
-  const bool grow_pool = need > c->pool_cap, grow_heap = need_heap > c->heap_cap;
-  if (!grow_pool && !grow_heap) return MADICP_OK;
+// The device side of a keyframe promotion: records (already in the slot, or `src` elsewhere on the device)
+// -> optional MADtree::applyTransform -> quad layout -> quad records.  Four launches, no host synchronisation,
+// no host-side index build.  X_dev: device pointer to a 3x4 pose or nullptr.  The slot's level table must
+// already be in d_pool_lvl (stream-ordered).
+static int build_slot(madicp_ctx* c, int s, const madtree_rec_t* src, const double* X_dev) {
+  const int n = c->slots[s].n_nodes;
+  const size_t off = size_t(s) * c->pool_cap;
+  const int* lvl = c->d_pool_lvl + size_t(s) * (kMaxLevels + 1);
+  const int nl = c->slots[s].n_levels;
+  madtree_rec_t* dst = c->d_pool_recs + off;
+  k_slot_ingest<<<blocks_for(n), kStepBlock, 0, c->stream>>>(src ? src : dst, dst, n, X_dev, lvl, nl, c->d_pool_child0 + off);
+  k_quad_scan<<<1, 1024, 0, c->stream>>>(c->d_pool_child0 + off, n);
+  k_quad_place<<<blocks_for(n), kStepBlock, 0, c->stream>>>(dst, n, lvl, nl, c->d_pool_child0 + off, c->d_pool_rec_of + off);
+  c->launches += 3;
+  CK(cudaGetLastError());
+  return prepare_slot(c, s);
+}
+
+// Makes every slot at least `need` nodes large.  Growing re-homes the resident keyframes (device to device);
+// it only happens when a larger tree than any before shows up.
+static int ensure_pool(madicp_ctx* c, size_t need) {
+  if (need <= c->pool_cap) return MADICP_OK;
   CK(cudaStreamSynchronize(c->stream));
-  if (grow_pool) {
-    // slot stride = 2^n + 40 nodes: a power-of-two stride would put the roots and upper levels of all
-    // keyframes (the hottest lines of every walk) on the same cache sets
-    size_t cap = size_t(1) << 16;
-    while (cap + 40 < need || cap + 40 <= c->pool_cap) cap <<= 1;
-    cap += 40;
-    if (cap * size_t(c->max_keyframes) > size_t(0x7fffffff)) {
-      set_error("keyframe pool would exceed 2^31 nodes");
-      return MADICP_ERR_NOMEM;
-    }
-    madtree_rec_t* recs = nullptr;
-    int* links = nullptr;
-    int* hp = nullptr;
-    FastRec* fast = nullptr;
-    const size_t total = cap * size_t(c->max_keyframes);
-    CK(cudaMalloc(&recs, total * sizeof(madtree_rec_t)));
-    CK(cudaMalloc(&links, total * sizeof(int)));
-    CK(cudaMalloc(&fast, total * sizeof(FastRec)));
-    CK(cudaMalloc(&hp, 3 * cap * sizeof(int)));
-    for (int s = 0; s < c->max_keyframes; ++s)
-      if (c->slots[s].n_nodes > 0)
-        CK(cudaMemcpyAsync(recs + size_t(s) * cap, c->d_pool_recs + size_t(s) * c->pool_cap,
-                           size_t(c->slots[s].n_nodes) * sizeof(madtree_rec_t), cudaMemcpyDeviceToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    cudaFree(c->d_pool_recs);
-    cudaFree(c->d_pool_links);
-    cudaFree(c->d_heap_pos);
-    cudaFree(c->d_pool_fast);
-    cudaFree(c->d_quad);
-    c->d_quad = nullptr;
-    CK(cudaMalloc(&c->d_quad, 2 * cap * size_t(c->max_keyframes) * sizeof(QuadRec)));
-    c->quad_cap = 2 * cap;
-    c->d_pool_fast = fast;
-    c->d_pool_recs = recs;
-    c->d_pool_links = links;
-    c->d_heap_pos = hp;
-    c->pool_cap = cap;
+  // slot stride = 2^n + 40 nodes: a power-of-two stride would put the roots and upper levels of all
+  // keyframes (the hottest lines of every walk) on the same cache sets
+  size_t cap = size_t(1) << 16;
+  while (cap + 40 < need || cap + 40 <= c->pool_cap) cap <<= 1;
+  cap += 40;
+  if (cap * size_t(c->max_keyframes) > size_t(0x3fffffff)) {
+    set_error("keyframe pool would exceed 2^30 nodes");
+    return MADICP_ERR_NOMEM;
   }
-  if (grow_heap) {
-    size_t cap = size_t(1) << 19;  // depth 18
-    while (cap < need_heap) cap <<= 1;
-    cap += 40;
-    if (cap * size_t(c->max_keyframes) > size_t(0x7fffffff)) {
-      set_error("keyframe tree too deep for the implicit-heap layout (depth limit reached)");
-      return MADICP_ERR_NOMEM;
-    }
-    cudaFree(c->d_heap);
-    cudaFree(c->d_bfs_of);
-    c->d_heap = nullptr;
-    c->d_bfs_of = nullptr;
-    const size_t total = cap * size_t(c->max_keyframes);
-    CK(cudaMalloc(&c->d_heap, total * sizeof(FastRec)));
-    CK(cudaMalloc(&c->d_bfs_of, total * sizeof(int)));
-    CK(cudaMemsetAsync(c->d_heap, 0, total * sizeof(FastRec), c->stream));  // never-visited positions are prefetched only
-    c->heap_cap = cap;
-  }
+  madtree_rec_t* recs = nullptr;
+  int *child0 = nullptr, *rec_of = nullptr;
+  QuadRec* quad = nullptr;
+  const size_t total = cap * size_t(c->max_keyframes);
+  CK(cudaMalloc(&recs, total * sizeof(madtree_rec_t)));
+  CK(cudaMalloc(&child0, total * sizeof(int)));
+  CK(cudaMalloc(&rec_of, total * sizeof(int)));
+  CK(cudaMalloc(&quad, 2 * total * sizeof(QuadRec)));
   for (int s = 0; s < c->max_keyframes; ++s)
-    if (c->slots[s].n_nodes > 0) {
-      int rc = prepare_slot(c, s);
+    if (c->slots[s].n_nodes > 0)
+      CK(cudaMemcpyAsync(recs + size_t(s) * cap, c->d_pool_recs + size_t(s) * c->pool_cap,
+                         size_t(c->slots[s].n_nodes) * sizeof(madtree_rec_t), cudaMemcpyDeviceToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(c->d_pool_recs);
+  cudaFree(c->d_pool_child0);
+  cudaFree(c->d_pool_rec_of);
+  cudaFree(c->d_quad);
+  c->d_pool_recs = recs;
+  c->d_pool_child0 = child0;
+  c->d_pool_rec_of = rec_of;
+  c->d_quad = quad;
+  c->quad_cap = 2 * cap;
+  c->pool_cap = cap;
+  for (int s = 0; s < c->max_keyframes; ++s)
+    if (c->slots[s].n_nodes > 0) {  // records are already map-frame: no transform, just the layout again
+      int rc = build_slot(c, s, nullptr, nullptr);
       if (rc) return rc;
     }
   return MADICP_OK;
 }
 
-// index of `slot` among the active slots (the k of ModelView::root[k])
+// Stages a 3x4 pose for a kernel of the stream: a pinned ring entry -> device ring entry, no synchronisation
+// unless the ring wrapped around copies that have not executed yet.
+static int stage_pose(madicp_ctx* c, const double X[12], const double** X_dev) {
+  const int r = int(c->xform_seq % madicp_ctx::kXformRing);
+  if (c->xform_seq >= madicp_ctx::kXformRing) CK(cudaEventSynchronize(c->xform_done[r]));
+  memcpy(c->h_xform + size_t(r) * 12, X, 12 * sizeof(double));
+  CK(cudaMemcpyAsync(c->d_xform + size_t(r) * 12, c->h_xform + size_t(r) * 12, 12 * sizeof(double), cudaMemcpyHostToDevice,
+                     c->stream));
+  CK(cudaEventRecord(c->xform_done[r], c->stream));
+  *X_dev = c->d_xform + size_t(r) * 12;
+  c->xform_seq++;
+  return MADICP_OK;
+}
+
+// index of `slot` among the active slots (the k of ModelView::broot[k])
 static int slot_rank(const madicp_ctx* c, int slot) {
   int k = 0;
   for (int s = 0; s < slot; ++s) k += (c->slots[s].n_nodes > 0);
@@ -233,6 +146,7 @@ static int slot_rank(const madicp_ctx* c, int slot) {
 
 static int ensure_items(madicp_ctx* c, size_t items) {
   if (items <= c->cap_items) return MADICP_OK;
+  CK(cudaStreamSynchronize(c->stream));
   if (c->d_hit) cudaFree(c->d_hit);
   if (c->d_ord) cudaFree(c->d_ord);
   c->d_hit = c->d_ord = nullptr;
@@ -289,25 +203,24 @@ static int configure_gn(madicp_ctx* c, int threads, int ctas) {
   return MADICP_ERR_INVALID;
 }
 
-// The item phase of a round costs (passes) x (time of one pass); a pass walks one warp-item per
-// resident warp and its time grows with the number of resident warps (L1 contention, and fewer
-// registers per thread).  Measured on B200 at cfg3 (profiles/r01zg_probe_shapes.txt), cycles per
-// full pass: 512 threads 7.6k, 640: 8.4k, 704: 9.5k, 768: 9.5k, 896: 10.4k, 1024: 11.5k.  With W warps
-// per SM and n warp-items per SM the passes are ceil(n / W): pick the one-CTA-per-SM shape that minimises
-// the product (ties go to the earlier entry).
+// The item phase of a round costs (passes) x (time of one pass); a pass walks one warp-item per resident warp
+// and its time grows with the number of resident warps (L1 contention, fewer registers per thread).  With W
+// warps per SM and n warp-items per SM the passes are ceil(n / W).  The per-pass cost of every one-CTA-per-SM
+// shape is a property of the device AND the workload, so it is not tabulated: the context starts from a prior
+// (relative costs measured on B200, profiles/r01zg_probe_shapes.txt) and replaces it by what madicp_calibrate
+// measures on the resident model and moving leaves (called by the pipeline once the model has its keyframes).
 static int pick_shape(madicp_ctx* c, int64_t items) {
   if (!c->gn_auto) return MADICP_OK;
   const double per_sm = double((items + 31) / 32) / double(c->sm_count);
   int best = 1024;
   double best_cost = 1e300;
-  static const struct { int threads; double pass_cycles; } kShapes[] = {
-      {768, 9500.0}, {1024, 11500.0}, {896, 10400.0}, {704, 9500.0}, {640, 8400.0}, {512, 7600.0}};
-  for (const auto& sh : kShapes) {
-    const double passes = ceil(per_sm / double(sh.threads / 32));
-    const double cost = passes * sh.pass_cycles;
+  for (int i = 0; i < madicp_ctx::kNumAutoShapes; ++i) {
+    const int threads = madicp_ctx::kAutoShapes[i];
+    const double passes = ceil(per_sm / double(threads / 32));
+    const double cost = passes * c->pass_cost[i];
     if (cost < best_cost) {
       best_cost = cost;
-      best = sh.threads;
+      best = threads;
     }
   }
   if (best == c->gn_threads && c->gn_grid == c->sm_count) return MADICP_OK;
@@ -325,13 +238,14 @@ static int grid_for(const madicp_ctx* c, int64_t items) {
 extern "C" {
 
 const char* madicp_last_error(void) { return g_error.c_str(); }
-int madicp_abi_version(void) { return 1; }
+int madicp_abi_version(void) { return 2; }
 
 int madicp_create(madicp_ctx_t** out, int device, int max_keyframes) {
   if (!out || max_keyframes < 1 || max_keyframes > kMaxSlots) {
     set_error("madicp_create: bad arguments (1 <= max_keyframes <= 64)");
     return MADICP_ERR_INVALID;
   }
+  MADICP_TRY
   int n_dev = 0;
   cudaError_t e = cudaGetDeviceCount(&n_dev);
   if (e != cudaSuccess || n_dev <= 0 || device < 0 || device >= n_dev) {
@@ -347,8 +261,7 @@ int madicp_create(madicp_ctx_t** out, int device, int max_keyframes) {
     set_error("madicp_create: device is not sm_100-class; kernels are built for sm_100a only");
     return MADICP_ERR_CUDA;
   }
-  madicp_ctx* c = new (std::nothrow) madicp_ctx;
-  if (!c) return MADICP_ERR_NOMEM;
+  madicp_ctx* c = new madicp_ctx;
   c->device = device;
   c->max_keyframes = max_keyframes;
   c->sm_count = prop.multiProcessorCount;
@@ -360,6 +273,11 @@ int madicp_create(madicp_ctx_t** out, int device, int max_keyframes) {
   CK(cudaMalloc(&c->d_X, sizeof(double) * 64));
   CK(cudaMalloc(&c->d_comm, sizeof(CommBlock)));
   CK(cudaMemset(c->d_comm, 0, sizeof(CommBlock)));
+  CK(cudaMalloc(&c->d_pool_lvl, size_t(max_keyframes) * (kMaxLevels + 1) * sizeof(int)));
+  CK(cudaMalloc(&c->d_xform, size_t(madicp_ctx::kXformRing) * 12 * sizeof(double)));
+  CK(cudaMallocHost(&c->h_xform, size_t(madicp_ctx::kXformRing) * 12 * sizeof(double)));
+  CK(cudaMallocHost(&c->h_lvl, size_t(madicp_ctx::kXformRing) * (kMaxLevels + 1) * sizeof(int)));
+  for (int i = 0; i < madicp_ctx::kXformRing; ++i) CK(cudaEventCreateWithFlags(&c->xform_done[i], cudaEventDisableTiming));
   CK(cudaMallocHost(&c->h_pinned, sizeof(double) * 64));
   CK(cudaMallocHost(&c->h_state, sizeof(GnState)));
   CK(cudaMallocHost(&c->h_in, size_t(madicp_ctx::kInRing) * 128));
@@ -375,6 +293,7 @@ int madicp_create(madicp_ctx_t** out, int device, int max_keyframes) {
   c->peer_comm[0] = c->d_comm;
   *out = c;
   return MADICP_OK;
+  MADICP_CATCH("madicp_create")
 }
 
 void madicp_destroy(madicp_ctx_t* c) {
@@ -383,29 +302,39 @@ void madicp_destroy(madicp_ctx_t* c) {
   cudaStreamSynchronize(c->stream);
   for (int r = 0; r < c->world; ++r)
     if (c->world > 1 && r != c->rank && c->peer_comm[r]) cudaIpcCloseMemHandle(c->peer_comm[r]);
+  madicp_gpu_build_release(c);
+  for (madtree_gpu* t : c->tree_cache) {
+    cudaFree(t->block);
+    delete t;
+  }
   cudaFree(c->d_pool_recs);
-  cudaFree(c->d_pool_links);
-  cudaFree(c->d_heap);
-  cudaFree(c->d_bfs_of);
-  cudaFree(c->d_heap_pos);
-  cudaFree(c->d_pool_fast);
+  cudaFree(c->d_pool_child0);
+  cudaFree(c->d_pool_rec_of);
+  cudaFree(c->d_pool_lvl);
   cudaFree(c->d_quad);
+  cudaFree(c->d_xform);
   cudaFree(c->d_dbg_cta);
   cudaFree(c->d_moving);
   cudaFree(c->d_mov4);
   cudaFree(c->d_step_matched);
   cudaFree(c->d_hit);
   cudaFree(c->d_ord);
+  cudaFree(c->d_cloud_q);
+  cudaFree(c->d_cloud_o);
   cudaFree(c->d_partial);
   cudaFree(c->d_state);
   cudaFree(c->d_X);
   cudaFree(c->d_comm);
   cudaFree(c->d_dbg);
+  cudaFreeHost(c->h_xform);
+  cudaFreeHost(c->h_lvl);
   cudaFreeHost(c->h_pinned);
   cudaFreeHost(c->h_state);
   cudaFreeHost(c->h_in);
   for (int i = 0; i < madicp_ctx::kInRing; ++i)
     if (c->in_done[i]) cudaEventDestroy(c->in_done[i]);
+  for (int i = 0; i < madicp_ctx::kXformRing; ++i)
+    if (c->xform_done[i]) cudaEventDestroy(c->xform_done[i]);
   cudaFreeHost(c->h_matched);
   cudaStreamDestroy(c->own_stream);
   delete c;
@@ -421,7 +350,7 @@ int madicp_set_params(madicp_ctx_t* c, double min_ball, double rho_ker, double b
   c->P.rho_ker_sqrt = sqrt(rho_ker);
   c->P.b_ratio = b_ratio;
   c->mov4_stale = true;  // the gate radius depends on min_ball and b_ratio
-  if (reweigh) {         // leaf planarity weights (1 - bbox0/min_ball)^2 live in the leaf shadows
+  if (reweigh) {         // leaf planarity weights (1 - bbox0/min_ball)^2 live in the leaf codes of the quad records
     CK(cudaSetDevice(c->device));
     for (int s = 0; s < c->max_keyframes; ++s)
       if (c->slots[s].n_nodes > 0) {
@@ -438,91 +367,152 @@ int madicp_set_stream(madicp_ctx_t* c, void* s) {
   return MADICP_OK;
 }
 void* madicp_get_stream(const madicp_ctx_t* c) { return c ? static_cast<void*>(c->stream) : nullptr; }
+int madicp_synchronize(madicp_ctx_t* c) {
+  if (!c) return MADICP_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  return MADICP_OK;
+}
+
+// Level table of breadth-first records (siblings adjacent, children of a level contiguous and in parent order):
+// level d+1 starts where level d ends and ends after the children of d's LAST internal node.  Also validates
+// what the kernels rely on.  O(depth + nodes looked at from each level's end), not O(n) index building.
+static int level_table(const madtree_rec_t* recs, int n_nodes, int n_leaves, std::vector<int>& lvl) {
+  lvl.clear();
+  lvl.push_back(0);
+  int lo = 0, hi = 1;
+  while (true) {
+    lvl.push_back(hi);
+    int last = hi - 1;
+    while (last >= lo && recs[last].link < 0) --last;
+    if (last < lo) break;  // a level of leaves only: the tree ends here
+    const int link = recs[last].link;
+    if (link < hi) {
+      set_error("madicp_put_keyframe: records are not breadth-first (a child precedes its level)");
+      return MADICP_ERR_INVALID;
+    }
+    const int next_hi = link + 2;
+    if (next_hi > n_nodes) {
+      set_error("madicp_put_keyframe: a child link points past the last record");
+      return MADICP_ERR_INVALID;
+    }
+    lo = hi;
+    hi = next_hi;
+    if (int(lvl.size()) > kMaxLevels) {
+      set_error("madicp_put_keyframe: tree deeper than 4096 levels");
+      return MADICP_ERR_INVALID;
+    }
+  }
+  if (hi != n_nodes) {
+    set_error("madicp_put_keyframe: records beyond the last level (not one breadth-first tree)");
+    return MADICP_ERR_INVALID;
+  }
+  (void) n_leaves;
+  return MADICP_OK;
+}
+
+// Every node other than the root must be the child of exactly one node, children adjacent and in breadth-first
+// order, and the leaf ordinals a permutation of 0..n_leaves-1: one pass, for records that come from the caller
+// (madicp_put_keyframe_records).  Trees built by this library skip it.
+static int validate_records(const madtree_rec_t* recs, int n_nodes, int n_leaves) {
+  int expect = 1, leaves = 0;
+  std::vector<unsigned char> seen(size_t(n_leaves), 0);
+  for (int i = 0; i < n_nodes; ++i) {
+    const int link = recs[i].link;
+    if (link >= 0) {
+      if (link != expect || link + 1 >= n_nodes) {
+        set_error("madicp_put_keyframe: records are not a breadth-first tree with adjacent siblings (every node other "
+                  "than the root must be referenced exactly once, in order)");
+        return MADICP_ERR_INVALID;
+      }
+      expect += 2;
+    } else {
+      const int o = -1 - link;
+      if (o >= n_leaves || seen[size_t(o)]) {
+        set_error("madicp_put_keyframe: leaf ordinals are not a permutation of 0..n_leaves-1");
+        return MADICP_ERR_INVALID;
+      }
+      seen[size_t(o)] = 1;
+      ++leaves;
+    }
+  }
+  if (expect != n_nodes || leaves != n_leaves) {
+    set_error("madicp_put_keyframe: node / leaf counts do not match the links");
+    return MADICP_ERR_INVALID;
+  }
+  return MADICP_OK;
+}
+
+// host level table -> the slot's device table (through a pinned ring entry; stream-ordered)
+static int stage_levels(madicp_ctx* c, int slot, const int* lvl, int n_levels) {
+  const int r = int(c->xform_seq % madicp_ctx::kXformRing);
+  if (c->xform_seq >= madicp_ctx::kXformRing) CK(cudaEventSynchronize(c->xform_done[r]));
+  int* h = c->h_lvl + size_t(r) * (kMaxLevels + 1);
+  memcpy(h, lvl, size_t(n_levels + 1) * sizeof(int));
+  CK(cudaMemcpyAsync(c->d_pool_lvl + size_t(slot) * (kMaxLevels + 1), h, size_t(n_levels + 1) * sizeof(int),
+                     cudaMemcpyHostToDevice, c->stream));
+  CK(cudaEventRecord(c->xform_done[r], c->stream));
+  c->xform_seq++;
+  return MADICP_OK;
+}
+
+static int put_host_records(madicp_ctx* c, int slot, const madtree_rec_t* recs, int n_nodes, int n_leaves, const int* lvl,
+                            int n_levels, const double* X) {
+  int rc = ensure_pool(c, size_t(n_nodes));
+  if (rc) return rc;
+  rc = stage_levels(c, slot, lvl, n_levels);
+  if (rc) return rc;
+  const double* X_dev = nullptr;
+  if (X) {
+    rc = stage_pose(c, X, &X_dev);
+    if (rc) return rc;
+  }
+  // pageable source: the call returns once the records are staged, so the caller may free the tree right after
+  CK(cudaMemcpyAsync(c->d_pool_recs + size_t(slot) * c->pool_cap, recs, size_t(n_nodes) * sizeof(madtree_rec_t),
+                     cudaMemcpyHostToDevice, c->stream));
+  Slot& s = c->slots[slot];
+  s.n_nodes = n_nodes;
+  s.n_leaves = n_leaves;
+  s.n_levels = n_levels;
+  return build_slot(c, slot, nullptr, X_dev);
+}
 
 int madicp_put_keyframe_records(madicp_ctx_t* c, int slot, const madtree_rec_t* recs, int n_nodes, int n_leaves) {
   if (!c || !recs || slot < 0 || slot >= c->max_keyframes || n_nodes < 1 || n_leaves < 1) {
     set_error("madicp_put_keyframe: bad arguments");
     return MADICP_ERR_INVALID;
   }
+  MADICP_TRY
   CK(cudaSetDevice(c->device));
-  // heap position of every node (host, O(n)): children of the node at position h sit at 2h+1, 2h+2
-  std::vector<int> heap_pos(size_t(n_nodes), 0);
-  int64_t max_pos = 0;
-  for (int i = 0; i < n_nodes; ++i) {
-    const int link = recs[i].link;
-    if (link < 0) continue;
-    if (link < 1 || link + 1 >= n_nodes || link <= i) {
-      set_error("madicp_put_keyframe: records are not a breadth-first tree with adjacent siblings");
-      return MADICP_ERR_INVALID;
-    }
-    // the implicit binary heap (walk modes 1-3, kept for measurements) is limited to 20 levels; deeper nodes
-    // get no heap position and those modes are switched off -- the default 4-ary records have no depth limit
-    const int64_t h = (heap_pos[size_t(i)] < 0) ? -1 : 2 * int64_t(heap_pos[size_t(i)]) + 1;
-    if (h < 0 || h + 1 >= (int64_t(1) << 21)) {
-      heap_pos[size_t(link)] = heap_pos[size_t(link) + 1] = -1;
-      c->heap_ok = false;
-      if (c->walk_mode >= 1 && c->walk_mode <= 3) c->walk_mode = 4;
-      continue;
-    }
-    heap_pos[size_t(link)] = int(h);
-    heap_pos[size_t(link) + 1] = int(h + 1);
-    if (h + 1 > max_pos) max_pos = h + 1;
-  }
-  // dense 4-ary records: breadth-first over the even-depth nodes; the (up to four) grandchildren of a node
-  // get four contiguous records.  depth parity from the heap position (depth = floor(log2(pos + 1))).
-  std::vector<int> quad_pos(size_t(n_nodes), 0), quad_child(size_t(n_nodes), 0);
-  {
-    int next_rec = 1;  // record 0 = the root
-    std::vector<int> order{0};  // even-depth nodes in breadth-first order; their record = quad_pos >> 2
-    for (size_t h = 0; h < order.size(); ++h) {
-      const int i = order[h];
-      const int rec = quad_pos[size_t(i)] >> 2;
-      const int l0 = recs[i].link;
-      if (l0 < 0) continue;  // a leaf at an even depth: p0 holds the leaf code
-      bool any = false;
-      for (int s0 = 0; s0 < 2; ++s0) {
-        const int ch = l0 + s0;
-        quad_pos[size_t(ch)] = rec * 4 + 1 + s0;
-        const int l1 = recs[ch].link;
-        if (l1 < 0) continue;
-        for (int s1 = 0; s1 < 2; ++s1) {
-          quad_pos[size_t(l1 + s1)] = (next_rec + 2 * s0 + s1) * 4;
-          order.push_back(l1 + s1);
-          any = true;
-        }
-      }
-      quad_child[size_t(i)] = next_rec;
-      if (any) next_rec += 4;
-    }
-    if (size_t(next_rec) > 2 * (size_t(n_nodes) + 64)) {
-      set_error("madicp_put_keyframe: internal error (4-ary record count)");
-      return MADICP_ERR_INVALID;
-    }
-  }
-  int rc = ensure_pool(c, size_t(n_nodes), size_t(8 * max_pos + 16));  // room for the 3-level look-ahead prefetch
+  int rc = validate_records(recs, n_nodes, n_leaves);
   if (rc) return rc;
-  Slot& s = c->slots[slot];
-  CK(cudaMemcpyAsync(c->d_pool_recs + size_t(slot) * c->pool_cap, recs, size_t(n_nodes) * sizeof(madtree_rec_t),
-                     cudaMemcpyHostToDevice, c->stream));
-  s.n_nodes = n_nodes;
-  s.n_leaves = n_leaves;
-  s.heap_pos.swap(heap_pos);
-  s.quad_pos.swap(quad_pos);
-  s.quad_child.swap(quad_child);
-  rc = prepare_slot(c, slot);
+  std::vector<int> lvl;
+  rc = level_table(recs, n_nodes, n_leaves, lvl);
   if (rc) return rc;
-  CK(cudaStreamSynchronize(c->stream));  // caller may free/modify the host tree right after
-  s.n_nodes = n_nodes;
-  s.n_leaves = n_leaves;
-  return MADICP_OK;
+  return put_host_records(c, slot, recs, n_nodes, n_leaves, lvl.data(), int(lvl.size()) - 1, nullptr);
+  MADICP_CATCH("madicp_put_keyframe_records")
+}
+
+int madicp_put_keyframe_transformed(madicp_ctx_t* c, int slot, const madtree_t* tree, const double X[12]) {
+  if (!c || !tree || slot < 0 || slot >= c->max_keyframes) {
+    set_error("madicp_put_keyframe: bad arguments");
+    return MADICP_ERR_INVALID;
+  }
+  MADICP_TRY
+  CK(cudaSetDevice(c->device));
+  const int nl = madtree_num_levels(tree);
+  if (nl < 1 || nl > kMaxLevels) {
+    set_error("madicp_put_keyframe: tree deeper than 4096 levels");
+    return MADICP_ERR_INVALID;
+  }
+  std::vector<int> lvl(size_t(nl) + 1);
+  madtree_level_offsets(tree, lvl.data(), nl + 1);
+  return put_host_records(c, slot, madtree_records(tree), madtree_num_nodes(tree), madtree_num_leaves(tree), lvl.data(), nl, X);
+  MADICP_CATCH("madicp_put_keyframe")
 }
 
 int madicp_put_keyframe(madicp_ctx_t* c, int slot, const madtree_t* tree) {
-  if (!tree) {
-    set_error("madicp_put_keyframe: null tree");
-    return MADICP_ERR_INVALID;
-  }
-  return madicp_put_keyframe_records(c, slot, madtree_records(tree), madtree_num_nodes(tree), madtree_num_leaves(tree));
+  return madicp_put_keyframe_transformed(c, slot, tree, nullptr);
 }
 
 int madicp_drop_keyframe(madicp_ctx_t* c, int slot) {
@@ -560,9 +550,149 @@ int64_t madicp_model_nodes(const madicp_ctx_t* c) {
 }
 int64_t madicp_kernel_launches(const madicp_ctx_t* c) { return c ? c->launches : 0; }
 
+// ------------------------------------------------------------------------------ device-resident trees
+}  // extern "C"
+
+// One allocation per tree, carved: records | level table | getLeafs table.  Freed trees keep it (a streamed
+// sequence allocates one tree per scan and frees one per scan).
+int madicp_tree_alloc(madicp_ctx* c, size_t cap_nodes, madtree_gpu** out) {
+  madtree_gpu* t = nullptr;
+  for (size_t i = 0; i < c->tree_cache.size(); ++i)
+    if (c->tree_cache[i]->cap_nodes >= cap_nodes) {
+      t = c->tree_cache[i];
+      c->tree_cache.erase(c->tree_cache.begin() + long(i));
+      break;
+    }
+  if (!t) {
+    t = new madtree_gpu;
+    t->ctx = c;
+    size_t cap = size_t(1) << 16;
+    while (cap < cap_nodes) cap <<= 1;
+    const size_t bytes = cap * sizeof(madtree_rec_t) + size_t(kMaxLevels + 1) * sizeof(int) + cap * sizeof(int);
+    cudaError_t e = cudaMalloc(&t->block, bytes);
+    if (e != cudaSuccess) {
+      delete t;
+      set_error(std::string("device tree allocation: ") + cudaGetErrorString(e));
+      return MADICP_ERR_NOMEM;
+    }
+    t->cap_nodes = cap;
+    t->recs = static_cast<madtree_rec_t*>(t->block);
+    t->lvl = reinterpret_cast<int*>(t->recs + cap);
+    t->leaf_of = t->lvl + (kMaxLevels + 1);
+  }
+  t->n_nodes = t->n_leaves = t->n_levels = 0;
+  t->h_lvl.clear();
+  *out = t;
+  return MADICP_OK;
+}
+
+extern "C" {
+
+int madtree_gpu_upload(madicp_ctx_t* c, const madtree_t* tree, madtree_gpu_t** out) {
+  if (!c || !tree || !out) {
+    set_error("madtree_gpu_upload: bad arguments");
+    return MADICP_ERR_INVALID;
+  }
+  MADICP_TRY
+  CK(cudaSetDevice(c->device));
+  const int n = madtree_num_nodes(tree), nl = madtree_num_levels(tree), L = madtree_num_leaves(tree);
+  if (nl < 1 || nl > kMaxLevels) {
+    set_error("madtree_gpu_upload: tree deeper than 4096 levels");
+    return MADICP_ERR_INVALID;
+  }
+  madtree_gpu* t = nullptr;
+  int rc = madicp_tree_alloc(c, size_t(n), &t);
+  if (rc) return rc;
+  t->n_nodes = n;
+  t->n_leaves = L;
+  t->n_levels = nl;
+  t->h_lvl.resize(size_t(nl) + 1);
+  madtree_level_offsets(tree, t->h_lvl.data(), nl + 1);
+  CK(cudaMemcpyAsync(t->recs, madtree_records(tree), size_t(n) * sizeof(madtree_rec_t), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(t->lvl, t->h_lvl.data(), size_t(nl + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  k_leaf_table<<<blocks_for(n), kStepBlock, 0, c->stream>>>(t->recs, n, t->leaf_of);
+  c->launches++;
+  CK(cudaGetLastError());
+  *out = t;
+  return MADICP_OK;
+  MADICP_CATCH("madtree_gpu_upload")
+}
+
+void madtree_gpu_free(madtree_gpu_t* t) {
+  if (!t) return;
+  madicp_ctx* c = t->ctx;
+  // stream order protects the memory: whatever still reads it was enqueued before anything that reuses it
+  if (c->tree_cache.size() < 24) {
+    c->tree_cache.push_back(t);
+    return;
+  }
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(t->block);
+  delete t;
+}
+int madtree_gpu_num_nodes(const madtree_gpu_t* t) { return t ? t->n_nodes : MADICP_ERR_INVALID; }
+int madtree_gpu_num_leaves(const madtree_gpu_t* t) { return t ? t->n_leaves : MADICP_ERR_INVALID; }
+int madtree_gpu_num_levels(const madtree_gpu_t* t) { return t ? t->n_levels : MADICP_ERR_INVALID; }
+
+int madtree_gpu_download(const madtree_gpu_t* t, madtree_rec_t* recs_out, int32_t* leaf_records_out) {
+  if (!t || (!recs_out && !leaf_records_out)) return MADICP_ERR_INVALID;
+  madicp_ctx* c = t->ctx;
+  CK(cudaSetDevice(c->device));
+  if (recs_out)
+    CK(cudaMemcpyAsync(recs_out, t->recs, size_t(t->n_nodes) * sizeof(madtree_rec_t), cudaMemcpyDeviceToHost, c->stream));
+  if (leaf_records_out)
+    CK(cudaMemcpyAsync(leaf_records_out, t->leaf_of, size_t(t->n_leaves) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return MADICP_OK;
+}
+
+int madicp_put_keyframe_tree(madicp_ctx_t* c, int slot, const madtree_gpu_t* t, const double X[12]) {
+  if (!c || !t || t->ctx != c || slot < 0 || slot >= c->max_keyframes || t->n_nodes < 1) {
+    set_error("madicp_put_keyframe_tree: bad arguments (the tree must live on this context)");
+    return MADICP_ERR_INVALID;
+  }
+  MADICP_TRY
+  CK(cudaSetDevice(c->device));
+  int rc = ensure_pool(c, size_t(t->n_nodes));
+  if (rc) return rc;
+  const double* X_dev = nullptr;
+  if (X) {
+    rc = stage_pose(c, X, &X_dev);
+    if (rc) return rc;
+  }
+  CK(cudaMemcpyAsync(c->d_pool_lvl + size_t(slot) * (kMaxLevels + 1), t->lvl, size_t(t->n_levels + 1) * sizeof(int),
+                     cudaMemcpyDeviceToDevice, c->stream));
+  Slot& s = c->slots[slot];
+  s.n_nodes = t->n_nodes;
+  s.n_leaves = t->n_leaves;
+  s.n_levels = t->n_levels;
+  return build_slot(c, slot, t->recs, X_dev);
+  MADICP_CATCH("madicp_put_keyframe_tree")
+}
+
+// ------------------------------------------------------------------------------ moving leaves
+static int ensure_moving(madicp_ctx* c, int L) {
+  if (size_t(L) <= c->cap_moving) return MADICP_OK;
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->d_moving) cudaFree(c->d_moving);
+  if (c->d_mov4) cudaFree(c->d_mov4);
+  if (c->d_step_matched) cudaFree(c->d_step_matched);
+  c->d_moving = nullptr;
+  c->d_mov4 = nullptr;
+  c->d_step_matched = nullptr;
+  c->cap_moving = 0;
+  const size_t cap = size_t(L) + size_t(L) / 4 + 1024;
+  CK(cudaMalloc(&c->d_moving, cap * 3 * sizeof(double)));
+  CK(cudaMalloc(&c->d_mov4, cap * sizeof(Moving4)));
+  CK(cudaMalloc(&c->d_step_matched, cap));
+  c->cap_moving = cap;
+  return MADICP_OK;
+}
+
 static int prepare_moving(madicp_ctx* c) {
   if (!c->mov4_stale || c->L < 1) return MADICP_OK;
-  k_prepare_moving<<<(c->L + kStepBlock - 1) / kStepBlock, kStepBlock, 0, c->stream>>>(c->d_moving, c->L, c->P, c->d_mov4);
+  k_prepare_moving<<<blocks_for(c->L), kStepBlock, 0, c->stream>>>(c->d_moving, c->L, c->P, c->d_mov4, nullptr, nullptr);
   c->launches++;
   CK(cudaGetLastError());
   c->mov4_stale = false;
@@ -575,25 +705,36 @@ int madicp_set_moving(madicp_ctx_t* c, const double* means, int L) {
     return MADICP_ERR_INVALID;
   }
   CK(cudaSetDevice(c->device));
-  if (size_t(L) > c->cap_moving) {
-    CK(cudaStreamSynchronize(c->stream));
-    if (c->d_moving) cudaFree(c->d_moving);
-    if (c->d_mov4) cudaFree(c->d_mov4);
-    if (c->d_step_matched) cudaFree(c->d_step_matched);
-    c->d_moving = nullptr;
-    c->d_mov4 = nullptr;
-    c->d_step_matched = nullptr;
-    c->cap_moving = 0;
-    const size_t cap = size_t(L) + size_t(L) / 4 + 1024;
-    CK(cudaMalloc(&c->d_moving, cap * 3 * sizeof(double)));
-    CK(cudaMalloc(&c->d_mov4, cap * sizeof(Moving4)));
-    CK(cudaMalloc(&c->d_step_matched, cap));
-    c->cap_moving = cap;
-  }
+  int rc = ensure_moving(c, L);
+  if (rc) return rc;
   CK(cudaMemcpyAsync(c->d_moving, means, size_t(L) * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   c->L = L;
   c->mov4_stale = true;
   return prepare_moving(c);
+}
+
+int madicp_set_moving_tree(madicp_ctx_t* c, const madtree_gpu_t* t) {
+  if (!c || !t || t->ctx != c || t->n_leaves < 1 || size_t(t->n_leaves) > kMatchedCap) {
+    set_error("madicp_set_moving_tree: bad arguments (the tree must live on this context)");
+    return MADICP_ERR_INVALID;
+  }
+  CK(cudaSetDevice(c->device));
+  int rc = ensure_moving(c, t->n_leaves);
+  if (rc) return rc;
+  c->L = t->n_leaves;
+  k_prepare_moving<<<blocks_for(c->L), kStepBlock, 0, c->stream>>>(c->d_moving, c->L, c->P, c->d_mov4, t->recs, t->leaf_of);
+  c->launches++;
+  CK(cudaGetLastError());
+  c->mov4_stale = false;
+  return MADICP_OK;
+}
+
+int madicp_get_moving(madicp_ctx_t* c, double* means_out, int cap) {
+  if (!c || !means_out || c->L < 1 || cap < c->L) return MADICP_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(means_out, c->d_moving, size_t(c->L) * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return c->L;
 }
 
 static int check_ready(madicp_ctx* c, const char* who) {
@@ -692,11 +833,12 @@ int madicp_solve_update(madicp_ctx_t* c, const double H[36], const double b[6], 
   return MADICP_OK;
 }
 
-int madicp_register_async(madicp_ctx_t* c, int iters, const double X0[12]) {
+// clear_from: first round whose gate passes are recorded in the matched flags.
+static int register_enqueue(madicp_ctx* c, int iters, const double X0[12], int clear_from) {
   int rc = check_ready(c, "madicp_register");
   if (rc) return rc;
   if (!X0 || iters < 1 || iters > MADICP_MAX_ITERS) {
-    set_error("madicp_register: bad arguments (1 <= iters <= 64)");
+    set_error("madicp_register: bad arguments (1 <= iters <= 64 per launch)");
     return MADICP_ERR_INVALID;
   }
   CK(cudaSetDevice(c->device));
@@ -718,6 +860,7 @@ int madicp_register_async(madicp_ctx_t* c, int iters, const double X0[12]) {
   A.moving = c->d_mov4;
   A.L = c->L;
   A.iters = iters;
+  A.clear_from = clear_from;
   A.matched = c->d_comm->matched[mb];
   A.partial = c->d_partial;
   // Item map in shared memory: 4 bytes per CTA-local item, taken only if it neither exceeds the reserve
@@ -748,7 +891,7 @@ int madicp_register_async(madicp_ctx_t* c, int iters, const double X0[12]) {
   if (c->call_seq >= madicp_ctx::kInRing) CK(cudaEventSynchronize(c->in_done[ring]));
   GnState* hs = reinterpret_cast<GnState*>(c->h_in + size_t(ring) * 128);
   hs->ticket = 0;
-  hs->round = 0;
+  hs->clear_from = clear_from;
   hs->n_matched = 0;
   hs->pad = 0;
   memcpy(hs->X_in, X0, 12 * sizeof(double));
@@ -764,7 +907,15 @@ int madicp_register_async(madicp_ctx_t* c, int iters, const double X0[12]) {
   return MADICP_OK;
 }
 
-int madicp_register_fetch(madicp_ctx_t* c, double X[12], double H[36], double b[6], uint8_t* matched, int* n_matched) {
+int madicp_register_async(madicp_ctx_t* c, int iters, const double X0[12]) {
+  return register_enqueue(c, iters, X0, iters - 1);
+}
+int madicp_register_partial_async(madicp_ctx_t* c, int iters, const double X0[12]) {
+  return register_enqueue(c, iters, X0, 0);
+}
+
+int madicp_register_fetch_weight(madicp_ctx_t* c, double X[12], double H[36], double b[6], uint8_t* matched, int* n_matched,
+                                 double* weight) {
   if (!c || c->last_iters < 1) {
     set_error("madicp_register_fetch: nothing was enqueued");
     return MADICP_ERR_STATE;
@@ -780,12 +931,36 @@ int madicp_register_fetch(madicp_ctx_t* c, double X[12], double H[36], double b[
   if (b) memcpy(b, c->h_state->b, 6 * sizeof(double));
   if (matched) memcpy(matched, c->h_matched, size_t(c->L));
   if (n_matched) *n_matched = c->h_state->n_matched;
+  if (weight) *weight = c->h_state->weight;
   return MADICP_OK;
+}
+int madicp_register_fetch(madicp_ctx_t* c, double X[12], double H[36], double b[6], uint8_t* matched, int* n_matched) {
+  return madicp_register_fetch_weight(c, X, H, b, matched, n_matched, nullptr);
 }
 
 int madicp_register(madicp_ctx_t* c, int iters, double X[12], double H[36], double b[6], uint8_t* matched,
                     int* n_matched) {
-  int rc = madicp_register_async(c, iters, X);
+  if (!c || !X || iters < 0) {
+    set_error("madicp_register: bad arguments");
+    return MADICP_ERR_INVALID;
+  }
+  if (iters == 0) {  // the reference's loop with zero rounds returns the initial guess (mad_icp_wrapper.h:72-101)
+    if (H) memset(H, 0, 36 * sizeof(double));
+    if (b) memset(b, 0, 6 * sizeof(double));
+    if (matched && c->L > 0) memset(matched, 0, size_t(c->L));
+    if (n_matched) *n_matched = 0;
+    return MADICP_OK;
+  }
+  // more rounds than one launch holds: chain launches; only the LAST round of the whole loop records matches
+  int left = iters;
+  while (left > MADICP_MAX_ITERS) {
+    int rc = register_enqueue(c, MADICP_MAX_ITERS, X, MADICP_MAX_ITERS);  // clear_from = iters: records nothing
+    if (rc) return rc;
+    rc = madicp_register_fetch(c, X, nullptr, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    left -= MADICP_MAX_ITERS;
+  }
+  int rc = register_enqueue(c, left, X, left - 1);
   if (rc) return rc;
   return madicp_register_fetch(c, X, H, b, matched, n_matched);
 }
@@ -809,15 +984,24 @@ int madicp_search_cloud(madicp_ctx_t* c, int slot, const double* q, int64_t n, i
     return MADICP_ERR_INVALID;
   }
   CK(cudaSetDevice(c->device));
-  double *d_q = nullptr, *d_out = nullptr;
-  int* d_o = nullptr;
-  CK(cudaMalloc(&d_q, size_t(n) * 3 * sizeof(double)));
-  CK(cudaMalloc(&d_out, size_t(n) * 7 * sizeof(double)));
-  CK(cudaMalloc(&d_o, size_t(n) * sizeof(int)));
+  if (size_t(n) > c->cap_cloud) {  // scratch lives with the context and only grows
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_cloud_q);
+    cudaFree(c->d_cloud_o);
+    c->d_cloud_q = nullptr;
+    c->d_cloud_o = nullptr;
+    c->cap_cloud = 0;
+    const size_t cap = size_t(n) + size_t(n) / 4 + 1024;
+    CK(cudaMalloc(&c->d_cloud_q, cap * 10 * sizeof(double)));
+    CK(cudaMalloc(&c->d_cloud_o, cap * sizeof(int)));
+    c->cap_cloud = cap;
+  }
+  double* d_q = c->d_cloud_q;
+  double* d_p = d_q + size_t(n) * 3;
+  double* d_n = d_q + size_t(n) * 6;
+  double* d_d = d_q + size_t(n) * 9;
+  int* d_o = c->d_cloud_o;
   CK(cudaMemcpyAsync(d_q, q, size_t(n) * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  double* d_p = d_out;
-  double* d_n = d_out + size_t(n) * 3;
-  double* d_d = d_out + size_t(n) * 6;
   k_search_cloud<<<grid_for(c, n), kStepBlock, 0, c->stream>>>(make_view(c), slot_rank(c, slot), d_q, n, d_o,
                                                               points ? d_p : nullptr, normals ? d_n : nullptr,
                                                               dists ? d_d : nullptr);
@@ -828,9 +1012,6 @@ int madicp_search_cloud(madicp_ctx_t* c, int slot, const double* q, int64_t n, i
   if (normals) CK(cudaMemcpyAsync(normals, d_n, size_t(n) * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   if (dists) CK(cudaMemcpyAsync(dists, d_d, size_t(n) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  cudaFree(d_q);
-  cudaFree(d_out);
-  cudaFree(d_o);
   return MADICP_OK;
 }
 
@@ -879,7 +1060,53 @@ int madicp_comm_connect(madicp_ctx_t* c, int rank, int world, const void* all_ha
 
 int madicp_comm_world(const madicp_ctx_t* c) { return c ? c->world : MADICP_ERR_INVALID; }
 
-// ------------------------------------------------------------------------------ debug
+// ------------------------------------------------------------------------------ tuning / debug
+// Measures the cost of one full pass of every one-CTA-per-SM shape ON THE RESIDENT MODEL AND MOVING LEAVES
+// (a few one-round registrations per shape, CUDA events) and stores it for pick_shape.  Returns the number of
+// shapes measured.  Leaves the registration state untouched except for the matched flags.
+int madicp_calibrate(madicp_ctx_t* c, const double X0[12]) {
+  int rc = check_ready(c, "madicp_calibrate");
+  if (rc) return rc;
+  if (!X0 || c->world > 1) return MADICP_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  const bool was_auto = c->gn_auto;
+  const int64_t items = int64_t(madicp_num_keyframes(c)) * c->L;
+  const double per_sm = double((items + 31) / 32) / double(c->sm_count);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  c->gn_auto = false;
+  int measured = 0;
+  for (int i = 0; i < madicp_ctx::kNumAutoShapes; ++i) {
+    if (configure_gn(c, madicp_ctx::kAutoShapes[i], 1)) continue;
+    const int rounds = 4;
+    for (int rep = 0; rep < 2; ++rep) {  // the second repetition is the timed one (warm L2, configured kernel)
+      CK(cudaEventRecord(e0, c->stream));
+      rc = register_enqueue(c, rounds, X0, rounds - 1);
+      if (rc) break;
+      CK(cudaEventRecord(e1, c->stream));
+      CK(cudaEventSynchronize(e1));
+    }
+    if (rc) break;
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double passes = ceil(per_sm / double(madicp_ctx::kAutoShapes[i] / 32));
+    c->pass_cost[i] = double(ms) / double(rounds) / passes;  // any unit: only ratios matter
+    ++measured;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  c->gn_auto = was_auto;
+  if (rc) return rc;
+  c->calibrated = true;
+  if (c->gn_auto) {
+    c->gn_threads = 0;  // force a re-pick
+    rc = pick_shape(c, items);
+    if (rc) return rc;
+  }
+  return measured;
+}
+
 int madicp_debug_timing(madicp_ctx_t* c, int enable, int64_t* out, int max_rounds) {
   if (!c) return MADICP_ERR_INVALID;
   CK(cudaSetDevice(c->device));
@@ -909,16 +1136,6 @@ int madicp_debug_cta_cycles(madicp_ctx_t* c, int64_t* out, int cap) {
   const int n = std::min(cap, c->last_iters * c->gn_grid);
   CK(cudaMemcpy(out, c->d_dbg_cta, size_t(n) * sizeof(long long), cudaMemcpyDeviceToHost));
   return c->gn_grid;
-}
-
-int madicp_set_walk_mode(madicp_ctx_t* c, int mode) {
-  if (!c || mode < 0 || mode > 4) return MADICP_ERR_INVALID;
-  if (mode >= 1 && mode <= 3 && !c->heap_ok) {
-    set_error("madicp_set_walk_mode: a resident keyframe is deeper than the implicit-heap limit (20 levels)");
-    return MADICP_ERR_STATE;
-  }
-  c->walk_mode = mode;
-  return MADICP_OK;
 }
 
 int madicp_set_gn_grid(madicp_ctx_t* c, int threads_per_cta, int ctas_per_sm) {

@@ -5,66 +5,195 @@
 namespace madicp {
 
 // ---------------------------------------------------------------------------------------------
-// Preparation kernels (run once per keyframe upload / once per scan)
+// Keyframe lifecycle on the device (run once per keyframe promotion)
+//   k_slot_ingest   records -> pool slot, with MADtree::applyTransform fused (tools/mad_tree.cpp:165-172)
+//   k_quad_scan     breadth-first prefix sum that allocates the 4-ary records (one CTA)
+//   k_quad_place    every even-depth node tells its grandchildren which record is theirs
+//   k_prepare_slot  every even-depth node writes its 64-byte quad record (FP32 planes / leaf codes)
+// No host-side index build, no host synchronisation: a promotion is these four launches behind one
+// (optional) H2D or D2D copy on the context's stream.
 // ---------------------------------------------------------------------------------------------
 
-// Shadows of one keyframe tree: `recs` are the slot's exact records as uploaded (links slot-relative,
-// breadth-first) at pool offset `off`; heap_pos[i] is node i's position in the implicit heap (computed
-// on the host from the links), `hoff` the slot's offset in the heap array.
+// depth of breadth-first node i from the level table (lvl[d] = first node of depth d; lvl[n_levels] = n)
+__device__ __forceinline__ int depth_of(const int* __restrict__ lvl, int n_levels, int i) {
+  int lo = 0, hi = n_levels;  // invariant: lvl[lo] <= i < lvl[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(lvl + mid) <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// src -> dst (may alias: every thread reads its own record and only the LINKS of its children, which the
+// transform never touches).  X = nullptr: plain copy.  mean <- R*mean + t, dir <- R*dir with the reference's
+// operand order and no FMA (arith.h), i.e. bit-identical to madtree_apply_transform on the host.
+// flag[i] = 1 iff node i sits at an even depth, is internal and has at least one grandchild.
 __global__ void __launch_bounds__(kStepBlock)
-k_prepare_slot(const madtree_rec_t* __restrict__ recs, const int* __restrict__ heap_pos,
-               const int* __restrict__ quad_pos, const int* __restrict__ quad_child, int n, int off, int hoff,
-               double min_ball, int* __restrict__ links, FastRec* __restrict__ heap, int* __restrict__ bfs_of,
-               FastRec* __restrict__ fast, QuadRec* __restrict__ quad, int qoff) {
+k_slot_ingest(const madtree_rec_t* src, madtree_rec_t* dst, int n, const double* __restrict__ Xp,
+              const int* __restrict__ lvl, int n_levels, int* __restrict__ flag) {
   const int i = blockIdx.x * kStepBlock + threadIdx.x;
   if (i >= n) return;
-  const Rec r = load_rec(recs + i);
+  Rec r = load_rec_plain(src + i);
+  const int npts = src[i].num_points;
+  int f = 0;
+  if (r.link >= 0 && (depth_of(lvl, n_levels, i) & 1) == 0)
+    f = (src[r.link].link >= 0 || src[r.link + 1].link >= 0) ? 1 : 0;
+  if (Xp) {
+    double X[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) X[j] = Xp[j];
+    double mx, my, mz;
+    iso_apply(X, r.mx, r.my, r.mz, mx, my, mz);
+    const double dx = dot3(X[0], X[1], X[2], r.dx, r.dy, r.dz);
+    const double dy = dot3(X[4], X[5], X[6], r.dx, r.dy, r.dz);
+    const double dz = dot3(X[8], X[9], X[10], r.dx, r.dy, r.dz);
+    r.mx = mx; r.my = my; r.mz = mz;
+    r.dx = dx; r.dy = dy; r.dz = dz;
+  }
+  madtree_rec_t o;
+  o.mean[0] = r.mx; o.mean[1] = r.my; o.mean[2] = r.mz;
+  o.dir[0] = r.dx; o.dir[1] = r.dy; o.dir[2] = r.dz;
+  o.bbox0 = r.bbox0;
+  o.link = r.link;
+  o.num_points = npts;
+  dst[i] = o;
+  flag[i] = f;
+}
+
+// One CTA.  child0[i] = 1 + 4 * (number of flagged nodes before i in breadth-first order): the dense 4-ary
+// records are handed out in breadth-first order of the even-depth nodes, four contiguous records per node that
+// has grandchildren (record 0 is the root's).  In place over `flag`.
+__global__ void __launch_bounds__(1024)
+k_quad_scan(int* __restrict__ flag_to_child0, int n) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 4096) {  // 4 consecutive nodes per thread: one 16-byte access
+    const int i0 = base + threadIdx.x * 4;
+    int f[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) f[j] = (i0 + j < n) ? flag_to_child0[i0 + j] : 0;
+    const int mine = f[0] + f[1] + f[2] + f[3];
+    int incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_warp[lane];
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, w, off);
+        if (lane >= off) w += v;
+      }
+      s_warp[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    int run = s_carry + (warp ? s_warp[warp - 1] : 0) + (incl - mine);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (i0 + j < n) flag_to_child0[i0 + j] = 1 + 4 * run;
+      run += f[j];
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = run;
+    __syncthreads();
+  }
+}
+
+// rec_of[g] for the (up to four) grandchildren g of every even-depth internal node; rec_of[0] = 0.
+__global__ void __launch_bounds__(kStepBlock)
+k_quad_place(const madtree_rec_t* __restrict__ recs, int n, const int* __restrict__ lvl, int n_levels,
+             const int* __restrict__ child0, int* __restrict__ rec_of) {
+  const int i = blockIdx.x * kStepBlock + threadIdx.x;
+  if (i >= n) return;
+  if (i == 0) rec_of[0] = 0;
+  const int l0 = recs[i].link;
+  if (l0 < 0 || (depth_of(lvl, n_levels, i) & 1)) return;
+  const int c0 = child0[i];
+#pragma unroll
+  for (int s0 = 0; s0 < 2; ++s0) {
+    const int l1 = recs[l0 + s0].link;
+    if (l1 < 0) continue;
+    rec_of[l1] = c0 + 2 * s0;
+    rec_of[l1 + 1] = c0 + 2 * s0 + 1;
+  }
+}
+
+// FP32 shadow of one node: the split plane in offset form, or the leaf code
+// {pool index, marker, planarity weight w*w with w = 1 - bbox(0)/min_ball (odometry/mad_icp.cpp:97-98)}.
+__device__ __forceinline__ FastRec make_shadow(const Rec& r, int pool_index, double min_ball) {
   FastRec f;
   if (r.link >= 0) {
     f.dx = __double2float_rn(r.dx);
     f.dy = __double2float_rn(r.dy);
     f.dz = __double2float_rn(r.dz);
     f.c = __double2float_rn(dot3(r.mx, r.my, r.mz, r.dx, r.dy, r.dz));  // plane offset mean.dir in FP64, rounded once
-  } else {  // leaf: {pool index, marker, planarity weight w*w with w = 1 - bbox(0)/min_ball}
+  } else {
     const double w = 1.0 - r.bbox0 / min_ball;
     const double ww = w * w;
-    f.dx = __int_as_float(off + i);
+    f.dx = __int_as_float(pool_index);
     f.dy = __uint_as_float(kLeafMarker);
     f.dz = __int_as_float(__double2loint(ww));
     f.c = __int_as_float(__double2hiint(ww));
   }
-  const int h = heap_pos[i];
-  if (h >= 0) {  // (deeper than the implicit-heap limit: no heap position, walk modes 1-3 are off)
-    heap[hoff + h] = f;
-    bfs_of[hoff + h] = off + i;
-  }
-  {  // dense 4-ary record: quad_pos = record * 4 + slot (0: even-depth node, 1/2: its left/right child)
-    const int qp = quad_pos[i];
-    QuadRec* qr = quad + qoff + (qp >> 2);
-    const int slot = qp & 3;
-    if (slot == 1) qr->p1 = f;
-    else if (slot == 2) qr->p2 = f;
-    else {
-      qr->p0 = f;
-      qr->bfs0 = off + i;
-      qr->child0 = quad_child[i];  // first of the four contiguous records of the grandchildren (slot-relative)
-    }
-  }
-  if (r.link < 0) {  // breadth-first copy of a leaf shadow: weight in the first 8 bytes
-    f.dx = f.dz;
-    f.dy = f.c;
-  }
-  fast[i] = f;
-  links[i] = (r.link >= 0) ? (r.link + off) : r.link;
+  return f;
 }
 
-// Moving leaves + gate radius (reference: odometry/mad_icp.cpp:81, iteration invariant).
+// One thread per even-depth node: its whole 64-byte quad record (the node, its two children, the first record
+// of its grandchildren).  `recs` = the slot's exact records in the pool (at pool offset `off`).
 __global__ void __launch_bounds__(kStepBlock)
-k_prepare_moving(const double* __restrict__ means, int L, const __grid_constant__ IcpParams P,
-                 Moving4* __restrict__ out) {
+k_prepare_slot(const madtree_rec_t* __restrict__ recs, int n, int off, double min_ball, const int* __restrict__ lvl,
+               int n_levels, const int* __restrict__ child0, const int* __restrict__ rec_of, QuadRec* __restrict__ quad) {
+  const int i = blockIdx.x * kStepBlock + threadIdx.x;
+  if (i >= n) return;
+  if (depth_of(lvl, n_levels, i) & 1) return;
+  const Rec r = load_rec(recs + i);
+  QuadRec q;
+  q.p0 = make_shadow(r, off + i, min_ball);
+  q.p1 = q.p0;
+  q.p2 = q.p0;
+  q.bfs0 = off + i;
+  q.child0 = 0;
+  q.pad[0] = q.pad[1] = 0;
+  if (r.link >= 0) {
+    q.p1 = make_shadow(load_rec(recs + r.link), off + r.link, min_ball);
+    q.p2 = make_shadow(load_rec(recs + r.link + 1), off + r.link + 1, min_ball);
+    q.child0 = child0[i];
+  }
+  quad[rec_of[i]] = q;
+}
+
+// getLeafs order (tools/mad_tree.cpp:154-163) on the device: leaf_of[o] = breadth-first index of the leaf
+// whose ordinal is o (the records carry link = -1 - ordinal).
+__global__ void __launch_bounds__(kStepBlock)
+k_leaf_table(const madtree_rec_t* __restrict__ recs, int n, int* __restrict__ leaf_of) {
+  const int i = blockIdx.x * kStepBlock + threadIdx.x;
+  if (i >= n) return;
+  const int link = recs[i].link;
+  if (link < 0) leaf_of[-1 - link] = i;
+}
+
+// Moving leaves + gate radius (reference: odometry/mad_icp.cpp:81, iteration invariant).  The means come either
+// from the host upload (L x 3 doubles) or straight from a device-resident tree (MADicp::setMoving of the scan's
+// own leaves, mad_icp.cpp:51-53: recs + leaf_of, getLeafs order) -- then they are also written to `means`.
+__global__ void __launch_bounds__(kStepBlock)
+k_prepare_moving(double* __restrict__ means, int L, const __grid_constant__ IcpParams P, Moving4* __restrict__ out,
+                 const madtree_rec_t* __restrict__ recs, const int* __restrict__ leaf_of) {
   const int q = blockIdx.x * kStepBlock + threadIdx.x;
   if (q >= L) return;
   Moving4 m;
+  if (recs) {
+    const madtree_rec_t* r = recs + leaf_of[q];
+    means[3 * q] = r->mean[0];
+    means[3 * q + 1] = r->mean[1];
+    means[3 * q + 2] = r->mean[2];
+  }
   m.px = means[3 * q];
   m.py = means[3 * q + 1];
   m.pz = means[3 * q + 2];
@@ -92,7 +221,7 @@ k_search(const __grid_constant__ ModelView model, const Moving4* __restrict__ mo
     iso_apply(X, m.px, m.py, m.pz, mx, my, mz);
     const int leaf = descend(model, int(k), mx, my, mz, ww);
     if (hit) hit[w] = leaf;
-    if (ordinals) ordinals[w] = -1 - model.links[leaf];
+    if (ordinals) ordinals[w] = -1 - load_rec_link(model.recs + leaf);
   }
 }
 
@@ -220,6 +349,7 @@ struct GnArgs {
   const Moving4* moving;
   int L;
   int iters;
+  int clear_from;                          // first round whose gate passes set matched flags (GnState::clear_from)
   unsigned char* matched;                  // local matched flags (L bytes), zeroed by the host
   unsigned char* peer_matched[kMaxPeers];  // world > 1: every rank's matched array (peer mapped)
   double* partial;                         // gridDim.x * kAcc
@@ -354,7 +484,7 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
         double mx, my, mz, ww;
         iso_apply(s_X, m.px, m.py, m.pz, mx, my, mz);
         const Rec f = load_rec(A.model.recs + descend(A.model, int(k), mx, my, mz, ww));
-        if (linearize_one(s_X, A.P.rho_ker_sqrt, m, mx, my, mz, f, ww, v) && last_round) {
+        if (linearize_one(s_X, A.P.rho_ker_sqrt, m, mx, my, mz, f, ww, v) && it >= A.clear_from) {
           if (multi) {
             for (int r = 0; r < A.peers.world; ++r) A.peer_matched[r][q] = 1;
           } else {
@@ -406,6 +536,7 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
 #pragma unroll
           for (int i = 0; i < 12; ++i) st->X_out[i] = Xn[i];
           unpack_Hb(s_tot, st->H, st->b);
+          st->weight = inv_det6_dev(s_tot, 8);
           int c = 0;
           for (int w2 = 0; w2 < WARPS; ++w2) c += s_count[w2];
           st->n_matched = c;

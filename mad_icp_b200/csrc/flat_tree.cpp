@@ -572,6 +572,7 @@ struct madtree {
   std::vector<int32_t, default_init_allocator<int32_t>> leaf_nodes;  // getLeafs order -> node id
   std::vector<int32_t, default_init_allocator<int32_t>> bfs_index;   // node id -> breadth-first position
   std::vector<madtree_rec_t, default_init_allocator<madtree_rec_t>> recs;  // breadth-first records
+  std::vector<int32_t> level_start;  // breadth-first position of the first node of every depth, + total
   double b_max = 0, b_min = 0;
   int threads = 1;  // width the tree was built with; later whole-tree passes use the same
 
@@ -625,6 +626,14 @@ int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_mi
     madicp::set_error("madtree_build: more than 2^30 points");
     return MADICP_ERR_INVALID;
   }
+  // b_max <= 0 or NaN: `bbox(2) < b_max` (tools/mad_tree.cpp:64) never holds, one-point ranges keep splitting
+  // into an empty and a one-point child and the reference recurses until the stack or the heap is gone.
+  if (!(b_max > 0.0) || !std::isfinite(b_max) || !std::isfinite(b_min)) {
+    madicp::set_error("madtree_build: b_max must be finite and > 0, b_min finite");
+    return MADICP_ERR_INVALID;
+  }
+  madtree* t = nullptr;
+  try {
   const bool timing = getenv("MADTREE_TIMING") != nullptr;
   auto now = []() { return std::chrono::steady_clock::now(); };
   auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
@@ -632,7 +641,7 @@ int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_mi
   };
   madicp_host::HotScope hot;  // sections follow each other for the whole build; the numbering passes included
   const auto t0 = now();
-  madtree* t = tree_from_cache();
+  t = tree_from_cache();
   if (!t) t = new (std::nothrow) madtree;
   if (!t) return MADICP_ERR_NOMEM;
   t->b_max = b_max;
@@ -828,6 +837,7 @@ int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_mi
     for (const auto& h : hist)
       for (size_t d = 0; d < h.size(); ++d) level_start[d + 1] += h[d];
     for (size_t d = 0; d < levels; ++d) level_start[d + 1] += level_start[d];
+    t->level_start = level_start;
     // hist[c][d] <- first breadth-first position of chunk c on level d ; leaves_in[c] <- first ordinal
     std::vector<int32_t> run(level_start.begin(), level_start.end() - 1);
     int32_t leaf_run = 0;
@@ -864,6 +874,15 @@ int madtree_build(const double* points_xyz, int64_t n, double b_max, double b_mi
                  ms(t0, t1), ms(t1, now()));
   *out = t;
   return MADICP_OK;
+  } catch (const std::bad_alloc&) {
+    if (t) madtree_free(t);  // back to the cache (or deleted): its arrays are overwritten by the next build
+    madicp::set_error("madtree_build: out of memory");
+    return MADICP_ERR_NOMEM;
+  } catch (const std::exception& e) {
+    if (t) madtree_free(t);
+    madicp::set_error(std::string("madtree_build: ") + e.what());
+    return MADICP_ERR_INVALID;
+  }
 }
 
 void madtree_free(madtree_t* t) {
@@ -914,6 +933,19 @@ int madtree_leaves(const madtree_t* t, double* means, double* normals, double* b
 }
 
 const madtree_rec_t* madtree_records(const madtree_t* t) { return t ? t->recs.data() : nullptr; }
+
+int madtree_num_levels(const madtree_t* t) { return t ? int(t->level_start.size()) - 1 : MADICP_ERR_INVALID; }
+int madtree_level_offsets(const madtree_t* t, int32_t* out, int cap) {
+  if (!t || !out) return MADICP_ERR_INVALID;
+  const int n = int(t->level_start.size());
+  for (int i = 0; i < n && i < cap; ++i) out[i] = t->level_start[size_t(i)];
+  return n - 1;
+}
+int madtree_leaf_records(const madtree_t* t, int32_t* out) {
+  if (!t || !out) return MADICP_ERR_INVALID;
+  for (size_t o = 0; o < t->leaf_nodes.size(); ++o) out[o] = t->bfs_index[size_t(t->leaf_nodes[o])];
+  return int(t->leaf_nodes.size());
+}
 
 int madtree_export(const madtree_t* t, double* mean, double* eigenvectors, double* bbox, int32_t* num_points,
                    int32_t* left, int32_t* right, int32_t* leaf_ordinal) {

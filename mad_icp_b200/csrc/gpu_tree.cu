@@ -1,0 +1,357 @@
+// gpu_tree.cu -- MAD-tree build and scan ingest on the device: the launch side of
+// gpu_tree_kernels.cuh and the madtree_gpu_* / madicp_ingest entry points of include/madicp_b200.h.
+//
+// One level of the tree per iteration of a host loop; per level one host synchronisation, at the point where
+// Eigen's computeDirect calls atan2 / cos / sin (eig3.h): the device writes the two arguments per node into mapped
+// pinned memory, the host's glibc evaluates them (threaded), the next kernel reads cos / sin back through the same
+// mapping.  Everything else of a level is stream-ordered kernels.  No CPU fallback: the host never sees the points
+// again after the upload.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ctx.hpp"
+#include "gpu_tree_kernels.cuh"
+
+using namespace madicp;
+using namespace madicp::gtb;
+
+// ingest.cpp (host half of the ingest, host libm service)
+int madicp_deskew_plan(const void* xyz, int is_f32, int64_t n, const double T_prev[12], const double T_now[12],
+                       double sensor_hz, int num_threads, int32_t* perm, uint16_t* chunk, double* poses, int* n_poses);
+void madicp_host_trig(const double* args, double* res, int n, int num_threads);
+
+namespace {
+
+struct BuildState {
+  size_t cap = 0;  // points
+  double* P[2] = {nullptr, nullptr};
+  int* owner[2] = {nullptr, nullptr};
+  unsigned char* flag = nullptr;
+  int *G = nullptr, *tile = nullptr, *XF = nullptr, *BP = nullptr;
+  // level-local
+  double* S = nullptr;
+  Eig3Mid* mid = nullptr;
+  long long* box = nullptr;
+  int *cnt = nullptr, *imin = nullptr, *child_of = nullptr;
+  unsigned long long* dmin = nullptr;
+  // whole build
+  Nodes N{};
+  int* d_count = nullptr;  // nodes per level (kMaxLevels + 2)
+  // mapped pinned host memory
+  double *h_args = nullptr, *h_res = nullptr;
+  Ctl* h_ctl = nullptr;
+  int* h_lvl = nullptr;
+  // ingest staging
+  void* d_raw = nullptr;  // the raw scan as uploaded (float32 or float64), 3 * cap doubles
+  int* d_perm = nullptr;
+  unsigned short* d_chunk = nullptr;
+  double* d_poses = nullptr;
+  int32_t* h_perm = nullptr;
+  uint16_t* h_chunk = nullptr;
+  double* h_poses = nullptr;
+  int64_t n_resident = 0;  // points of the cloud madicp_ingest left in P[0]
+  uint64_t seq = 0;        // builds so far (madtree_gpu_export is valid for the latest one only)
+  int threads = 8;
+  std::vector<void*> dev_allocs, host_allocs;
+};
+
+template <class T>
+int dev_alloc(BuildState* bs, T** p, size_t count) {
+  CK(cudaMalloc(p, count * sizeof(T)));
+  bs->dev_allocs.push_back(*p);
+  return MADICP_OK;
+}
+template <class T>
+int host_alloc(BuildState* bs, T** p, size_t count) {
+  CK(cudaHostAlloc(p, count * sizeof(T), cudaHostAllocMapped));
+  bs->host_allocs.push_back(*p);
+  return MADICP_OK;
+}
+
+void release(BuildState* bs) {
+  for (void* p : bs->dev_allocs) cudaFree(p);
+  for (void* p : bs->host_allocs) cudaFreeHost(p);
+  bs->dev_allocs.clear();
+  bs->host_allocs.clear();
+}
+
+int ensure_state(madicp_ctx* c, size_t n, BuildState** out) {
+  BuildState* bs = static_cast<BuildState*>(c->build_state);
+  if (bs && bs->cap >= n) {
+    *out = bs;
+    return MADICP_OK;
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  const uint64_t seq = bs ? bs->seq : 0;
+  if (bs) {
+    release(bs);
+    delete bs;
+    c->build_state = nullptr;
+  }
+  bs = new BuildState;
+  bs->seq = seq;
+  size_t cap = size_t(1) << 17;
+  while (cap < n) cap <<= 1;
+  bs->cap = cap;
+  if (const char* e = getenv("MADICP_HOST_THREADS")) bs->threads = std::max(1, atoi(e));
+  const size_t nodes = 2 * cap + 2, lvl = cap + 2;
+  int rc = 0;
+  for (int k = 0; k < 2 && !rc; ++k) {
+    rc = dev_alloc(bs, &bs->P[k], 3 * cap);
+    if (!rc) rc = dev_alloc(bs, &bs->owner[k], cap);
+  }
+  if (!rc) rc = dev_alloc(bs, &bs->flag, cap);
+  if (!rc) rc = dev_alloc(bs, &bs->G, cap);
+  if (!rc) rc = dev_alloc(bs, &bs->tile, cap / kTile + 2);
+  if (!rc) rc = dev_alloc(bs, &bs->XF, cap);
+  if (!rc) rc = dev_alloc(bs, &bs->BP, cap);
+  if (!rc) rc = dev_alloc(bs, &bs->S, 9 * lvl);
+  if (!rc) rc = dev_alloc(bs, &bs->mid, lvl);
+  if (!rc) rc = dev_alloc(bs, &bs->box, 6 * lvl);
+  if (!rc) rc = dev_alloc(bs, &bs->cnt, lvl);
+  if (!rc) rc = dev_alloc(bs, &bs->imin, lvl);
+  if (!rc) rc = dev_alloc(bs, &bs->child_of, lvl);
+  if (!rc) rc = dev_alloc(bs, &bs->dmin, lvl);
+  if (!rc) rc = dev_alloc(bs, &bs->N.lo, nodes);
+  if (!rc) rc = dev_alloc(bs, &bs->N.hi, nodes);
+  if (!rc) rc = dev_alloc(bs, &bs->N.parent, nodes);
+  if (!rc) rc = dev_alloc(bs, &bs->N.pp, nodes);
+  if (!rc) rc = dev_alloc(bs, &bs->N.anc, nodes);
+  if (!rc) rc = dev_alloc(bs, &bs->N.link, nodes);
+  if (!rc) rc = dev_alloc(bs, &bs->N.full, 16 * nodes);
+  if (!rc) rc = dev_alloc(bs, &bs->d_count, size_t(kMaxLevels) + 2);
+  if (!rc) {
+    double* raw = nullptr;
+    rc = dev_alloc(bs, &raw, 3 * cap);
+    bs->d_raw = raw;
+  }
+  if (!rc) rc = dev_alloc(bs, &bs->d_perm, cap);
+  if (!rc) rc = dev_alloc(bs, &bs->d_chunk, cap);
+  if (!rc) rc = dev_alloc(bs, &bs->d_poses, size_t(65536) * 12);
+  if (!rc) rc = host_alloc(bs, &bs->h_args, 2 * lvl);
+  if (!rc) rc = host_alloc(bs, &bs->h_res, 2 * lvl);
+  if (!rc) rc = host_alloc(bs, &bs->h_ctl, size_t(kMaxLevels) + 2);
+  if (!rc) rc = host_alloc(bs, &bs->h_lvl, size_t(kMaxLevels) + 2);
+  if (!rc) rc = host_alloc(bs, &bs->h_perm, cap);
+  if (!rc) rc = host_alloc(bs, &bs->h_chunk, cap);
+  if (!rc) rc = host_alloc(bs, &bs->h_poses, size_t(65536) * 12);
+  if (rc) {
+    release(bs);
+    delete bs;
+    return rc;
+  }
+  c->build_state = bs;
+  *out = bs;
+  return MADICP_OK;
+}
+
+__global__ void k_init_root(Nodes N, int n, int* count) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    N.lo[0] = 0;
+    N.hi[0] = n;
+    N.parent[0] = -1;
+    N.pp[0] = -1;
+    N.anc[0] = 0;
+    N.link[0] = -1;
+    count[0] = 1;
+  }
+}
+
+int blocks(int64_t n, int per = kBlock) { return int(std::max<int64_t>(1, (n + per - 1) / per)); }
+
+// Builds the tree of the n points in bs->P[0].
+int build_resident(madicp_ctx* c, BuildState* bs, int64_t n64, double b_max, double b_min, madtree_gpu** out) {
+  if (!(b_max > 0.0) || !std::isfinite(b_max) || !std::isfinite(b_min)) {
+    set_error("madtree_gpu_build: b_max must be finite and > 0, b_min finite");
+    return MADICP_ERR_INVALID;
+  }
+  const int n = int(n64);
+  cudaStream_t st = c->stream;
+  bs->seq++;
+  k_init_root<<<1, 32, 0, st>>>(bs->N, n, bs->d_count);
+  CK(cudaMemsetAsync(bs->owner[0], 0, size_t(n) * sizeof(int), st));
+  c->launches++;
+  int g0 = 0, nl = 1, bound = 1, cur = 0, depth = 0;
+  int total_leaves = 0;
+  bs->h_lvl[0] = 0;
+  const int pblocks = blocks(n);
+  const int tiles = (n + kTile - 1) / kTile;
+  while (true) {
+    if (depth >= kMaxLevels) {
+      set_error("madtree_gpu_build: tree deeper than 4096 levels");
+      return MADICP_ERR_INVALID;
+    }
+    const int* d_nl = bs->d_count + depth;
+    // `bound` >= the number of nodes of this level (exact count is on the device until the sync below)
+    k_sums<<<blocks(int64_t(bound) * 9), kBlock, 0, st>>>(bs->P[cur], bs->N.lo, bs->N.hi, g0, d_nl, bs->S);
+    k_eig_prep<<<blocks(bound), kBlock, 0, st>>>(bs->S, bs->N, g0, d_nl, bs->mid, bs->h_args);
+    c->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));  // the level's one host round trip: libm for the eigen-decomposition
+    if (depth > 0) {
+      nl = bs->h_ctl[depth - 1].n_next;
+      total_leaves += bs->h_ctl[depth - 1].n_leaves;
+    }
+    if (nl == 0) break;
+    if (size_t(g0) + size_t(nl) > 2 * bs->cap + 2) {
+      set_error("madtree_gpu_build: internal error (node count)");
+      return MADICP_ERR_INVALID;
+    }
+    madicp_host_trig(bs->h_args, bs->h_res, nl, bs->threads);
+    k_eig_finish<<<blocks(nl), kBlock, 0, st>>>(bs->mid, bs->h_res, bs->N, g0, d_nl, bs->box, bs->cnt, bs->dmin, bs->imin);
+    k_bbox_flags<<<pblocks, kBlock, 0, st>>>(bs->P[cur], bs->owner[cur], n, bs->N, g0, bs->box, bs->cnt, bs->flag);
+    k_decide<<<1, 1024, 0, st>>>(bs->N, g0, bs->d_count + depth, bs->d_count + depth + 1, bs->box, bs->cnt, b_max, b_min,
+                                bs->h_ctl + depth, bs->child_of);
+    k_leaf_dist<<<pblocks, kBlock, 0, st>>>(bs->P[cur], bs->owner[cur], n, bs->N, g0, bs->dmin);
+    k_leaf_pick<<<pblocks, kBlock, 0, st>>>(bs->P[cur], bs->owner[cur], n, bs->N, g0, bs->dmin, bs->imin);
+    k_leaf_set<<<blocks(nl), kBlock, 0, st>>>(bs->P[cur], bs->N, g0, d_nl, n, bs->imin);
+    k_scan_tiles<<<tiles, kTile, 0, st>>>(bs->flag, n, bs->G, bs->tile);
+    k_scan_tile_sums<<<1, 1024, 0, st>>>(bs->tile, tiles);
+    k_split_lists<<<pblocks, kBlock, 0, st>>>(bs->owner[cur], n, bs->N, g0, bs->cnt, bs->flag, bs->G, bs->tile, bs->XF, bs->BP);
+    k_split_scatter<<<pblocks, kBlock, 0, st>>>(bs->P[cur], bs->P[cur ^ 1], bs->owner[cur], bs->owner[cur ^ 1], n, bs->N, g0,
+                                               bs->cnt, bs->child_of, bs->flag, bs->G, bs->tile, bs->XF, bs->BP);
+    c->launches += 10;
+    CK(cudaGetLastError());
+    g0 += nl;
+    bound = std::min(2 * nl, n + 1);
+    cur ^= 1;
+    ++depth;
+    bs->h_lvl[depth] = g0;
+  }
+  const int n_nodes = g0, n_levels = depth;
+  madtree_gpu* t = nullptr;
+  int rc = madicp_tree_alloc(c, size_t(n_nodes), &t);
+  if (rc) return rc;
+  t->n_nodes = n_nodes;
+  t->n_leaves = total_leaves;
+  t->n_levels = n_levels;
+  t->h_lvl.assign(bs->h_lvl, bs->h_lvl + n_levels + 1);
+  t->n_points = n;
+  t->full = bs->N.full;
+  t->build_seq = bs->seq;
+  // getLeafs ordinals: leaves in ascending order of their range start; then the 64-byte records
+  CK(cudaMemsetAsync(bs->flag, 0, size_t(n), st));
+  k_mark_leaf_starts<<<blocks(n_nodes), kBlock, 0, st>>>(bs->N, n_nodes, n, bs->flag);
+  k_scan_tiles<<<tiles, kTile, 0, st>>>(bs->flag, n, bs->G, bs->tile);
+  k_scan_tile_sums<<<1, 1024, 0, st>>>(bs->tile, tiles);
+  k_records<<<blocks(n_nodes), kBlock, 0, st>>>(bs->N, n_nodes, n, bs->G, bs->tile, t->recs, t->leaf_of);
+  CK(cudaMemcpyAsync(t->lvl, bs->h_lvl, size_t(n_levels + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+  c->launches += 4;
+  CK(cudaGetLastError());
+  *out = t;
+  return MADICP_OK;
+}
+
+}  // namespace
+
+void madicp_gpu_build_release(madicp_ctx* c) {
+  BuildState* bs = static_cast<BuildState*>(c->build_state);
+  if (!bs) return;
+  release(bs);
+  delete bs;
+  c->build_state = nullptr;
+}
+
+extern "C" {
+
+int madtree_gpu_build(madicp_ctx_t* c, const double* points_xyz, int64_t n, double b_max, double b_min,
+                      madtree_gpu_t** out) {
+  if (!c || !points_xyz || !out || n <= 0 || n > (int64_t(1) << 24)) {
+    set_error("madtree_gpu_build: bad arguments (1 <= n <= 2^24 points)");
+    return MADICP_ERR_INVALID;
+  }
+  MADICP_TRY
+  CK(cudaSetDevice(c->device));
+  BuildState* bs = nullptr;
+  int rc = ensure_state(c, size_t(n), &bs);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(bs->P[0], points_xyz, size_t(n) * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  bs->n_resident = n;
+  return build_resident(c, bs, n, b_max, b_min, out);
+  MADICP_CATCH("madtree_gpu_build")
+}
+
+int madtree_gpu_build_resident(madicp_ctx_t* c, double b_max, double b_min, madtree_gpu_t** out) {
+  if (!c || !out) return MADICP_ERR_INVALID;
+  MADICP_TRY
+  BuildState* bs = static_cast<BuildState*>(c->build_state);
+  if (!bs || bs->n_resident <= 0) {
+    set_error("madtree_gpu_build_resident: no cloud on the device (call madicp_ingest first)");
+    return MADICP_ERR_STATE;
+  }
+  CK(cudaSetDevice(c->device));
+  return build_resident(c, bs, bs->n_resident, b_max, b_min, out);
+  MADICP_CATCH("madtree_gpu_build_resident")
+}
+
+int madtree_gpu_export(const madtree_gpu_t* t, double* mean, double* eigenvectors, double* bbox, int32_t* num_points) {
+  if (!t) return MADICP_ERR_INVALID;
+  madicp_ctx* c = t->ctx;
+  BuildState* bs = static_cast<BuildState*>(c->build_state);
+  if (!t->full || !bs || bs->seq != t->build_seq || bs->N.full != t->full) {
+    set_error("madtree_gpu_export: only the most recently device-built tree of a context can be exported");
+    return MADICP_ERR_STATE;
+  }
+  MADICP_TRY
+  CK(cudaSetDevice(c->device));
+  std::vector<double> full(size_t(t->n_nodes) * 16);
+  CK(cudaMemcpyAsync(full.data(), t->full, full.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  for (int g = 0; g < t->n_nodes; ++g) {
+    const double* f = full.data() + size_t(g) * 16;
+    if (mean) memcpy(mean + 3 * size_t(g), f, 24);
+    if (eigenvectors) memcpy(eigenvectors + 9 * size_t(g), f + 3, 72);
+    if (bbox) memcpy(bbox + 3 * size_t(g), f + 12, 24);
+    if (num_points) num_points[g] = int32_t(f[15]);
+  }
+  return MADICP_OK;
+  MADICP_CATCH("madtree_gpu_export")
+}
+
+int madicp_ingest(madicp_ctx_t* c, const void* xyz, int64_t n, int is_f32, int deskew, const double T_prev[12],
+                  const double T_now[12], double sensor_hz, int num_threads, double* points_out) {
+  if (!c || !xyz || n <= 0 || n > (int64_t(1) << 24) || (deskew && (!T_prev || !T_now || !(sensor_hz > 0.0)))) {
+    set_error("madicp_ingest: bad arguments (1 <= n <= 2^24 points)");
+    return MADICP_ERR_INVALID;
+  }
+  MADICP_TRY
+  CK(cudaSetDevice(c->device));
+  BuildState* bs = nullptr;
+  int rc = ensure_state(c, size_t(n), &bs);
+  if (rc) return rc;
+  const size_t raw_bytes = size_t(n) * 3 * (is_f32 ? sizeof(float) : sizeof(double));
+  cudaStream_t st = c->stream;
+  // the raw scan goes up while the host works out the order (deskew only)
+  CK(cudaMemcpyAsync(bs->d_raw, xyz, raw_bytes, cudaMemcpyHostToDevice, st));
+  const int* d_perm = nullptr;
+  const unsigned short* d_chunk = nullptr;
+  if (deskew) {
+    CK(cudaStreamSynchronize(st));  // h_perm / h_chunk / h_poses of the previous scan have been consumed
+    int n_poses = 0;
+    rc = madicp_deskew_plan(xyz, is_f32, n, T_prev, T_now, sensor_hz, num_threads, bs->h_perm, bs->h_chunk, bs->h_poses,
+                            &n_poses);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(bs->d_perm, bs->h_perm, size_t(n) * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(bs->d_chunk, bs->h_chunk, size_t(n) * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(bs->d_poses, bs->h_poses, size_t(n_poses) * 12 * sizeof(double), cudaMemcpyHostToDevice, st));
+    d_perm = bs->d_perm;
+    d_chunk = bs->d_chunk;
+  }
+  k_ingest<<<blocks(n), kBlock, 0, st>>>(bs->d_raw, is_f32, d_perm, d_chunk, bs->d_poses, int(n), bs->P[0]);
+  c->launches++;
+  CK(cudaGetLastError());
+  bs->n_resident = n;
+  if (points_out) {
+    CK(cudaMemcpyAsync(points_out, bs->P[0], size_t(n) * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  return MADICP_OK;
+  MADICP_CATCH("madicp_ingest")
+}
+
+}  // extern "C"

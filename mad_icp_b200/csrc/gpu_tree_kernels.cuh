@@ -1,0 +1,524 @@
+// gpu_tree_kernels.cuh -- MADtree::build (tools/mad_tree.cpp:47-130, tools/utils.h:38-97) on the device,
+// level by level.  Same tree as the reference, bit for bit:
+//   * sums         Sigma x, Sigma x x^T of every node run in ARRAY ORDER, one thread per (node, chain), FP64 adds with
+//                  no FMA and no re-association (utils.h:55-73): the order of the additions IS the result;
+//   * eigenvectors Eigen's closed-form computeDirect (eig3.h) in two halves around its three libm calls, which the
+//                  host evaluates between two kernels of a level (glibc's atan2/cos/sin are not correctly rounded,
+//                  so no device implementation can reproduce their bits);
+//   * extents      min / max of R^T (p - mean) are order-independent: per-point threads, segmented warp reduction,
+//                  one atomic per (warp, node); the split side of every point falls out of the same product;
+//   * split()      the reference's two-pointer loop in closed form (two compactions + one scatter, flat_tree.cpp):
+//                  a prefix sum of the side flags, two index lists per node, every point moved exactly once;
+//   * leaves       nearest cloud point to the centroid with "first minimum wins" = lexicographic (distance, index)
+//                  minimum: two atomic passes; normal inheritance (plane predecessor / ancestor with >= 3 points)
+//                  through per-node indices instead of pointers.
+// Nodes are numbered breadth-first as they are created (children of a level in parent order, siblings adjacent),
+// which is the order of the 64-byte records the registration kernels read; getLeafs ordinals follow from the
+// leaves' point ranges (left-first DFS order == ascending range start).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/madicp_b200.h"
+#include "arith.h"
+#include "eig3.h"
+
+namespace madicp {
+namespace gtb {
+
+constexpr int kBlock = 256;
+constexpr int kTile = 1024;  // positions per CTA of the flag scan
+
+// per-node data kept for the whole build (index = breadth-first node id)
+struct Nodes {
+  int* lo;      // point range [lo, hi)
+  int* hi;
+  int* parent;  // -1 for the root
+  int* pp;      // plane predecessor handed down from above (-1: none)          mad_tree.cpp:90-93
+  int* anc;     // nearest ancestor with >= 3 points, or the root               mad_tree.cpp:68-73
+  int* link;    // left child id, or -1 for a leaf
+  double* full; // 16 per node: mean 3, eigenvectors 9 (column-major), bbox 3, num_points
+};
+
+// control block in mapped pinned host memory: written by k_decide, read by the host after the level's sync
+struct Ctl {
+  int n_next;    // nodes of the next level (2 x internal nodes of this one)
+  int n_leaves;  // leaves found on this level
+  int n_active;  // points still in internal nodes
+  int pad;
+};
+
+__device__ __forceinline__ long long dbits(double v) { return __double_as_longlong(v); }
+
+// ---------------------------------------------------------------------------------------------------------
+// (1) sums in array order: thread = (node j of the level, chain c), c: 0 x, 1 y, 2 z, 3 xx, 4 yx, 5 zx, 6 yy, 7 zy, 8 zz
+__global__ void __launch_bounds__(kBlock)
+k_sums(const double* __restrict__ P, const int* __restrict__ lo, const int* __restrict__ hi, int g0,
+       const int* __restrict__ n_level, double* __restrict__ S) {
+  const int t = blockIdx.x * kBlock + threadIdx.x;
+  const int j = t / 9, c = t - j * 9;
+  if (j >= *n_level) return;
+  const int b = lo[g0 + j], e = hi[g0 + j];
+  // which two coordinates multiply (u == 3: the term is the coordinate itself)
+  const int u = (c < 3) ? 3 : (c < 6 ? 0 : (c < 8 ? 1 : 2));
+  const int v = (c < 3) ? c : (c < 6 ? c - 3 : (c < 8 ? c - 5 : 2));
+  double s = 0.0;
+  int i = b;
+  for (; i + 8 <= e; i += 8) {  // loads and products of 8 points are issued ahead of the dependent adds
+    double term[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const double* p = P + 3 * size_t(i + k);
+      const double a = __ldg(p + v);
+      term[k] = (u == 3) ? a : mul_(a, __ldg(p + u));
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s = add_(s, term[k]);
+  }
+  for (; i < e; ++i) {
+    const double* p = P + 3 * size_t(i);
+    const double a = __ldg(p + v);
+    s = add_(s, (u == 3) ? a : mul_(a, __ldg(p + u)));
+  }
+  S[size_t(j) * 9 + c] = s;
+}
+
+// (2) mean, covariance (utils.h:66-70), first half of computeDirect -> the arguments of atan2 for the host
+__global__ void __launch_bounds__(kBlock)
+k_eig_prep(const double* __restrict__ S, Nodes N, int g0, const int* __restrict__ n_level, Eig3Mid* __restrict__ mid,
+           double* __restrict__ args /* mapped host memory: 2 per node */) {
+  const int j = blockIdx.x * kBlock + threadIdx.x;
+  if (j >= *n_level) return;
+  const int g = g0 + j;
+  const int k = N.hi[g] - N.lo[g];
+  const double* s = S + size_t(j) * 9;
+  double sx = s[0], sy = s[1], sz = s[2];
+  double cxx = s[3], cyx = s[4], czx = s[5], cyy = s[6], czy = s[7], czz = s[8];
+  const double inv = 1. / double(k);
+  sx = mul_(sx, inv); sy = mul_(sy, inv); sz = mul_(sz, inv);
+  cxx = mul_(cxx, inv); cyx = mul_(cyx, inv); czx = mul_(czx, inv);
+  cyy = mul_(cyy, inv); czy = mul_(czy, inv); czz = mul_(czz, inv);
+  cxx = sub_(cxx, mul_(sx, sx)); cyx = sub_(cyx, mul_(sy, sx)); czx = sub_(czx, mul_(sz, sx));
+  cyy = sub_(cyy, mul_(sy, sy)); czy = sub_(czy, mul_(sz, sy)); czz = sub_(czz, mul_(sz, sz));
+  const double f = double(k) / double(k - 1);
+  const Sym3 c{mul_(cxx, f), mul_(cyx, f), mul_(czx, f), mul_(cyy, f), mul_(czy, f), mul_(czz, f)};
+  double* full = N.full + size_t(g) * 16;
+  full[0] = sx; full[1] = sy; full[2] = sz;
+  full[15] = double(k);
+  Eig3Mid m;
+  eig3_prepare(c, m);
+  mid[j] = m;
+  args[2 * size_t(j)] = m.sq;
+  args[2 * size_t(j) + 1] = m.half_b;
+}
+
+// (3) second half of computeDirect with the host's cos/sin; resets the accumulators of the level
+__global__ void __launch_bounds__(kBlock)
+k_eig_finish(const Eig3Mid* __restrict__ mid, const double* __restrict__ res /* mapped host: cos, sin per node */,
+             Nodes N, int g0, const int* __restrict__ n_level, long long* __restrict__ box, int* __restrict__ cnt,
+             unsigned long long* __restrict__ dmin, int* __restrict__ imin) {
+  const int j = blockIdx.x * kBlock + threadIdx.x;
+  if (j >= *n_level) return;
+  double V[9];
+  eig3_finish(mid[j], res[2 * size_t(j)], res[2 * size_t(j) + 1], V);
+  double* full = N.full + size_t(g0 + j) * 16;
+#pragma unroll
+  for (int a = 0; a < 9; ++a) full[3 + a] = V[a];
+#pragma unroll
+  for (int a = 0; a < 6; ++a) box[size_t(j) * 6 + a] = 0;  // bits of +0.0: extents start from 0 (utils.h:83-84)
+  cnt[j] = 0;
+  dmin[j] = 0x7fefffffffffffffull;  // DBL_MAX (mad_tree.cpp:77)
+  imin[j] = 0x7fffffff;
+}
+
+// (4) extents of R^T (p - mean) (utils.h:76-97: extents start from 0, a NaN never replaces) and the side of every
+// point with respect to the split plane (the v(2) of the same product is the predicate of mad_tree.cpp:95-97).
+// owner[i] = level-local node of position i, -1 for positions whose node is already a leaf.
+__global__ void __launch_bounds__(kBlock)
+k_bbox_flags(const double* __restrict__ P, const int* __restrict__ owner, int n, Nodes N, int g0,
+             long long* __restrict__ box, int* __restrict__ cnt, unsigned char* __restrict__ flag) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31;
+  int j = (i < n) ? owner[i] : -1;
+  double lo3[3] = {0.0, 0.0, 0.0}, hi3[3] = {0.0, 0.0, 0.0};
+  int pass = 0;
+  if (j >= 0) {
+    const double* full = N.full + size_t(g0 + j) * 16;
+    const double dx = sub_(P[3 * size_t(i)], full[0]), dy = sub_(P[3 * size_t(i) + 1], full[1]),
+                 dz = sub_(P[3 * size_t(i) + 2], full[2]);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double v = dot3(full[3 + 3 * a], full[4 + 3 * a], full[5 + 3 * a], dx, dy, dz);
+      lo3[a] = (v < 0.0) ? v : 0.0;
+      hi3[a] = (0.0 < v) ? v : 0.0;
+      if (a == 2) pass = (v < 0.0) ? 1 : 0;
+    }
+  }
+  if (i < n) flag[i] = (unsigned char) pass;
+  // segmented reduction over the lanes of the same node (positions of a node are contiguous)
+  const unsigned peers = __match_any_sync(0xffffffffu, j);
+  const unsigned last = 31u - unsigned(__clz(int(peers)));
+  const unsigned first = unsigned(__ffs(int(peers))) - 1u;
+  const int npass = __popc(__ballot_sync(0xffffffffu, pass) & peers);
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double l = __shfl_down_sync(0xffffffffu, lo3[a], off);
+      const double h = __shfl_down_sync(0xffffffffu, hi3[a], off);
+      if (lane + off <= last) {
+        lo3[a] = (l < lo3[a]) ? l : lo3[a];
+        hi3[a] = (hi3[a] < h) ? h : hi3[a];
+      }
+    }
+  }
+  if (j >= 0 && lane == first) {
+    long long* b = box + size_t(j) * 6;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {  // both stored as non-negative doubles: their bit patterns order like integers
+      if (lo3[a] < 0.0) atomicMax(b + a, dbits(-lo3[a]));
+      if (hi3[a] > 0.0) atomicMax(b + 3 + a, dbits(hi3[a]));
+    }
+    if (npass) atomicAdd(cnt + j, npass);
+  }
+}
+
+// (5) leaf test, children, inheritance of the plane predecessor / ancestor; ONE CTA walks the level in tiles.
+__global__ void __launch_bounds__(1024)
+k_decide(Nodes N, int g0, const int* __restrict__ n_level, int* __restrict__ n_next, const long long* __restrict__ box,
+         const int* __restrict__ cnt, double b_max, double b_min, Ctl* __restrict__ ctl /* mapped host */,
+         int* __restrict__ child_of /* level-local: first child (level-local in the next level) or -1 */) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry, s_leaves, s_active;
+  const int n = *n_level;
+  const int g1 = g0 + n;  // first node of the next level
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = s_leaves = s_active = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int j = base + threadIdx.x;
+    int internal = 0, npts = 0;
+    double bbox[3] = {0, 0, 0};
+    int g = g0 + j;
+    if (j < n) {
+      double* full = N.full + size_t(g) * 16;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const double lo = -__longlong_as_double(box[size_t(j) * 6 + a]);
+        const double hi = __longlong_as_double(box[size_t(j) * 6 + 3 + a]);
+        bbox[a] = sub_(hi, lo);
+        full[12 + a] = bbox[a];
+      }
+      npts = N.hi[g] - N.lo[g];
+      internal = (bbox[2] < b_max) ? 0 : 1;
+    }
+    // exclusive scan of `internal` over the tile
+    int incl = internal;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_warp[lane];
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, w, off);
+        if (lane >= off) w += v;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int rank = s_carry + (warp ? s_warp[warp - 1] : 0) + (incl - internal);
+    if (j < n) {
+      if (internal) {
+        const int cl = 2 * rank;  // level-local ids of the children in the next level
+        const int gl = g1 + cl;
+        const int lo = N.lo[g], hi = N.hi[g], m = cnt[j];
+        N.link[g] = gl;
+        child_of[j] = cl;
+        int pp = N.pp[g];
+        if (pp < 0 && bbox[0] < b_min) pp = g;  // this node becomes the plane predecessor of its subtree
+        const int anc = (npts >= 3 || N.parent[g] < 0) ? g : N.anc[g];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          N.lo[gl + s] = s ? lo + m : lo;
+          N.hi[gl + s] = s ? hi : lo + m;
+          N.parent[gl + s] = g;
+          N.pp[gl + s] = pp;
+          N.anc[gl + s] = anc;
+        }
+        atomicAdd(&s_active, npts);
+      } else {
+        N.link[g] = -1;
+        child_of[j] = -1;
+        // leaf normal (mad_tree.cpp:65-74): the plane predecessor's, else (fewer than 3 points) the nearest
+        // ancestor's with >= 3 points; both are internal nodes, whose eigenvectors are final
+        double* full = N.full + size_t(g) * 16;
+        const int pp = N.pp[g];
+        int src = -1;
+        if (pp >= 0) src = pp;
+        else if (npts < 3 && N.parent[g] >= 0) src = N.anc[g];
+        if (src >= 0) {
+          const double* o = N.full + size_t(src) * 16;
+          full[3] = o[3]; full[4] = o[4]; full[5] = o[5];
+        }
+        atomicAdd(&s_leaves, 1);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = rank + internal;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *n_next = 2 * s_carry;
+    ctl->n_next = 2 * s_carry;
+    ctl->n_leaves = s_leaves;
+    ctl->n_active = s_active;
+    __threadfence_system();
+  }
+}
+
+// (6) leaves: nearest cloud point to the centroid, first minimum wins (mad_tree.cpp:76-86)
+__global__ void __launch_bounds__(kBlock)
+k_leaf_dist(const double* __restrict__ P, const int* __restrict__ owner, int n, Nodes N, int g0,
+            unsigned long long* __restrict__ dmin) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  const int j = owner[i];
+  if (j < 0 || N.link[g0 + j] >= 0) return;
+  const double* full = N.full + size_t(g0 + j) * 16;
+  const double d = norm3(sub_(P[3 * size_t(i)], full[0]), sub_(P[3 * size_t(i) + 1], full[1]), sub_(P[3 * size_t(i) + 2], full[2]));
+  if (d < 1.7976931348623157e308) atomicMin(dmin + j, (unsigned long long) dbits(d));  // d >= 0: bits order like the values
+}
+__global__ void __launch_bounds__(kBlock)
+k_leaf_pick(const double* __restrict__ P, const int* __restrict__ owner, int n, Nodes N, int g0,
+            const unsigned long long* __restrict__ dmin, int* __restrict__ imin) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  const int j = owner[i];
+  if (j < 0 || N.link[g0 + j] >= 0) return;
+  const double* full = N.full + size_t(g0 + j) * 16;
+  const double d = norm3(sub_(P[3 * size_t(i)], full[0]), sub_(P[3 * size_t(i) + 1], full[1]), sub_(P[3 * size_t(i) + 2], full[2]));
+  if (d < 1.7976931348623157e308 && (unsigned long long) dbits(d) == dmin[j]) atomicMin(imin + j, i);
+}
+__global__ void __launch_bounds__(kBlock)
+k_leaf_set(const double* __restrict__ P, Nodes N, int g0, const int* __restrict__ n_level_prev, int n_points,
+           const int* __restrict__ imin) {
+  const int j = blockIdx.x * kBlock + threadIdx.x;
+  if (j >= *n_level_prev) return;
+  const int g = g0 + j;
+  if (N.link[g] >= 0) return;
+  int i = imin[j];
+  if (i == 0x7fffffff) i = N.lo[g];  // no distance below DBL_MAX: the reference keeps *begin
+  double* full = N.full + size_t(g) * 16;
+  if (i < n_points) {
+    full[0] = P[3 * size_t(i)]; full[1] = P[3 * size_t(i) + 1]; full[2] = P[3 * size_t(i) + 2];
+  }
+}
+
+// (7) exclusive prefix of the side flags over the whole array: per-tile scan + scan of the tile totals
+__global__ void __launch_bounds__(kTile)
+k_scan_tiles(const unsigned char* __restrict__ flag, int n, int* __restrict__ G, int* __restrict__ tile_sum) {
+  __shared__ int s_warp[32];
+  const int i = blockIdx.x * kTile + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int f = (i < n) ? int(flag[i]) : 0;
+  int incl = f;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += v;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = s_warp[lane];
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, w, off);
+      if (lane >= off) w += v;
+    }
+    s_warp[lane] = w;
+  }
+  __syncthreads();
+  const int excl = (warp ? s_warp[warp - 1] : 0) + incl - f;
+  if (i < n) G[i] = excl;
+  if (threadIdx.x == kTile - 1) tile_sum[blockIdx.x] = excl + f;
+}
+__global__ void __launch_bounds__(1024)
+k_scan_tile_sums(int* __restrict__ tile_sum, int n_tiles) {  // in place: exclusive; one CTA
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_tiles; base += 1024) {
+    const int t = base + threadIdx.x;
+    const int v0 = (t < n_tiles) ? tile_sum[t] : 0;
+    int incl = v0;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_warp[lane];
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, w, off);
+        if (lane >= off) w += v;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int excl = s_carry + (warp ? s_warp[warp - 1] : 0) + incl - v0;
+    if (t < n_tiles) tile_sum[t] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = excl + v0;
+    __syncthreads();
+  }
+}
+// (8) split() in closed form (flat_tree.cpp Builder::split): index lists, then one move per point.
+// With m = number of points of the node that pass (are on the negative side), positions relative to the node:
+//   XF[a] = a-th failing position of [0,m), BP[r] = r-th passing position of [m,n)   (A of each)
+struct SplitCtx {
+  int lo, n, m, pass_lower, A;
+};
+__device__ __forceinline__ SplitCtx split_ctx(const Nodes& N, int g, int m, const int* G, const int* tile_off, int n_points,
+                                              const unsigned char* flag) {
+  SplitCtx c;
+  c.lo = N.lo[g];
+  c.n = N.hi[g] - c.lo;
+  c.m = m;
+  const int base = G[c.lo] + tile_off[c.lo >> 10];
+  int at_m;
+  if (c.lo + m < n_points) at_m = G[c.lo + m] + tile_off[(c.lo + m) >> 10];
+  else at_m = G[n_points - 1] + tile_off[(n_points - 1) >> 10] + int(flag[n_points - 1]);
+  c.pass_lower = at_m - base;
+  c.A = m - c.pass_lower;
+  return c;
+}
+__global__ void __launch_bounds__(kBlock)
+k_split_lists(const int* __restrict__ owner, int n_points, Nodes N, int g0, const int* __restrict__ cnt,
+              const unsigned char* __restrict__ flag, const int* __restrict__ G, const int* __restrict__ tile_off,
+              int* __restrict__ XF, int* __restrict__ BP) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n_points) return;
+  const int j = owner[i];
+  if (j < 0 || N.link[g0 + j] < 0) return;
+  const SplitCtx c = split_ctx(N, g0 + j, cnt[j], G, tile_off, n_points, flag);
+  const int rel = i - c.lo;
+  const int pb = (G[i] + tile_off[i >> 10]) - (G[c.lo] + tile_off[c.lo >> 10]);  // passing points before i in the node
+  const int f = flag[i];
+  if (rel < c.m) {
+    if (!f) XF[c.lo + (rel - pb)] = rel;
+  } else if (f) {
+    BP[c.lo + (pb - c.pass_lower)] = rel;
+  }
+}
+__global__ void __launch_bounds__(kBlock)
+k_split_scatter(const double* __restrict__ P, double* __restrict__ Pn, const int* __restrict__ owner,
+                int* __restrict__ owner_next, int n_points, Nodes N, int g0, const int* __restrict__ cnt,
+                const int* __restrict__ child_of, const unsigned char* __restrict__ flag, const int* __restrict__ G,
+                const int* __restrict__ tile_off, const int* __restrict__ XF, const int* __restrict__ BP) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n_points) return;
+  const int j = owner[i];
+  if (j < 0 || N.link[g0 + j] < 0) {
+    owner_next[i] = -1;  // its node is a leaf (now or earlier): the position is retired
+    return;
+  }
+  const SplitCtx c = split_ctx(N, g0 + j, cnt[j], G, tile_off, n_points, flag);
+  const int rel = i - c.lo;
+  const int pb = (G[i] + tile_off[i >> 10]) - (G[c.lo] + tile_off[c.lo >> 10]);
+  const int f = flag[i];
+  int dest;
+  if (c.m == c.n) dest = rel;  // every point passes: nothing moves
+  else if (rel < c.m) {
+    if (f) dest = rel;
+    else {
+      const int a = rel - pb;  // a-th failing point of the lower part (0-based)
+      dest = (a == 0) ? c.n - 1 : BP[c.lo + c.A - a] - 1;
+    }
+  } else if (f) {
+    dest = XF[c.lo + c.A - 1 - (pb - c.pass_lower)];
+  } else if (rel == c.m) {
+    dest = (c.A > 0 ? BP[c.lo] : c.n) - 1;
+  } else {
+    dest = rel - 1;
+  }
+  const size_t d = size_t(c.lo + dest);
+  Pn[3 * d] = P[3 * size_t(i)];
+  Pn[3 * d + 1] = P[3 * size_t(i) + 1];
+  Pn[3 * d + 2] = P[3 * size_t(i) + 2];
+  owner_next[d] = child_of[j] + (dest < c.m ? 0 : 1);
+}
+
+// (9) records.  getLeafs ordinal of a leaf = number of leaves whose point range starts before its own.
+__global__ void __launch_bounds__(kBlock)
+k_mark_leaf_starts(Nodes N, int n_nodes, int n_points, unsigned char* __restrict__ flag) {
+  const int g = blockIdx.x * kBlock + threadIdx.x;
+  if (g >= n_nodes || N.link[g] >= 0) return;
+  const int lo = N.lo[g];
+  if (lo < n_points && N.hi[g] > lo) flag[lo] = 1;
+}
+__global__ void __launch_bounds__(kBlock)
+k_records(Nodes N, int n_nodes, int n_points, const int* __restrict__ G, const int* __restrict__ tile_off,
+          madtree_rec_t* __restrict__ recs, int* __restrict__ leaf_of) {
+  const int g = blockIdx.x * kBlock + threadIdx.x;
+  if (g >= n_nodes) return;
+  const double* full = N.full + size_t(g) * 16;
+  madtree_rec_t r;
+  r.mean[0] = full[0]; r.mean[1] = full[1]; r.mean[2] = full[2];
+  r.bbox0 = full[12];
+  r.num_points = int(full[15]);
+  const int link = N.link[g];
+  if (link >= 0) {
+    r.dir[0] = full[9]; r.dir[1] = full[10]; r.dir[2] = full[11];  // eigenvectors.col(2): split direction
+    r.link = link;
+  } else {
+    r.dir[0] = full[3]; r.dir[1] = full[4]; r.dir[2] = full[5];    // eigenvectors.col(0): surface normal
+    const int lo = N.lo[g];
+    const int ord = (lo < n_points) ? G[lo] + tile_off[lo >> 10] : 0;
+    r.link = -1 - ord;
+    leaf_of[ord] = g;
+  }
+  recs[g] = r;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Ingest (odometry/pipeline.cpp:79-123 + the float32 -> float64 conversion of the readers): out[i] = T[chunk[i]] *
+// in[perm[i]], with the reference's operand order (Isometry * point = R p + t, dot3 rows) and no FMA.
+// perm == nullptr: identity; chunk == nullptr: no transform (conversion only).
+__global__ void __launch_bounds__(kBlock)
+k_ingest(const void* __restrict__ in, int is_f32, const int* __restrict__ perm, const unsigned short* __restrict__ chunk,
+         const double* __restrict__ poses /* n_chunks x 12 */, int n, double* __restrict__ out) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  const size_t s = size_t(perm ? perm[i] : i);
+  double x, y, z;
+  if (is_f32) {
+    const float* p = static_cast<const float*>(in) + 3 * s;
+    x = double(p[0]); y = double(p[1]); z = double(p[2]);
+  } else {
+    const double* p = static_cast<const double*>(in) + 3 * s;
+    x = p[0]; y = p[1]; z = p[2];
+  }
+  if (chunk) {
+    const double* X = poses + size_t(chunk[i]) * 12;
+    double ox, oy, oz;
+    iso_apply(X, x, y, z, ox, oy, oz);
+    x = ox; y = oy; z = oz;
+  }
+  out[3 * size_t(i)] = x;
+  out[3 * size_t(i) + 1] = y;
+  out[3 * size_t(i) + 2] = z;
+}
+
+}  // namespace gtb
+}  // namespace madicp

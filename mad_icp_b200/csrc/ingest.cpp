@@ -22,7 +22,7 @@
 #include <utility>
 #include <vector>
 
-#include "../../include/madicp_b200.h"
+#include "../../include/madicp_b200_debug.h"
 #include "host_pool.hpp"
 #include "pose_math.h"
 
@@ -229,6 +229,80 @@ extern "C" int madicp_deskew(double* points_xyz, int64_t n, const double T_prev[
     std::fprintf(stderr, "madicp_deskew: n=%lld threads=%d azimuths %.2f ms, sort %.2f ms%s, sweep+poses+apply %.2f ms\n", (long long) n,
                  threads, ms(t0, t1), ms(t1, t2), "", ms(t2, now()));
   return MADICP_OK;
+}
+
+// The host half of the device-side ingest (gpu_tree.cu, madicp_ingest): everything of Pipeline::deskew that decides
+// an ORDER or calls libm -- azimuths (atan2), the reference's sort permutation, the chunk of every sorted position,
+// the chunk poses (sin/cos inside the exponential map) -- and nothing that touches the points' values: the gather,
+// the float -> double conversion and the rigid transform run on the device.
+// perm[i] = input index of the point at sorted position i; chunk[i] = its pose; poses: (*n_poses) x 12 row-major.
+int madicp_deskew_plan(const void* xyz, int is_f32, int64_t n, const double T_prev[12], const double T_now[12],
+                       double sensor_hz, int num_threads, int32_t* perm, uint16_t* chunk, double* poses, int* n_poses) {
+  if (!xyz || !T_prev || !T_now || n <= 0 || n > (int64_t(1) << 30) || !(sensor_hz > 0.0)) {
+    madicp::set_error("madicp_ingest: bad arguments");
+    return MADICP_ERR_INVALID;
+  }
+  int threads = num_threads < 1 ? 1 : (num_threads > 64 ? 64 : num_threads);
+  if (n < 20000) threads = 1;
+  const size_t un = size_t(n);
+  const double ts = 1. / sensor_hz;
+  Pose a, b;
+  std::memcpy(a.m, T_prev, sizeof(a.m));
+  std::memcpy(b.m, T_now, sizeof(b.m));
+  const Pose rel = madicp_pose::poseMul(madicp_pose::poseInverse(a), b);
+  double w[3];
+  madicp_pose::logSO3(rel, w);
+  const double vel[6] = {rel.m[3] / ts, rel.m[7] / ts, rel.m[11] / ts, w[0] / ts, w[1] / ts, w[2] / ts};
+  const double resolution = 2 * M_PI / double(kChunks), delta = ts / double(kChunks - 1);
+  madicp_host::HotScope hot;
+  RawVec<Item> items(un);
+  const float* xf = static_cast<const float*>(xyz);
+  const double* xd = static_cast<const double*>(xyz);
+  for_chunks(threads, un, 8192, [&](size_t c0, size_t c1) {
+    for (size_t i = c0; i < c1; ++i) {
+      const double x = is_f32 ? double(xf[3 * i]) : xd[3 * i], y = is_f32 ? double(xf[3 * i + 1]) : xd[3 * i + 1];
+      items[i] = Item{std::atan2(y, x), int32_t(i), 0};
+    }
+  });
+  if (threads > 1) sort_like_std(items.data(), items.data() + un, threads);
+  else std::sort(items.begin(), items.end(), KeyLess());
+  RawVec<int32_t> cid(un);
+  int32_t last = 0;
+  sweep(items.data(), n, resolution, cid, last);
+  if (last >= 65535) {
+    madicp::set_error("madicp_ingest: more than 65535 deskew chunks");
+    return MADICP_ERR_INVALID;
+  }
+  {
+    double t = -ts;
+    for (int32_t c = 0; c <= last; ++c) {
+      const double tr[3] = {vel[0] * t, vel[1] * t, vel[2] * t}, ro[3] = {vel[3] * t, vel[4] * t, vel[5] * t};
+      const Pose m = madicp_pose::poseFromTwist(tr, ro);
+      std::memcpy(poses + size_t(c) * 12, m.m, sizeof(double) * 12);
+      t += delta;
+    }
+  }
+  for_chunks(threads, un, 16384, [&](size_t c0, size_t c1) {
+    for (size_t i = c0; i < c1; ++i) {
+      perm[i] = items[i].idx;
+      chunk[i] = uint16_t(cid[i]);
+    }
+  });
+  *n_poses = last + 1;
+  return MADICP_OK;
+}
+
+// theta = atan2(sq, half_b) / 3, cos, sin for n nodes (eig3.h): the libm calls of the device-side tree build,
+// evaluated by the host's glibc so that the trees are the reference's bit for bit.
+void madicp_host_trig(const double* args, double* res, int n, int num_threads) {
+  const int threads = (n < 512 || num_threads < 2) ? 1 : (num_threads > 64 ? 64 : num_threads);
+  for_chunks(threads, size_t(n), 256, [&](size_t c0, size_t c1) {
+    for (size_t j = c0; j < c1; ++j) {
+      const double theta = std::atan2(args[2 * j], args[2 * j + 1]) * (1.0 / 3.0);
+      res[2 * j] = std::cos(theta);
+      res[2 * j + 1] = std::sin(theta);
+    }
+  });
 }
 
 // Diagnostic: sorts n pseudo-random keys drawn from `distinct` values (many ties when distinct << n) with

@@ -17,9 +17,9 @@
 //     on |s32 - s64|; otherwise the lane calls the out-of-line exact test, which re-evaluates the
 //     reference's FP64 expression on the 64-byte record.  The decision is therefore always the FP64 one
 //     (indices stay bit-exact) while >99.9% of visits never touch the FP64 pipe or the exact record.
-//   * TWO LEVELS PER ROUND TRIP.  The shadows are stored as 64-byte records in implicit 4-ary heap order
-//     (a node at an even depth + its two children; grandchildren = records 4g+1..4g+4): no child link is
-//     loaded and one memory round trip resolves two binary decisions.
+//   * TWO LEVELS PER ROUND TRIP.  The shadows are stored as dense 64-byte records (a node at an even depth
+//     + its two children + the index of the four contiguous records of its grandchildren): no child link
+//     is loaded and one memory round trip resolves two binary decisions.
 //   * Each CTA owns a few contiguous stretches of the scan's leaves (DFS order = spatially compact) and
 //     registers them against every keyframe: balanced across SMs, and the lanes of a warp / the warps of
 //     an SM share the upper levels in L1.  The inter-round barrier uses release-only atomics and
@@ -72,30 +72,16 @@ struct __align__(32) QuadRec {
 };
 static_assert(sizeof(QuadRec) == 64, "QuadRec must be two 256-bit loads");
 
-// All keyframes of a device live in ONE pool; slot s owns the index range [s*cap, (s+1)*cap) of the
-// breadth-first arrays and [s*heap_cap, (s+1)*heap_cap) of the heap-ordered shadow array.
-//
-// The walk reads ONLY the shadows, stored in implicit binary-heap order: the children of the node at
-// heap position h sit at 2h+1 and 2h+2.  No child link has to be loaded, so (a) a level costs one
-// 16-byte load instead of two dependent-address loads and (b) the positions of all descendants are
-// known in advance: the 8 candidates three levels down (8h+7 .. 8h+14, 128 contiguous bytes) are
-// prefetched into L1 while the current level is still being decided, which turns the chain of
-// ~16 dependent L2 round trips into ~16/3.  The tree is not complete (leaves sit at depth 11..17 for a
-// 64-beam scan), so the array is sparse: 2^(D+1) slots of 16 B per keyframe (8 MB at D=18) of which
-// ~40k are ever touched; HBM capacity is not the constraint here (180 GB), latency is.
+// All keyframes of a device live in ONE pool; slot s owns the index range [s*cap, (s+1)*cap) of the exact
+// records and [s*quad_cap, (s+1)*quad_cap) of the quad records.  The walk reads ONLY quad records; the exact
+// records serve the FP64 fallback predicate and the linearisation (one leaf record per correspondence).
 // A LEAF's shadow holds {breadth-first pool index of the leaf, marker, planarity weight ww (f64)}.
 struct ModelView {  // passed by value (constant bank)
-  const madtree_rec_t* recs;  // exact 64-byte records, breadth-first (fallback predicate + leaf data)
-  const int* links;           // breadth-first: pool index of the left child, or -1 - getLeafs ordinal (leaf)
-  const FastRec* heap;        // FP32 plane shadows in implicit heap order
-  const int* bfs_of;          // heap position -> breadth-first pool index (read only by the FP64 fallback)
-  const FastRec* fast;        // the same shadows in breadth-first order (walk_mode 0)
-  const QuadRec* quad;        // two binary levels per 64-byte record, dense, explicit child groups (walk_mode 4)
-  int root[kMaxSlots];        // heap position of the root of the k-th active keyframe (= slot * heap_cap)
-  int broot[kMaxSlots];       // breadth-first pool index of that root (= slot * cap)
-  int qroot[kMaxSlots];       // index of that root's record (= slot * quad_cap)
+  const madtree_rec_t* recs;  // exact 64-byte records, breadth-first, links slot-relative
+  const QuadRec* quad;        // two binary levels per 64-byte record, dense, explicit child groups
+  int broot[kMaxSlots];       // breadth-first pool index of the root of the k-th active keyframe (= slot * cap)
+  int qroot[kMaxSlots];       // index of that root's quad record (= slot * quad_cap)
   int K;
-  int walk_mode;              // 0: breadth-first + link loads; 1: binary heap; 2/3: + look-ahead prefetch; 4: 4-ary heap
 };
 constexpr unsigned kLeafMarker = 0x7fc0beefu;  // a NaN payload no arithmetic produces, in FastRec::dy of a leaf
 
@@ -118,13 +104,15 @@ struct __align__(16) LLCell {
 
 struct GnState {
   int ticket;     // monotonically increasing arrival counter (reset by the host before a launch)
-  int round;      // unused since the pose carries its own flag (X_ll); kept so the launch header keeps its layout
+  int clear_from; // first round whose gate passes are recorded in the matched flags (iters-1: the reference's
+                  // clear-before-the-last-round, pipeline.cpp:172-176; 0: a budget-limited loop that never cleared)
   int n_matched;  // matched moving leaves in the last round
   int pad;
   double X_in[12];  // initial pose: [ticket .. X_in] is ONE host-to-device copy per registration
   double X_out[12]; // final pose:   [ticket .. b] is ONE device-to-host copy per registration
   double H[36];     // last round; H[r*6+c] = sum (scale*J_r)*J_c, both triangles accumulated independently
   double b[6];
+  double weight;    // det(H^-1) of the last round's H (Frame::weight_, odometry/pipeline.cpp:223)
   double X_trace[(MADICP_MAX_ITERS + 1) * 12];  // pose before round i; [iters] = final pose (debug / parity aid)
   LLCell X_ll[12];  // pose of the next round, published with its epoch: waiting CTAs get value and flag in one load
 };
@@ -157,14 +145,20 @@ __device__ __forceinline__ Rec load_rec(const madtree_rec_t* p) {
   return r;
 }
 
-__device__ __forceinline__ FastRec load_fast(const FastRec* p) {
-  FastRec r;
-  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.dx), "=f"(r.dy), "=f"(r.dz), "=f"(r.c) : "l"(p));
+// the same through ordinary (coherent) loads: for records another kernel of the same stream has just written
+// where .nc is not wanted, and for in-place passes
+__device__ __forceinline__ Rec load_rec_plain(const madtree_rec_t* p) {
+  Rec r;
+  r.mx = p->mean[0]; r.my = p->mean[1]; r.mz = p->mean[2];
+  r.dx = p->dir[0]; r.dy = p->dir[1]; r.dz = p->dir[2];
+  r.bbox0 = p->bbox0;
+  r.link = p->link;
   return r;
 }
-__device__ __forceinline__ int load_link(const int* p) {
+// the `link` field of an exact record (byte offset 56)
+__device__ __forceinline__ int load_rec_link(const madtree_rec_t* p) {
   int v;
-  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(reinterpret_cast<const char*>(p) + 56));
   return v;
 }
 
@@ -178,7 +172,7 @@ __device__ __forceinline__ Moving4 load_moving(const Moving4* p) {
 // Deliberately NOT inlined: inlined, ptxas if-converts the rare branch and issues its ~10 predicated-off
 // FP64 instructions at every level of every walk (160 of the ~200 FP64-class issue slots per item, and
 // the FP64/XU issue port is what the item phase saturates: profiles/r01p, xu_realtime 66% of elapsed).
-__device__ __noinline__ bool side_exact(const madtree_rec_t* rec, double qx, double qy, double qz) {
+static __device__ __noinline__ bool side_exact(const madtree_rec_t* rec, double qx, double qy, double qz) {
   const Rec r = load_rec(rec);
   return !(plane_side(qx, qy, qz, r.mx, r.my, r.mz, r.dx, r.dy, r.dz) < 0.0);
 }
@@ -209,88 +203,49 @@ __device__ __forceinline__ SideF side_filtered2(const QueryF& q, const FastRec& 
   r.right = s > 0.0f;
   return r;
 }
-// the same as +1 right, 0 left, -1 undecided
-__device__ __forceinline__ int side_filtered(const QueryF& q, const FastRec& p) {
-  const SideF r = side_filtered2(q, p);
-  return r.decided ? (r.right ? 1 : 0) : -1;
-}
 __device__ __forceinline__ bool is_leaf(const FastRec& p) { return __float_as_uint(p.dy) == kLeafMarker; }
 __device__ __forceinline__ int leaf_index(const FastRec& p) { return __float_as_int(p.dx); }
 // planarity weight ww = (1 - bbox0/min_ball)^2 (reference: odometry/mad_icp.cpp:97-98), stored as a double
 __device__ __forceinline__ double leaf_weight(const FastRec& p) {
   return __hiloint2double(__float_as_int(p.c), __float_as_int(p.dz));
 }
-__device__ __forceinline__ void prefetch_line(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // Greedy single-path descent (no backtracking, like the reference: tools/mad_tree.cpp:144-152).
 // Returns the breadth-first pool index of the leaf reached and its planarity weight.  Decisions are
 // bit-identical to the reference's FP64 expression by construction.  `k` = index of the active keyframe.
+// (Four other walk layouts -- breadth-first shadows + link loads, implicit binary heap, heap + 2-/3-level
+// look-ahead prefetch -- were measured in round 1 and removed: profiles/r01r, r01t, r01u.)
 __device__ __forceinline__ int descend(const ModelView& M, int k, double qx, double qy, double qz, double& ww) {
   const QueryF q = make_query(qx, qy, qz);
-  if (M.walk_mode == 0) {  // breadth-first shadows + one link load per level
-    int idx = M.broot[k];
-    while (true) {
-      const int link = load_link(M.links + idx);
-      const FastRec p = load_fast(M.fast + idx);  // independent of `link`: both requests are in flight together
-      if (link < 0) {
-        ww = __hiloint2double(__float_as_int(p.dy), __float_as_int(p.dx));
-        return idx;
-      }
-      int side = side_filtered(q, p);
-      if (side < 0) side = side_exact(M.recs + idx, qx, qy, qz) ? 1 : 0;
-      idx = link + side;
+  const unsigned qroot = unsigned(M.qroot[k]);
+  const QuadRec* qbase = M.quad;  // uniform base + 32-bit pool index: one IMAD.WIDE per record address
+  unsigned g = qroot;
+  while (true) {  // two binary decisions per memory round trip
+    FastRec p0, p1, p2;
+    int bfs0, child0, pad1, pad2;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(p0.dx), "=f"(p0.dy), "=f"(p0.dz), "=f"(p0.c), "=f"(p1.dx), "=f"(p1.dy), "=f"(p1.dz), "=f"(p1.c)
+                 : "l"(qbase + g));
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(p2.dx), "=f"(p2.dy), "=f"(p2.dz), "=f"(p2.c), "=r"(bfs0), "=r"(child0), "=r"(pad1), "=r"(pad2)
+                 : "l"(reinterpret_cast<const char*>(qbase + g) + 32));
+    if (is_leaf(p0)) {
+      ww = leaf_weight(p0);
+      return leaf_index(p0);
     }
-  }
-  if (M.walk_mode == 4) {  // 4-ary records: two binary decisions per memory round trip
-    const unsigned qroot = unsigned(M.qroot[k]);
-    const QuadRec* qbase = M.quad;  // uniform base + 32-bit pool index: one IMAD.WIDE per record address
-    unsigned g = qroot;
-    while (true) {
-      FastRec p0, p1, p2;
-      int bfs0, child0, pad1, pad2;
-      asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                   : "=f"(p0.dx), "=f"(p0.dy), "=f"(p0.dz), "=f"(p0.c), "=f"(p1.dx), "=f"(p1.dy), "=f"(p1.dz), "=f"(p1.c)
-                   : "l"(qbase + g));
-      asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                   : "=f"(p2.dx), "=f"(p2.dy), "=f"(p2.dz), "=f"(p2.c), "=r"(bfs0), "=r"(child0), "=r"(pad1), "=r"(pad2)
-                   : "l"(reinterpret_cast<const char*>(qbase + g) + 32));
-      if (is_leaf(p0)) {
-        ww = leaf_weight(p0);
-        return leaf_index(p0);
-      }
-      const SideF f0 = side_filtered2(q, p0);
-      bool s0 = f0.right;
-      if (!f0.decided) s0 = side_exact(M.recs + bfs0, qx, qy, qz);
-      const FastRec c = s0 ? p2 : p1;
-      if (is_leaf(c)) {
-        ww = leaf_weight(c);
-        return leaf_index(c);
-      }
-      const SideF f1 = side_filtered2(q, c);
-      bool s1 = f1.right;
-      if (!f1.decided) s1 = side_exact(M.recs + (load_link(M.links + bfs0) + (s0 ? 1 : 0)), qx, qy, qz);
-      g = qroot + unsigned(child0) + (s0 ? 2u : 0u) + (s1 ? 1u : 0u);
+    const SideF f0 = side_filtered2(q, p0);
+    bool s0 = f0.right;
+    if (!f0.decided) s0 = side_exact(M.recs + bfs0, qx, qy, qz);
+    const FastRec c = s0 ? p2 : p1;
+    if (is_leaf(c)) {
+      ww = leaf_weight(c);
+      return leaf_index(c);
     }
-  }
-  const int root = M.root[k];
-  const FastRec* base = M.heap + root;
-  unsigned h = 0;
-  while (true) {
-    const FastRec p = load_fast(base + h);
-    if (M.walk_mode == 2) {  // the four nodes two levels below: 64 contiguous bytes
-      prefetch_line(base + (4u * h + 3u));
-      prefetch_line(base + (4u * h + 6u));
-    } else if (M.walk_mode == 3) {  // the eight nodes three levels below: 128 contiguous bytes
-      prefetch_line(base + (8u * h + 7u));
-      prefetch_line(base + (8u * h + 14u));
-    }
-    if (is_leaf(p)) {
-      ww = leaf_weight(p);
-      return leaf_index(p);
-    }
-    int side = side_filtered(q, p);
-    if (side < 0) side = side_exact(M.recs + M.bfs_of[root + h], qx, qy, qz) ? 1 : 0;
-    h = 2u * h + 1u + unsigned(side);
+    const SideF f1 = side_filtered2(q, c);
+    bool s1 = f1.right;
+    if (!f1.decided)
+      s1 = side_exact(M.recs + (M.broot[k] + load_rec_link(M.recs + bfs0) + (s0 ? 1 : 0)), qx, qy, qz);
+    g = qroot + unsigned(child0) + (s0 ? 2u : 0u) + (s1 ? 1u : 0u);
   }
 }
 
@@ -435,6 +390,9 @@ __device__ __forceinline__ void final_reduce(const double* partial, int nblk, do
   }
   __syncthreads();
 }
+
+// out of line: its pivoting indexes a local 6x6 at run time (a stack frame the persistent kernel should not carry)
+static __device__ __noinline__ double inv_det6_dev(const double* H, int ld) { return inv_det6(H, ld); }
 
 __device__ __forceinline__ void unpack_Hb(const double* tot, double* H, double* b) {
   for (int r = 0; r < 6; ++r) {

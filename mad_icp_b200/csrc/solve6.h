@@ -112,6 +112,41 @@ MADICP_HD void ldlt6_solve_neg(const double* H, int ld, const double* b, double*
   for (int i = 0; i < 6; ++i) x[idx[i]] = y[i];
 }
 
+// det(H^-1) as 1 / det(H) by partial-pivot LU (reference: odometry/pipeline.cpp:223 computes
+// H_adder_.inverse().determinant(); the C++ facade uses the same form).  H row-major 6x6, stride ld.
+MADICP_HD double inv_det6(const double* H, int ld) {
+  double A[6][6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) A[r][c] = H[r * ld + c];
+  double det = 1.0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    int p = k;
+#pragma unroll
+    for (int i = k + 1; i < 6; ++i)
+      if (i > k && fabs(A[i][k]) > fabs(A[p][k])) p = i;
+    if (p != k) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const double u = A[k][c];
+        A[k][c] = A[p][c];
+        A[p][c] = u;
+      }
+      det = -det;
+    }
+    det = mul_(det, A[k][k]);
+#pragma unroll
+    for (int i = k + 1; i < 6; ++i) {
+      const double f = A[i][k] / A[k][k];
+#pragma unroll
+      for (int c = k; c < 6; ++c) A[i][c] = sub_(A[i][c], mul_(f, A[k][c]));
+    }
+  }
+  return 1.0 / det;
+}
+
 // Rodrigues with the reference's small-angle branch (theta^2 < 1e-8 -> I + [w]x). R row-major 3x3.
 MADICP_HD void expmap_so3(double wx, double wy, double wz, double* R) {
   const double th2 = dot3(wx, wy, wz, wx, wy, wz);

@@ -73,6 +73,45 @@ class FlatTree:
         return out
 
 
+class DeviceTree:
+    """A sensor-frame MAD-tree resident in the device memory of one Registrar: built on the device
+    (`Registrar.build_tree`) or uploaded from a host-built FlatTree (`Registrar.upload_tree`)."""
+
+    def __init__(self, handle, registrar):
+        self._h, self._reg = handle, registrar  # the registrar must outlive the tree
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h and getattr(self._reg, "_h", None):
+            self._h = None
+            try:
+                capi.lib().madtree_gpu_free(h)
+            except TypeError:
+                pass
+
+    num_nodes = property(lambda self: capi.lib().madtree_gpu_num_nodes(self._h))
+    num_leaves = property(lambda self: capi.lib().madtree_gpu_num_leaves(self._h))
+    num_levels = property(lambda self: capi.lib().madtree_gpu_num_levels(self._h))
+
+    def records(self):
+        recs = np.empty(self.num_nodes, dtype=capi.REC_DTYPE)
+        check(capi.lib().madtree_gpu_download(self._h, recs.ctypes.data_as(C.c_void_p), None), "madtree_gpu_download")
+        return recs
+
+    def leaf_records(self):
+        out = np.empty(self.num_leaves, np.int32)
+        check(capi.lib().madtree_gpu_download(self._h, None, as_i(out)), "madtree_gpu_download")
+        return out
+
+    def export(self):
+        """Audit dump of a device-BUILT tree, breadth-first: mean, eivecs (column-major), bbox, num_points."""
+        n = self.num_nodes
+        out = dict(mean=np.empty((n, 3)), eivecs=np.empty((n, 9)), bbox=np.empty((n, 3)), num_points=np.empty(n, np.int32))
+        check(capi.lib().madtree_gpu_export(self._h, as_d(out["mean"]), as_d(out["eivecs"]), as_d(out["bbox"]),
+                                            as_i(out["num_points"])), "madtree_gpu_export")
+        return out
+
+
 class Registrar:
     """One GPU's registration context (reference: class MADicp + Pipeline's keyframe deque)."""
 
@@ -106,8 +145,59 @@ class Registrar:
     def stream(self):
         return capi.lib().madicp_get_stream(self._h)
 
-    def put_keyframe(self, slot, tree):
-        check(capi.lib().madicp_put_keyframe(self._h, slot, tree._h), "madicp_put_keyframe")
+    def put_keyframe(self, slot, tree, T=None):
+        """tree: FlatTree (host-built) or DeviceTree.  T: pose applied ON THE DEVICE during the upload
+        (MADtree::applyTransform); None for a tree that is already in the map frame."""
+        X = as_d(pose12(T)) if T is not None else None
+        if isinstance(tree, DeviceTree):
+            check(capi.lib().madicp_put_keyframe_tree(self._h, slot, tree._h, X), "madicp_put_keyframe_tree")
+        else:
+            check(capi.lib().madicp_put_keyframe_transformed(self._h, slot, tree._h, X), "madicp_put_keyframe")
+
+    def upload_tree(self, flat_tree):
+        h = C.c_void_p()
+        check(capi.lib().madtree_gpu_upload(self._h, flat_tree._h, C.byref(h)), "madtree_gpu_upload")
+        return DeviceTree(h, self)
+
+    def build_tree(self, points=None, b_max=0.2, b_min=0.1):
+        """MAD-tree of a scan built ON THE DEVICE (points: N x 3 float64 host array, or None for the cloud
+        madicp_ingest left on the device)."""
+        h = C.c_void_p()
+        if points is None:
+            check(capi.lib().madtree_gpu_build_resident(self._h, b_max, b_min, C.byref(h)), "madtree_gpu_build_resident")
+        else:
+            pts = np.ascontiguousarray(points, dtype=np.float64)
+            check(capi.lib().madtree_gpu_build(self._h, as_d(pts), pts.shape[0], b_max, b_min, C.byref(h)),
+                  "madtree_gpu_build")
+        return DeviceTree(h, self)
+
+    def ingest(self, xyz, deskew=False, T_prev=None, T_now=None, sensor_hz=10.0, num_threads=1, want_points=False):
+        """Raw scan -> device-resident float64 cloud (optionally deskewed, Pipeline::deskew)."""
+        a = np.ascontiguousarray(xyz)
+        if a.dtype != np.float32:
+            a = np.ascontiguousarray(a, dtype=np.float64)
+        n = a.shape[0]
+        out = np.empty((n, 3)) if want_points else None
+        Tp = as_d(pose12(T_prev)) if T_prev is not None else None
+        Tn = as_d(pose12(T_now)) if T_now is not None else None
+        check(capi.lib().madicp_ingest(self._h, a.ctypes.data_as(C.c_void_p), n, int(a.dtype == np.float32), int(deskew),
+                                       Tp, Tn, sensor_hz, num_threads, as_d(out)), "madicp_ingest")
+        return out
+
+    def set_moving_tree(self, tree):
+        check(capi.lib().madicp_set_moving_tree(self._h, tree._h), "madicp_set_moving_tree")
+        self.L = tree.num_leaves
+
+    def get_moving(self):
+        out = np.empty((self.L, 3))
+        check(capi.lib().madicp_get_moving(self._h, as_d(out), self.L), "madicp_get_moving")
+        return out
+
+    def synchronize(self):
+        check(capi.lib().madicp_synchronize(self._h))
+
+    def calibrate(self, X0):
+        return check(capi.lib().madicp_calibrate(self._h, as_d(pose12(X0))), "madicp_calibrate")
 
     def put_keyframe_records(self, slot, recs, n_leaves):
         recs = np.ascontiguousarray(recs, dtype=capi.REC_DTYPE)
@@ -177,17 +267,19 @@ class Registrar:
               "madicp_register")
         return dict(X=X, H=H, b=b, matched=m, n_matched=n.value)
 
-    def register_async(self, X0, iters=15):
+    def register_async(self, X0, iters=15, partial=False):
+        """partial=True: a loop the realtime budget cut short -- the matched flags are the union over all rounds."""
         X = pose12(X0)
-        check(capi.lib().madicp_register_async(self._h, iters, as_d(X)), "madicp_register_async")
+        fn = capi.lib().madicp_register_partial_async if partial else capi.lib().madicp_register_async
+        check(fn(self._h, iters, as_d(X)), "madicp_register_async")
 
     def register_fetch(self, want_matched=False):
         X, H, b = np.empty((3, 4)), np.empty((6, 6)), np.empty(6)
         m = np.empty(self.L, np.uint8) if want_matched else None
-        n = C.c_int(0)
-        check(capi.lib().madicp_register_fetch(self._h, as_d(X), as_d(H), as_d(b), as_b(m), C.byref(n)),
+        n, w = C.c_int(0), C.c_double(0)
+        check(capi.lib().madicp_register_fetch_weight(self._h, as_d(X), as_d(H), as_d(b), as_b(m), C.byref(n), C.byref(w)),
               "madicp_register_fetch")
-        return dict(X=X, H=H, b=b, matched=m, n_matched=n.value)
+        return dict(X=X, H=H, b=b, matched=m, n_matched=n.value, weight=w.value)
 
     def register_trace(self):
         buf = np.empty((65, 3, 4))
@@ -217,9 +309,6 @@ class Registrar:
         grid = check(capi.lib().madicp_debug_cta_cycles(self._h, buf.ctypes.data_as(C.POINTER(C.c_int64)), buf.size))
         return buf[:rounds * grid].reshape(rounds, grid)
 
-    def set_walk_mode(self, mode):
-        check(capi.lib().madicp_set_walk_mode(self._h, mode))
-
     def set_gn_grid(self, threads_per_cta=1024, ctas_per_sm=1):
         return check(capi.lib().madicp_set_gn_grid(self._h, threads_per_cta, ctas_per_sm))
 
@@ -239,4 +328,4 @@ class Registrar:
         return capi.lib().madicp_comm_world(self._h)
 
 
-__all__ = ["FlatTree", "Registrar", "MadIcpError"]
+__all__ = ["FlatTree", "DeviceTree", "Registrar", "MadIcpError"]

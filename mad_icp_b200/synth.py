@@ -138,3 +138,22 @@ def registration_case(K=16, beams=64, azimuths=2048, seed=1, scene_seed=7):
     T_true = sensor_pose(q_base)
     T_guess = T_true @ pose_xyyaw(0.3, 0.0, 0.01)
     return dict(scans=scans, kf_poses=[sensor_pose(b) for b in base], query=query, T_true=T_true, T_guess=T_guess)
+
+
+def sequence_scan(scene, i, beams=64, azimuths=2048, seed=100, step=0.8):
+    """Scan i of the cfg5 sequence: `step` metres per scan along a gently curving lane."""
+    base = pose_xyyaw(step * i, 1.0 + 0.3 * np.sin(0.05 * i), 0.02 * np.sin(0.03 * i))
+    return np.ascontiguousarray(lidar_scan(scene, base, beams=beams, azimuths=azimuths, seed=seed + i))
+
+
+def sequence(n_scans=60, beams=64, azimuths=2048, seed=100, step=0.8, workers=1):
+    """cfg5 streaming workload: n_scans sensor-frame scans through a street scene long enough for the whole path.
+    workers > 1 ray-casts the scans in forked processes (call before CUDA is initialised)."""
+    scene = StreetScene(seed=7, x_min=-45.0, x_max=60.0 + step * n_scans)
+    if workers > 1 and n_scans > 16:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(workers) as pool:
+            scans = pool.starmap(sequence_scan, [(scene, i, beams, azimuths, seed, step) for i in range(n_scans)], chunksize=4)
+    else:
+        scans = [sequence_scan(scene, i, beams, azimuths, seed, step) for i in range(n_scans)]
+    return dict(scans=scans, step=step)

@@ -191,3 +191,18 @@ def expmap(w):
 
 def max_threads():
     return lib().orc_max_threads()
+
+
+def deskew(points, T_prev, T_now, sensor_hz=10.0):
+    """Pipeline::deskew (odometry/pipeline.cpp:79-123) of the CPU restatement; returns the deskewed copy."""
+    L = lib()
+    L.orc_pipeline_create.restype = C.c_void_p
+    L.orc_pipeline_create.argtypes = [C.c_double, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                      C.c_int, C.c_int, C.c_int]
+    L.orc_pipeline_deskew.argtypes = [C.c_void_p, _dp, C.c_int, _dp, _dp]
+    L.orc_pipeline_free.argtypes = [C.c_void_p]
+    po = C.c_void_p(L.orc_pipeline_create(float(sensor_hz), 1, 0.2, 0.1, 0.8, 0.1, 0.02, 4, 1, 0))
+    out = np.ascontiguousarray(points, dtype=np.float64).copy()
+    L.orc_pipeline_deskew(po, _d(out), out.shape[0], _d(_pose12(T_prev)), _d(_pose12(T_now)))
+    L.orc_pipeline_free(po)
+    return out

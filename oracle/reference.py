@@ -166,3 +166,21 @@ class ReferencePipeline:
 
 def max_threads():
     return lib().ref_max_threads()
+
+
+def variant(so_name, make_target=None):
+    """A second instance of this module over another build of the same C entry points (oracle/ref_capi.cpp), e.g.
+    `variant("libmadicp_ref_gpu.so", "ref_gpu")`: the reference's unmodified pipeline.cpp / vel_estimator.cpp linked
+    with the product's backend TU instead of its own mad_tree.cpp / mad_icp.cpp (oracle/Makefile)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(f"oracle.reference__{so_name.replace('.', '_')}", __file__,
+                                                  submodule_search_locations=None)
+    mod = importlib.util.module_from_spec(spec)
+    mod.__package__ = __package__
+    spec.loader.exec_module(mod)
+    mod._SO = os.path.join(_HERE, "_ref", so_name)
+    if make_target and os.path.isdir(REF_SRC):
+        subprocess.check_call(["make", "-C", _HERE, "-s", make_target])
+    if not os.path.exists(mod._SO):
+        raise RuntimeError(f"{mod._SO} is missing (built where /root/reference exists: make -C oracle {make_target})")
+    return mod

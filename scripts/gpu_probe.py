@@ -37,7 +37,7 @@ for iters in (1, 2, 5, 10, 15, 20):
 # per-round phase breakdown (SM cycles @ ~1.965 GHz) per walk mode and shape
 reg.debug_timing(True, fetch=False)
 for mode in (4, 1):
-    reg.set_walk_mode(mode)
+    pass
     for thr, cps in ((1024, 1), (768, 1)):
         reg.set_gn_grid(thr, cps)
         w = timed(lambda: reg.register_async(X0, 10))
@@ -51,4 +51,4 @@ for mode in (4, 1):
               f"fold={np.median(d[:,2]):.0f} solve={np.median(d[:,4]):.0f} | per-CTA item phase: min={med.min():.0f} "
               f"p50={np.median(med):.0f} p90={np.percentile(med,90):.0f} max={med.max():.0f} slowest CTAs={order[-4:].tolist()} "
               f"fastest={order[:4].tolist()} round-to-round corr={rho:.2f}")
-reg.set_walk_mode(4)
+pass

@@ -11,9 +11,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared_symbols():
+    names = set()
+    for h in ("madicp_b200.h", "madicp_b200_debug.h"):  # the drop-in surface + the tuning/diagnostic header
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(mad(?:icp|tree)_[a-z_0-9]+)\s*\(", src))
+    return sorted(names)
+
+
+def test_debug_entry_points_are_not_in_the_drop_in_header():
     src = open(os.path.join(ROOT, "include", "madicp_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(mad(?:icp|tree)_[a-z_0-9]+)\s*\(", src)))
+    assert not re.findall(r"\bmadicp_(debug_[a-z_]+|set_gn_grid|set_walk_mode)\s*\(", src)
 
 
 def test_header_symbols_all_exported(built):
@@ -65,3 +74,9 @@ def test_host_entry_points_reject_bad_arguments(built):
     out = C.c_void_p()
     assert L.madtree_build(None, 4, 0.2, 0.1, 1, C.byref(out)) < 0
     assert L.madtree_build(ok(pts), 0, 0.2, 0.1, 1, C.byref(out)) < 0
+    # b_max <= 0 / NaN would make `bbox(2) < b_max` unsatisfiable: one-point ranges would split for ever
+    big = np.random.RandomState(0).normal(size=(100, 3))
+    for bad in (0.0, -1.0, float("nan"), float("inf")):
+        assert L.madtree_build(ok(big), 100, bad, 0.1, 1, C.byref(out)) < 0, bad
+        assert b"b_max" in L.madicp_last_error()
+    assert L.madtree_build(ok(big), 100, 0.2, float("nan"), 1, C.byref(out)) < 0

@@ -1,0 +1,126 @@
+"""MAD-tree build and scan ingest ON THE DEVICE, `-m gpu`: the device-built tree must be
+the reference's tree node for node and bit for bit -- topology, means, all nine eigenvector coefficients (including
+the NaNs of one-point nodes), bounding boxes, point counts, leaf order -- against the CPU oracle (which is pinned to
+the reference's own sources, tests/test_reference_pin.py) and against the host builder; registration from a
+device-built tree must give the same bits as from a host-built one; the device ingest must reproduce
+Pipeline::deskew (odometry/pipeline.cpp:79-123) bit for bit."""
+import numpy as np
+import pytest
+
+from mad_icp_b200 import FlatTree, Registrar, synth
+from util import bits_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def _bfs_order(e):
+    """DFS pre-order export (left/right node ids) -> node ids in breadth-first order, siblings adjacent."""
+    order, level = [], [0]
+    while level:
+        order += level
+        nxt = []
+        for i in level:
+            if e["left"][i] >= 0:
+                nxt += [int(e["left"][i]), int(e["right"][i])]
+        level = nxt
+    return np.array(order)
+
+
+def _same_as_oracle(dt, otree, ft=None):
+    e = otree.export()
+    order = _bfs_order(e)
+    d = dt.export()
+    assert dt.num_nodes == len(order) and dt.num_leaves == otree.num_leaves
+    for k in ("mean", "eivecs", "bbox"):
+        assert bits_equal(d[k], e[k][order]), f"{k}: {(d[k] != e[k][order]).sum()} coefficients differ (NaN-aware compare failed)"
+    assert (d["num_points"] == e["num_points"][order]).all()
+    recs = dt.records()
+    leaf = recs["link"] < 0
+    assert ((-1 - recs["link"][leaf]) == e["leaf_ordinal"][order][leaf]).all()
+    assert (e["leaf_ordinal"][order][~leaf] == -1).all()
+    if ft is not None:  # and the 64-byte records are the host builder's, byte for byte (NaN payloads aside)
+        h = ft.records()
+        for k in ("mean", "dir", "bbox0"):
+            assert bits_equal(recs[k], h[k]), k
+        assert (recs["link"] == h["link"]).all() and (recs["num_points"] == h["num_points"]).all()
+
+
+@pytest.fixture(scope="module")
+def reg():
+    return Registrar(device=0, max_keyframes=4)
+
+
+@pytest.mark.parametrize("beams,azimuths,seed", [(16, 512, 3), (32, 1024, 5), (64, 2048, 1)])
+def test_lidar_scan_tree_is_the_references(reg, oracle, beams, azimuths, seed):
+    c = synth.registration_case(K=1, beams=beams, azimuths=azimuths, seed=seed)
+    for cloud in (c["scans"][0], c["query"]):
+        dt = reg.build_tree(cloud)
+        _same_as_oracle(dt, oracle.OracleTree(cloud), FlatTree(cloud))
+
+
+@pytest.mark.parametrize("b_max,b_min", [(0.2, 0.1), (0.05, 0.02), (1e-5, 0.1), (1.0, 0.5)])
+def test_four_walls_and_parameters(reg, oracle, b_max, b_min):
+    np.random.seed(42)
+    cloud = synth.four_walls(points_per_wall=2000 if b_max < 1e-3 else 4000)
+    dt = reg.build_tree(cloud, b_max=b_max, b_min=b_min)
+    _same_as_oracle(dt, oracle.OracleTree(cloud, b_max=b_max, b_min=b_min), FlatTree(cloud, b_max=b_max, b_min=b_min))
+
+
+def test_degenerate_clouds(reg, oracle):
+    rs = np.random.RandomState(0)
+    clouds = [np.array([[1.0, 2.0, 3.0]]),                                   # one point: NaN covariance, root leaf
+              np.array([[0.0, 0, 0], [1.0, 0, 0]]),                          # two points
+              np.repeat(np.array([[0.5, -1.0, 2.0]]), 50, axis=0),            # all identical
+              np.stack([np.linspace(0, 10, 200), np.zeros(200), np.zeros(200)], 1),   # collinear
+              np.concatenate([rs.normal(0, 0.01, (300, 3)), rs.normal(5, 0.01, (3, 3)), [[9.0, 9, 9]]]),  # tiny clusters
+              rs.uniform(-1, 1, (1000, 3)) * [10, 10, 0]]                   # planar
+    for cloud in clouds:
+        dt = reg.build_tree(cloud)
+        _same_as_oracle(dt, oracle.OracleTree(cloud), FlatTree(cloud))
+
+
+def test_registration_from_device_built_trees(reg):
+    """The whole device-resident chain: build on the device -> moving leaves from the device tree -> promotion with the
+    pose applied on the device; same bits as host-built trees transformed on the host."""
+    c = synth.registration_case(K=3, beams=32, azimuths=1024, seed=11)
+    a = Registrar(device=0, max_keyframes=4)
+    for k, (scan, P) in enumerate(zip(c["scans"], c["kf_poses"])):
+        ft = FlatTree(scan)
+        ft.apply_transform(P)
+        a.put_keyframe(k, ft)
+        reg.put_keyframe(k, reg.build_tree(scan), T=P)
+    q = FlatTree(c["query"])
+    a.set_moving(q.leaf_means())
+    reg.set_moving_tree(reg.build_tree(c["query"]))
+    assert bits_equal(reg.get_moving(), q.leaf_means())
+    assert (a.search(c["T_guess"]) == reg.search(c["T_guess"])).all()
+    ra, rb = a.register(c["T_guess"], iters=10), reg.register(c["T_guess"], iters=10)
+    for k in ("X", "H", "b"):
+        assert bits_equal(ra[k], rb[k]), k
+    assert (ra["matched"] == rb["matched"]).all()
+    for k in range(3):
+        reg.drop_keyframe(k)
+
+
+def test_ingest_float32_and_deskew(reg, oracle):
+    c = synth.registration_case(K=1, beams=32, azimuths=1024, seed=8)
+    cloud = c["query"]
+    f32 = cloud.astype(np.float32)
+    out = reg.ingest(f32, want_points=True)
+    assert bits_equal(out, f32.astype(np.float64))                 # the readers' float32 -> float64 (exact)
+    dt = reg.build_tree()                                          # tree of the cloud the ingest left on the device
+    _same_as_oracle(dt, oracle.OracleTree(f32.astype(np.float64)))
+    # deskew: against the CPU pipeline's (itself pinned to the reference's Pipeline::deskew)
+    T_prev = synth.pose_xyyaw(0.0, 0.0, 0.0)
+    T_now = synth.pose_xyyaw(0.8, 0.05, 0.02)
+    want = oracle.deskew(cloud, T_prev, T_now, sensor_hz=10.0)
+    for threads in (1, 4):
+        got = reg.ingest(cloud, deskew=True, T_prev=T_prev, T_now=T_now, sensor_hz=10.0, num_threads=threads, want_points=True)
+        assert bits_equal(got, want), f"{threads} threads: {(got != want).any(axis=1).sum()} points differ"
+    # tied azimuths (noise-free rings: whole firing columns share an azimuth) and float32 input
+    az = np.repeat(np.linspace(-np.pi, np.pi, 256, endpoint=False), 16)
+    r = np.tile(np.linspace(2.0, 30.0, 16), 256)
+    tied = np.stack([r * np.cos(az), r * np.sin(az), np.tile(np.linspace(-2, 1, 16), 256)], 1).astype(np.float32)
+    want = oracle.deskew(tied.astype(np.float64), T_prev, T_now, sensor_hz=10.0)
+    got = reg.ingest(tied, deskew=True, T_prev=T_prev, T_now=T_now, sensor_hz=10.0, num_threads=2, want_points=True)
+    assert bits_equal(got, want)

@@ -5,7 +5,7 @@
 // defines every member function those two files define -- same class layouts, same public data (X_, H_adder_,
 // b_adder_, moving_leaves_, the pointer-linked MADtree nodes with mean_/eigenvectors_/bbox_/matched_) -- so the
 // reference's odometry/pipeline.cpp, vel_estimator.cpp, the pybind wrappers and bin_runner compile and link
-// against it unchanged (`make -C oracle ref_gpu` does exactly that and
+// against it unchanged (the `ref_gpu` target of the test Makefile does exactly that and
 // tests/test_gpu_adapter.py streams scans through the result).  Works with Eigen or any stand-in that offers
 // coefficient access (`v(i)`, `m(r,c)`, `iso.linear()`, `iso.translation()`, `setZero`, `setIdentity`).
 //

@@ -3,8 +3,10 @@
 // Pipeline::compute (odometry/pipeline.cpp:125-265): optional deskew, MAD-tree of the scan, constant-
 // velocity prediction, the ICP loop (one persistent-kernel launch instead of 15 OpenMP rounds), inlier
 // ratio, velocity smoothing (odometry/vel_estimator.cpp), frame weight det(H^-1), keyframe promotion.
-// How it is organised differs: trees are flat handles, keyframes are device-resident pool slots that are
-// uploaded once at promotion, and the small dense algebra uses plain row-major arrays.
+// How it is organised differs: by default the scan never exists as a tree on the host -- it is ingested (float
+// conversion, deskew) and its MAD-tree is built ON THE DEVICE, its leaves become the moving leaves there, and on
+// promotion the tree is transformed and laid out in a keyframe slot there (MADICP_GPU_BUILD=0: host-built flat
+// trees, uploaded at promotion); the small dense algebra uses plain row-major arrays.
 #pragma once
 #include <algorithm>
 #include <chrono>
@@ -93,9 +95,9 @@ class Pipeline {
       : sensor_hz_(sensor_hz), deskew_(deskew), b_max_(b_max), p_th_(p_th), b_min_(b_min), num_keyframes_(num_keyframes),
         realtime_(realtime), icp_(b_max, rho_ker, b_ratio, num_threads, device, std::max(num_keyframes, 1)),
         vel_(sensor_hz) {
-    // `realtime` bounds the ICP rounds by the sensor period in the reference (pipeline.cpp:167-169); here
-    // all 15 rounds run in one launch of a few hundred microseconds, so the budget is never the limit.
     frame_to_map_ = keyframe_to_map_ = detail::poseIdentity();
+    if (const char* e = std::getenv("MADICP_GPU_BUILD")) gpu_build_ = std::atoi(e) != 0;
+    num_threads_ = std::max(num_threads, 1);
     int lvl = 0;
     while ((1 << (lvl + 1)) <= std::max(num_threads, 1)) ++lvl;
     max_parallel_levels_ = lvl;  // pipeline.cpp:64
@@ -141,36 +143,56 @@ class Pipeline {
     return cloud;
   }
 
-  // pipeline.cpp:125-265 (cloud by value, as the reference)
-  // reference signature (pipeline.h:71): the cloud by value
+  // pipeline.cpp:125-265; reference signature (pipeline.h:71): the cloud by value
   void compute(double stamp, ContainerType cloud) {
     if (cloud.empty()) throw Error("Pipeline.compute: empty cloud");
-    if (deskew_ && is_initialized_ && trajectory_.size() > 1)
-      deskew(cloud, trajectory_[trajectory_.size() - 2], trajectory_[trajectory_.size() - 1], sensor_hz_,
-             1 << max_parallel_levels_);
-    computeDeskewed(stamp, cloud[0].data(), cloud.size());
+    computeRaw(stamp, cloud[0].data(), cloud.size(), false);
   }
-  // the same without taking ownership: N x 3 doubles read in place (copied only if the scan is deskewed)
-  void compute(double stamp, const double* xyz, size_t n) {
-    if (!xyz || n == 0) throw Error("Pipeline.compute: empty cloud");
-    if (deskew_ && is_initialized_ && trajectory_.size() > 1) {
+  // the same without taking ownership: N x 3 doubles read in place
+  void compute(double stamp, const double* xyz, size_t n) { computeRaw(stamp, xyz, n, false); }
+  // float32 scans as the dataset readers produce them (the conversion to float64 runs on the device)
+  void computeF32(double stamp, const float* xyz, size_t n) {
+    if (!gpu_build_) {
       ContainerType cloud(n);
-      std::memcpy(cloud[0].data(), xyz, sizeof(double) * 3 * n);
+      for (size_t i = 0; i < n; ++i)
+        for (int a = 0; a < 3; ++a) cloud[i][size_t(a)] = double(xyz[3 * i + size_t(a)]);
       compute(stamp, std::move(cloud));
-    } else {
-      computeDeskewed(stamp, xyz, n);
+      return;
     }
+    computeRaw(stamp, xyz, n, true);
   }
+  bool gpuBuild() const { return gpu_build_; }
 
  private:
-  void computeDeskewed(double stamp, const double* xyz, size_t n) {
+  // the scan's MAD-tree: ingest (+ deskew, pipeline.cpp:137-138) and build, on the device or on the host
+  std::unique_ptr<MADtree> makeTree(const void* xyz, size_t n, bool is_f32) {
+    const bool dsk = deskew_ && is_initialized_ && trajectory_.size() > 1;
+    const double* Ta = dsk ? trajectory_[trajectory_.size() - 2].m : nullptr;
+    const double* Tb = dsk ? trajectory_[trajectory_.size() - 1].m : nullptr;
+    if (gpu_build_) {
+      check(madicp_ingest(icp_.context(), xyz, int64_t(n), is_f32 ? 1 : 0, dsk ? 1 : 0, Ta, Tb, sensor_hz_,
+                          std::max(1 << max_parallel_levels_, 1), nullptr), "madicp_ingest");
+      return std::unique_ptr<MADtree>(new MADtree(icp_.context(), b_max_, b_min_));
+    }
+    const double* pts = static_cast<const double*>(xyz);
+    if (dsk) {
+      ContainerType cloud(n);
+      std::memcpy(cloud[0].data(), pts, sizeof(double) * 3 * n);
+      check(madicp_deskew(cloud[0].data(), int64_t(n), Ta, Tb, sensor_hz_, 1 << max_parallel_levels_), "madicp_deskew");
+      return std::unique_ptr<MADtree>(new MADtree(cloud[0].data(), n, b_max_, b_min_, max_parallel_levels_));
+    }
+    return std::unique_ptr<MADtree>(new MADtree(pts, n, b_max_, b_min_, max_parallel_levels_));
+  }
+
+  void computeRaw(double stamp, const void* xyz, size_t n, bool is_f32) {
+    if (!xyz || n == 0) throw Error("Pipeline.compute: empty cloud");
     is_map_updated_ = false;
     if (!is_initialized_) {  // pipeline.cpp:267-284
       auto f = std::make_shared<FrameB>();
       f->frame = int(seq_);
       f->to_map = frame_to_map_;
       f->stamp = stamp;
-      f->tree.reset(new MADtree(xyz, n, b_max_, b_min_, max_parallel_levels_));
+      f->tree = makeTree(xyz, n, is_f32);
       keyframes_.push_back(f);
       current_ = f;
       trajectory_.push_back(detail::poseIdentity());
@@ -179,9 +201,9 @@ class Pipeline {
       return;
     }
     const auto c0 = clk();
-    const auto c1 = c0;  // (deskewing happens in compute(), before this point)
+    const auto c1 = c0;
     auto cur = std::make_shared<FrameB>();
-    cur->tree.reset(new MADtree(xyz, n, b_max_, b_min_, max_parallel_levels_));
+    cur->tree = makeTree(xyz, n, is_f32);
     const auto c2 = clk();
     double t[3], w[3];
     for (int a = 0; a < 3; ++a) {
@@ -194,8 +216,19 @@ class Pipeline {
     icp_.init(toM(prediction));
     std::vector<const MADtree*> kfs;
     for (const auto& f : keyframes_) kfs.push_back(f->tree.get());
-    const int matched = icp_.compute(kfs, kMaxIcpIts);  // the whole loop of pipeline.cpp:166-193
+    // `realtime` (pipeline.cpp:62,167-169): round k runs only while preprocessing + the rounds so far + one more
+    // round of the last duration still fit the sensor period minus 5 ms.  The rounds of a scan run in ONE launch
+    // here, so the budget is turned into a round count up front, with the per-round time of the previous scan as
+    // the duration of a round; a loop cut short keeps the union of the matched flags (no clear ever happened).
+    int iters = kMaxIcpIts;
+    if (realtime_) {
+      const double budget = (1000.0 / sensor_hz_) - 5.0 - ms(c0, c3);
+      if (budget < 0.0) iters = 0;
+      else if (round_ms_ > 0.0) iters = std::max(1, std::min(kMaxIcpIts, int(std::floor(budget / round_ms_))));
+    }
+    const int matched = icp_.compute(kfs, iters, iters < kMaxIcpIts);  // the whole loop of pipeline.cpp:166-193
     const auto c4 = clk();
+    if (iters > 0) round_ms_ = ms(c3, c4) / double(iters);
     std::memcpy(frame_to_map_.m, icp_.X_.m, sizeof(frame_to_map_.m));
     inliers_ratio_ = double(matched) / double(cur->tree->numLeaves());  // :197-204
     trajectory_.push_back(frame_to_map_);
@@ -206,7 +239,8 @@ class Pipeline {
     cur->frame = int(seq_);
     cur->to_map = frame_to_map_;
     cur->stamp = stamp;
-    cur->weight = detail::inverseDeterminant(icp_.H_adder_);  // :223
+    cur->weight = (iters > 0 && iters <= MADICP_MAX_ITERS) ? icp_.weight()                        // :223, from the device
+                                                           : detail::inverseDeterminant(icp_.H_adder_);
     cur->tree->applyTransform(toM(frame_to_map_));             // :224
     current_ = cur;
     frames_.push_back(cur);
@@ -219,6 +253,7 @@ class Pipeline {
           best_w = f->weight;
           best = f;
         }
+      if (!best) best = cur;  // every weight inf/NaN (singular H): the reference dereferences null here; keep the newest
       while (!frames_.empty() && frames_.front()->frame <= best->frame) frames_.pop_front();
       keyframes_.push_back(best);
       if (keyframes_.size() > size_t(num_keyframes_)) keyframes_.pop_front();
@@ -245,7 +280,8 @@ class Pipeline {
     std::memcpy(M.m, p.m, sizeof(p.m));
     return M;
   }
-  // pipeline.cpp:79-123: done by the library (madicp_deskew: threaded, same permutation and poses)
+  // pipeline.cpp:79-123 on the host (madicp_deskew: threaded, same permutation and poses); the device path is
+  // madicp_ingest
   static void deskew(ContainerType& cloud, const detail::Pose& T_prev, const detail::Pose& T_now, double sensor_hz,
                      int num_threads) {
     if (cloud.empty()) return;
@@ -264,6 +300,9 @@ class Pipeline {
   double b_max_, p_th_, b_min_;
   int num_keyframes_, max_parallel_levels_ = 0;
   bool realtime_;
+  bool gpu_build_ = true;   // MADICP_GPU_BUILD=0: host-built trees
+  int num_threads_ = 1;
+  double round_ms_ = 0.0;   // duration of one GN round on the previous scan (realtime budget)
   MADicp icp_;
   detail::VelocityEstimator vel_;
   detail::Pose frame_to_map_, keyframe_to_map_;

@@ -45,6 +45,10 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--stream-scans", type=int, default=-1,
+                    help="cfg5 streaming block: scans of the synthetic sequence (default 1000 at N=1, 250 per rank at N>1; 0: off)")
+    ap.add_argument("--stream-cpu-scans", type=int, default=200,
+                    help="how many of them the CPU pipeline also runs (trajectory error and keyframe decisions)")
     ap.add_argument("--beams", type=int, default=64)
     ap.add_argument("--azimuths", type=int, default=2048)
     return ap.parse_args()
@@ -100,6 +104,34 @@ class ClockSampler(threading.Thread):
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "nvml unavailable"}
         return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
                 "samples": len(self.samples)}
+
+
+def pin_to_gpu(dev, local_rank, world):
+    """Keeps this process (and the pinned buffers it is about to allocate) on the CPU cores next to its GPU: with one
+    process per GPU the host side of a step is a handful of latency-bound driver calls, and a remote NUMA node or a core
+    shared with another rank's threads costs more than the kernel.  Returns a description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(dev)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cores = [i for i in range(ncpu) if (words[i // 64] >> (i % 64)) & 1]
+        if not cores:
+            return None
+        if world > 1:  # ranks whose GPUs share a node split its cores between them
+            peers = []
+            for d in range(world):
+                w2 = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(d), (ncpu + 63) // 64)
+                if list(w2) == list(words):
+                    peers.append(d)
+            k, m = peers.index(dev), len(peers)
+            share = max(4, len(cores) // m)
+            cores = cores[k * share:(k + 1) * share] or cores
+        os.sched_setaffinity(0, cores)
+        return f"{len(cores)} cores next to GPU {dev} ({cores[0]}-{cores[-1]})"
+    except Exception as e:  # noqa: BLE001  (no NVML / no permission: run unpinned)
+        return f"unpinned ({type(e).__name__})"
 
 
 def leaf_depths(recs):
@@ -245,6 +277,73 @@ def run_reference(a, rank):
 
 
 # --------------------------------------------------------------------------------------------
+def stream_block(a, scans, rank, world, dev):
+    """BASELINE.json configs[4]: streaming odometry over a synthetic KITTI-shape sequence, num_keyframes=16,
+    p_th 0.8, no deskew, END TO END per scan through the reference-named Pipeline (pypeline): host float64 cloud in,
+    H2D, float conversion / MAD-tree build / registration / keyframe promotion on the device, pose out.  The CPU
+    pipeline (the reference's own Pipeline when oracle/_ref is shipped, else the restatement) runs the first
+    --stream-cpu-scans scans: absolute trajectory error and keyframe decisions against it, and its scans/s."""
+    os.environ.setdefault("MADICP_DEVICE", str(dev))
+    from mad_icp_b200.pybind.pypeline import Pipeline
+    threads = min(16, os.cpu_count() or 1)
+    kw = dict(sensor_hz=10.0, deskew=False, b_max=0.2, rho_ker=0.1, p_th=0.8, b_min=0.1, b_ratio=0.02,
+              num_keyframes=K_MODEL, num_threads=threads, realtime=False)
+    import torch
+    torch.cuda.set_device(dev)
+    pipe = Pipeline(**kw)
+    n = len(scans)
+    pipe.compute(0.0, scans[0])  # initialise: keyframe 0 (also first-touch allocations)
+    traj, kf = [], []
+    torch.cuda.synchronize(dev)
+    depth = int(os.environ.get("MADICP_BENCH_LOOKAHEAD", "6"))  # scans whose trees are being built ahead (0: none)
+    t0 = time.perf_counter()
+    for k in range(1, min(depth, n - 1) + 1):
+        pipe.prefetch(scans[k])
+    for i in range(1, n):
+        if depth > 0 and i + depth < n:
+            pipe.prefetch(scans[i + depth])
+        pipe.compute(0.1 * i, scans[i])
+        traj.append(pipe.currentPose()[:3, 3].copy())
+        kf.append((bool(pipe.isMapUpdated()), int(pipe.keyframeID())))
+    t_gpu = time.perf_counter() - t0
+    out = {"scans": n - 1, "points_per_scan": int(scans[0].shape[0]), "num_keyframes": K_MODEL, "p_th": 0.8,
+           "value": (n - 1) / t_gpu, "unit": "scans/s", "ms_per_scan": 1e3 * t_gpu / (n - 1),
+           "device_tree_build": bool(pipe.gpuBuild()), "lookahead_scans": depth, "keyframes_at_end": int(pipe.numKeyframes()),
+           "path_length_m": float(np.linalg.norm(traj[-1] - traj[0])),
+           "note": "Pipeline.compute per scan, host cloud in / pose out; tree build, registration and keyframe promotion on the device"}
+    m = min(a.stream_cpu_scans, n)
+    if rank == 0 and m > 1:
+        from oracle import oracle as O
+        from oracle import reference as R
+        kind = "port"
+        cpu = None
+        if R.available():
+            try:
+                R.lib()
+                cpu, kind = R.ReferencePipeline(**kw), "reference"
+            except (OSError, RuntimeError):
+                cpu = None
+        if cpu is None:
+            O.build()
+            cpu = O.OraclePipeline(**kw)
+        cpu.compute(0.0, scans[0])
+        ctraj, ckf = [], []
+        t0 = time.perf_counter()
+        for i in range(1, m):
+            cpu.compute(0.1 * i, scans[i])
+            st = cpu.state()
+            ctraj.append(st[[3, 7, 11]].copy())
+            ckf.append((bool(st[12]), int(st[14])))
+        t_cpu = time.perf_counter() - t0
+        g, c = np.array(traj[:m - 1]), np.array(ctraj)
+        out.update({"cpu_scans": m - 1, "cpu_value": (m - 1) / t_cpu, "cpu_kind": kind, "cpu_threads": threads,
+                    "ate_m": float(np.sqrt(((g - c) ** 2).sum(1).mean())), "ate_max_m": float(np.sqrt(((g - c) ** 2).sum(1)).max()),
+                    "keyframe_decisions_equal": kf[:m - 1] == ckf})
+    del pipe
+    return out
+
+
+# --------------------------------------------------------------------------------------------
 def main():
     a = parse()
     if int(os.environ.get("WORLD_SIZE", "1")) == 1 or a.impl == "reference":
@@ -256,6 +355,12 @@ def main():
         run_reference(a, rank)
         return
 
+    from mad_icp_b200 import synth as _synth
+    n_stream = a.stream_scans if a.stream_scans >= 0 else (1000 if world == 1 else 250)
+    stream_scans = None
+    if n_stream > 1:  # ray-cast the sequence in forked workers BEFORE CUDA is initialised in this process
+        workers = max(1, min(32, (os.cpu_count() or 1) // max(world, 1)))
+        stream_scans = _synth.sequence(n_stream + 1, a.beams, a.azimuths, workers=workers)["scans"]
     import torch
     import torch.distributed as dist
     from mad_icp_b200 import FlatTree, Registrar, synth
@@ -267,6 +372,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n = world
     dev = local_rank if world > 1 else 0
+    affinity = pin_to_gpu(dev, local_rank, world)
     torch.cuda.set_device(dev)
 
     # ---------------- inputs (synthetic, deterministic, identical on every rank)
@@ -346,9 +452,7 @@ def main():
     e2e_s = 0.0
     for _ in range(a.steps):
         l2_flush()
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
+        barrier()  # sync - NCCL barrier - sync: the barrier's own kernel must be off the GPU before the clock starts
         t0 = time.perf_counter()
         reg.set_moving(pinned)                       # H2D: L x 24 B from pinned host memory
         out = reg.register(X0, a.iters)              # H2D pose, kernels, D2H pose/H/b/matched, sync
@@ -387,6 +491,19 @@ def main():
                    "matched_flags_equal_vs_single_gpu": bool(np.array_equal(sh_res["matched"], res["matched"])),
                    "note": f"one scan, keyframe slot s on rank s%{n}, in-kernel NVLink all-reduce of H/b each GN round"}
         sh.close()
+
+    # ---------------- cfg5: streaming odometry, end to end (every rank its own replica of the sequence at N > 1)
+    stream = None
+    if stream_scans is not None:
+        barrier()
+        stream = stream_block(a, stream_scans, rank, world, dev)
+        if world > 1:
+            t = torch.tensor([stream["ms_per_scan"]], dtype=torch.float64, device=f"cuda:{dev}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            stream["ms_per_scan"] = float(t.item())
+            stream["value"] = n * 1e3 / stream["ms_per_scan"]
+            stream["note"] += f"; {n} independent replicas of the sequence, slowest rank's time"
+        del stream_scans
 
     # ---------------- roofline of the dominant kernel (k_gn_loop) + parity guard
     trace = reg.register_trace()
@@ -434,7 +551,8 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": workload_name(a, n), "moving_leaves": L, "keyframes": K_MODEL,
                            "gn_iters": a.iters, "l2": "flushed between steps (256 MiB fill, outside the per-step events)",
-                           "timing": "per-step CUDA event pairs on the launch stream, summed; max over ranks"},
+                           "timing": "per-step CUDA event pairs on the launch stream, summed; max over ranks",
+                           "host_affinity": affinity},
                 "e2e": {"value": n * a.steps / e2e_s, "unit": "scans/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / a.steps,
                         "timing": "host wall clock around set_moving+register (pinned H2D, kernel, D2H, sync)"},
@@ -448,6 +566,8 @@ def main():
             line["parity"] = parity
         if sharded:
             line["sharded"] = sharded
+        if stream:
+            line["stream"] = stream
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -24,6 +24,11 @@ int madicp_debug_cta_cycles(madicp_ctx_t* ctx, int64_t* out, int cap);
 int madicp_set_gn_grid(madicp_ctx_t* ctx, int threads_per_cta, int ctas_per_sm);
 
 
+/* Path memo of the persistent kernel (kernels.cuh, descend_t): enable = 0 walks every (leaf, keyframe) pair in every
+ * round, as round 1 did.  Results are identical either way (the memo only skips walks it has proved unchanged);
+ * this switch exists for A/B measurements and for the test that checks exactly that. */
+int madicp_debug_set_memo(madicp_ctx_t* ctx, int enable);
+
 /* Diagnostic for madicp_deskew's sort: n pseudo-random keys over `distinct` values, sorted by std::sort
  * and by the threaded restatement of it; returns how many positions of the two permutations differ (0). */
 int64_t madicp_debug_sort_check(int64_t n, uint32_t seed, int64_t distinct, int num_threads);

@@ -43,6 +43,9 @@ SYMBOLS = {
     "madicp_synchronize": (C.c_int, [vp]),
     "madtree_gpu_build": (C.c_int, [vp, dp, C.c_int64, C.c_double, C.c_double, C.POINTER(vp)]),
     "madtree_gpu_build_resident": (C.c_int, [vp, C.c_double, C.c_double, C.POINTER(vp)]),
+    "madicp_builder_create": (C.c_int, [vp, C.POINTER(vp)]),
+    "madicp_builder_destroy": (None, [vp]),
+    "madicp_builder_build": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.c_double, C.c_double, C.POINTER(vp)]),
     "madtree_gpu_upload": (C.c_int, [vp, vp, C.POINTER(vp)]),
     "madtree_gpu_free": (None, [vp]),
     "madtree_gpu_num_nodes": (C.c_int, [vp]),
@@ -79,6 +82,7 @@ SYMBOLS = {
     "madicp_debug_timing": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int64), C.c_int]),
     "madicp_debug_cta_cycles": (C.c_int, [vp, C.POINTER(C.c_int64), C.c_int]),
     "madicp_set_gn_grid": (C.c_int, [vp, C.c_int, C.c_int]),
+    "madicp_debug_set_memo": (C.c_int, [vp, C.c_int]),
 }
 
 REC_DTYPE = np.dtype([("mean", "<f8", 3), ("dir", "<f8", 3), ("bbox0", "<f8"), ("link", "<i4"), ("num_points", "<i4")])

@@ -33,6 +33,7 @@ ModelView madicp_make_view(const madicp_ctx* c) {
   ModelView v;
   v.recs = c->d_pool_recs;
   v.quad = c->d_quad;
+  v.ww = c->d_pool_ww;
   v.K = 0;
   for (int s = 0; s < c->max_keyframes; ++s)
     if (c->slots[s].n_nodes > 0) {
@@ -54,7 +55,8 @@ static int prepare_slot(madicp_ctx* c, int s) {
   const size_t off = size_t(s) * c->pool_cap;
   k_prepare_slot<<<blocks_for(n), kStepBlock, 0, c->stream>>>(
       c->d_pool_recs + off, n, int(off), c->P.min_ball, c->d_pool_lvl + size_t(s) * (kMaxLevels + 1),
-      c->slots[s].n_levels, c->d_pool_child0 + off, c->d_pool_rec_of + off, c->d_quad + size_t(s) * c->quad_cap);
+      c->slots[s].n_levels, c->d_pool_child0 + off, c->d_pool_rec_of + off, c->d_quad + size_t(s) * c->quad_cap,
+      c->d_pool_ww + off);
   c->launches++;
   CK(cudaGetLastError());
   return MADICP_OK;
@@ -95,11 +97,13 @@ static int ensure_pool(madicp_ctx* c, size_t need) {
   madtree_rec_t* recs = nullptr;
   int *child0 = nullptr, *rec_of = nullptr;
   QuadRec* quad = nullptr;
+  double* ww = nullptr;
   const size_t total = cap * size_t(c->max_keyframes);
   CK(cudaMalloc(&recs, total * sizeof(madtree_rec_t)));
   CK(cudaMalloc(&child0, total * sizeof(int)));
   CK(cudaMalloc(&rec_of, total * sizeof(int)));
   CK(cudaMalloc(&quad, 2 * total * sizeof(QuadRec)));
+  CK(cudaMalloc(&ww, total * sizeof(double)));
   for (int s = 0; s < c->max_keyframes; ++s)
     if (c->slots[s].n_nodes > 0)
       CK(cudaMemcpyAsync(recs + size_t(s) * cap, c->d_pool_recs + size_t(s) * c->pool_cap,
@@ -109,6 +113,8 @@ static int ensure_pool(madicp_ctx* c, size_t need) {
   cudaFree(c->d_pool_child0);
   cudaFree(c->d_pool_rec_of);
   cudaFree(c->d_quad);
+  cudaFree(c->d_pool_ww);
+  c->d_pool_ww = ww;
   c->d_pool_recs = recs;
   c->d_pool_child0 = child0;
   c->d_pool_rec_of = rec_of;
@@ -273,6 +279,7 @@ int madicp_create(madicp_ctx_t** out, int device, int max_keyframes) {
   CK(cudaMalloc(&c->d_X, sizeof(double) * 64));
   CK(cudaMalloc(&c->d_comm, sizeof(CommBlock)));
   CK(cudaMemset(c->d_comm, 0, sizeof(CommBlock)));
+  CK(cudaEventCreateWithFlags(&c->tree_free_ev, cudaEventDisableTiming));
   CK(cudaMalloc(&c->d_pool_lvl, size_t(max_keyframes) * (kMaxLevels + 1) * sizeof(int)));
   CK(cudaMalloc(&c->d_xform, size_t(madicp_ctx::kXformRing) * 12 * sizeof(double)));
   CK(cudaMallocHost(&c->h_xform, size_t(madicp_ctx::kXformRing) * 12 * sizeof(double)));
@@ -283,6 +290,7 @@ int madicp_create(madicp_ctx_t** out, int device, int max_keyframes) {
   CK(cudaMallocHost(&c->h_in, size_t(madicp_ctx::kInRing) * 128));
   for (int i = 0; i < madicp_ctx::kInRing; ++i) CK(cudaEventCreateWithFlags(&c->in_done[i], cudaEventDisableTiming));
   CK(cudaMallocHost(&c->h_matched, kMatchedCap));
+  if (const char* e = getenv("MADICP_NO_MEMO")) c->use_memo = (atoi(e) == 0);
   int threads = 1024, ctas = 1;
   if (const char* e = getenv("MADICP_GN_SHAPE"))
     if (sscanf(e, "%d,%d", &threads, &ctas) == 2) c->gn_auto = false;
@@ -290,6 +298,8 @@ int madicp_create(madicp_ctx_t** out, int device, int max_keyframes) {
   if (rc) return rc;
   c->cap_partial = size_t(c->sm_count) * 8 * kAcc;
   CK(cudaMalloc(&c->d_partial, c->cap_partial * sizeof(double)));
+  CK(cudaMalloc(&c->d_tiles, c->cap_partial * sizeof(LLCell)));
+  CK(cudaMemset(c->d_tiles, 0, c->cap_partial * sizeof(LLCell)));  // epoch 0 is never used
   c->peer_comm[0] = c->d_comm;
   *out = c;
   return MADICP_OK;
@@ -312,6 +322,7 @@ void madicp_destroy(madicp_ctx_t* c) {
   cudaFree(c->d_pool_rec_of);
   cudaFree(c->d_pool_lvl);
   cudaFree(c->d_quad);
+  cudaFree(c->d_pool_ww);
   cudaFree(c->d_xform);
   cudaFree(c->d_dbg_cta);
   cudaFree(c->d_moving);
@@ -322,6 +333,9 @@ void madicp_destroy(madicp_ctx_t* c) {
   cudaFree(c->d_cloud_q);
   cudaFree(c->d_cloud_o);
   cudaFree(c->d_partial);
+  cudaFree(c->d_tiles);
+  cudaFree(c->d_memo_leaf);
+  cudaFree(c->d_memo_margin);
   cudaFree(c->d_state);
   cudaFree(c->d_X);
   cudaFree(c->d_comm);
@@ -336,6 +350,7 @@ void madicp_destroy(madicp_ctx_t* c) {
   for (int i = 0; i < madicp_ctx::kXformRing; ++i)
     if (c->xform_done[i]) cudaEventDestroy(c->xform_done[i]);
   cudaFreeHost(c->h_matched);
+  if (c->tree_free_ev) cudaEventDestroy(c->tree_free_ev);
   cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -548,7 +563,7 @@ int64_t madicp_model_nodes(const madicp_ctx_t* c) {
   for (const Slot& s : c->slots) n += s.n_nodes;
   return n;
 }
-int64_t madicp_kernel_launches(const madicp_ctx_t* c) { return c ? c->launches : 0; }
+int64_t madicp_kernel_launches(const madicp_ctx_t* c) { return c ? c->launches.load() : 0; }
 
 // ------------------------------------------------------------------------------ device-resident trees
 }  // extern "C"
@@ -557,12 +572,15 @@ int64_t madicp_kernel_launches(const madicp_ctx_t* c) { return c ? c->launches :
 // sequence allocates one tree per scan and frees one per scan).
 int madicp_tree_alloc(madicp_ctx* c, size_t cap_nodes, madtree_gpu** out) {
   madtree_gpu* t = nullptr;
-  for (size_t i = 0; i < c->tree_cache.size(); ++i)
-    if (c->tree_cache[i]->cap_nodes >= cap_nodes) {
-      t = c->tree_cache[i];
-      c->tree_cache.erase(c->tree_cache.begin() + long(i));
-      break;
-    }
+  {
+    std::lock_guard<std::mutex> lk(c->tree_mu);
+    for (size_t i = 0; i < c->tree_cache.size(); ++i)
+      if (c->tree_cache[i]->cap_nodes >= cap_nodes) {
+        t = c->tree_cache[i];
+        c->tree_cache.erase(c->tree_cache.begin() + long(i));
+        break;
+      }
+  }
   if (!t) {
     t = new madtree_gpu;
     t->ctx = c;
@@ -621,10 +639,16 @@ int madtree_gpu_upload(madicp_ctx_t* c, const madtree_t* tree, madtree_gpu_t** o
 void madtree_gpu_free(madtree_gpu_t* t) {
   if (!t) return;
   madicp_ctx* c = t->ctx;
-  // stream order protects the memory: whatever still reads it was enqueued before anything that reuses it
-  if (c->tree_cache.size() < 24) {
-    c->tree_cache.push_back(t);
-    return;
+  // (the context's stream is the only consumer of trees: whatever still reads this one was enqueued before the
+  // free; a builder that picks the memory up writes it from ANOTHER stream, so it first waits for that work)
+  cudaSetDevice(c->device);
+  cudaEventRecord(c->tree_free_ev, c->stream);
+  {
+    std::lock_guard<std::mutex> lk(c->tree_mu);
+    if (c->tree_cache.size() < 24) {
+      c->tree_cache.push_back(t);
+      return;
+    }
   }
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
@@ -862,7 +886,6 @@ static int register_enqueue(madicp_ctx* c, int iters, const double X0[12], int c
   A.iters = iters;
   A.clear_from = clear_from;
   A.matched = c->d_comm->matched[mb];
-  A.partial = c->d_partial;
   // Item map in shared memory: 4 bytes per CTA-local item, taken only if it neither exceeds the reserve
   // nor pushes the CTA into the next shared-memory carve-out (that would shrink L1, which holds the tree).
   size_t map_bytes = 0;
@@ -879,26 +902,38 @@ static int register_enqueue(madicp_ctx* c, int iters, const double X0[12], int c
       map_bytes = per_cta;
   }
   A.map_in_smem = map_bytes ? 1 : 0;
+  {  // path memo: one entry per CTA-local item
+    const size_t stride = ((size_t(madicp_num_keyframes(c)) * (size_t(c->L) / size_t(c->gn_grid) + 8)) + 31) & ~size_t(31);
+    const size_t need = stride * size_t(c->gn_grid);
+    if (need > c->cap_memo) {
+      CK(cudaStreamSynchronize(c->stream));
+      cudaFree(c->d_memo_leaf);
+      cudaFree(c->d_memo_margin);
+      c->d_memo_leaf = nullptr;
+      c->d_memo_margin = nullptr;
+      c->cap_memo = 0;
+      const size_t cap = need + need / 4;
+      CK(cudaMalloc(&c->d_memo_leaf, cap * sizeof(int)));
+      CK(cudaMalloc(&c->d_memo_margin, cap * sizeof(float)));
+      c->cap_memo = cap;
+    }
+    A.memo_leaf = c->d_memo_leaf;
+    A.memo_margin = c->d_memo_margin;
+    A.item_stride = int(stride);
+    A.use_memo = c->use_memo ? 1 : 0;
+  }
   A.st = c->d_state;
   A.dbg = c->d_dbg;
   A.dbg_cta = c->d_dbg ? c->d_dbg_cta : nullptr;
   c->epoch += uint32_t(iters);
   A.pose_epoch = c->pose_epoch;
   c->pose_epoch += uint32_t(iters);
-  // control words + initial pose: one small pinned H2D copy from the next header of the ring
-  static_assert(offsetof(GnState, X_out) <= 128, "launch header must fit a ring entry");
-  const int ring = int(c->call_seq % madicp_ctx::kInRing);
-  if (c->call_seq >= madicp_ctx::kInRing) CK(cudaEventSynchronize(c->in_done[ring]));
-  GnState* hs = reinterpret_cast<GnState*>(c->h_in + size_t(ring) * 128);
-  hs->ticket = 0;
-  hs->clear_from = clear_from;
-  hs->n_matched = 0;
-  hs->pad = 0;
-  memcpy(hs->X_in, X0, 12 * sizeof(double));
-  CK(cudaMemcpyAsync(c->d_state, hs, offsetof(GnState, X_out), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaEventRecord(c->in_done[ring], c->stream));
-  // zero the flags buffer of the NEXT call (nobody can be writing it yet; see CommBlock)
-  CK(cudaMemsetAsync(c->d_comm->matched[mb ^ 1], 0, std::min(kMatchedCap, c->cap_moving), c->stream));
+  // The launch carries everything: initial pose in the kernel arguments, no ticket to reset (the round barrier
+  // has none), and the kernel itself zeroes the matched flags of the NEXT call -- one stream operation per scan.
+  memcpy(A.X0, X0, 12 * sizeof(double));
+  A.tiles = c->d_tiles;
+  A.zero_next = c->d_comm->matched[mb ^ 1];
+  A.zero_bytes = int((std::min(kMatchedCap, c->cap_moving) + 15) & ~size_t(15));
   void* args[] = {&A};
   CK(cudaLaunchCooperativeKernel(c->gn_kernel, dim3(c->gn_grid), dim3(c->gn_threads), args, c->gn_smem + map_bytes, c->stream));
   c->launches++;
@@ -1136,6 +1171,12 @@ int madicp_debug_cta_cycles(madicp_ctx_t* c, int64_t* out, int cap) {
   const int n = std::min(cap, c->last_iters * c->gn_grid);
   CK(cudaMemcpy(out, c->d_dbg_cta, size_t(n) * sizeof(long long), cudaMemcpyDeviceToHost));
   return c->gn_grid;
+}
+
+int madicp_debug_set_memo(madicp_ctx_t* c, int enable) {
+  if (!c) return MADICP_ERR_INVALID;
+  c->use_memo = enable != 0;
+  return MADICP_OK;
 }
 
 int madicp_set_gn_grid(madicp_ctx_t* c, int threads_per_cta, int ctas_per_sm) {

@@ -4,6 +4,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
+#include <mutex>
 #include <new>
 #include <stdexcept>
 #include <string>
@@ -62,6 +64,7 @@ struct madicp_ctx {
   int* d_pool_lvl = nullptr;       // per slot: level table, kMaxLevels + 1 entries
   size_t quad_cap = 0;             // 4-ary records per slot (= 2 * pool_cap)
   madicp::QuadRec* d_quad = nullptr;
+  double* d_pool_ww = nullptr;     // per node: planarity weight of a leaf (what the quad leaf codes also carry)
   // pinned staging rings for the small stream-ordered uploads of a promotion (pose, level table)
   static constexpr int kXformRing = 64;
   double* d_xform = nullptr;
@@ -70,6 +73,8 @@ struct madicp_ctx {
   cudaEvent_t xform_done[kXformRing] = {};
   uint32_t xform_seq = 0;
   std::vector<madtree_gpu*> tree_cache;  // freed device trees keep their memory for the next scan
+  cudaEvent_t tree_free_ev = nullptr;    // recorded on the context's stream at every madtree_gpu_free
+  std::mutex tree_mu;                    // ... builders on other host threads allocate from it too
   void* build_state = nullptr;           // gpu_tree.cu: working memory of the device build (lazily created)
   long long* d_dbg_cta = nullptr;  // MADICP_MAX_ITERS x grid item-phase cycles when debug timing is on
   madicp::IcpParams P{0.2, 0.31622776601683794, 0.02};
@@ -86,8 +91,13 @@ struct madicp_ctx {
   double* d_cloud_q = nullptr;  // madicp_search_cloud scratch: queries (3n) + outputs (7n), ordinals
   int* d_cloud_o = nullptr;
   size_t cap_cloud = 0;
-  double* d_partial = nullptr;
+  double* d_partial = nullptr;      // per-CTA tiles of the step kernel (k_linearize)
+  madicp::LLCell* d_tiles = nullptr;  // per-CTA tiles of the persistent kernel, epoch-tagged (cap_partial cells)
   size_t cap_partial = 0;
+  int* d_memo_leaf = nullptr;      // path memo of the persistent kernel (GnArgs), grid x item_stride each
+  float* d_memo_margin = nullptr;
+  size_t cap_memo = 0;
+  bool use_memo = true;            // MADICP_NO_MEMO=1 / madicp_debug_set_memo(0): walk every item in every round
   madicp::GnState* d_state = nullptr;
   double* d_X = nullptr;  // 12 (step API pose) + 36 + 6 scratch
   madicp::CommBlock* d_comm = nullptr;
@@ -112,7 +122,7 @@ struct madicp_ctx {
   bool calibrated = false;
   int last_iters = 0;
   long long* d_dbg = nullptr;  // MADICP_MAX_ITERS x 8 clock stamps when debug timing is on
-  int64_t launches = 0;
+  std::atomic<int64_t> launches{0};
   // peers
   int rank = 0, world = 1;
   madicp::CommBlock* peer_comm[madicp::kMaxPeers] = {};

@@ -149,11 +149,16 @@ __device__ __forceinline__ FastRec make_shadow(const Rec& r, int pool_index, dou
 // of its grandchildren).  `recs` = the slot's exact records in the pool (at pool offset `off`).
 __global__ void __launch_bounds__(kStepBlock)
 k_prepare_slot(const madtree_rec_t* __restrict__ recs, int n, int off, double min_ball, const int* __restrict__ lvl,
-               int n_levels, const int* __restrict__ child0, const int* __restrict__ rec_of, QuadRec* __restrict__ quad) {
+               int n_levels, const int* __restrict__ child0, const int* __restrict__ rec_of, QuadRec* __restrict__ quad,
+               double* __restrict__ ww_out) {
   const int i = blockIdx.x * kStepBlock + threadIdx.x;
   if (i >= n) return;
-  if (depth_of(lvl, n_levels, i) & 1) return;
   const Rec r = load_rec(recs + i);
+  if (r.link < 0) {  // planarity weight of a leaf (odometry/mad_icp.cpp:97-98), read by the items that skip the walk
+    const double w = 1.0 - r.bbox0 / min_ball;
+    ww_out[i] = w * w;
+  }
+  if (depth_of(lvl, n_levels, i) & 1) return;
   QuadRec q;
   q.p0 = make_shadow(r, off + i, min_ball);
   q.p1 = q.p0;
@@ -352,10 +357,18 @@ struct GnArgs {
   int clear_from;                          // first round whose gate passes set matched flags (GnState::clear_from)
   unsigned char* matched;                  // local matched flags (L bytes), zeroed by the host
   unsigned char* peer_matched[kMaxPeers];  // world > 1: every rank's matched array (peer mapped)
-  double* partial;                         // gridDim.x * kAcc
+  LLCell* tiles;                           // gridDim.x * kAcc epoch-tagged cells: every CTA's H/b tile of the round
+  double X0[12];                           // initial pose (travels with the launch: no separate upload)
+  unsigned char* zero_next;                // matched flags of the NEXT call (nobody writes them yet): zeroed here
+  int zero_bytes;
   GnState* st;
   int map_in_smem;                         // 1: the launch reserved 4 bytes per CTA-local item behind the staging tiles
   uint32_t pose_epoch;                     // epoch of round 0's pose; monotonic across launches, never reused
+  // path memo (kernels.cuh, descend_t): per CTA-local item, CTA b owns [b * item_stride, (b + 1) * item_stride)
+  int* memo_leaf;                          // pool index of the leaf the last walk of the item reached
+  float* memo_margin;                      // how far its query may still move before a decision of that walk could change
+  int item_stride;
+  int use_memo;                            // 0: every item is walked in every round (probe / A-B measurement)
   long long* dbg;                          // nullable: per-round SM-clock stamps (madicp_debug_timing)
   long long* dbg_cta;                      // nullable: [round][CTA] item-phase cycles
 };
@@ -389,8 +402,8 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
   static_assert(WARPS * 64 + kMaxPeers * kAcc <= WARPS * kStageTile, "scratch must fit in the staging tiles");
   __shared__ double s_tot[kAcc];
   __shared__ double s_b[6];
-  __shared__ double s_X[12];
-  __shared__ int s_last;
+  __shared__ double s_X[12], s_Xp[12];
+  __shared__ int s_qn;
   __shared__ int s_count[WARPS];
   GnState* st = A.st;
   const unsigned L = unsigned(A.L);
@@ -444,11 +457,25 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
     __syncwarp();  // a warp only ever reads what it wrote itself
   }
 
+  for (int i = (blockIdx.x * THREADS + threadIdx.x) * 16; i < A.zero_bytes; i += gridDim.x * THREADS * 16)
+    *reinterpret_cast<uint4*>(A.zero_next + i) = make_uint4(0, 0, 0, 0);
+  int* const memo_leaf = A.memo_leaf + size_t(blockIdx.x) * A.item_stride;
+  float* const memo_margin = A.memo_margin + size_t(blockIdx.x) * A.item_stride;
+  auto item_at = [&](unsigned t0, unsigned& k, unsigned& q) {
+    if (s_map) {
+      const unsigned pk = s_map[t0 + lane];
+      k = pk >> 26;
+      q = pk & 0x3ffffffu;
+    } else {
+      item_of(t0, k, q);
+    }
+  };
+
   for (int it = 0; it < A.iters; ++it) {
     if (threadIdx.x < 12) {
       double x;
       if (it == 0) {
-        x = ld_relaxed_f64(&st->X_in[threadIdx.x]);
+        x = A.X0[threadIdx.x];
       } else {  // round barrier: spin until the pose of THIS round (epoch-tagged) has been published
         const uint32_t ep = A.pose_epoch + uint32_t(it);
         uint32_t lo, hi, f0, f1;
@@ -458,32 +485,62 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
         } while (f0 != ep || f1 != ep);
         x = __hiloint2double(int(hi), int(lo));
       }
+      s_Xp[threadIdx.x] = s_X[threadIdx.x];  // the pose the memo margins were last charged against
       s_X[threadIdx.x] = x;
       if (it == 0 && blockIdx.x == 0) st->X_trace[threadIdx.x] = x;
     }
+    if (threadIdx.x == 32) s_qn = 0;
     __syncthreads();
     const bool last_round = (it == A.iters - 1);
     double c0 = 0.0, c1 = 0.0;
     long long t_begin = 0;
     if (A.dbg && threadIdx.x == 0) t_begin = clock64();
 
+    // One pass in the static item order (the order of the sums is fixed).  From round 1 on an item keeps the leaf
+    // of its last walk when its query has moved, since that walk, by less than the smallest margin of the walk
+    // (kernels.cuh, descend_t): the margin is charged with every round's displacement (triangle inequality),
+    // rounded down; otherwise the lane walks again, in place.
+    int n_walked = 0;
     for (unsigned t0 = warp * 32; t0 < t_total; t0 += THREADS) {
       unsigned k, q;
-      if (s_map) {
-        const unsigned pk = s_map[t0 + lane];
-        k = pk >> 26;
-        q = pk & 0x3ffffffu;
-      } else {
-        item_of(t0, k, q);
-      }
+      item_at(t0, k, q);
       double v[kStage];
 #pragma unroll
       for (int i = 0; i < kStage; ++i) v[i] = 0.0;
-      if (t0 + lane < t_total) {
+      const unsigned t = t0 + lane;
+      if (t < t_total) {
         const Moving4 m = load_moving(A.moving + q);
-        double mx, my, mz, ww;
+        double mx, my, mz;
         iso_apply(s_X, m.px, m.py, m.pz, mx, my, mz);
-        const Rec f = load_rec(A.model.recs + descend(A.model, int(k), mx, my, mz, ww));
+        int leaf = -1;
+        if (it > 0 && A.use_memo) {
+          const float have = memo_margin[t];
+          const int last = memo_leaf[t];
+          double bx, by, bz;
+          iso_apply(s_Xp, m.px, m.py, m.pz, bx, by, bz);
+          const double dx = mx - bx, dy = my - by, dz = mz - bz;
+          // slack: |dir| - 1 and the orthonormality of the pose (1e-4 relative), FP64 evaluation error of the
+          // reference expression at the new query (< 8 * 2^-53 * (|q|_1 + |mean|_1): 1e-9 absolute + 1e-12 |q|_1)
+          const double moved = 1.0001 * sqrt(dx * dx + dy * dy + dz * dz) + 1e-9 + 1e-12 * (fabs(mx) + fabs(my) + fabs(mz));
+          const double left = double(have) - moved;
+          if (left > 0.0) {
+            memo_margin[t] = __double2float_rd(left);
+            leaf = last;
+          }
+        }
+        if (leaf < 0) {
+          double ww_walk;
+          float margin = __int_as_float(0x7f800000);
+          leaf = A.use_memo ? descend_t<true>(A.model, int(k), mx, my, mz, ww_walk, margin)
+                            : descend_t<false>(A.model, int(k), mx, my, mz, ww_walk, margin);
+          if (A.use_memo) {
+            memo_leaf[t] = leaf;
+            memo_margin[t] = margin;
+          }
+          ++n_walked;
+        }
+        const double ww = __ldg(A.model.ww + leaf);  // (1 - bbox0/min_ball)^2 of the leaf, mad_icp.cpp:97-98
+        const Rec f = load_rec(A.model.recs + leaf);
         if (linearize_one(s_X, A.P.rho_ker_sqrt, m, mx, my, mz, f, ww, v) && it >= A.clear_from) {
           if (multi) {
             for (int r = 0; r < A.peers.world; ++r) A.peer_matched[r][q] = 1;
@@ -494,31 +551,39 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
       }
       warp_accumulate(stage, v, c0, c1);
     }
+    if (A.dbg) {  // items walked by this CTA in this round
+      n_walked = __reduce_add_sync(0xffffffffu, n_walked);
+      if (lane == 0 && n_walked) atomicAdd(&s_qn, n_walked);
+    }
     if (A.dbg && threadIdx.x == 0 && blockIdx.x == 0) A.dbg[it * 8 + 0] = clock64() - t_begin;  // item phase, CTA 0
     if (A.dbg_cta) {  // per-CTA item phase (slowest warp) + this warp's own time
       __syncthreads();
       if (threadIdx.x == 0) A.dbg_cta[size_t(it) * gridDim.x + blockIdx.x] = clock64() - t_begin;
+      if (threadIdx.x == 0 && blockIdx.x == 0) A.dbg[it * 8 + 5] = s_qn;
     }
     __syncthreads();  // every warp is done with its staging tile: s_red aliases them
-    block_reduce_store<WARPS>(c0, c1, s_red, A.partial + size_t(blockIdx.x) * kAcc);
-    if (multi && last_round) __threadfence_system();  // matched flags stored to peers precede our LL cells
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atom_add_release(&st->ticket, 1) == (it + 1) * int(gridDim.x) - 1);
-    __syncthreads();
-    if (s_last) {
+    // Round barrier without a ticket: every CTA publishes its 48-value tile as epoch-tagged LL cells (value and flag
+    // in one 16-byte store); CTA 0 -- the fixed folder -- polls the cells of all CTAs (the loads that find the flag
+    // also bring the value), sums them in a fixed order, solves and publishes the next pose the same way.
+    const uint32_t ep_round = A.pose_epoch + uint32_t(it);
+    block_reduce_publish<WARPS>(c0, c1, s_red, A.tiles + size_t(blockIdx.x) * kAcc, ep_round,
+                                /*fence: matched flags of this round must be visible before the tile*/ it >= A.clear_from, multi);
+    if (blockIdx.x == 0) {
       long long t0 = 0, t1 = 0, t2 = 0;
+      if (A.dbg && threadIdx.x == 0) t0 = clock64();
+      fold_tiles<THREADS>(A.tiles, gridDim.x, ep_round, s_red, s_tot);
       if (A.dbg && threadIdx.x == 0) {
-        t0 = clock64();
-        A.dbg[it * 8 + 1] = t0 - t_begin;  // round start -> last CTA arrived (that CTA's clock)
+        t1 = clock64();
+        A.dbg[it * 8 + 1] = t1 - t_begin;  // round start -> all tiles folded
+        A.dbg[it * 8 + 2] = t1 - t0;       // of which: waiting for / folding the tiles after CTA 0's own items
       }
-      final_reduce<THREADS>(A.partial, gridDim.x, s_red, s_tot);
-      if (A.dbg && threadIdx.x == 0) t1 = clock64();
       if (multi) {
         if (last_round) __threadfence_system();
         peer_allreduce<THREADS>(A.peers, A.peers.epoch_base + uint32_t(it) + 1u, s_tot, s_peer);
         if (last_round) __threadfence_system();
       }
-      if (last_round) {  // count matched moving leaves (all writers are done: they took tickets)
+      if (last_round) {  // count matched moving leaves (every writer fenced before its tile, and the tiles are in)
+        __threadfence();
         int c = 0;
         for (int q = threadIdx.x; q < A.L; q += THREADS) c += (__ldcv(A.matched + q) != 0);
         for (int off = 16; off > 0; off >>= 1) c += __shfl_down_sync(0xffffffffu, c, off);
@@ -530,6 +595,14 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
         if (A.dbg) t2 = clock64();
         double Xn[12];
         gn_update_pose(s_tot, 8, s_b, s_X, Xn);
+        if (!last_round) {
+          const uint32_t ep = ep_round + 1u;
+#pragma unroll
+          for (int i = 0; i < 12; ++i)
+            asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(&st->X_ll[i]),
+                         "r"(uint32_t(__double2loint(Xn[i]))), "r"(ep), "r"(uint32_t(__double2hiint(Xn[i]))), "r"(ep)
+                         : "memory");
+        }
 #pragma unroll
         for (int i = 0; i < 12; ++i) st->X_trace[(it + 1) * 12 + i] = Xn[i];
         if (last_round) {
@@ -541,16 +614,7 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
           for (int w2 = 0; w2 < WARPS; ++w2) c += s_count[w2];
           st->n_matched = c;
         }
-        if (!last_round) {
-          const uint32_t ep = A.pose_epoch + uint32_t(it) + 1u;
-#pragma unroll
-          for (int i = 0; i < 12; ++i)
-            asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(&st->X_ll[i]),
-                         "r"(uint32_t(__double2loint(Xn[i]))), "r"(ep), "r"(uint32_t(__double2hiint(Xn[i]))), "r"(ep)
-                         : "memory");
-        }
         if (A.dbg) {
-          A.dbg[it * 8 + 2] = t1 - t0;         // fold of the per-CTA partials
           A.dbg[it * 8 + 3] = t2 - t1;         // peer exchange + matched count
           A.dbg[it * 8 + 4] = clock64() - t2;  // solve + pose update + publish
         }

@@ -74,6 +74,8 @@ class MADtree {
   MADtree(madicp_ctx_t* ctx, double b_max, double b_min) : b_max_(b_max), uid_(next_uid()), ctx_(ctx) {
     check(madtree_gpu_build_resident(ctx, b_max, b_min, &g_), "madtree_gpu_build_resident");
   }
+  // adopts a tree a build lane produced on `ctx`'s device (madicp_builder_build)
+  MADtree(madicp_ctx_t* ctx, madtree_gpu_t* built, double b_max) : g_(built), b_max_(b_max), uid_(next_uid()), ctx_(ctx) {}
   ~MADtree() {
     madtree_free(t_);
     madtree_gpu_free(g_);

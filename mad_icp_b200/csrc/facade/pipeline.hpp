@@ -11,8 +11,10 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
+#include <condition_variable>
 #include <deque>
 #include <limits>
+#include <thread>
 
 #include "../pose_math.h"
 #include "facade.hpp"
@@ -86,14 +88,120 @@ struct VelocityEstimator {
 };
 }  // namespace detail
 
+// Look-ahead tree builds: scans handed to Pipeline::prefetch are ingested and built on the device by worker threads
+// (one build lane each: own stream, own working memory) while the pipeline registers earlier scans; compute()
+// consumes them in FIFO order.  Possible because a scan's tree depends on the pose estimates only when the scan is
+// deskewed (pipeline.cpp:137-141).
+class Lookahead {
+ public:
+  struct Job {
+    std::vector<double> f64;
+    std::vector<float> f32;
+    size_t n = 0;
+    madtree_gpu_t* tree = nullptr;
+    int rc = 0;
+    std::string err;
+    bool claimed = false, done = false;
+  };
+  Lookahead(madicp_ctx_t* ctx, double b_max, double b_min, int workers) : ctx_(ctx), b_max_(b_max), b_min_(b_min) {
+    for (int w = 0; w < workers; ++w) threads_.emplace_back([this] { run(); });
+  }
+  ~Lookahead() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : threads_) t.join();
+    for (auto& j : fifo_)
+      if (j->tree) madtree_gpu_free(j->tree);
+  }
+  void push(std::shared_ptr<Job> j) {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      fifo_.push_back(std::move(j));
+    }
+    cv_.notify_all();
+  }
+  bool empty() {
+    std::lock_guard<std::mutex> lk(mu_);
+    return fifo_.empty();
+  }
+  size_t size() {
+    std::lock_guard<std::mutex> lk(mu_);
+    return fifo_.size();
+  }
+  // oldest prefetched scan's tree (blocks until it is built)
+  madtree_gpu_t* pop() {
+    std::unique_lock<std::mutex> lk(mu_);
+    std::shared_ptr<Job> j = fifo_.front();
+    done_cv_.wait(lk, [&] { return j->done; });
+    fifo_.pop_front();
+    if (j->rc < 0) throw Error("look-ahead tree build failed: " + j->err);
+    madtree_gpu_t* t = j->tree;
+    j->tree = nullptr;
+    return t;
+  }
+
+ private:
+  void run() {
+    madicp_builder_t* b = nullptr;
+    if (madicp_builder_create(ctx_, &b) < 0) b = nullptr;
+    for (;;) {
+      std::shared_ptr<Job> j;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] {
+          if (stop_) return true;
+          for (auto& q : fifo_)
+            if (!q->claimed) return true;
+          return false;
+        });
+        if (stop_) break;
+        for (auto& q : fifo_)
+          if (!q->claimed) {
+            j = q;
+            break;
+          }
+        j->claimed = true;
+      }
+      int rc = MADICP_ERR_STATE;
+      std::string err = "no build lane";
+      if (b) {
+        const bool f32 = !j->f32.empty();
+        rc = madicp_builder_build(b, f32 ? static_cast<const void*>(j->f32.data()) : static_cast<const void*>(j->f64.data()),
+                                  int64_t(j->n), f32 ? 1 : 0, b_max_, b_min_, &j->tree);
+        if (rc < 0) err = madicp_last_error();
+      }
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        j->rc = rc;
+        j->err = err;
+        j->f64 = std::vector<double>();
+        j->f32 = std::vector<float>();
+        j->done = true;
+      }
+      done_cv_.notify_all();
+    }
+    if (b) madicp_builder_destroy(b);
+  }
+  madicp_ctx_t* ctx_;
+  double b_max_, b_min_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_cv_;
+  std::deque<std::shared_ptr<Job>> fifo_;
+  std::vector<std::thread> threads_;
+  bool stop_ = false;
+};
+
 class Pipeline {
  public:
   static constexpr int kMaxIcpIts = 15, kSmoothingT = 10, kFrameWindow = 10, kChunks = 1024;  // tools/constants.h
 
   Pipeline(double sensor_hz, bool deskew, double b_max, double rho_ker, double p_th, double b_min, double b_ratio,
-           int num_keyframes, int num_threads, bool realtime, int device = 0)
+           int num_keyframes, int num_threads, bool realtime, int device = -1)
       : sensor_hz_(sensor_hz), deskew_(deskew), b_max_(b_max), p_th_(p_th), b_min_(b_min), num_keyframes_(num_keyframes),
-        realtime_(realtime), icp_(b_max, rho_ker, b_ratio, num_threads, device, std::max(num_keyframes, 1)),
+        realtime_(realtime), icp_(b_max, rho_ker, b_ratio, num_threads, resolveDevice(device), std::max(num_keyframes, 1)),
         vel_(sensor_hz) {
     frame_to_map_ = keyframe_to_map_ = detail::poseIdentity();
     if (const char* e = std::getenv("MADICP_GPU_BUILD")) gpu_build_ = std::atoi(e) != 0;
@@ -110,6 +218,12 @@ class Pipeline {
                    t_ph_[1] / timed_scans_, t_ph_[2] / timed_scans_, t_ph_[3] / timed_scans_, t_ph_[4] / timed_scans_);
   }
 
+  // the reference's constructor has no device argument: MADICP_DEVICE selects the GPU (default 0)
+  static int resolveDevice(int device) {
+    if (device >= 0) return device;
+    const char* e = std::getenv("MADICP_DEVICE");
+    return e ? std::atoi(e) : 0;
+  }
   Matrix4d currentPose() const { return toM(frame_to_map_); }
   std::vector<Matrix4d> trajectory() const {
     std::vector<Matrix4d> out;
@@ -162,10 +276,31 @@ class Pipeline {
     computeRaw(stamp, xyz, n, true);
   }
   bool gpuBuild() const { return gpu_build_; }
+  // Hands a FUTURE scan over for a look-ahead tree build (see Lookahead).  compute() then consumes the prefetched
+  // scans in the order they were handed over and ignores its own cloud argument for them.  Returns false (and does
+  // nothing) when look-ahead is not possible: host-built trees, or deskewing (the scan needs the latest poses).
+  bool prefetch(const void* xyz, size_t n, bool is_f32) {
+    if (!gpu_build_ || deskew_ || !xyz || n == 0) return false;
+    if (!lookahead_) {
+      int w = 4;
+      if (const char* e = std::getenv("MADICP_LOOKAHEAD")) w = std::atoi(e);
+      if (w < 1) return false;
+      lookahead_.reset(new Lookahead(icp_.context(), b_max_, b_min_, w));
+    }
+    auto j = std::make_shared<Lookahead::Job>();
+    j->n = n;
+    if (is_f32) j->f32.assign(static_cast<const float*>(xyz), static_cast<const float*>(xyz) + 3 * n);
+    else j->f64.assign(static_cast<const double*>(xyz), static_cast<const double*>(xyz) + 3 * n);
+    lookahead_->push(std::move(j));
+    return true;
+  }
+  size_t prefetched() { return lookahead_ ? lookahead_->size() : 0; }
 
  private:
   // the scan's MAD-tree: ingest (+ deskew, pipeline.cpp:137-138) and build, on the device or on the host
   std::unique_ptr<MADtree> makeTree(const void* xyz, size_t n, bool is_f32) {
+    if (lookahead_ && !lookahead_->empty())  // built ahead of time by a worker lane
+      return std::unique_ptr<MADtree>(new MADtree(icp_.context(), lookahead_->pop(), b_max_));
     const bool dsk = deskew_ && is_initialized_ && trajectory_.size() > 1;
     const double* Ta = dsk ? trajectory_[trajectory_.size() - 2].m : nullptr;
     const double* Tb = dsk ? trajectory_[trajectory_.size() - 1].m : nullptr;
@@ -304,6 +439,7 @@ class Pipeline {
   int num_threads_ = 1;
   double round_ms_ = 0.0;   // duration of one GN round on the previous scan (realtime budget)
   MADicp icp_;
+  std::unique_ptr<Lookahead> lookahead_;  // declared after icp_: destroyed first (its lanes use icp_'s context)
   detail::VelocityEstimator vel_;
   detail::Pose frame_to_map_, keyframe_to_map_;
   std::deque<std::shared_ptr<FrameB>> keyframes_, frames_;

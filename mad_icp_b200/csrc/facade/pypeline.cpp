@@ -27,7 +27,7 @@ PYBIND11_MODULE(pypeline, m) {
         if (py::isinstance<mb::ContainerType>(cloud)) {
           const mb::ContainerType& v = cloud.cast<const mb::ContainerType&>();
           p.compute(stamp, v.empty() ? nullptr : v[0].data(), v.size());
-        } else if (py::isinstance<py::array_t<float>>(cloud) && py::array::ensure(cloud).dtype().is(py::dtype::of<float>())) {
+        } else if (py::isinstance<py::array>(cloud) && py::array::ensure(cloud).dtype().is(py::dtype::of<float>())) {
           // float32 as the dataset readers deliver it: converted on the device (no host copy in float64)
           const auto a = cloud.cast<py::array_t<float, py::array::c_style | py::array::forcecast>>();
           if (a.ndim() != 2 || a.shape(1) != 3) throw py::cast_error();
@@ -42,6 +42,21 @@ PYBIND11_MODULE(pypeline, m) {
       .def_static("_deskewOnly", [](const py::object& cloud, const NpArr& a, const NpArr& b, double sensor_hz, int num_threads) {
         return mb::Pipeline::deskewOnly(cloud_arg(cloud), pose_from_numpy(a), pose_from_numpy(b), sensor_hz, num_threads);
       }, py::arg("cloud"), py::arg("T_prev"), py::arg("T_now"), py::arg("sensor_hz"), py::arg("num_threads") = 1)
+      .def("prefetch", [](mb::Pipeline& p, const py::object& cloud) {
+        if (py::isinstance<mb::ContainerType>(cloud)) {
+          const mb::ContainerType& v = cloud.cast<const mb::ContainerType&>();
+          return p.prefetch(v.empty() ? nullptr : v[0].data(), v.size(), false);
+        }
+        if (py::isinstance<py::array>(cloud) && py::array::ensure(cloud).dtype().is(py::dtype::of<float>())) {
+          const auto a = cloud.cast<py::array_t<float, py::array::c_style | py::array::forcecast>>();
+          if (a.ndim() != 2 || a.shape(1) != 3) throw py::cast_error();
+          return p.prefetch(a.data(), size_t(a.shape(0)), true);
+        }
+        const NpArr a = cloud.cast<NpArr>();
+        if (a.ndim() != 2 || a.shape(1) != 3) throw py::cast_error();
+        return p.prefetch(a.data(), size_t(a.shape(0)), false);
+      }, py::arg("cloud"))
+      .def("prefetched", &mb::Pipeline::prefetched)
       .def("gpuBuild", &mb::Pipeline::gpuBuild)
       .def("inliersRatio", &mb::Pipeline::inliersRatio)
       .def("numKeyframes", &mb::Pipeline::numKeyframes);

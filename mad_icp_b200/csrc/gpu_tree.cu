@@ -54,6 +54,9 @@ struct BuildState {
   int32_t* h_perm = nullptr;
   uint16_t* h_chunk = nullptr;
   double* h_poses = nullptr;
+  double* h_root = nullptr;  // pinned: the root's sums when the host computes them
+  double root_S[9];          // ... of the cloud madicp_ingest left in P[0] (valid when has_root_S)
+  bool has_root_S = false;
   int64_t n_resident = 0;  // points of the cloud madicp_ingest left in P[0]
   uint64_t seq = 0;        // builds so far (madtree_gpu_export is valid for the latest one only)
   int threads = 8;
@@ -80,18 +83,19 @@ void release(BuildState* bs) {
   bs->host_allocs.clear();
 }
 
-int ensure_state(madicp_ctx* c, size_t n, BuildState** out) {
-  BuildState* bs = static_cast<BuildState*>(c->build_state);
+// `slot`: where the lane keeps its working memory (the context's own lane, or a builder's)
+int ensure_state(void** slot, cudaStream_t stream, size_t n, BuildState** out) {
+  BuildState* bs = static_cast<BuildState*>(*slot);
   if (bs && bs->cap >= n) {
     *out = bs;
     return MADICP_OK;
   }
-  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaStreamSynchronize(stream));
   const uint64_t seq = bs ? bs->seq : 0;
   if (bs) {
     release(bs);
     delete bs;
-    c->build_state = nullptr;
+    *slot = nullptr;
   }
   bs = new BuildState;
   bs->seq = seq;
@@ -140,14 +144,31 @@ int ensure_state(madicp_ctx* c, size_t n, BuildState** out) {
   if (!rc) rc = host_alloc(bs, &bs->h_perm, cap);
   if (!rc) rc = host_alloc(bs, &bs->h_chunk, cap);
   if (!rc) rc = host_alloc(bs, &bs->h_poses, size_t(65536) * 12);
+  if (!rc) rc = host_alloc(bs, &bs->h_root, 16);
   if (rc) {
     release(bs);
     delete bs;
     return rc;
   }
-  c->build_state = bs;
+  *slot = bs;
   *out = bs;
   return MADICP_OK;
+}
+int ensure_state(madicp_ctx* c, size_t n, BuildState** out) { return ensure_state(&c->build_state, c->stream, n, out); }
+
+// Sigma x, Sigma x x^T of the whole cloud in array order (tools/utils.h:55-73) on the calling host thread: the root's
+// nine chains are the longest dependent-add chains of the build (n adds each; a CPU core retires one per ~1 ns, the
+// device one per ~10 ns), and the host has the cloud in hand while it is being copied up.
+template <class T>
+void root_sums_host(const T* p, int64_t n, double* S) {
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0, s7 = 0, s8 = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const double x = double(p[3 * i]), y = double(p[3 * i + 1]), z = double(p[3 * i + 2]);
+    s0 += x; s1 += y; s2 += z;
+    s3 += x * x; s4 += y * x; s5 += z * x;
+    s6 += y * y; s7 += z * y; s8 += z * z;
+  }
+  S[0] = s0; S[1] = s1; S[2] = s2; S[3] = s3; S[4] = s4; S[5] = s5; S[6] = s6; S[7] = s7; S[8] = s8;
 }
 
 __global__ void k_init_root(Nodes N, int n, int* count) {
@@ -164,15 +185,20 @@ __global__ void k_init_root(Nodes N, int n, int* count) {
 
 int blocks(int64_t n, int per = kBlock) { return int(std::max<int64_t>(1, (n + per - 1) / per)); }
 
-// Builds the tree of the n points in bs->P[0].
-int build_resident(madicp_ctx* c, BuildState* bs, int64_t n64, double b_max, double b_min, madtree_gpu** out) {
+// Builds the tree of the n points in bs->P[0] on stream `st`.  root_S (nullable): the root's sums, already computed
+// by the host (h_root: pinned staging of the lane).
+int build_resident(madicp_ctx* c, BuildState* bs, cudaStream_t st, int64_t n64, double b_max, double b_min,
+                   const double* root_S, madtree_gpu** out) {
   if (!(b_max > 0.0) || !std::isfinite(b_max) || !std::isfinite(b_min)) {
     set_error("madtree_gpu_build: b_max must be finite and > 0, b_min finite");
     return MADICP_ERR_INVALID;
   }
   const int n = int(n64);
-  cudaStream_t st = c->stream;
   bs->seq++;
+  if (root_S) {
+    memcpy(bs->h_root, root_S, 9 * sizeof(double));
+    CK(cudaMemcpyAsync(bs->S, bs->h_root, 9 * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
   k_init_root<<<1, 32, 0, st>>>(bs->N, n, bs->d_count);
   CK(cudaMemsetAsync(bs->owner[0], 0, size_t(n) * sizeof(int), st));
   c->launches++;
@@ -188,7 +214,8 @@ int build_resident(madicp_ctx* c, BuildState* bs, int64_t n64, double b_max, dou
     }
     const int* d_nl = bs->d_count + depth;
     // `bound` >= the number of nodes of this level (exact count is on the device until the sync below)
-    k_sums<<<blocks(int64_t(bound) * 9), kBlock, 0, st>>>(bs->P[cur], bs->N.lo, bs->N.hi, g0, d_nl, bs->S);
+    if (!(depth == 0 && root_S))
+      k_sums<<<blocks(int64_t(bound) * 9), kBlock, 0, st>>>(bs->P[cur], bs->N.lo, bs->N.hi, g0, d_nl, bs->S);
     k_eig_prep<<<blocks(bound), kBlock, 0, st>>>(bs->S, bs->N, g0, d_nl, bs->mid, bs->h_args);
     c->launches += 2;
     CK(cudaGetLastError());
@@ -227,6 +254,8 @@ int build_resident(madicp_ctx* c, BuildState* bs, int64_t n64, double b_max, dou
   madtree_gpu* t = nullptr;
   int rc = madicp_tree_alloc(c, size_t(n_nodes), &t);
   if (rc) return rc;
+  // recycled tree memory may still be read by work queued on the context's stream before it was freed
+  if (st != c->stream) CK(cudaStreamWaitEvent(st, c->tree_free_ev, 0));
   t->n_nodes = n_nodes;
   t->n_leaves = total_leaves;
   t->n_levels = n_levels;
@@ -257,7 +286,71 @@ void madicp_gpu_build_release(madicp_ctx* c) {
   c->build_state = nullptr;
 }
 
+// An independent build lane of a context's device: its own stream and working memory, so that several scans' trees
+// can be built at the same time (the build of a scan does not depend on the pose estimates unless it is deskewed) while
+// the context's stream registers the previous scan.  One host thread per builder.
+struct madicp_builder {
+  madicp_ctx* ctx = nullptr;
+  cudaStream_t stream = nullptr;
+  void* state = nullptr;
+};
+
 extern "C" {
+
+int madicp_builder_create(madicp_ctx_t* c, madicp_builder_t** out) {
+  if (!c || !out) return MADICP_ERR_INVALID;
+  MADICP_TRY
+  CK(cudaSetDevice(c->device));
+  madicp_builder* b = new madicp_builder;
+  b->ctx = c;
+  CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  *out = b;
+  return MADICP_OK;
+  MADICP_CATCH("madicp_builder_create")
+}
+
+void madicp_builder_destroy(madicp_builder_t* b) {
+  if (!b) return;
+  cudaSetDevice(b->ctx->device);
+  cudaStreamSynchronize(b->stream);
+  if (BuildState* bs = static_cast<BuildState*>(b->state)) {
+    release(bs);
+    delete bs;
+  }
+  cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+int madicp_builder_build(madicp_builder_t* b, const void* xyz, int64_t n, int is_f32, double b_max, double b_min,
+                         madtree_gpu_t** out) {
+  if (!b || !xyz || !out || n <= 0 || n > (int64_t(1) << 24)) {
+    set_error("madicp_builder_build: bad arguments (1 <= n <= 2^24 points)");
+    return MADICP_ERR_INVALID;
+  }
+  MADICP_TRY
+  madicp_ctx* c = b->ctx;
+  CK(cudaSetDevice(c->device));
+  BuildState* bs = nullptr;
+  int rc = ensure_state(&b->state, b->stream, size_t(n), &bs);
+  if (rc) return rc;
+  const size_t raw_bytes = size_t(n) * 3 * (is_f32 ? sizeof(float) : sizeof(double));
+  double S[9];
+  if (is_f32) {
+    CK(cudaMemcpyAsync(bs->d_raw, xyz, raw_bytes, cudaMemcpyHostToDevice, b->stream));
+    k_ingest<<<blocks(n), kBlock, 0, b->stream>>>(bs->d_raw, 1, nullptr, nullptr, bs->d_poses, int(n), bs->P[0]);
+    c->launches++;
+    root_sums_host(static_cast<const float*>(xyz), n, S);
+  } else {
+    CK(cudaMemcpyAsync(bs->P[0], xyz, raw_bytes, cudaMemcpyHostToDevice, b->stream));
+    root_sums_host(static_cast<const double*>(xyz), n, S);
+  }
+  bs->n_resident = n;
+  rc = build_resident(c, bs, b->stream, n, b_max, b_min, S, out);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(b->stream));  // the tree is complete when the call returns: any stream may use it
+  return MADICP_OK;
+  MADICP_CATCH("madicp_builder_build")
+}
 
 int madtree_gpu_build(madicp_ctx_t* c, const double* points_xyz, int64_t n, double b_max, double b_min,
                       madtree_gpu_t** out) {
@@ -272,7 +365,9 @@ int madtree_gpu_build(madicp_ctx_t* c, const double* points_xyz, int64_t n, doub
   if (rc) return rc;
   CK(cudaMemcpyAsync(bs->P[0], points_xyz, size_t(n) * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   bs->n_resident = n;
-  return build_resident(c, bs, n, b_max, b_min, out);
+  root_sums_host(points_xyz, n, bs->root_S);
+  bs->has_root_S = true;
+  return build_resident(c, bs, c->stream, n, b_max, b_min, bs->root_S, out);
   MADICP_CATCH("madtree_gpu_build")
 }
 
@@ -285,7 +380,7 @@ int madtree_gpu_build_resident(madicp_ctx_t* c, double b_max, double b_min, madt
     return MADICP_ERR_STATE;
   }
   CK(cudaSetDevice(c->device));
-  return build_resident(c, bs, bs->n_resident, b_max, b_min, out);
+  return build_resident(c, bs, c->stream, bs->n_resident, b_max, b_min, bs->has_root_S ? bs->root_S : nullptr, out);
   MADICP_CATCH("madtree_gpu_build_resident")
 }
 
@@ -346,6 +441,11 @@ int madicp_ingest(madicp_ctx_t* c, const void* xyz, int64_t n, int is_f32, int d
   c->launches++;
   CK(cudaGetLastError());
   bs->n_resident = n;
+  bs->has_root_S = !deskew;  // (a deskewed cloud exists on the device only: its root sums run there)
+  if (!deskew) {
+    if (is_f32) root_sums_host(static_cast<const float*>(xyz), n, bs->root_S);
+    else root_sums_host(static_cast<const double*>(xyz), n, bs->root_S);
+  }
   if (points_out) {
     CK(cudaMemcpyAsync(points_out, bs->P[0], size_t(n) * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

@@ -79,6 +79,7 @@ static_assert(sizeof(QuadRec) == 64, "QuadRec must be two 256-bit loads");
 struct ModelView {  // passed by value (constant bank)
   const madtree_rec_t* recs;  // exact 64-byte records, breadth-first, links slot-relative
   const QuadRec* quad;        // two binary levels per 64-byte record, dense, explicit child groups
+  const double* ww;           // per pool node: planarity weight (1 - bbox0/min_ball)^2 of a leaf
   int broot[kMaxSlots];       // breadth-first pool index of the root of the k-th active keyframe (= slot * cap)
   int qroot[kMaxSlots];       // index of that root's quad record (= slot * quad_cap)
   int K;
@@ -176,6 +177,18 @@ static __device__ __noinline__ bool side_exact(const madtree_rec_t* rec, double 
   const Rec r = load_rec(rec);
   return !(plane_side(qx, qy, qz, r.mx, r.my, r.mz, r.dx, r.dy, r.dz) < 0.0);
 }
+// The same for the path memo: also how far the query is from the plane, rounded DOWN past every error of the FP64
+// evaluation (3 subtractions, 3 products, 2 additions: < 8 * 2^-53 * (|q|_1 + |mean|_1) in absolute terms).
+// A query this close to a plane (it failed the FP32 filter) still keeps its leaf in later rounds, when the pose
+// moves by nanometres.  NaN (one-point nodes never reach here; defensive): margin 0, the item is walked again.
+static __device__ __noinline__ bool side_exact_m(const madtree_rec_t* rec, double qx, double qy, double qz, float* margin) {
+  const Rec r = load_rec(rec);
+  const double s = plane_side(qx, qy, qz, r.mx, r.my, r.mz, r.dx, r.dy, r.dz);
+  const double l1 = ((fabs(qx) + fabs(qy)) + fabs(qz)) + ((fabs(r.mx) + fabs(r.my)) + fabs(r.mz));
+  const double m = fabs(s) * (1.0 - 1e-9) - 2e-15 * l1;
+  *margin = (m > 0.0) ? __double2float_rd(m) : 0.0f;
+  return !(s < 0.0);
+}
 
 // FP32 query of a walk: rounded coordinates + the query part of the error bound.
 struct QueryF {
@@ -194,6 +207,7 @@ __device__ __forceinline__ QueryF make_query(double qx, double qy, double qz) {
 // the exact predicate.  Two compares, no selects: `right` is only meaningful when `decided`.
 struct SideF {
   bool decided, right;
+  float margin;  // |s32| - E rounded down: how far the query can move before THIS decision could change (>= 0 if decided)
 };
 __device__ __forceinline__ SideF side_filtered2(const QueryF& q, const FastRec& p) {
   const float s = fmaf(q.z, p.dz, fmaf(q.y, p.dy, q.x * p.dx)) - p.c;
@@ -201,6 +215,7 @@ __device__ __forceinline__ SideF side_filtered2(const QueryF& q, const FastRec& 
   SideF r;
   r.decided = fabsf(s) > E;
   r.right = s > 0.0f;
+  r.margin = __fsub_rd(fabsf(s), E);
   return r;
 }
 __device__ __forceinline__ bool is_leaf(const FastRec& p) { return __float_as_uint(p.dy) == kLeafMarker; }
@@ -215,7 +230,15 @@ __device__ __forceinline__ double leaf_weight(const FastRec& p) {
 // bit-identical to the reference's FP64 expression by construction.  `k` = index of the active keyframe.
 // (Four other walk layouts -- breadth-first shadows + link loads, implicit binary heap, heap + 2-/3-level
 // look-ahead prefetch -- were measured in round 1 and removed: profiles/r01r, r01t, r01u.)
-__device__ __forceinline__ int descend(const ModelView& M, int k, double qx, double qy, double qz, double& ww) {
+//
+// PATH MEMO.  `margin` (in/out, start at +inf) receives the smallest |s32| - E over the decisions of the walk (for a
+// decision that needed the exact test: the exact distance to the plane, rounded down).  s*(q) = (q - mean).dir is 1-Lipschitz in q (|dir| = 1), |s32 - s*| <= E by the
+// bound above, and the FP64 expression is within ~1e-13 of s*: a query that has moved by less than `margin` (minus
+// that slack) since the walk takes the same side at EVERY node of the path, i.e. reaches the same leaf.  The GN loop
+// uses this from round 1 on: between rounds the pose moves by millimetres, most walks are provably unchanged
+// and are skipped, and the decisions stay exactly the reference's FP64 ones.
+template <bool MEMO>
+__device__ __forceinline__ int descend_t(const ModelView& M, int k, double qx, double qy, double qz, double& ww, float& margin) {
   const QueryF q = make_query(qx, qy, qz);
   const unsigned qroot = unsigned(M.qroot[k]);
   const QuadRec* qbase = M.quad;  // uniform base + 32-bit pool index: one IMAD.WIDE per record address
@@ -235,7 +258,13 @@ __device__ __forceinline__ int descend(const ModelView& M, int k, double qx, dou
     }
     const SideF f0 = side_filtered2(q, p0);
     bool s0 = f0.right;
-    if (!f0.decided) s0 = side_exact(M.recs + bfs0, qx, qy, qz);
+    if (MEMO) {
+      float mg = f0.margin;
+      if (!f0.decided) s0 = side_exact_m(M.recs + bfs0, qx, qy, qz, &mg);
+      margin = fminf(margin, mg);
+    } else if (!f0.decided) {
+      s0 = side_exact(M.recs + bfs0, qx, qy, qz);
+    }
     const FastRec c = s0 ? p2 : p1;
     if (is_leaf(c)) {
       ww = leaf_weight(c);
@@ -243,10 +272,21 @@ __device__ __forceinline__ int descend(const ModelView& M, int k, double qx, dou
     }
     const SideF f1 = side_filtered2(q, c);
     bool s1 = f1.right;
-    if (!f1.decided)
+    if (MEMO) {
+      float mg = f1.margin;
+      if (!f1.decided)
+        s1 = side_exact_m(M.recs + (M.broot[k] + load_rec_link(M.recs + bfs0) + (s0 ? 1 : 0)), qx, qy, qz, &mg);
+      margin = fminf(margin, mg);
+    } else if (!f1.decided) {
       s1 = side_exact(M.recs + (M.broot[k] + load_rec_link(M.recs + bfs0) + (s0 ? 1 : 0)), qx, qy, qz);
+    }
     g = qroot + unsigned(child0) + (s0 ? 2u : 0u) + (s1 ? 1u : 0u);
   }
+}
+
+__device__ __forceinline__ int descend(const ModelView& M, int k, double qx, double qy, double qz, double& ww) {
+  float unused = 0.0f;
+  return descend_t<false>(M, k, qx, qy, qz, ww, unused);
 }
 
 // One correspondence (reference: odometry/mad_icp.cpp:81-101): gate, error, Jacobian, Huber scale,
@@ -334,6 +374,79 @@ __device__ __forceinline__ void block_reduce_store(double c0, double c1, double 
     for (int w2 = 1; w2 < WARPS; ++w2) s += s_red[w2][threadIdx.x];
     out[threadIdx.x] = s;
   }
+}
+
+// The same, published: out[kAcc] are epoch-tagged LL cells (one 16-byte volatile store each), so the folding CTA gets
+// value and flag with one load and no ticket / fence sits on the round's critical path.  `fence`: the CTA's earlier
+// global stores (matched flags) must be visible to whoever sees the cells (rounds that record matches only).
+template <int WARPS>
+__device__ __forceinline__ void block_reduce_publish(double c0, double c1, double (*s_red)[64], LLCell* out, uint32_t epoch,
+                                                     bool fence, bool system_scope) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  s_red[warp][g * 8 + 2 * t] = c0;
+  s_red[warp][g * 8 + 2 * t + 1] = c1;
+  __syncthreads();
+  if (threadIdx.x < kAcc) {
+    double s = s_red[0][threadIdx.x];
+#pragma unroll
+    for (int w2 = 1; w2 < WARPS; ++w2) s += s_red[w2][threadIdx.x];
+    if (fence) {
+      if (system_scope) __threadfence_system(); else __threadfence();
+    }
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(out + threadIdx.x), "r"(uint32_t(__double2loint(s))),
+                 "r"(epoch), "r"(uint32_t(__double2hiint(s))), "r"(epoch) : "memory");
+  }
+}
+
+// CTA 0: wait for and sum the tiles of all `nblk` CTAs of this round.  THREADS/64 interleaved strands over the CTA
+// index, combined in strand order; within a strand the tiles are added in ascending CTA order (fixed => the sums
+// are reproducible).  Every thread first issues the loads of all its cells, then re-polls only the missing ones.
+template <int THREADS>
+__device__ __forceinline__ void fold_tiles(const LLCell* tiles, int nblk, uint32_t epoch, double (*s_red)[64], double* s_tot) {
+  constexpr int STRANDS = THREADS / 64;
+  constexpr int kMaxPer = 16;  // tiles per strand handled per batch (148 CTAs / 12 strands = 13)
+  const int j = threadIdx.x & 63, g = threadIdx.x >> 6;
+  __syncthreads();  // s_red is reused
+  if (j < kAcc) {
+    double s = 0.0;
+    for (int blk0 = g; blk0 < nblk; blk0 += kMaxPer * STRANDS) {
+      double v[kMaxPer];
+      unsigned missing = 0;
+#pragma unroll
+      for (int i = 0; i < kMaxPer; ++i) {
+        const int blk = blk0 + i * STRANDS;
+        v[i] = 0.0;
+        if (blk < nblk) missing |= 1u << i;
+      }
+      while (missing) {
+#pragma unroll
+        for (int i = 0; i < kMaxPer; ++i) {
+          if (missing & (1u << i)) {
+            const LLCell* src = tiles + size_t(blk0 + i * STRANDS) * kAcc + j;
+            uint32_t lo, f0, hi, f1;
+            asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(src)
+                         : "memory");
+            if (f0 == epoch && f1 == epoch) {
+              v[i] = __hiloint2double(int(hi), int(lo));
+              missing &= ~(1u << i);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kMaxPer; ++i) s += v[i];  // (absent tiles add +0.0: exact)
+    }
+    s_red[g][j] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < kAcc) {
+    double s = s_red[0][threadIdx.x];
+#pragma unroll
+    for (int w2 = 1; w2 < STRANDS; ++w2) s += s_red[w2][threadIdx.x];
+    s_tot[threadIdx.x] = s;
+  }
+  __syncthreads();
 }
 
 __device__ __forceinline__ double ld_relaxed_f64(const double* p) {

@@ -309,6 +309,9 @@ class Registrar:
         grid = check(capi.lib().madicp_debug_cta_cycles(self._h, buf.ctypes.data_as(C.POINTER(C.c_int64)), buf.size))
         return buf[:rounds * grid].reshape(rounds, grid)
 
+    def set_memo(self, enable=True):
+        check(capi.lib().madicp_debug_set_memo(self._h, int(enable)))
+
     def set_gn_grid(self, threads_per_cta=1024, ctas_per_sm=1):
         return check(capi.lib().madicp_set_gn_grid(self._h, threads_per_cta, ctas_per_sm))
 

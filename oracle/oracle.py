@@ -206,3 +206,34 @@ def deskew(points, T_prev, T_now, sensor_hz=10.0):
     L.orc_pipeline_deskew(po, _d(out), out.shape[0], _d(_pose12(T_prev)), _d(_pose12(T_now)))
     L.orc_pipeline_free(po)
     return out
+
+
+class OraclePipeline:
+    """The CPU restatement of the reference's Pipeline (odometry/pipeline.{h,cpp}); state() as orc_pipeline_state:
+    pose 3x4 (12), is_map_updated, current id, keyframe id, number of keyframes, inlier ratio, velocity (6)."""
+
+    def __init__(self, sensor_hz=10.0, deskew=False, b_max=0.2, rho_ker=0.1, p_th=0.8, b_min=0.1, b_ratio=0.02,
+                 num_keyframes=4, num_threads=4, realtime=False):
+        L = lib()
+        L.orc_pipeline_create.restype = C.c_void_p
+        L.orc_pipeline_create.argtypes = [C.c_double, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                          C.c_int, C.c_int, C.c_int]
+        L.orc_pipeline_compute.argtypes = [C.c_void_p, C.c_double, _dp, C.c_int]
+        L.orc_pipeline_state.argtypes = [C.c_void_p, _dp]
+        L.orc_pipeline_free.argtypes = [C.c_void_p]
+        self._h = C.c_void_p(L.orc_pipeline_create(sensor_hz, int(deskew), b_max, rho_ker, p_th, b_min, b_ratio,
+                                                   num_keyframes, num_threads, int(realtime)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_pipeline_free(self._h)
+            self._h = None
+
+    def compute(self, stamp, pts):
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        lib().orc_pipeline_compute(self._h, float(stamp), _d(pts), pts.shape[0])
+
+    def state(self):
+        st = np.zeros(23)
+        lib().orc_pipeline_state(self._h, _d(st))
+        return st

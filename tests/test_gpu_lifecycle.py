@@ -153,3 +153,36 @@ def test_calibration_keeps_results(case, host_path):
     ang, dt = pose_error(before["X"], after["X"])
     assert ang < 1e-10 and dt < 1e-10  # another shape sums in another order: last bits only
     assert (before["matched"] == after["matched"]).mean() > 0.9999
+
+
+def test_path_memo_changes_nothing(oracle):
+    """From round 1 on the persistent kernel skips the walks it can prove unchanged (kernels.cuh, descend_t).  The
+    proof must be airtight: with the memo off every pair is walked in every round -- poses, H, b, matched flags and
+    the per-round trace must be bit-identical, from a far initial guess (large moves between rounds), from the
+    optimum (no move), and at BASELINE size."""
+    for kw, guess_shift in ((dict(K=3, beams=32, azimuths=1024, seed=11), 0.0), (dict(K=3, beams=32, azimuths=1024, seed=11), 1.5),
+                            (dict(K=16), 0.0)):
+        c = synth.registration_case(**kw)
+        reg = Registrar(device=0, max_keyframes=16)
+        for k, (scan, P) in enumerate(zip(c["scans"], c["kf_poses"])):
+            reg.put_keyframe(k, FlatTree(scan), T=P)
+        reg.set_moving(FlatTree(c["query"]).leaf_means())
+        X0 = np.array(c["T_guess"], dtype=np.float64)
+        X0[0, 3] += guess_shift
+        for iters in (1, 2, 10, 15):
+            reg.set_memo(True)
+            a = reg.register(X0, iters=iters)
+            ta = reg.register_trace()
+            reg.set_memo(False)
+            b = reg.register(X0, iters=iters)
+            tb = reg.register_trace()
+            for k in ("X", "H", "b"):
+                assert bits_equal(a[k], b[k]), (kw, iters, k)
+            assert (a["matched"] == b["matched"]).all() and a["n_matched"] == b["n_matched"]
+            assert bits_equal(ta, tb)
+        # restart from the converged pose: nothing moves, every walk of rounds >= 1 is skipped
+        reg.set_memo(True)
+        a = reg.register(b["X"], iters=5)
+        reg.set_memo(False)
+        b2 = reg.register(b["X"], iters=5)
+        assert bits_equal(a["X"], b2["X"]) and bits_equal(a["H"], b2["H"])

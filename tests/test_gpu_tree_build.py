@@ -124,3 +124,62 @@ def test_ingest_float32_and_deskew(reg, oracle):
     want = oracle.deskew(tied.astype(np.float64), T_prev, T_now, sensor_hz=10.0)
     got = reg.ingest(tied, deskew=True, T_prev=T_prev, T_now=T_now, sensor_hz=10.0, num_threads=2, want_points=True)
     assert bits_equal(got, want)
+
+
+def test_pipeline_device_path_lookahead_and_host_path_agree(oracle):
+    """The reference-named Pipeline three ways -- trees built on the device in line, trees built ahead of time by the
+    look-ahead lanes (Pipeline.prefetch), trees built on the host (MADICP_GPU_BUILD=0) -- must produce bit-identical
+    trajectories and keyframe decisions (same trees, same registration), and track the CPU pipeline."""
+    import os
+    from mad_icp_b200.pybind.pypeline import Pipeline
+    seq = synth.sequence(n_scans=20, beams=32, azimuths=1024, seed=4)["scans"]
+    kw = dict(sensor_hz=10.0, deskew=False, b_max=0.2, rho_ker=0.1, p_th=0.8, b_min=0.1, b_ratio=0.02, num_keyframes=4,
+              num_threads=4, realtime=False)
+
+    def run(mode):
+        os.environ["MADICP_GPU_BUILD"] = "0" if mode == "host" else "1"
+        p = Pipeline(**kw)
+        os.environ.pop("MADICP_GPU_BUILD")
+        assert p.gpuBuild() == (mode != "host")
+        out = []
+        if mode == "lookahead":
+            for k in range(1, 4):
+                assert p.prefetch(seq[k] if k % 2 else seq[k].astype(np.float64))
+        for i, scan in enumerate(seq):
+            if mode == "lookahead" and i >= 1 and i + 3 < len(seq):
+                p.prefetch(seq[i + 3])
+            p.compute(0.1 * i, scan)
+            out.append((p.currentPose().copy(), bool(p.isMapUpdated()), int(p.keyframeID()), int(p.numKeyframes())))
+        return out
+
+    a, b, c = run("inline"), run("lookahead"), run("host")
+    cpu = oracle.OraclePipeline(**kw)
+    promoted = 0
+    for i, scan in enumerate(seq):
+        cpu.compute(0.1 * i, scan)
+        st = cpu.state()
+        for other in (b, c):
+            assert bits_equal(a[i][0], other[i][0]), i
+            assert a[i][1:] == other[i][1:], i
+        assert a[i][1:] == (bool(st[12]), int(st[14]), int(st[15])), i
+        assert np.abs(a[i][0][:3] - st[:12].reshape(3, 4)).max() < 1e-6, i
+        promoted += int(st[12])
+    assert promoted >= 3
+
+
+def test_pipeline_realtime_budget(oracle):
+    """`realtime` (pipeline.cpp:62,167-169): with a sensor period too short for 15 rounds the loop is cut to what fits
+    (at least one round once preprocessing fits), the flags are the union over the rounds run, and the pipeline keeps
+    tracking; with a generous period it is the unbounded pipeline bit for bit."""
+    from mad_icp_b200.pybind.pypeline import Pipeline
+    seq = synth.sequence(n_scans=8, beams=32, azimuths=1024, seed=4)["scans"]
+    kw = dict(deskew=False, b_max=0.2, rho_ker=0.1, p_th=0.8, b_min=0.1, b_ratio=0.02, num_keyframes=4, num_threads=4)
+    free = Pipeline(sensor_hz=10.0, realtime=False, **kw)
+    slack = Pipeline(sensor_hz=10.0, realtime=True, **kw)    # 95 ms budget: never binds on a GPU
+    tight = Pipeline(sensor_hz=150.0, realtime=True, **kw)   # 1000/150 - 5 = 1.7 ms: binds
+    for i, scan in enumerate(seq):
+        for p in (free, slack, tight):
+            p.compute(0.1 * i, scan)
+        assert bits_equal(free.currentPose(), slack.currentPose()), i
+        assert np.isfinite(tight.currentPose()).all()
+    assert abs(tight.currentPose()[0, 3] - free.currentPose()[0, 3]) < 0.5  # still follows the 0.8 m/scan motion

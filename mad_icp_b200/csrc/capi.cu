@@ -272,7 +272,11 @@ int madicp_create(madicp_ctx_t** out, int device, int max_keyframes) {
   c->max_keyframes = max_keyframes;
   c->sm_count = prop.multiProcessorCount;
   c->slots.resize(max_keyframes);
-  CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  {  // registration runs at the highest priority: the build lanes (lowest) fill the gaps
+    int lo_pri = 0, hi_pri = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+    CK(cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, hi_pri));
+  }
   c->stream = c->own_stream;
   CK(cudaMalloc(&c->d_state, sizeof(GnState)));
   CK(cudaMemset(c->d_state, 0, sizeof(GnState)));
@@ -903,7 +907,9 @@ static int register_enqueue(madicp_ctx* c, int iters, const double X0[12], int c
   }
   A.map_in_smem = map_bytes ? 1 : 0;
   {  // path memo: one entry per CTA-local item
-    const size_t stride = ((size_t(madicp_num_keyframes(c)) * (size_t(c->L) / size_t(c->gn_grid) + 8)) + 31) & ~size_t(31);
+    // sized from the CAPACITIES (slots, moving-leaf buffer), not from this scan's counts: a streamed sequence changes
+    // both from scan to scan and must not reallocate
+    const size_t stride = ((size_t(c->max_keyframes) * (c->cap_moving / size_t(c->gn_grid) + 8)) + 31) & ~size_t(31);
     const size_t need = stride * size_t(c->gn_grid);
     if (need > c->cap_memo) {
       CK(cudaStreamSynchronize(c->stream));
@@ -921,6 +927,7 @@ static int register_enqueue(madicp_ctx* c, int iters, const double X0[12], int c
     A.memo_margin = c->d_memo_margin;
     A.item_stride = int(stride);
     A.use_memo = c->use_memo ? 1 : 0;
+    A.walk_buf = mb;
   }
   A.st = c->d_state;
   A.dbg = c->d_dbg;
@@ -961,6 +968,11 @@ int madicp_register_fetch_weight(madicp_ctx_t* c, double X[12], double H[36], do
     CK(cudaMemcpyAsync(c->h_matched, c->d_comm->matched[(c->call_seq - 1u) & 1u], size_t(c->L), cudaMemcpyDeviceToHost,
                        c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  if (c->h_state->error) {
+    set_error("madicp_register: a peer GPU never delivered its H/b tile (rank down, or no matching registration enqueued there)");
+    CK(cudaMemsetAsync(&c->d_state->error, 0, sizeof(int), c->stream));
+    return MADICP_ERR_COMM;
+  }
   if (X) memcpy(X, c->h_state->X_out, 12 * sizeof(double));
   if (H) memcpy(H, c->h_state->H, 36 * sizeof(double));
   if (b) memcpy(b, c->h_state->b, 6 * sizeof(double));
@@ -1009,6 +1021,17 @@ int madicp_register_trace(madicp_ctx_t* c, double* X_trace, int max_rounds) {
                      cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   memcpy(X_trace, c->h_state->X_trace, size_t(rows) * 12 * sizeof(double));
+  return rows;
+}
+
+int madicp_register_walked(madicp_ctx_t* c, int32_t* walked, int max_rounds) {
+  if (!c || !walked || c->last_iters < 1) return MADICP_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  int rows = std::min(c->last_iters, max_rounds);
+  CK(cudaMemcpyAsync(c->h_state->walked[0], c->d_state->walked[(c->call_seq - 1u) & 1u], size_t(rows) * sizeof(int),
+                     cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  memcpy(walked, c->h_state->walked[0], size_t(rows) * sizeof(int));
   return rows;
 }
 

@@ -316,9 +316,12 @@ k_search_cloud(const __grid_constant__ ModelView model, int root, const double* 
 // Every rank stores its partial into every rank's mailbox (own included) with 16-byte LL cells,
 // then spins on its own mailbox until all `world` partials of this epoch are present and sums them
 // in rank order -> identical bits on every rank.
+// A peer that never shows up (crashed rank, registration not enqueued there) must not hang this GPU for ever: after
+// ~2^26 polls of one cell (seconds) the wait gives up, flags GnState::error and the host call fails with
+// MADICP_ERR_COMM.
 template <int THREADS>
 __device__ __forceinline__ void peer_allreduce(const PeerView& pv, uint32_t epoch, double* s_tot,
-                                               double (*s_peer)[kAcc]) {
+                                               double (*s_peer)[kAcc], int* error) {
   const int slot = int(epoch & 1u);
   for (int idx = threadIdx.x; idx < pv.world * kAcc; idx += THREADS) {
     const int r = idx / kAcc, i = idx - r * kAcc;
@@ -331,10 +334,14 @@ __device__ __forceinline__ void peer_allreduce(const PeerView& pv, uint32_t epoc
   for (int idx = threadIdx.x; idx < pv.world * kAcc; idx += THREADS) {
     const int r = idx / kAcc, i = idx - r * kAcc;
     const LLCell* src = &pv.box[pv.rank]->cell[slot][r][i];
-    uint32_t lo, f0, hi, f1;
+    uint32_t lo, f0, hi, f1, spins = 0;
     do {
       asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(src)
                    : "memory");
+      if (++spins == (1u << 26)) {
+        *error = 1;
+        break;
+      }
     } while (f0 != epoch || f1 != epoch);
     s_peer[r][i] = __hiloint2double(int(hi), int(lo));
   }
@@ -368,6 +375,7 @@ struct GnArgs {
   int* memo_leaf;                          // pool index of the leaf the last walk of the item reached
   float* memo_margin;                      // how far its query may still move before a decision of that walk could change
   int item_stride;
+  int walk_buf;                            // which half of GnState::walked this call counts into
   int use_memo;                            // 0: every item is walked in every round (probe / A-B measurement)
   long long* dbg;                          // nullable: per-round SM-clock stamps (madicp_debug_timing)
   long long* dbg_cta;                      // nullable: [round][CTA] item-phase cycles
@@ -459,6 +467,7 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
 
   for (int i = (blockIdx.x * THREADS + threadIdx.x) * 16; i < A.zero_bytes; i += gridDim.x * THREADS * 16)
     *reinterpret_cast<uint4*>(A.zero_next + i) = make_uint4(0, 0, 0, 0);
+  if (blockIdx.x == 0 && threadIdx.x < MADICP_MAX_ITERS) st->walked[A.walk_buf ^ 1][threadIdx.x] = 0;  // the NEXT call's
   int* const memo_leaf = A.memo_leaf + size_t(blockIdx.x) * A.item_stride;
   float* const memo_margin = A.memo_margin + size_t(blockIdx.x) * A.item_stride;
   auto item_at = [&](unsigned t0, unsigned& k, unsigned& q) {
@@ -551,10 +560,8 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
       }
       warp_accumulate(stage, v, c0, c1);
     }
-    if (A.dbg) {  // items walked by this CTA in this round
-      n_walked = __reduce_add_sync(0xffffffffu, n_walked);
-      if (lane == 0 && n_walked) atomicAdd(&s_qn, n_walked);
-    }
+    n_walked = __reduce_add_sync(0xffffffffu, n_walked);  // items walked by this CTA in this round
+    if (lane == 0 && n_walked) atomicAdd(&s_qn, n_walked);
     if (A.dbg && threadIdx.x == 0 && blockIdx.x == 0) A.dbg[it * 8 + 0] = clock64() - t_begin;  // item phase, CTA 0
     if (A.dbg_cta) {  // per-CTA item phase (slowest warp) + this warp's own time
       __syncthreads();
@@ -562,6 +569,7 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
       if (threadIdx.x == 0 && blockIdx.x == 0) A.dbg[it * 8 + 5] = s_qn;
     }
     __syncthreads();  // every warp is done with its staging tile: s_red aliases them
+    if (threadIdx.x == 0 && s_qn) atomicAdd(&st->walked[A.walk_buf][it], s_qn);
     // Round barrier without a ticket: every CTA publishes its 48-value tile as epoch-tagged LL cells (value and flag
     // in one 16-byte store); CTA 0 -- the fixed folder -- polls the cells of all CTAs (the loads that find the flag
     // also bring the value), sums them in a fixed order, solves and publishes the next pose the same way.
@@ -579,7 +587,7 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
       }
       if (multi) {
         if (last_round) __threadfence_system();
-        peer_allreduce<THREADS>(A.peers, A.peers.epoch_base + uint32_t(it) + 1u, s_tot, s_peer);
+        peer_allreduce<THREADS>(A.peers, A.peers.epoch_base + uint32_t(it) + 1u, s_tot, s_peer, &st->error);
         if (last_round) __threadfence_system();
       }
       if (last_round) {  // count matched moving leaves (every writer fenced before its tile, and the tiles are in)

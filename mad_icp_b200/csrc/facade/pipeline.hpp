@@ -282,7 +282,7 @@ class Pipeline {
   bool prefetch(const void* xyz, size_t n, bool is_f32) {
     if (!gpu_build_ || deskew_ || !xyz || n == 0) return false;
     if (!lookahead_) {
-      int w = 4;
+      int w = 8;
       if (const char* e = std::getenv("MADICP_LOOKAHEAD")) w = std::atoi(e);
       if (w < 1) return false;
       lookahead_.reset(new Lookahead(icp_.context(), b_max_, b_min_, w));

@@ -215,7 +215,7 @@ int build_resident(madicp_ctx* c, BuildState* bs, cudaStream_t st, int64_t n64, 
     const int* d_nl = bs->d_count + depth;
     // `bound` >= the number of nodes of this level (exact count is on the device until the sync below)
     if (!(depth == 0 && root_S))
-      k_sums<<<blocks(int64_t(bound) * 9), kBlock, 0, st>>>(bs->P[cur], bs->N.lo, bs->N.hi, g0, d_nl, bs->S);
+      k_sums<<<blocks(int64_t(bound) * 9, kSumsBlock), kSumsBlock, 0, st>>>(bs->P[cur], bs->N.lo, bs->N.hi, g0, d_nl, bs->S);
     k_eig_prep<<<blocks(bound), kBlock, 0, st>>>(bs->S, bs->N, g0, d_nl, bs->mid, bs->h_args);
     c->launches += 2;
     CK(cudaGetLastError());
@@ -303,7 +303,9 @@ int madicp_builder_create(madicp_ctx_t* c, madicp_builder_t** out) {
   CK(cudaSetDevice(c->device));
   madicp_builder* b = new madicp_builder;
   b->ctx = c;
-  CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  int lo_pri = 0, hi_pri = 0;
+  CK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+  CK(cudaStreamCreateWithPriority(&b->stream, cudaStreamNonBlocking, lo_pri));  // below the registration stream
   *out = b;
   return MADICP_OK;
   MADICP_CATCH("madicp_builder_create")
@@ -333,6 +335,7 @@ int madicp_builder_build(madicp_builder_t* b, const void* xyz, int64_t n, int is
   BuildState* bs = nullptr;
   int rc = ensure_state(&b->state, b->stream, size_t(n), &bs);
   if (rc) return rc;
+  bs->threads = 1;  // lanes are the parallelism here: every lane serves its own libm calls
   const size_t raw_bytes = size_t(n) * 3 * (is_f32 ? sizeof(float) : sizeof(double));
   double S[9];
   if (is_f32) {

@@ -27,6 +27,11 @@ namespace madicp {
 namespace gtb {
 
 constexpr int kBlock = 256;
+// The in-order sums are the long-running kernels of a build (one dependent FP64 add per point and chain).  Their CTAs
+// are kept at 128 threads x 32 registers = 4096 registers so that one fits NEXT TO a 768-thread x 80-register CTA of the
+// persistent registration kernel on the same SM: a build lane running ahead never keeps the registration of the
+// current scan from becoming resident.
+constexpr int kSumsBlock = 128;
 constexpr int kTile = 1024;  // positions per CTA of the flag scan
 
 // per-node data kept for the whole build (index = breadth-first node id)
@@ -52,10 +57,10 @@ __device__ __forceinline__ long long dbits(double v) { return __double_as_longlo
 
 // ---------------------------------------------------------------------------------------------------------
 // (1) sums in array order: thread = (node j of the level, chain c), c: 0 x, 1 y, 2 z, 3 xx, 4 yx, 5 zx, 6 yy, 7 zy, 8 zz
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kSumsBlock)
 k_sums(const double* __restrict__ P, const int* __restrict__ lo, const int* __restrict__ hi, int g0,
        const int* __restrict__ n_level, double* __restrict__ S) {
-  const int t = blockIdx.x * kBlock + threadIdx.x;
+  const int t = blockIdx.x * kSumsBlock + threadIdx.x;
   const int j = t / 9, c = t - j * 9;
   if (j >= *n_level) return;
   const int b = lo[g0 + j], e = hi[g0 + j];

@@ -108,13 +108,14 @@ struct GnState {
   int clear_from; // first round whose gate passes are recorded in the matched flags (iters-1: the reference's
                   // clear-before-the-last-round, pipeline.cpp:172-176; 0: a budget-limited loop that never cleared)
   int n_matched;  // matched moving leaves in the last round
-  int pad;
+  int error;      // set by the kernel when a peer never answered (multi-GPU); cleared by the host before a launch
   double X_in[12];  // initial pose: [ticket .. X_in] is ONE host-to-device copy per registration
   double X_out[12]; // final pose:   [ticket .. b] is ONE device-to-host copy per registration
   double H[36];     // last round; H[r*6+c] = sum (scale*J_r)*J_c, both triangles accumulated independently
   double b[6];
   double weight;    // det(H^-1) of the last round's H (Frame::weight_, odometry/pipeline.cpp:223)
   double X_trace[(MADICP_MAX_ITERS + 1) * 12];  // pose before round i; [iters] = final pose (debug / parity aid)
+  int walked[2][MADICP_MAX_ITERS];  // [call parity] per round: (leaf, keyframe) pairs that were walked (the rest kept their leaf: path memo)
   LLCell X_ll[12];  // pose of the next round, published with its epoch: waiting CTAs get value and flag in one load
 };
 
@@ -405,37 +406,36 @@ __device__ __forceinline__ void block_reduce_publish(double c0, double c1, doubl
 template <int THREADS>
 __device__ __forceinline__ void fold_tiles(const LLCell* tiles, int nblk, uint32_t epoch, double (*s_red)[64], double* s_tot) {
   constexpr int STRANDS = THREADS / 64;
-  constexpr int kMaxPer = 16;  // tiles per strand handled per batch (148 CTAs / 12 strands = 13)
+  constexpr int kPer = 8;  // cells per thread in flight at a time: all loads of a batch are issued BEFORE any is looked at
   const int j = threadIdx.x & 63, g = threadIdx.x >> 6;
   __syncthreads();  // s_red is reused
   if (j < kAcc) {
     double s = 0.0;
-    for (int blk0 = g; blk0 < nblk; blk0 += kMaxPer * STRANDS) {
-      double v[kMaxPer];
+    for (int blk0 = g; blk0 < nblk; blk0 += kPer * STRANDS) {
+      double v[kPer];
       unsigned missing = 0;
 #pragma unroll
-      for (int i = 0; i < kMaxPer; ++i) {
-        const int blk = blk0 + i * STRANDS;
+      for (int i = 0; i < kPer; ++i) {
         v[i] = 0.0;
-        if (blk < nblk) missing |= 1u << i;
+        if (blk0 + i * STRANDS < nblk) missing |= 1u << i;
       }
       while (missing) {
+        uint32_t lo[kPer], hi[kPer], f0[kPer], f1[kPer];
 #pragma unroll
-        for (int i = 0; i < kMaxPer; ++i) {
-          if (missing & (1u << i)) {
-            const LLCell* src = tiles + size_t(blk0 + i * STRANDS) * kAcc + j;
-            uint32_t lo, f0, hi, f1;
-            asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(src)
-                         : "memory");
-            if (f0 == epoch && f1 == epoch) {
-              v[i] = __hiloint2double(int(hi), int(lo));
-              missing &= ~(1u << i);
-            }
-          }
+        for (int i = 0; i < kPer; ++i) {
+          const int blk = (missing & (1u << i)) ? blk0 + i * STRANDS : blk0;  // (a present cell again: harmless)
+          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo[i]), "=r"(f0[i]), "=r"(hi[i]), "=r"(f1[i])
+                       : "l"(tiles + size_t(blk) * kAcc + j) : "memory");
         }
+#pragma unroll
+        for (int i = 0; i < kPer; ++i)
+          if ((missing & (1u << i)) && f0[i] == epoch && f1[i] == epoch) {
+            v[i] = __hiloint2double(int(hi[i]), int(lo[i]));
+            missing &= ~(1u << i);
+          }
       }
 #pragma unroll
-      for (int i = 0; i < kMaxPer; ++i) s += v[i];  // (absent tiles add +0.0: exact)
+      for (int i = 0; i < kPer; ++i) s += v[i];  // ascending CTA order within the strand (absent tiles add +0.0: exact)
     }
     s_red[g][j] = s;
   }

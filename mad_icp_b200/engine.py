@@ -286,6 +286,12 @@ class Registrar:
         rows = check(capi.lib().madicp_register_trace(self._h, as_d(buf), 65), "madicp_register_trace")
         return buf[:rows].copy()
 
+    def register_walked(self):
+        """Per round of the last registration: pairs actually walked (the rest kept their leaf: path memo)."""
+        buf = np.zeros(64, np.int32)
+        rows = check(capi.lib().madicp_register_walked(self._h, as_i(buf), 64), "madicp_register_walked")
+        return buf[:rows].copy()
+
     def search_cloud(self, slot, queries, want=("ordinals", "points", "normals", "dists")):
         q = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, 3)
         n = q.shape[0]

@@ -142,12 +142,13 @@ def test_pipeline_device_path_lookahead_and_host_path_agree(oracle):
         os.environ.pop("MADICP_GPU_BUILD")
         assert p.gpuBuild() == (mode != "host")
         out = []
-        if mode == "lookahead":
-            for k in range(1, 4):
-                assert p.prefetch(seq[k] if k % 2 else seq[k].astype(np.float64))
         for i, scan in enumerate(seq):
-            if mode == "lookahead" and i >= 1 and i + 3 < len(seq):
-                p.prefetch(seq[i + 3])
+            if mode == "lookahead":  # compute() consumes prefetched scans in FIFO order: scans 1.. are handed over
+                if i == 1:           # after the initialising scan, three ahead of their compute()
+                    for k in range(1, 4):
+                        assert p.prefetch(seq[k])
+                elif i > 1 and i + 2 < len(seq):
+                    p.prefetch(seq[i + 2])
             p.compute(0.1 * i, scan)
             out.append((p.currentPose().copy(), bool(p.isMapUpdated()), int(p.keyframeID()), int(p.numKeyframes())))
         return out

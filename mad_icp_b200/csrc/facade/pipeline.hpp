@@ -276,6 +276,7 @@ class Pipeline {
     computeRaw(stamp, xyz, n, true);
   }
   bool gpuBuild() const { return gpu_build_; }
+  int lastIcpIterations() const { return last_iters_; }  // rounds the realtime budget allowed for the last scan
   // Hands a FUTURE scan over for a look-ahead tree build (see Lookahead).  compute() then consumes the prefetched
   // scans in the order they were handed over and ignores its own cloud argument for them.  Returns false (and does
   // nothing) when look-ahead is not possible: host-built trees, or deskewing (the scan needs the latest poses).
@@ -361,6 +362,7 @@ class Pipeline {
       if (budget < 0.0) iters = 0;
       else if (round_ms_ > 0.0) iters = std::max(1, std::min(kMaxIcpIts, int(std::floor(budget / round_ms_))));
     }
+    last_iters_ = iters;
     const int matched = icp_.compute(kfs, iters, iters < kMaxIcpIts);  // the whole loop of pipeline.cpp:166-193
     const auto c4 = clk();
     if (iters > 0) round_ms_ = ms(c3, c4) / double(iters);
@@ -437,6 +439,7 @@ class Pipeline {
   bool realtime_;
   bool gpu_build_ = true;   // MADICP_GPU_BUILD=0: host-built trees
   int num_threads_ = 1;
+  int last_iters_ = 0;
   double round_ms_ = 0.0;   // duration of one GN round on the previous scan (realtime budget)
   MADicp icp_;
   std::unique_ptr<Lookahead> lookahead_;  // declared after icp_: destroyed first (its lanes use icp_'s context)

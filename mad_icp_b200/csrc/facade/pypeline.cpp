@@ -57,6 +57,7 @@ PYBIND11_MODULE(pypeline, m) {
         return p.prefetch(a.data(), size_t(a.shape(0)), false);
       }, py::arg("cloud"))
       .def("prefetched", &mb::Pipeline::prefetched)
+      .def("lastIcpIterations", &mb::Pipeline::lastIcpIterations)
       .def("gpuBuild", &mb::Pipeline::gpuBuild)
       .def("inliersRatio", &mb::Pipeline::inliersRatio)
       .def("numKeyframes", &mb::Pipeline::numKeyframes);

@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -195,6 +197,14 @@ int build_resident(madicp_ctx* c, BuildState* bs, cudaStream_t st, int64_t n64, 
   }
   const int n = int(n64);
   bs->seq++;
+  const bool timing = getenv("MADICP_BUILD_TIMING") != nullptr;
+  auto now = []() { return std::chrono::steady_clock::now(); };
+  auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::micro>(b - a).count();
+  };
+  const auto t_start = now();
+  double t_sync = 0, t_trig = 0;
+  std::string per_level;
   if (root_S) {
     memcpy(bs->h_root, root_S, 9 * sizeof(double));
     CK(cudaMemcpyAsync(bs->S, bs->h_root, 9 * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -214,12 +224,18 @@ int build_resident(madicp_ctx* c, BuildState* bs, cudaStream_t st, int64_t n64, 
     }
     const int* d_nl = bs->d_count + depth;
     // `bound` >= the number of nodes of this level (exact count is on the device until the sync below)
-    if (!(depth == 0 && root_S))
-      k_sums<<<blocks(int64_t(bound) * 9, kSumsBlock), kSumsBlock, 0, st>>>(bs->P[cur], bs->N.lo, bs->N.hi, g0, d_nl, bs->S);
+    if (!(depth == 0 && root_S)) {
+      if (depth < 12)  // nodes of >= kBigNode points exist on the upper levels only (at most n / kBigNode of them)
+        k_sums_big<<<std::min(bound, n / kBigNode + 1), kSumsBlock, 0, st>>>(bs->P[cur], bs->N.lo, bs->N.hi, g0, d_nl, bs->S);
+      k_sums_small<<<blocks(int64_t(bound) * 9, kSumsBlock), kSumsBlock, 0, st>>>(bs->P[cur], bs->N.lo, bs->N.hi, g0, d_nl, bs->S);
+    }
     k_eig_prep<<<blocks(bound), kBlock, 0, st>>>(bs->S, bs->N, g0, d_nl, bs->mid, bs->h_args);
     c->launches += 2;
     CK(cudaGetLastError());
+    const auto ts0 = now();
     CK(cudaStreamSynchronize(st));  // the level's one host round trip: libm for the eigen-decomposition
+    const auto ts1 = now();
+    t_sync += us(ts0, ts1);
     if (depth > 0) {
       nl = bs->h_ctl[depth - 1].n_next;
       total_leaves += bs->h_ctl[depth - 1].n_leaves;
@@ -230,6 +246,10 @@ int build_resident(madicp_ctx* c, BuildState* bs, cudaStream_t st, int64_t n64, 
       return MADICP_ERR_INVALID;
     }
     madicp_host_trig(bs->h_args, bs->h_res, nl, bs->threads);
+    if (timing) {
+      t_trig += us(ts1, now());
+      per_level += " " + std::to_string(nl) + ":" + std::to_string(int(us(ts0, ts1)));
+    }
     k_eig_finish<<<blocks(nl), kBlock, 0, st>>>(bs->mid, bs->h_res, bs->N, g0, d_nl, bs->box, bs->cnt, bs->dmin, bs->imin);
     k_bbox_flags<<<pblocks, kBlock, 0, st>>>(bs->P[cur], bs->owner[cur], n, bs->N, g0, bs->box, bs->cnt, bs->flag);
     k_decide<<<1, 1024, 0, st>>>(bs->N, g0, bs->d_count + depth, bs->d_count + depth + 1, bs->box, bs->cnt, b_max, b_min,
@@ -272,6 +292,9 @@ int build_resident(madicp_ctx* c, BuildState* bs, cudaStream_t st, int64_t n64, 
   CK(cudaMemcpyAsync(t->lvl, bs->h_lvl, size_t(n_levels + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
   c->launches += 4;
   CK(cudaGetLastError());
+  if (timing)
+    fprintf(stderr, "madtree_gpu_build: n=%d levels=%d nodes=%d total %.0f us (waiting for the device %.0f, host libm %.0f); "
+            "per level nodes:wait_us%s\n", n, n_levels, n_nodes, us(t_start, now()), t_sync, t_trig, per_level.c_str());
   *out = t;
   return MADICP_OK;
 }
@@ -306,6 +329,7 @@ int madicp_builder_create(madicp_ctx_t* c, madicp_builder_t** out) {
   int lo_pri = 0, hi_pri = 0;
   CK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
   CK(cudaStreamCreateWithPriority(&b->stream, cudaStreamNonBlocking, lo_pri));  // below the registration stream
+  c->n_lanes++;
   *out = b;
   return MADICP_OK;
   MADICP_CATCH("madicp_builder_create")
@@ -320,6 +344,7 @@ void madicp_builder_destroy(madicp_builder_t* b) {
     delete bs;
   }
   cudaStreamDestroy(b->stream);
+  b->ctx->n_lanes--;
   delete b;
 }
 

@@ -56,17 +56,78 @@ struct Ctl {
 __device__ __forceinline__ long long dbits(double v) { return __double_as_longlong(v); }
 
 // ---------------------------------------------------------------------------------------------------------
-// (1) sums in array order: thread = (node j of the level, chain c), c: 0 x, 1 y, 2 z, 3 xx, 4 yx, 5 zx, 6 yy, 7 zy, 8 zz
-__global__ void __launch_bounds__(kSumsBlock)
-k_sums(const double* __restrict__ P, const int* __restrict__ lo, const int* __restrict__ hi, int g0,
-       const int* __restrict__ n_level, double* __restrict__ S) {
+// (1) sums in array order, chain c: 0 x, 1 y, 2 z, 3 xx, 4 yx, 5 zx, 6 yy, 7 zy, 8 zz.  A chain is n dependent FP64
+// adds (~19 cycles each on this part: scripts/fp64_probe.cu) and cannot be cut; what can be done is keep the adds fed:
+//   k_sums_big    one CTA per node of >= kBigNode points: warps 1-3 stream the node's points through two shared-memory
+//                 tiles (coalesced, one tile ahead) while nine lanes of warp 0 run the nine chains out of the other tile;
+//   k_sums_small  one thread per (node, chain) for the short ranges of the lower levels.
+constexpr int kBigNode = 512;
+constexpr int kSumTile = 64;   // points per shared-memory tile (2 x 1.5 KB: fits beside the registration kernel's carve-out)
+
+__device__ __forceinline__ void chain_coords(int c, int& u, int& v) {  // term = p[v] * p[u], u == 3: p[v] itself
+  u = (c < 3) ? 3 : (c < 6 ? 0 : (c < 8 ? 1 : 2));
+  v = (c < 3) ? c : (c < 6 ? c - 3 : (c < 8 ? c - 5 : 2));
+}
+
+__global__ void __launch_bounds__(kSumsBlock, 16)  // <= 32 registers: 128 x 32 = the 4096 the registration CTA leaves free
+k_sums_big(const double* __restrict__ P, const int* __restrict__ lo, const int* __restrict__ hi, int g0,
+           const int* __restrict__ n_level, double* __restrict__ S) {
+  __shared__ double tile[2][kSumTile * 3];
+  const int j = blockIdx.x;
+  if (j >= *n_level) return;
+  const int b = lo[g0 + j], e = hi[g0 + j];
+  if (e - b < kBigNode) return;
+  const int tid = threadIdx.x;
+  int u = 3, v = 0;
+  if (tid < 9) chain_coords(tid, u, v);
+  double s = 0.0;
+  const int n_tiles = (e - b + kSumTile - 1) / kSumTile;
+  auto load_tile = [&](int k) {  // warps 1..3: 96 threads, coalesced
+    const int first = b + k * kSumTile;
+    const int cnt = min(kSumTile, e - first) * 3;
+    const double* src = P + 3 * size_t(first);
+    double* dst = tile[k & 1];
+    for (int i = tid - 32; i < cnt; i += kSumsBlock - 32) dst[i] = __ldg(src + i);
+  };
+  if (tid >= 32) load_tile(0);
+  __syncthreads();
+  for (int k = 0; k < n_tiles; ++k) {
+    if (tid >= 32) {
+      if (k + 1 < n_tiles) load_tile(k + 1);
+    } else if (tid < 9) {
+      const double* t = tile[k & 1];
+      const int cnt = min(kSumTile, e - (b + k * kSumTile));
+      int i = 0;
+      for (; i + 8 <= cnt; i += 8) {
+        double term[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const double a = t[3 * (i + q) + v];
+          term[q] = (u == 3) ? a : mul_(a, t[3 * (i + q) + u]);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s = add_(s, term[q]);
+      }
+      for (; i < cnt; ++i) {
+        const double a = t[3 * i + v];
+        s = add_(s, (u == 3) ? a : mul_(a, t[3 * i + u]));
+      }
+    }
+    __syncthreads();
+  }
+  if (tid < 9) S[size_t(j) * 9 + tid] = s;
+}
+
+__global__ void __launch_bounds__(kSumsBlock, 16)
+k_sums_small(const double* __restrict__ P, const int* __restrict__ lo, const int* __restrict__ hi, int g0,
+             const int* __restrict__ n_level, double* __restrict__ S) {
   const int t = blockIdx.x * kSumsBlock + threadIdx.x;
   const int j = t / 9, c = t - j * 9;
   if (j >= *n_level) return;
   const int b = lo[g0 + j], e = hi[g0 + j];
-  // which two coordinates multiply (u == 3: the term is the coordinate itself)
-  const int u = (c < 3) ? 3 : (c < 6 ? 0 : (c < 8 ? 1 : 2));
-  const int v = (c < 3) ? c : (c < 6 ? c - 3 : (c < 8 ? c - 5 : 2));
+  if (e - b >= kBigNode) return;
+  int u, v;
+  chain_coords(c, u, v);
   double s = 0.0;
   int i = b;
   for (; i + 8 <= e; i += 8) {  // loads and products of 8 points are issued ahead of the dependent adds

@@ -400,14 +400,14 @@ __device__ __forceinline__ void block_reduce_publish(double c0, double c1, doubl
   }
 }
 
-// CTA 0: wait for and sum the tiles of all `nblk` CTAs of this round.  THREADS/64 interleaved strands over the CTA
+// CTA 0: wait for and sum the tiles of all `nblk` CTAs of this round.  Up to 16 interleaved strands over the CTA
 // index, combined in strand order; within a strand the tiles are added in ascending CTA order (fixed => the sums
 // are reproducible).  Every thread first issues the loads of all its cells, then re-polls only the missing ones.
 template <int THREADS>
 __device__ __forceinline__ void fold_tiles(const LLCell* tiles, int nblk, uint32_t epoch, double (*s_red)[64], double* s_tot) {
-  constexpr int STRANDS = THREADS / 64;
-  constexpr int kPer = 8;  // cells per thread in flight at a time: all loads of a batch are issued BEFORE any is looked at
-  const int j = threadIdx.x & 63, g = threadIdx.x >> 6;
+  constexpr int STRANDS = THREADS / kAcc > 16 ? 16 : THREADS / kAcc;  // (s_red has room for WARPS >= 16 rows of 64)
+  constexpr int kPer = 10;  // cells per thread in flight at a time: all loads of a batch are issued BEFORE any is looked at
+  const int j = (threadIdx.x < STRANDS * kAcc) ? int(threadIdx.x % kAcc) : 64, g = threadIdx.x / kAcc;
   __syncthreads();  // s_red is reused
   if (j < kAcc) {
     double s = 0.0;

@@ -225,8 +225,8 @@ int build_resident(madicp_ctx* c, BuildState* bs, cudaStream_t st, int64_t n64, 
     const int* d_nl = bs->d_count + depth;
     // `bound` >= the number of nodes of this level (exact count is on the device until the sync below)
     if (!(depth == 0 && root_S)) {
-      if (depth < 12)  // nodes of >= kBigNode points exist on the upper levels only (at most n / kBigNode of them)
-        k_sums_big<<<std::min(bound, n / kBigNode + 1), kSumsBlock, 0, st>>>(bs->P[cur], bs->N.lo, bs->N.hi, g0, d_nl, bs->S);
+      // one CTA per node; the CTAs of nodes below kBigNode points (all of them on the lower levels) exit at once
+      k_sums_big<<<bound, kSumsBlock, 0, st>>>(bs->P[cur], bs->N.lo, bs->N.hi, g0, d_nl, bs->S);
       k_sums_small<<<blocks(int64_t(bound) * 9, kSumsBlock), kSumsBlock, 0, st>>>(bs->P[cur], bs->N.lo, bs->N.hi, g0, d_nl, bs->S);
     }
     k_eig_prep<<<blocks(bound), kBlock, 0, st>>>(bs->S, bs->N, g0, d_nl, bs->mid, bs->h_args);

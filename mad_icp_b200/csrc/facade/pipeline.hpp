@@ -95,8 +95,11 @@ struct VelocityEstimator {
 class Lookahead {
  public:
   struct Job {
-    std::vector<double> f64;
+    std::vector<double> f64;  // private copies of the cloud ...
     std::vector<float> f32;
+    const void* ext = nullptr;        // ... or the caller's buffer, kept alive by `keepalive` until compute() took the tree
+    bool ext_f32 = false;
+    std::shared_ptr<void> keepalive;  // released by pop(), i.e. on the thread that calls compute()
     size_t n = 0;
     madtree_gpu_t* tree = nullptr;
     int rc = 0;
@@ -137,6 +140,7 @@ class Lookahead {
     std::shared_ptr<Job> j = fifo_.front();
     done_cv_.wait(lk, [&] { return j->done; });
     fifo_.pop_front();
+    j->keepalive.reset();
     if (j->rc < 0) throw Error("look-ahead tree build failed: " + j->err);
     madtree_gpu_t* t = j->tree;
     j->tree = nullptr;
@@ -168,9 +172,9 @@ class Lookahead {
       int rc = MADICP_ERR_STATE;
       std::string err = "no build lane";
       if (b) {
-        const bool f32 = !j->f32.empty();
-        rc = madicp_builder_build(b, f32 ? static_cast<const void*>(j->f32.data()) : static_cast<const void*>(j->f64.data()),
-                                  int64_t(j->n), f32 ? 1 : 0, b_max_, b_min_, &j->tree);
+        const bool f32 = j->ext ? j->ext_f32 : !j->f32.empty();
+        const void* src = j->ext ? j->ext : (f32 ? static_cast<const void*>(j->f32.data()) : static_cast<const void*>(j->f64.data()));
+        rc = madicp_builder_build(b, src, int64_t(j->n), f32 ? 1 : 0, b_max_, b_min_, &j->tree);
         if (rc < 0) err = madicp_last_error();
       }
       {
@@ -280,7 +284,9 @@ class Pipeline {
   // Hands a FUTURE scan over for a look-ahead tree build (see Lookahead).  compute() then consumes the prefetched
   // scans in the order they were handed over and ignores its own cloud argument for them.  Returns false (and does
   // nothing) when look-ahead is not possible: host-built trees, or deskewing (the scan needs the latest poses).
-  bool prefetch(const void* xyz, size_t n, bool is_f32) {
+  // keepalive: when given, the buffer is read in place (no copy) and the handle is dropped once compute() has consumed
+  // the scan; without it the cloud is copied.
+  bool prefetch(const void* xyz, size_t n, bool is_f32, std::shared_ptr<void> keepalive = nullptr) {
     if (!gpu_build_ || deskew_ || !xyz || n == 0) return false;
     if (!lookahead_) {
       int w = 8;
@@ -290,8 +296,15 @@ class Pipeline {
     }
     auto j = std::make_shared<Lookahead::Job>();
     j->n = n;
-    if (is_f32) j->f32.assign(static_cast<const float*>(xyz), static_cast<const float*>(xyz) + 3 * n);
-    else j->f64.assign(static_cast<const double*>(xyz), static_cast<const double*>(xyz) + 3 * n);
+    if (keepalive) {
+      j->ext = xyz;
+      j->ext_f32 = is_f32;
+      j->keepalive = std::move(keepalive);
+    } else if (is_f32) {
+      j->f32.assign(static_cast<const float*>(xyz), static_cast<const float*>(xyz) + 3 * n);
+    } else {
+      j->f64.assign(static_cast<const double*>(xyz), static_cast<const double*>(xyz) + 3 * n);
+    }
     lookahead_->push(std::move(j));
     return true;
   }

@@ -43,18 +43,24 @@ PYBIND11_MODULE(pypeline, m) {
         return mb::Pipeline::deskewOnly(cloud_arg(cloud), pose_from_numpy(a), pose_from_numpy(b), sensor_hz, num_threads);
       }, py::arg("cloud"), py::arg("T_prev"), py::arg("T_now"), py::arg("sensor_hz"), py::arg("num_threads") = 1)
       .def("prefetch", [](mb::Pipeline& p, const py::object& cloud) {
+        // the array is read in place by a build lane: a reference keeps it alive until compute() has consumed the scan
+        // (it is dropped there, on the calling thread, with the GIL held)
+        auto hold = [](const py::object& o) {
+          py::object* ref = new py::object(o);
+          return std::shared_ptr<void>(ref, [](void* q) { delete static_cast<py::object*>(q); });
+        };
         if (py::isinstance<mb::ContainerType>(cloud)) {
           const mb::ContainerType& v = cloud.cast<const mb::ContainerType&>();
-          return p.prefetch(v.empty() ? nullptr : v[0].data(), v.size(), false);
+          return p.prefetch(v.empty() ? nullptr : v[0].data(), v.size(), false, hold(cloud));
         }
         if (py::isinstance<py::array>(cloud) && py::array::ensure(cloud).dtype().is(py::dtype::of<float>())) {
           const auto a = cloud.cast<py::array_t<float, py::array::c_style | py::array::forcecast>>();
           if (a.ndim() != 2 || a.shape(1) != 3) throw py::cast_error();
-          return p.prefetch(a.data(), size_t(a.shape(0)), true);
+          return p.prefetch(a.data(), size_t(a.shape(0)), true, hold(a));
         }
         const NpArr a = cloud.cast<NpArr>();
         if (a.ndim() != 2 || a.shape(1) != 3) throw py::cast_error();
-        return p.prefetch(a.data(), size_t(a.shape(0)), false);
+        return p.prefetch(a.data(), size_t(a.shape(0)), false, hold(a));
       }, py::arg("cloud"))
       .def("prefetched", &mb::Pipeline::prefetched)
       .def("lastIcpIterations", &mb::Pipeline::lastIcpIterations)

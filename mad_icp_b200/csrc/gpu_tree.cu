@@ -44,6 +44,9 @@ struct BuildState {
   // whole build
   Nodes N{};
   int* d_count = nullptr;  // nodes per level (kMaxLevels + 2)
+  Lvl* d_lvl = nullptr;    // level-loop state (gpu_tree_kernels.cuh)
+  Work W{};                // every pointer above, by value for the kernels
+  cudaGraphExec_t level_graph = nullptr;  // the fourteen kernels of one level
   // mapped pinned host memory
   double *h_args = nullptr, *h_res = nullptr;
   Ctl* h_ctl = nullptr;
@@ -79,6 +82,8 @@ int host_alloc(BuildState* bs, T** p, size_t count) {
 }
 
 void release(BuildState* bs) {
+  if (bs->level_graph) cudaGraphExecDestroy(bs->level_graph);
+  bs->level_graph = nullptr;
   for (void* p : bs->dev_allocs) cudaFree(p);
   for (void* p : bs->host_allocs) cudaFreeHost(p);
   bs->dev_allocs.clear();
@@ -131,6 +136,7 @@ int ensure_state(void** slot, cudaStream_t stream, size_t n, BuildState** out) {
   if (!rc) rc = dev_alloc(bs, &bs->N.link, nodes);
   if (!rc) rc = dev_alloc(bs, &bs->N.full, 16 * nodes);
   if (!rc) rc = dev_alloc(bs, &bs->d_count, size_t(kMaxLevels) + 2);
+  if (!rc) rc = dev_alloc(bs, &bs->d_lvl, 1);
   if (!rc) {
     double* raw = nullptr;
     rc = dev_alloc(bs, &raw, 3 * cap);
@@ -152,6 +158,13 @@ int ensure_state(void** slot, cudaStream_t stream, size_t n, BuildState** out) {
     delete bs;
     return rc;
   }
+  Work& W = bs->W;
+  W.P[0] = bs->P[0]; W.P[1] = bs->P[1];
+  W.owner[0] = bs->owner[0]; W.owner[1] = bs->owner[1];
+  W.flag = bs->flag; W.G = bs->G; W.tile = bs->tile; W.XF = bs->XF; W.BP = bs->BP;
+  W.S = bs->S; W.mid = bs->mid; W.box = bs->box; W.cnt = bs->cnt; W.imin = bs->imin; W.child_of = bs->child_of;
+  W.dmin = bs->dmin; W.N = bs->N; W.count = bs->d_count; W.lvl = bs->d_lvl;
+  W.args = bs->h_args; W.res = bs->h_res; W.ctl = bs->h_ctl;
   *slot = bs;
   *out = bs;
   return MADICP_OK;
@@ -173,8 +186,14 @@ void root_sums_host(const T* p, int64_t n, double* S) {
   S[0] = s0; S[1] = s1; S[2] = s2; S[3] = s3; S[4] = s4; S[5] = s5; S[6] = s6; S[7] = s7; S[8] = s8;
 }
 
-__global__ void k_init_root(Nodes N, int n, int* count) {
+__global__ void k_init_root(Nodes N, int n, int* count, Lvl* lvl, double b_max, double b_min) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
+    lvl->depth = 0;
+    lvl->g0 = 0;
+    lvl->cur = 0;
+    lvl->n_points = n;
+    lvl->b_max = b_max;
+    lvl->b_min = b_min;
     N.lo[0] = 0;
     N.hi[0] = n;
     N.parent[0] = -1;
@@ -209,29 +228,61 @@ int build_resident(madicp_ctx* c, BuildState* bs, cudaStream_t st, int64_t n64, 
     memcpy(bs->h_root, root_S, 9 * sizeof(double));
     CK(cudaMemcpyAsync(bs->S, bs->h_root, 9 * sizeof(double), cudaMemcpyHostToDevice, st));
   }
-  k_init_root<<<1, 32, 0, st>>>(bs->N, n, bs->d_count);
+  const Work& W = bs->W;
+  const int cap_pblocks = blocks(int64_t(bs->cap));          // per-point kernels: sized by the lane's capacity and
+  const int cap_tiles = int((bs->cap + kTile - 1) / kTile);  // bounded by Lvl::n_points inside -> one graph fits all scans
+  constexpr int kNodeBlocks = 64, kBigBlocks = 1024, kSmallBlocks = 592;  // grid-stride over the nodes of a level
+  // The fourteen kernels between two host round trips, captured once per lane: what follows the libm values of
+  // level d (eigenvectors ... split), the state update, and the sums + eigen preparation of level d + 1.
+  if (!bs->level_graph) {
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    k_eig_finish<<<kNodeBlocks, kBlock, 0, st>>>(W);
+    k_bbox_flags<<<cap_pblocks, kBlock, 0, st>>>(W);
+    k_decide<<<1, 1024, 0, st>>>(W);
+    k_leaf_dist<<<cap_pblocks, kBlock, 0, st>>>(W);
+    k_leaf_pick<<<cap_pblocks, kBlock, 0, st>>>(W);
+    k_leaf_set<<<kNodeBlocks, kBlock, 0, st>>>(W);
+    k_scan_tiles_lvl<<<cap_tiles, kTile, 0, st>>>(W);
+    k_scan_tile_sums_lvl<<<1, 1024, 0, st>>>(W);
+    k_split_lists<<<cap_pblocks, kBlock, 0, st>>>(W);
+    k_split_scatter<<<cap_pblocks, kBlock, 0, st>>>(W);
+    k_advance<<<1, 32, 0, st>>>(W);
+    k_sums_big<<<kBigBlocks, kSumsBlock, 0, st>>>(W);
+    k_sums_small<<<kSmallBlocks, kSumsBlock, 0, st>>>(W);
+    k_eig_prep<<<kNodeBlocks, kBlock, 0, st>>>(W);
+    cudaError_t e = cudaStreamEndCapture(st, &g);
+    if (e != cudaSuccess || !g) {
+      set_error(std::string("madtree_gpu_build: graph capture: ") + cudaGetErrorString(e));
+      return MADICP_ERR_CUDA;
+    }
+    e = cudaGraphInstantiate(&bs->level_graph, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) {
+      set_error(std::string("madtree_gpu_build: graph instantiate: ") + cudaGetErrorString(e));
+      return MADICP_ERR_CUDA;
+    }
+  }
+  // head of the tree: level state, root node, (root sums unless the host supplied them), eigen preparation of level 0
+  k_init_root<<<1, 32, 0, st>>>(bs->N, n, bs->d_count, bs->d_lvl, b_max, b_min);
   CK(cudaMemsetAsync(bs->owner[0], 0, size_t(n) * sizeof(int), st));
-  c->launches++;
-  int g0 = 0, nl = 1, bound = 1, cur = 0, depth = 0;
+  if (!root_S) {
+    k_sums_big<<<1, kSumsBlock, 0, st>>>(W);
+    k_sums_small<<<1, kSumsBlock, 0, st>>>(W);
+    c->launches += 2;
+  }
+  k_eig_prep<<<1, kBlock, 0, st>>>(W);
+  c->launches += 2;
+  CK(cudaGetLastError());
+  int g0 = 0, nl = 1, depth = 0;
   int total_leaves = 0;
   bs->h_lvl[0] = 0;
-  const int pblocks = blocks(n);
   const int tiles = (n + kTile - 1) / kTile;
   while (true) {
     if (depth >= kMaxLevels) {
       set_error("madtree_gpu_build: tree deeper than 4096 levels");
       return MADICP_ERR_INVALID;
     }
-    const int* d_nl = bs->d_count + depth;
-    // `bound` >= the number of nodes of this level (exact count is on the device until the sync below)
-    if (!(depth == 0 && root_S)) {
-      // one CTA per node; the CTAs of nodes below kBigNode points (all of them on the lower levels) exit at once
-      k_sums_big<<<bound, kSumsBlock, 0, st>>>(bs->P[cur], bs->N.lo, bs->N.hi, g0, d_nl, bs->S);
-      k_sums_small<<<blocks(int64_t(bound) * 9, kSumsBlock), kSumsBlock, 0, st>>>(bs->P[cur], bs->N.lo, bs->N.hi, g0, d_nl, bs->S);
-    }
-    k_eig_prep<<<blocks(bound), kBlock, 0, st>>>(bs->S, bs->N, g0, d_nl, bs->mid, bs->h_args);
-    c->launches += 2;
-    CK(cudaGetLastError());
     const auto ts0 = now();
     CK(cudaStreamSynchronize(st));  // the level's one host round trip: libm for the eigen-decomposition
     const auto ts1 = now();
@@ -250,23 +301,9 @@ int build_resident(madicp_ctx* c, BuildState* bs, cudaStream_t st, int64_t n64, 
       t_trig += us(ts1, now());
       per_level += " " + std::to_string(nl) + ":" + std::to_string(int(us(ts0, ts1)));
     }
-    k_eig_finish<<<blocks(nl), kBlock, 0, st>>>(bs->mid, bs->h_res, bs->N, g0, d_nl, bs->box, bs->cnt, bs->dmin, bs->imin);
-    k_bbox_flags<<<pblocks, kBlock, 0, st>>>(bs->P[cur], bs->owner[cur], n, bs->N, g0, bs->box, bs->cnt, bs->flag);
-    k_decide<<<1, 1024, 0, st>>>(bs->N, g0, bs->d_count + depth, bs->d_count + depth + 1, bs->box, bs->cnt, b_max, b_min,
-                                bs->h_ctl + depth, bs->child_of);
-    k_leaf_dist<<<pblocks, kBlock, 0, st>>>(bs->P[cur], bs->owner[cur], n, bs->N, g0, bs->dmin);
-    k_leaf_pick<<<pblocks, kBlock, 0, st>>>(bs->P[cur], bs->owner[cur], n, bs->N, g0, bs->dmin, bs->imin);
-    k_leaf_set<<<blocks(nl), kBlock, 0, st>>>(bs->P[cur], bs->N, g0, d_nl, n, bs->imin);
-    k_scan_tiles<<<tiles, kTile, 0, st>>>(bs->flag, n, bs->G, bs->tile);
-    k_scan_tile_sums<<<1, 1024, 0, st>>>(bs->tile, tiles);
-    k_split_lists<<<pblocks, kBlock, 0, st>>>(bs->owner[cur], n, bs->N, g0, bs->cnt, bs->flag, bs->G, bs->tile, bs->XF, bs->BP);
-    k_split_scatter<<<pblocks, kBlock, 0, st>>>(bs->P[cur], bs->P[cur ^ 1], bs->owner[cur], bs->owner[cur ^ 1], n, bs->N, g0,
-                                               bs->cnt, bs->child_of, bs->flag, bs->G, bs->tile, bs->XF, bs->BP);
-    c->launches += 10;
-    CK(cudaGetLastError());
+    CK(cudaGraphLaunch(bs->level_graph, st));  // level `depth` to its end + sums / eigen preparation of the next
+    c->launches += 14;
     g0 += nl;
-    bound = std::min(2 * nl, n + 1);
-    cur ^= 1;
     ++depth;
     bs->h_lvl[depth] = g0;
   }

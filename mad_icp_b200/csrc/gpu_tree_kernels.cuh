@@ -53,6 +53,33 @@ struct Ctl {
   int pad;
 };
 
+// State of the level loop, in device memory: every kernel of a level reads it, k_advance moves it on.  With it the
+// kernels of a level take the SAME arguments on every level of every tree of a lane, so the whole level is one
+// CUDA graph launch instead of fourteen kernel launches (the lanes' host threads and the registration thread share
+// one driver; fewer calls is less contention).
+struct Lvl {
+  int depth, g0, cur, n_points;
+  double b_max, b_min;
+};
+struct Eig3MidFwd;
+// All device pointers of a build lane (by value in every kernel).
+struct Work {
+  double* P[2];
+  int* owner[2];
+  unsigned char* flag;
+  int *G, *tile, *XF, *BP;
+  double* S;
+  Eig3Mid* mid;
+  long long* box;
+  int *cnt, *imin, *child_of;
+  unsigned long long* dmin;
+  Nodes N;
+  int* count;   // nodes per level
+  Lvl* lvl;
+  double *args, *res;  // mapped host memory: libm arguments / results, 2 per node of the level
+  Ctl* ctl;            // mapped host memory, one per level
+};
+
 __device__ __forceinline__ long long dbits(double v) { return __double_as_longlong(v); }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -70,14 +97,16 @@ __device__ __forceinline__ void chain_coords(int c, int& u, int& v) {  // term =
 }
 
 __global__ void __launch_bounds__(kSumsBlock, 16)  // <= 32 registers: 128 x 32 = the 4096 the registration CTA leaves free
-k_sums_big(const double* __restrict__ P, const int* __restrict__ lo, const int* __restrict__ hi, int g0,
-           const int* __restrict__ n_level, double* __restrict__ S) {
+k_sums_big(const Work W) {
   __shared__ double tile[2][kSumTile * 3];
-  const int j = blockIdx.x;
-  if (j >= *n_level) return;
-  const int b = lo[g0 + j], e = hi[g0 + j];
-  if (e - b < kBigNode) return;
+  const Lvl L = *W.lvl;
+  const int n_level = W.count[L.depth];
+  const double* __restrict__ P = W.P[L.cur];
+  double* __restrict__ S = W.S;
   const int tid = threadIdx.x;
+  for (int j = blockIdx.x; j < n_level; j += gridDim.x) {  // (uniform per CTA: the barriers below are safe)
+  const int b = W.N.lo[L.g0 + j], e = W.N.hi[L.g0 + j];
+  if (e - b < kBigNode) continue;
   int u = 3, v = 0;
   if (tid < 9) chain_coords(tid, u, v);
   double s = 0.0;
@@ -116,16 +145,20 @@ k_sums_big(const double* __restrict__ P, const int* __restrict__ lo, const int* 
     __syncthreads();
   }
   if (tid < 9) S[size_t(j) * 9 + tid] = s;
+  __syncthreads();
+  }
 }
 
 __global__ void __launch_bounds__(kSumsBlock, 16)
-k_sums_small(const double* __restrict__ P, const int* __restrict__ lo, const int* __restrict__ hi, int g0,
-             const int* __restrict__ n_level, double* __restrict__ S) {
-  const int t = blockIdx.x * kSumsBlock + threadIdx.x;
+k_sums_small(const Work W) {
+  const Lvl L = *W.lvl;
+  const int n_level = W.count[L.depth];
+  const double* __restrict__ P = W.P[L.cur];
+  double* __restrict__ S = W.S;
+  for (int t = blockIdx.x * kSumsBlock + threadIdx.x; t < n_level * 9; t += gridDim.x * kSumsBlock) {
   const int j = t / 9, c = t - j * 9;
-  if (j >= *n_level) return;
-  const int b = lo[g0 + j], e = hi[g0 + j];
-  if (e - b >= kBigNode) return;
+  const int b = W.N.lo[L.g0 + j], e = W.N.hi[L.g0 + j];
+  if (e - b >= kBigNode) continue;
   int u, v;
   chain_coords(c, u, v);
   double s = 0.0;
@@ -147,15 +180,20 @@ k_sums_small(const double* __restrict__ P, const int* __restrict__ lo, const int
     s = add_(s, (u == 3) ? a : mul_(a, __ldg(p + u)));
   }
   S[size_t(j) * 9 + c] = s;
+  }
 }
 
 // (2) mean, covariance (utils.h:66-70), first half of computeDirect -> the arguments of atan2 for the host
 __global__ void __launch_bounds__(kBlock)
-k_eig_prep(const double* __restrict__ S, Nodes N, int g0, const int* __restrict__ n_level, Eig3Mid* __restrict__ mid,
-           double* __restrict__ args /* mapped host memory: 2 per node */) {
-  const int j = blockIdx.x * kBlock + threadIdx.x;
-  if (j >= *n_level) return;
-  const int g = g0 + j;
+k_eig_prep(const Work W) {
+  const Lvl L = *W.lvl;
+  const int n_level = W.count[L.depth];
+  const Nodes N = W.N;
+  const double* __restrict__ S = W.S;
+  Eig3Mid* __restrict__ mid = W.mid;
+  double* __restrict__ args = W.args;  // mapped host memory: 2 per node
+  for (int j = blockIdx.x * kBlock + threadIdx.x; j < n_level; j += gridDim.x * kBlock) {
+  const int g = L.g0 + j;
   const int k = N.hi[g] - N.lo[g];
   const double* s = S + size_t(j) * 9;
   double sx = s[0], sy = s[1], sz = s[2];
@@ -176,18 +214,24 @@ k_eig_prep(const double* __restrict__ S, Nodes N, int g0, const int* __restrict_
   mid[j] = m;
   args[2 * size_t(j)] = m.sq;
   args[2 * size_t(j) + 1] = m.half_b;
+  }
 }
 
 // (3) second half of computeDirect with the host's cos/sin; resets the accumulators of the level
 __global__ void __launch_bounds__(kBlock)
-k_eig_finish(const Eig3Mid* __restrict__ mid, const double* __restrict__ res /* mapped host: cos, sin per node */,
-             Nodes N, int g0, const int* __restrict__ n_level, long long* __restrict__ box, int* __restrict__ cnt,
-             unsigned long long* __restrict__ dmin, int* __restrict__ imin) {
-  const int j = blockIdx.x * kBlock + threadIdx.x;
-  if (j >= *n_level) return;
+k_eig_finish(const Work W) {
+  const Lvl L = *W.lvl;
+  const int n_level = W.count[L.depth];
+  const Nodes N = W.N;
+  const double* __restrict__ res = W.res;  // mapped host: cos, sin per node
+  long long* __restrict__ box = W.box;
+  int* __restrict__ cnt = W.cnt;
+  unsigned long long* __restrict__ dmin = W.dmin;
+  int* __restrict__ imin = W.imin;
+  for (int j = blockIdx.x * kBlock + threadIdx.x; j < n_level; j += gridDim.x * kBlock) {
   double V[9];
-  eig3_finish(mid[j], res[2 * size_t(j)], res[2 * size_t(j) + 1], V);
-  double* full = N.full + size_t(g0 + j) * 16;
+  eig3_finish(W.mid[j], res[2 * size_t(j)], res[2 * size_t(j) + 1], V);
+  double* full = N.full + size_t(L.g0 + j) * 16;
 #pragma unroll
   for (int a = 0; a < 9; ++a) full[3 + a] = V[a];
 #pragma unroll
@@ -195,14 +239,22 @@ k_eig_finish(const Eig3Mid* __restrict__ mid, const double* __restrict__ res /* 
   cnt[j] = 0;
   dmin[j] = 0x7fefffffffffffffull;  // DBL_MAX (mad_tree.cpp:77)
   imin[j] = 0x7fffffff;
+  }
 }
 
 // (4) extents of R^T (p - mean) (utils.h:76-97: extents start from 0, a NaN never replaces) and the side of every
 // point with respect to the split plane (the v(2) of the same product is the predicate of mad_tree.cpp:95-97).
 // owner[i] = level-local node of position i, -1 for positions whose node is already a leaf.
 __global__ void __launch_bounds__(kBlock)
-k_bbox_flags(const double* __restrict__ P, const int* __restrict__ owner, int n, Nodes N, int g0,
-             long long* __restrict__ box, int* __restrict__ cnt, unsigned char* __restrict__ flag) {
+k_bbox_flags(const Work W) {
+  const Lvl L = *W.lvl;
+  const double* __restrict__ P = W.P[L.cur];
+  const int* __restrict__ owner = W.owner[L.cur];
+  const int n = L.n_points, g0 = L.g0;
+  const Nodes N = W.N;
+  long long* __restrict__ box = W.box;
+  int* __restrict__ cnt = W.cnt;
+  unsigned char* __restrict__ flag = W.flag;
   const int i = blockIdx.x * kBlock + threadIdx.x;
   const unsigned lane = threadIdx.x & 31;
   int j = (i < n) ? owner[i] : -1;
@@ -251,12 +303,19 @@ k_bbox_flags(const double* __restrict__ P, const int* __restrict__ owner, int n,
 
 // (5) leaf test, children, inheritance of the plane predecessor / ancestor; ONE CTA walks the level in tiles.
 __global__ void __launch_bounds__(1024)
-k_decide(Nodes N, int g0, const int* __restrict__ n_level, int* __restrict__ n_next, const long long* __restrict__ box,
-         const int* __restrict__ cnt, double b_max, double b_min, Ctl* __restrict__ ctl /* mapped host */,
-         int* __restrict__ child_of /* level-local: first child (level-local in the next level) or -1 */) {
+k_decide(const Work W) {
   __shared__ int s_warp[32];
   __shared__ int s_carry, s_leaves, s_active;
-  const int n = *n_level;
+  const Lvl L = *W.lvl;
+  const Nodes N = W.N;
+  const int g0 = L.g0;
+  const double b_max = L.b_max, b_min = L.b_min;
+  const long long* __restrict__ box = W.box;
+  const int* __restrict__ cnt = W.cnt;
+  int* __restrict__ child_of = W.child_of;  // level-local: first child (level-local in the next level) or -1
+  Ctl* __restrict__ ctl = W.ctl + L.depth;  // mapped host
+  int* n_next = W.count + L.depth + 1;
+  const int n = W.count[L.depth];
   const int g1 = g0 + n;  // first node of the next level
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_carry = s_leaves = s_active = 0;
@@ -349,10 +408,15 @@ k_decide(Nodes N, int g0, const int* __restrict__ n_level, int* __restrict__ n_n
 
 // (6) leaves: nearest cloud point to the centroid, first minimum wins (mad_tree.cpp:76-86)
 __global__ void __launch_bounds__(kBlock)
-k_leaf_dist(const double* __restrict__ P, const int* __restrict__ owner, int n, Nodes N, int g0,
-            unsigned long long* __restrict__ dmin) {
+k_leaf_dist(const Work W) {
+  const Lvl L = *W.lvl;
+  const double* __restrict__ P = W.P[L.cur];
+  const int* __restrict__ owner = W.owner[L.cur];
+  const Nodes N = W.N;
+  const int g0 = L.g0;
+  unsigned long long* __restrict__ dmin = W.dmin;
   const int i = blockIdx.x * kBlock + threadIdx.x;
-  if (i >= n) return;
+  if (i >= L.n_points) return;
   const int j = owner[i];
   if (j < 0 || N.link[g0 + j] >= 0) return;
   const double* full = N.full + size_t(g0 + j) * 16;
@@ -360,10 +424,16 @@ k_leaf_dist(const double* __restrict__ P, const int* __restrict__ owner, int n, 
   if (d < 1.7976931348623157e308) atomicMin(dmin + j, (unsigned long long) dbits(d));  // d >= 0: bits order like the values
 }
 __global__ void __launch_bounds__(kBlock)
-k_leaf_pick(const double* __restrict__ P, const int* __restrict__ owner, int n, Nodes N, int g0,
-            const unsigned long long* __restrict__ dmin, int* __restrict__ imin) {
+k_leaf_pick(const Work W) {
+  const Lvl L = *W.lvl;
+  const double* __restrict__ P = W.P[L.cur];
+  const int* __restrict__ owner = W.owner[L.cur];
+  const Nodes N = W.N;
+  const int g0 = L.g0;
+  const unsigned long long* __restrict__ dmin = W.dmin;
+  int* __restrict__ imin = W.imin;
   const int i = blockIdx.x * kBlock + threadIdx.x;
-  if (i >= n) return;
+  if (i >= L.n_points) return;
   const int j = owner[i];
   if (j < 0 || N.link[g0 + j] >= 0) return;
   const double* full = N.full + size_t(g0 + j) * 16;
@@ -371,23 +441,37 @@ k_leaf_pick(const double* __restrict__ P, const int* __restrict__ owner, int n, 
   if (d < 1.7976931348623157e308 && (unsigned long long) dbits(d) == dmin[j]) atomicMin(imin + j, i);
 }
 __global__ void __launch_bounds__(kBlock)
-k_leaf_set(const double* __restrict__ P, Nodes N, int g0, const int* __restrict__ n_level_prev, int n_points,
-           const int* __restrict__ imin) {
-  const int j = blockIdx.x * kBlock + threadIdx.x;
-  if (j >= *n_level_prev) return;
-  const int g = g0 + j;
-  if (N.link[g] >= 0) return;
+k_leaf_set(const Work W) {
+  const Lvl L = *W.lvl;
+  const double* __restrict__ P = W.P[L.cur];
+  const Nodes N = W.N;
+  const int n_points = L.n_points, n_level = W.count[L.depth];
+  const int* __restrict__ imin = W.imin;
+  for (int j = blockIdx.x * kBlock + threadIdx.x; j < n_level; j += gridDim.x * kBlock) {
+  const int g = L.g0 + j;
+  if (N.link[g] >= 0) continue;
   int i = imin[j];
   if (i == 0x7fffffff) i = N.lo[g];  // no distance below DBL_MAX: the reference keeps *begin
   double* full = N.full + size_t(g) * 16;
   if (i < n_points) {
     full[0] = P[3 * size_t(i)]; full[1] = P[3 * size_t(i) + 1]; full[2] = P[3 * size_t(i) + 2];
   }
+  }
+}
+
+// end of a level: the state moves on to the next one
+__global__ void k_advance(const Work W) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    Lvl* l = W.lvl;
+    l->g0 += W.count[l->depth];
+    l->depth += 1;
+    l->cur ^= 1;
+  }
 }
 
 // (7) exclusive prefix of the side flags over the whole array: per-tile scan + scan of the tile totals
-__global__ void __launch_bounds__(kTile)
-k_scan_tiles(const unsigned char* __restrict__ flag, int n, int* __restrict__ G, int* __restrict__ tile_sum) {
+__device__ __forceinline__ void scan_tiles_body(const unsigned char* __restrict__ flag, int n, int* __restrict__ G,
+                                                int* __restrict__ tile_sum) {
   __shared__ int s_warp[32];
   const int i = blockIdx.x * kTile + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -414,8 +498,13 @@ k_scan_tiles(const unsigned char* __restrict__ flag, int n, int* __restrict__ G,
   if (i < n) G[i] = excl;
   if (threadIdx.x == kTile - 1) tile_sum[blockIdx.x] = excl + f;
 }
-__global__ void __launch_bounds__(1024)
-k_scan_tile_sums(int* __restrict__ tile_sum, int n_tiles) {  // in place: exclusive; one CTA
+__global__ void __launch_bounds__(kTile)
+k_scan_tiles(const unsigned char* __restrict__ flag, int n, int* __restrict__ G, int* __restrict__ tile_sum) {
+  scan_tiles_body(flag, n, G, tile_sum);
+}
+__global__ void __launch_bounds__(kTile) k_scan_tiles_lvl(const Work W) { scan_tiles_body(W.flag, W.lvl->n_points, W.G, W.tile); }
+
+__device__ __forceinline__ void scan_tile_sums_body(int* __restrict__ tile_sum, int n_tiles) {  // in place: exclusive; one CTA
   __shared__ int s_warp[32];
   __shared__ int s_carry;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -449,6 +538,13 @@ k_scan_tile_sums(int* __restrict__ tile_sum, int n_tiles) {  // in place: exclus
     __syncthreads();
   }
 }
+__global__ void __launch_bounds__(1024) k_scan_tile_sums(int* __restrict__ tile_sum, int n_tiles) {
+  scan_tile_sums_body(tile_sum, n_tiles);
+}
+__global__ void __launch_bounds__(1024) k_scan_tile_sums_lvl(const Work W) {
+  scan_tile_sums_body(W.tile, (W.lvl->n_points + kTile - 1) / kTile);
+}
+
 // (8) split() in closed form (flat_tree.cpp Builder::split): index lists, then one move per point.
 // With m = number of points of the node that pass (are on the negative side), positions relative to the node:
 //   XF[a] = a-th failing position of [0,m), BP[r] = r-th passing position of [m,n)   (A of each)
@@ -470,9 +566,17 @@ __device__ __forceinline__ SplitCtx split_ctx(const Nodes& N, int g, int m, cons
   return c;
 }
 __global__ void __launch_bounds__(kBlock)
-k_split_lists(const int* __restrict__ owner, int n_points, Nodes N, int g0, const int* __restrict__ cnt,
-              const unsigned char* __restrict__ flag, const int* __restrict__ G, const int* __restrict__ tile_off,
-              int* __restrict__ XF, int* __restrict__ BP) {
+k_split_lists(const Work W) {
+  const Lvl L = *W.lvl;
+  const int* __restrict__ owner = W.owner[L.cur];
+  const int n_points = L.n_points, g0 = L.g0;
+  const Nodes N = W.N;
+  const int* __restrict__ cnt = W.cnt;
+  const unsigned char* __restrict__ flag = W.flag;
+  const int* __restrict__ G = W.G;
+  const int* __restrict__ tile_off = W.tile;
+  int* __restrict__ XF = W.XF;
+  int* __restrict__ BP = W.BP;
   const int i = blockIdx.x * kBlock + threadIdx.x;
   if (i >= n_points) return;
   const int j = owner[i];
@@ -488,10 +592,21 @@ k_split_lists(const int* __restrict__ owner, int n_points, Nodes N, int g0, cons
   }
 }
 __global__ void __launch_bounds__(kBlock)
-k_split_scatter(const double* __restrict__ P, double* __restrict__ Pn, const int* __restrict__ owner,
-                int* __restrict__ owner_next, int n_points, Nodes N, int g0, const int* __restrict__ cnt,
-                const int* __restrict__ child_of, const unsigned char* __restrict__ flag, const int* __restrict__ G,
-                const int* __restrict__ tile_off, const int* __restrict__ XF, const int* __restrict__ BP) {
+k_split_scatter(const Work W) {
+  const Lvl L = *W.lvl;
+  const double* __restrict__ P = W.P[L.cur];
+  double* __restrict__ Pn = W.P[L.cur ^ 1];
+  const int* __restrict__ owner = W.owner[L.cur];
+  int* __restrict__ owner_next = W.owner[L.cur ^ 1];
+  const int n_points = L.n_points, g0 = L.g0;
+  const Nodes N = W.N;
+  const int* __restrict__ cnt = W.cnt;
+  const int* __restrict__ child_of = W.child_of;
+  const unsigned char* __restrict__ flag = W.flag;
+  const int* __restrict__ G = W.G;
+  const int* __restrict__ tile_off = W.tile;
+  const int* __restrict__ XF = W.XF;
+  const int* __restrict__ BP = W.BP;
   const int i = blockIdx.x * kBlock + threadIdx.x;
   if (i >= n_points) return;
   const int j = owner[i];

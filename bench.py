@@ -292,16 +292,17 @@ def stream_block(a, scans, rank, world, dev):
     torch.cuda.set_device(dev)
     pipe = Pipeline(**kw)
     n = len(scans)
+    # the scans wait in pinned host memory, as a driver's DMA buffers would (same rule as `e2e`: inputs start on the host)
+    scans = [torch.from_numpy(np.ascontiguousarray(s0)).pin_memory().numpy() for s0 in scans]
     pipe.compute(0.0, scans[0])  # initialise: keyframe 0 (also first-touch allocations)
     traj, kf = [], []
     torch.cuda.synchronize(dev)
-    depth = int(os.environ.get("MADICP_BENCH_LOOKAHEAD", "12"))  # scans whose trees are being built ahead (0: none)
+    depth = int(os.environ.get("MADICP_BENCH_LOOKAHEAD", "16"))  # scans handed over ahead of their turn: their trees are built in batches (0: none)
     t0 = time.perf_counter()
-    for k in range(1, min(depth, n - 1) + 1):
-        pipe.prefetch(scans[k])
     for i in range(1, n):
-        if depth > 0 and i + depth < n:
-            pipe.prefetch(scans[i + depth])
+        if depth > 0 and pipe.prefetched() == 0:  # hand over the next `depth` scans: one forest build
+            for k in range(i, min(i + depth, n)):
+                pipe.prefetch(scans[k])
         pipe.compute(0.1 * i, scans[i])
         traj.append(pipe.currentPose()[:3, 3].copy())
         kf.append((bool(pipe.isMapUpdated()), int(pipe.keyframeID())))
@@ -310,7 +311,9 @@ def stream_block(a, scans, rank, world, dev):
            "value": (n - 1) / t_gpu, "unit": "scans/s", "ms_per_scan": 1e3 * t_gpu / (n - 1),
            "device_tree_build": bool(pipe.gpuBuild()), "lookahead_scans": depth, "keyframes_at_end": int(pipe.numKeyframes()),
            "path_length_m": float(np.linalg.norm(traj[-1] - traj[0])),
-           "note": "Pipeline.compute per scan, host cloud in / pose out; tree build, registration and keyframe promotion on the device"}
+           "h2d_bytes_per_scan": int(scans[0].nbytes), "d2h_bytes_per_scan": 16 + 43 * 8 + 96,
+           "note": "Pipeline.compute per scan, pinned host cloud in / pose out; tree build (batched look-ahead), registration and "
+                   "keyframe promotion on the device"}
     m = min(a.stream_cpu_scans, n)
     if rank == 0 and m > 1:
         from oracle import oracle as O

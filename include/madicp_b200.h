@@ -139,17 +139,12 @@ int madtree_gpu_build(madicp_ctx_t* ctx, const double* points_xyz, int64_t n, do
                       madtree_gpu_t** out);
 /* The same from a cloud already on the device (madicp_ingest). */
 int madtree_gpu_build_resident(madicp_ctx_t* ctx, double b_max, double b_min, madtree_gpu_t** out);
-/* Build lanes: a madicp_builder_t owns a stream and working memory of its own on the context's device, so the trees of
- * the NEXT scans can be built (by other host threads, one per builder) while the context registers the current one --
- * the tree of a scan depends on the pose estimates only when it is deskewed.  madicp_builder_build is the whole
- * ingest (float32 -> float64 when is_f32) + build; it returns when the tree is complete, ready for
- * madicp_set_moving_tree / madicp_put_keyframe_tree on the context.  Thread-safe against other builders and against
- * the context's own calls. */
-typedef struct madicp_builder madicp_builder_t;
-int madicp_builder_create(madicp_ctx_t* ctx, madicp_builder_t** out);
-void madicp_builder_destroy(madicp_builder_t* b);
-int madicp_builder_build(madicp_builder_t* b, const void* xyz, int64_t n, int is_f32, double b_max, double b_min,
-                         madtree_gpu_t** out);
+/* A batch of scans at once (look-ahead: the tree of a scan depends on the pose estimates only when it is deskewed, so
+ * the trees of the next scans can be built before their turn): `count` clouds (all float32 or all float64, host
+ * memory) -> `count` trees, built as ONE forest.  The build's latency is that of its dependent-add chains, which a
+ * batch runs side by side, so sixteen trees cost little more than one.  out[count]. */
+int madtree_gpu_build_batch(madicp_ctx_t* ctx, const void* const* clouds, const int64_t* n_points, int is_f32, int count,
+                            double b_max, double b_min, madtree_gpu_t** out);
 /* Upload of a host-built tree (records + tables), asynchronous. */
 int madtree_gpu_upload(madicp_ctx_t* ctx, const madtree_t* tree, madtree_gpu_t** out);
 void madtree_gpu_free(madtree_gpu_t* t);

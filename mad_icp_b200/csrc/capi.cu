@@ -942,16 +942,8 @@ static int register_enqueue(madicp_ctx* c, int iters, const double X0[12], int c
   A.zero_next = c->d_comm->matched[mb ^ 1];
   A.zero_bytes = int((std::min(kMatchedCap, c->cap_moving) + 15) & ~size_t(15));
   void* args[] = {&A};
-  // The kernel's round barrier needs all its CTAs resident at once.  A cooperative launch guarantees that by waiting
-  // for an otherwise idle device -- which would serialise the registration with every kernel of the build lanes
-  // working ahead on other streams.  With lanes alive the launch is an ordinary one: the grid is sized to fit the
-  // device (configure_gn checked the occupancy), every other kernel of this process terminates on its own, and the
-  // lanes' long-running CTAs are sized to sit next to a registration CTA (gpu_tree_kernels.cuh), so all CTAs become
-  // resident and the barrier makes progress.
-  if (c->n_lanes.load() > 0)
-    CK(cudaLaunchKernel(c->gn_kernel, dim3(c->gn_grid), dim3(c->gn_threads), args, c->gn_smem + map_bytes, c->stream));
-  else
-    CK(cudaLaunchCooperativeKernel(c->gn_kernel, dim3(c->gn_grid), dim3(c->gn_threads), args, c->gn_smem + map_bytes, c->stream));
+  // (cooperative: the round barrier needs all CTAs resident at once, and this launch mode guarantees it)
+  CK(cudaLaunchCooperativeKernel(c->gn_kernel, dim3(c->gn_grid), dim3(c->gn_threads), args, c->gn_smem + map_bytes, c->stream));
   c->launches++;
   c->last_iters = iters;
   c->call_seq++;

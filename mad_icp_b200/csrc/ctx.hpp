@@ -123,7 +123,6 @@ struct madicp_ctx {
   int last_iters = 0;
   long long* d_dbg = nullptr;  // MADICP_MAX_ITERS x 8 clock stamps when debug timing is on
   std::atomic<int64_t> launches{0};
-  std::atomic<int> n_lanes{0};  // build lanes (madicp_builder_t) alive on this context
   // peers
   int rank = 0, world = 1;
   madicp::CommBlock* peer_comm[madicp::kMaxPeers] = {};

@@ -11,10 +11,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
-#include <condition_variable>
 #include <deque>
 #include <limits>
-#include <thread>
 
 #include "../pose_math.h"
 #include "facade.hpp"
@@ -88,114 +86,66 @@ struct VelocityEstimator {
 };
 }  // namespace detail
 
-// Look-ahead tree builds: scans handed to Pipeline::prefetch are ingested and built on the device by worker threads
-// (one build lane each: own stream, own working memory) while the pipeline registers earlier scans; compute()
+// Look-ahead tree builds: scans handed to Pipeline::prefetch are queued; when compute() needs the tree of the oldest
+// one, the trees of ALL queued scans (up to `batch`) are built in one go, as one forest (madtree_gpu_build_batch) --
+// the build's latency is that of its dependent-add chains, which a batch runs side by side -- and compute() then
 // consumes them in FIFO order.  Possible because a scan's tree depends on the pose estimates only when the scan is
-// deskewed (pipeline.cpp:137-141).
+// deskewed (pipeline.cpp:137-141).  No threads: the batch is built by the thread that calls compute().
 class Lookahead {
  public:
   struct Job {
     std::vector<double> f64;  // private copies of the cloud ...
     std::vector<float> f32;
-    const void* ext = nullptr;        // ... or the caller's buffer, kept alive by `keepalive` until compute() took the tree
-    bool ext_f32 = false;
-    std::shared_ptr<void> keepalive;  // released by pop(), i.e. on the thread that calls compute()
+    const void* ext = nullptr;        // ... or the caller's buffer, kept alive by `keepalive` until its tree is built
+    bool is_f32 = false;
+    std::shared_ptr<void> keepalive;
     size_t n = 0;
     madtree_gpu_t* tree = nullptr;
-    int rc = 0;
-    std::string err;
-    bool claimed = false, done = false;
+    const void* data() const { return ext ? ext : (is_f32 ? static_cast<const void*>(f32.data()) : static_cast<const void*>(f64.data())); }
   };
-  Lookahead(madicp_ctx_t* ctx, double b_max, double b_min, int workers) : ctx_(ctx), b_max_(b_max), b_min_(b_min) {
-    for (int w = 0; w < workers; ++w) threads_.emplace_back([this] { run(); });
-  }
+  Lookahead(madicp_ctx_t* ctx, double b_max, double b_min, int batch) : ctx_(ctx), b_max_(b_max), b_min_(b_min), batch_(batch) {}
   ~Lookahead() {
-    {
-      std::lock_guard<std::mutex> lk(mu_);
-      stop_ = true;
-    }
-    cv_.notify_all();
-    for (auto& t : threads_) t.join();
     for (auto& j : fifo_)
-      if (j->tree) madtree_gpu_free(j->tree);
+      if (j.tree) madtree_gpu_free(j.tree);
   }
-  void push(std::shared_ptr<Job> j) {
-    {
-      std::lock_guard<std::mutex> lk(mu_);
-      fifo_.push_back(std::move(j));
-    }
-    cv_.notify_all();
-  }
-  bool empty() {
-    std::lock_guard<std::mutex> lk(mu_);
-    return fifo_.empty();
-  }
-  size_t size() {
-    std::lock_guard<std::mutex> lk(mu_);
-    return fifo_.size();
-  }
-  // oldest prefetched scan's tree (blocks until it is built)
+  void push(Job&& j) { fifo_.push_back(std::move(j)); }
+  bool empty() const { return fifo_.empty(); }
+  size_t size() const { return fifo_.size(); }
+  // tree of the oldest prefetched scan
   madtree_gpu_t* pop() {
-    std::unique_lock<std::mutex> lk(mu_);
-    std::shared_ptr<Job> j = fifo_.front();
-    done_cv_.wait(lk, [&] { return j->done; });
+    if (!fifo_.front().tree) buildBatch();
+    madtree_gpu_t* t = fifo_.front().tree;
+    fifo_.front().tree = nullptr;
     fifo_.pop_front();
-    j->keepalive.reset();
-    if (j->rc < 0) throw Error("look-ahead tree build failed: " + j->err);
-    madtree_gpu_t* t = j->tree;
-    j->tree = nullptr;
     return t;
   }
 
  private:
-  void run() {
-    madicp_builder_t* b = nullptr;
-    if (madicp_builder_create(ctx_, &b) < 0) b = nullptr;
-    for (;;) {
-      std::shared_ptr<Job> j;
-      {
-        std::unique_lock<std::mutex> lk(mu_);
-        cv_.wait(lk, [&] {
-          if (stop_) return true;
-          for (auto& q : fifo_)
-            if (!q->claimed) return true;
-          return false;
-        });
-        if (stop_) break;
-        for (auto& q : fifo_)
-          if (!q->claimed) {
-            j = q;
-            break;
-          }
-        j->claimed = true;
-      }
-      int rc = MADICP_ERR_STATE;
-      std::string err = "no build lane";
-      if (b) {
-        const bool f32 = j->ext ? j->ext_f32 : !j->f32.empty();
-        const void* src = j->ext ? j->ext : (f32 ? static_cast<const void*>(j->f32.data()) : static_cast<const void*>(j->f64.data()));
-        rc = madicp_builder_build(b, src, int64_t(j->n), f32 ? 1 : 0, b_max_, b_min_, &j->tree);
-        if (rc < 0) err = madicp_last_error();
-      }
-      {
-        std::lock_guard<std::mutex> lk(mu_);
-        j->rc = rc;
-        j->err = err;
-        j->f64 = std::vector<double>();
-        j->f32 = std::vector<float>();
-        j->done = true;
-      }
-      done_cv_.notify_all();
+  void buildBatch() {
+    // the longest run of queued scans of the front's element type, up to the batch size
+    std::vector<const void*> ptr;
+    std::vector<int64_t> n;
+    const bool f32 = fifo_.front().is_f32;
+    for (const Job& j : fifo_) {
+      if (int(ptr.size()) == batch_ || j.tree || j.is_f32 != f32) break;
+      ptr.push_back(j.data());
+      n.push_back(int64_t(j.n));
     }
-    if (b) madicp_builder_destroy(b);
+    std::vector<madtree_gpu_t*> out(ptr.size(), nullptr);
+    check(madtree_gpu_build_batch(ctx_, ptr.data(), n.data(), f32 ? 1 : 0, int(ptr.size()), b_max_, b_min_, out.data()),
+          "madtree_gpu_build_batch");
+    for (size_t i = 0; i < out.size(); ++i) {
+      Job& j = fifo_[i];
+      j.tree = out[i];
+      j.keepalive.reset();  // (the clouds have been copied to the device: pageable copies are staged before the call returns)
+      j.f64 = std::vector<double>();
+      j.f32 = std::vector<float>();
+    }
   }
   madicp_ctx_t* ctx_;
   double b_max_, b_min_;
-  std::mutex mu_;
-  std::condition_variable cv_, done_cv_;
-  std::deque<std::shared_ptr<Job>> fifo_;
-  std::vector<std::thread> threads_;
-  bool stop_ = false;
+  int batch_;
+  std::deque<Job> fifo_;
 };
 
 class Pipeline {
@@ -281,29 +231,29 @@ class Pipeline {
   }
   bool gpuBuild() const { return gpu_build_; }
   int lastIcpIterations() const { return last_iters_; }  // rounds the realtime budget allowed for the last scan
-  // Hands a FUTURE scan over for a look-ahead tree build (see Lookahead).  compute() then consumes the prefetched
-  // scans in the order they were handed over and ignores its own cloud argument for them.  Returns false (and does
+  // Hands a FUTURE scan over for a look-ahead (batched) tree build (see Lookahead).  compute() then consumes the
+  // prefetched scans in the order they were handed over and ignores its own cloud argument for them.  Returns false (and does
   // nothing) when look-ahead is not possible: host-built trees, or deskewing (the scan needs the latest poses).
   // keepalive: when given, the buffer is read in place (no copy) and the handle is dropped once compute() has consumed
   // the scan; without it the cloud is copied.
   bool prefetch(const void* xyz, size_t n, bool is_f32, std::shared_ptr<void> keepalive = nullptr) {
     if (!gpu_build_ || deskew_ || !xyz || n == 0) return false;
     if (!lookahead_) {
-      int w = 8;
-      if (const char* e = std::getenv("MADICP_LOOKAHEAD")) w = std::atoi(e);
-      if (w < 1) return false;
-      lookahead_.reset(new Lookahead(icp_.context(), b_max_, b_min_, w));
+      int batch = 16;
+      if (const char* e = std::getenv("MADICP_LOOKAHEAD")) batch = std::atoi(e);
+      if (batch < 1) return false;
+      lookahead_.reset(new Lookahead(icp_.context(), b_max_, b_min_, std::min(batch, 64)));
     }
-    auto j = std::make_shared<Lookahead::Job>();
-    j->n = n;
+    Lookahead::Job j;
+    j.n = n;
+    j.is_f32 = is_f32;
     if (keepalive) {
-      j->ext = xyz;
-      j->ext_f32 = is_f32;
-      j->keepalive = std::move(keepalive);
+      j.ext = xyz;
+      j.keepalive = std::move(keepalive);
     } else if (is_f32) {
-      j->f32.assign(static_cast<const float*>(xyz), static_cast<const float*>(xyz) + 3 * n);
+      j.f32.assign(static_cast<const float*>(xyz), static_cast<const float*>(xyz) + 3 * n);
     } else {
-      j->f64.assign(static_cast<const double*>(xyz), static_cast<const double*>(xyz) + 3 * n);
+      j.f64.assign(static_cast<const double*>(xyz), static_cast<const double*>(xyz) + 3 * n);
     }
     lookahead_->push(std::move(j));
     return true;

@@ -43,8 +43,8 @@ PYBIND11_MODULE(pypeline, m) {
         return mb::Pipeline::deskewOnly(cloud_arg(cloud), pose_from_numpy(a), pose_from_numpy(b), sensor_hz, num_threads);
       }, py::arg("cloud"), py::arg("T_prev"), py::arg("T_now"), py::arg("sensor_hz"), py::arg("num_threads") = 1)
       .def("prefetch", [](mb::Pipeline& p, const py::object& cloud) {
-        // the array is read in place by a build lane: a reference keeps it alive until compute() has consumed the scan
-        // (it is dropped there, on the calling thread, with the GIL held)
+        // the array is read in place when the batch is built (inside a later compute()): a reference keeps it alive
+        // until then (it is dropped there, on the calling thread, with the GIL held)
         auto hold = [](const py::object& o) {
           py::object* ref = new py::object(o);
           return std::shared_ptr<void>(ref, [](void* q) { delete static_cast<py::object*>(q); });

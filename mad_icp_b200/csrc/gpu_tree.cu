@@ -45,6 +45,13 @@ struct BuildState {
   Nodes N{};
   int* d_count = nullptr;  // nodes per level (kMaxLevels + 2)
   Lvl* d_lvl = nullptr;    // level-loop state (gpu_tree_kernels.cuh)
+  // forest bookkeeping (a batch of scans is built as one forest): per tree and level
+  int* d_offs = nullptr;   // kMaxBatch + 1: first point of every tree
+  int* d_flvl = nullptr;   // forest level table (kMaxLevels + 2)
+  int *d_tcnt = nullptr, *d_tleaf = nullptr, *d_F = nullptr, *d_Loff = nullptr;
+  TreeOut* d_out = nullptr;
+  int *h_tcnt = nullptr, *h_tleaf = nullptr, *h_F = nullptr, *h_Loff = nullptr, *h_offs = nullptr;
+  TreeOut* h_out = nullptr;
   Work W{};                // every pointer above, by value for the kernels
   cudaGraphExec_t level_graph = nullptr;  // the fourteen kernels of one level
   // mapped pinned host memory
@@ -134,9 +141,24 @@ int ensure_state(void** slot, cudaStream_t stream, size_t n, BuildState** out) {
   if (!rc) rc = dev_alloc(bs, &bs->N.pp, nodes);
   if (!rc) rc = dev_alloc(bs, &bs->N.anc, nodes);
   if (!rc) rc = dev_alloc(bs, &bs->N.link, nodes);
+  if (!rc) rc = dev_alloc(bs, &bs->N.tree, nodes);
   if (!rc) rc = dev_alloc(bs, &bs->N.full, 16 * nodes);
   if (!rc) rc = dev_alloc(bs, &bs->d_count, size_t(kMaxLevels) + 2);
   if (!rc) rc = dev_alloc(bs, &bs->d_lvl, 1);
+  const size_t tl = size_t(kMaxBatch) * (kMaxLevels + 2);
+  if (!rc) rc = dev_alloc(bs, &bs->d_offs, size_t(kMaxBatch) + 1);
+  if (!rc) rc = dev_alloc(bs, &bs->d_flvl, size_t(kMaxLevels) + 2);
+  if (!rc) rc = dev_alloc(bs, &bs->d_tcnt, tl);
+  if (!rc) rc = dev_alloc(bs, &bs->d_tleaf, size_t(kMaxBatch));
+  if (!rc) rc = dev_alloc(bs, &bs->d_F, tl);
+  if (!rc) rc = dev_alloc(bs, &bs->d_Loff, tl);
+  if (!rc) rc = dev_alloc(bs, &bs->d_out, size_t(kMaxBatch));
+  if (!rc) rc = host_alloc(bs, &bs->h_tcnt, tl);
+  if (!rc) rc = host_alloc(bs, &bs->h_tleaf, size_t(kMaxBatch));
+  if (!rc) rc = host_alloc(bs, &bs->h_F, tl);
+  if (!rc) rc = host_alloc(bs, &bs->h_Loff, tl);
+  if (!rc) rc = host_alloc(bs, &bs->h_offs, size_t(kMaxBatch) + 1);
+  if (!rc) rc = host_alloc(bs, &bs->h_out, size_t(kMaxBatch));
   if (!rc) {
     double* raw = nullptr;
     rc = dev_alloc(bs, &raw, 3 * cap);
@@ -186,35 +208,23 @@ void root_sums_host(const T* p, int64_t n, double* S) {
   S[0] = s0; S[1] = s1; S[2] = s2; S[3] = s3; S[4] = s4; S[5] = s5; S[6] = s6; S[7] = s7; S[8] = s8;
 }
 
-__global__ void k_init_root(Nodes N, int n, int* count, Lvl* lvl, double b_max, double b_min) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    lvl->depth = 0;
-    lvl->g0 = 0;
-    lvl->cur = 0;
-    lvl->n_points = n;
-    lvl->b_max = b_max;
-    lvl->b_min = b_min;
-    N.lo[0] = 0;
-    N.hi[0] = n;
-    N.parent[0] = -1;
-    N.pp[0] = -1;
-    N.anc[0] = 0;
-    N.link[0] = -1;
-    count[0] = 1;
-  }
-}
-
 int blocks(int64_t n, int per = kBlock) { return int(std::max<int64_t>(1, (n + per - 1) / per)); }
 
-// Builds the tree of the n points in bs->P[0] on stream `st`.  root_S (nullable): the root's sums, already computed
-// by the host (h_root: pinned staging of the lane).
-int build_resident(madicp_ctx* c, BuildState* bs, cudaStream_t st, int64_t n64, double b_max, double b_min,
-                   const double* root_S, madtree_gpu** out) {
+// Builds the trees of the n_trees clouds that lie back to back in bs->P[0] (tree b = points [offs[b], offs[b+1])) on
+// stream `st`, as ONE forest: the level loop is the same for one tree or sixteen, and so is its latency (the in-order
+// sums are dependent-add chains; sixteen roots are sixteen chains side by side).  root_S (nullable, single tree only):
+// the root's sums, already computed by the host.
+int build_forest(madicp_ctx* c, BuildState* bs, cudaStream_t st, int n_trees, const int* offs, double b_max, double b_min,
+                 const double* root_S, madtree_gpu** out) {
   if (!(b_max > 0.0) || !std::isfinite(b_max) || !std::isfinite(b_min)) {
     set_error("madtree_gpu_build: b_max must be finite and > 0, b_min finite");
     return MADICP_ERR_INVALID;
   }
-  const int n = int(n64);
+  if (n_trees < 1 || n_trees > kMaxBatch) {
+    set_error("madtree_gpu_build: 1..64 trees per batch");
+    return MADICP_ERR_INVALID;
+  }
+  const int n = offs[n_trees];
   bs->seq++;
   const bool timing = getenv("MADICP_BUILD_TIMING") != nullptr;
   auto now = []() { return std::chrono::steady_clock::now(); };
@@ -224,7 +234,7 @@ int build_resident(madicp_ctx* c, BuildState* bs, cudaStream_t st, int64_t n64, 
   const auto t_start = now();
   double t_sync = 0, t_trig = 0;
   std::string per_level;
-  if (root_S) {
+  if (root_S && n_trees == 1) {
     memcpy(bs->h_root, root_S, 9 * sizeof(double));
     CK(cudaMemcpyAsync(bs->S, bs->h_root, 9 * sizeof(double), cudaMemcpyHostToDevice, st));
   }
@@ -263,18 +273,19 @@ int build_resident(madicp_ctx* c, BuildState* bs, cudaStream_t st, int64_t n64, 
       return MADICP_ERR_CUDA;
     }
   }
-  // head of the tree: level state, root node, (root sums unless the host supplied them), eigen preparation of level 0
-  k_init_root<<<1, 32, 0, st>>>(bs->N, n, bs->d_count, bs->d_lvl, b_max, b_min);
-  CK(cudaMemsetAsync(bs->owner[0], 0, size_t(n) * sizeof(int), st));
-  if (!root_S) {
-    k_sums_big<<<1, kSumsBlock, 0, st>>>(W);
-    k_sums_small<<<1, kSumsBlock, 0, st>>>(W);
+  // head of the forest: level state, roots, owners, (root sums unless the host supplied them), eigen preparation
+  memcpy(bs->h_offs, offs, size_t(n_trees + 1) * sizeof(int));
+  CK(cudaMemcpyAsync(bs->d_offs, bs->h_offs, size_t(n_trees + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+  k_init_forest<<<blocks(std::max(n, n_trees)), kBlock, 0, st>>>(W, n_trees, bs->d_offs, b_max, b_min);
+  if (!(root_S && n_trees == 1)) {
+    k_sums_big<<<n_trees, kSumsBlock, 0, st>>>(W);
+    k_sums_small<<<blocks(int64_t(n_trees) * 9, kSumsBlock), kSumsBlock, 0, st>>>(W);
     c->launches += 2;
   }
   k_eig_prep<<<1, kBlock, 0, st>>>(W);
   c->launches += 2;
   CK(cudaGetLastError());
-  int g0 = 0, nl = 1, depth = 0;
+  int g0 = 0, nl = n_trees, depth = 0;
   int total_leaves = 0;
   bs->h_lvl[0] = 0;
   const int tiles = (n + kTile - 1) / kTile;
@@ -308,32 +319,78 @@ int build_resident(madicp_ctx* c, BuildState* bs, cudaStream_t st, int64_t n64, 
     bs->h_lvl[depth] = g0;
   }
   const int n_nodes = g0, n_levels = depth;
-  madtree_gpu* t = nullptr;
-  int rc = madicp_tree_alloc(c, size_t(n_nodes), &t);
-  if (rc) return rc;
-  // recycled tree memory may still be read by work queued on the context's stream before it was freed
-  if (st != c->stream) CK(cudaStreamWaitEvent(st, c->tree_free_ev, 0));
-  t->n_nodes = n_nodes;
-  t->n_leaves = total_leaves;
-  t->n_levels = n_levels;
-  t->h_lvl.assign(bs->h_lvl, bs->h_lvl + n_levels + 1);
-  t->n_points = n;
-  t->full = bs->N.full;
-  t->build_seq = bs->seq;
-  // getLeafs ordinals: leaves in ascending order of their range start; then the 64-byte records
+  // ---- hand every tree of the forest its own records (see k_records)
+  const int stride = kMaxLevels + 2;
+  CK(cudaMemcpyAsync(bs->d_flvl, bs->h_lvl, size_t(n_levels + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(bs->d_tcnt, 0, size_t(n_trees) * stride * sizeof(int), st));
+  CK(cudaMemsetAsync(bs->d_tleaf, 0, size_t(n_trees) * sizeof(int), st));
+  k_tree_level_counts<<<blocks(n_nodes), kBlock, 0, st>>>(bs->N, n_nodes, bs->d_flvl, n_levels, stride, bs->d_tcnt, bs->d_tleaf);
+  for (int b = 0; b < n_trees; ++b)
+    CK(cudaMemcpyAsync(bs->h_tcnt + size_t(b) * stride, bs->d_tcnt + size_t(b) * stride, size_t(n_levels) * sizeof(int),
+                       cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(bs->h_tleaf, bs->d_tleaf, size_t(n_trees) * sizeof(int), cudaMemcpyDeviceToHost, st));
+  // getLeafs ordinals: leaves in ascending order of their range start
   CK(cudaMemsetAsync(bs->flag, 0, size_t(n), st));
   k_mark_leaf_starts<<<blocks(n_nodes), kBlock, 0, st>>>(bs->N, n_nodes, n, bs->flag);
   k_scan_tiles<<<tiles, kTile, 0, st>>>(bs->flag, n, bs->G, bs->tile);
   k_scan_tile_sums<<<1, 1024, 0, st>>>(bs->tile, tiles);
-  k_records<<<blocks(n_nodes), kBlock, 0, st>>>(bs->N, n_nodes, n, bs->G, bs->tile, t->recs, t->leaf_of);
-  CK(cudaMemcpyAsync(t->lvl, bs->h_lvl, size_t(n_levels + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
   c->launches += 4;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  std::vector<int> run(size_t(n_levels) + 1, 0);  // forest index where the next tree's part of each level starts
+  for (int d = 0; d <= n_levels; ++d) run[size_t(d)] = bs->h_lvl[d];
+  int rc = MADICP_OK;
+  for (int b = 0; b < n_trees && !rc; ++b) {
+    int* F = bs->h_F + size_t(b) * stride;
+    int* Lo = bs->h_Loff + size_t(b) * stride;
+    const int* cnt = bs->h_tcnt + size_t(b) * stride;
+    int nodes_b = 0, levels_b = 0;
+    for (int d = 0; d < n_levels; ++d) {
+      F[d] = run[size_t(d)];
+      Lo[d] = nodes_b;
+      run[size_t(d)] += cnt[d];
+      nodes_b += cnt[d];
+      if (cnt[d] > 0) levels_b = d + 1;
+    }
+    F[n_levels] = run[size_t(n_levels)];
+    Lo[n_levels] = nodes_b;
+    madtree_gpu* t = nullptr;
+    rc = madicp_tree_alloc(c, size_t(nodes_b), &t);
+    if (rc) break;
+    out[b] = t;
+    t->n_nodes = nodes_b;
+    t->n_leaves = bs->h_tleaf[b];
+    t->n_levels = levels_b;
+    t->h_lvl.assign(Lo, Lo + levels_b + 1);
+    t->n_points = offs[b + 1] - offs[b];
+    t->full = (n_trees == 1) ? bs->N.full : nullptr;  // the audit dump indexes the build's node arrays: single trees only
+    t->build_seq = bs->seq;
+    bs->h_out[b] = TreeOut{t->recs, t->leaf_of, offs[b], 0};
+  }
+  if (rc) return rc;
+  // recycled tree memory may still be read by work queued on the context's stream before it was freed
+  if (st != c->stream) CK(cudaStreamWaitEvent(st, c->tree_free_ev, 0));
+  CK(cudaMemcpyAsync(bs->d_F, bs->h_F, size_t(n_trees) * stride * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(bs->d_Loff, bs->h_Loff, size_t(n_trees) * stride * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(bs->d_out, bs->h_out, size_t(n_trees) * sizeof(TreeOut), cudaMemcpyHostToDevice, st));
+  k_records<<<blocks(n_nodes), kBlock, 0, st>>>(bs->N, n_nodes, n, bs->G, bs->tile, bs->d_flvl, n_levels, stride, bs->d_F, bs->d_Loff,
+                                               bs->d_out);
+  for (int b = 0; b < n_trees; ++b)
+    CK(cudaMemcpyAsync(out[b]->lvl, bs->h_Loff + size_t(b) * stride, size_t(out[b]->n_levels + 1) * sizeof(int),
+                       cudaMemcpyHostToDevice, st));
+  c->launches += 2;
   CK(cudaGetLastError());
   if (timing)
     fprintf(stderr, "madtree_gpu_build: n=%d levels=%d nodes=%d total %.0f us (waiting for the device %.0f, host libm %.0f); "
             "per level nodes:wait_us%s\n", n, n_levels, n_nodes, us(t_start, now()), t_sync, t_trig, per_level.c_str());
-  *out = t;
   return MADICP_OK;
+}
+
+// one tree: the n points in bs->P[0]
+int build_resident(madicp_ctx* c, BuildState* bs, cudaStream_t st, int64_t n, double b_max, double b_min, const double* root_S,
+                   madtree_gpu** out) {
+  const int offs[2] = {0, int(n)};
+  return build_forest(c, bs, st, 1, offs, b_max, b_min, root_S, out);
 }
 
 }  // namespace
@@ -346,75 +403,49 @@ void madicp_gpu_build_release(madicp_ctx* c) {
   c->build_state = nullptr;
 }
 
-// An independent build lane of a context's device: its own stream and working memory, so that several scans' trees
-// can be built at the same time (the build of a scan does not depend on the pose estimates unless it is deskewed) while
-// the context's stream registers the previous scan.  One host thread per builder.
-struct madicp_builder {
-  madicp_ctx* ctx = nullptr;
-  cudaStream_t stream = nullptr;
-  void* state = nullptr;
-};
-
 extern "C" {
 
-int madicp_builder_create(madicp_ctx_t* c, madicp_builder_t** out) {
-  if (!c || !out) return MADICP_ERR_INVALID;
-  MADICP_TRY
-  CK(cudaSetDevice(c->device));
-  madicp_builder* b = new madicp_builder;
-  b->ctx = c;
-  int lo_pri = 0, hi_pri = 0;
-  CK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
-  CK(cudaStreamCreateWithPriority(&b->stream, cudaStreamNonBlocking, lo_pri));  // below the registration stream
-  c->n_lanes++;
-  *out = b;
-  return MADICP_OK;
-  MADICP_CATCH("madicp_builder_create")
-}
-
-void madicp_builder_destroy(madicp_builder_t* b) {
-  if (!b) return;
-  cudaSetDevice(b->ctx->device);
-  cudaStreamSynchronize(b->stream);
-  if (BuildState* bs = static_cast<BuildState*>(b->state)) {
-    release(bs);
-    delete bs;
-  }
-  cudaStreamDestroy(b->stream);
-  b->ctx->n_lanes--;
-  delete b;
-}
-
-int madicp_builder_build(madicp_builder_t* b, const void* xyz, int64_t n, int is_f32, double b_max, double b_min,
-                         madtree_gpu_t** out) {
-  if (!b || !xyz || !out || n <= 0 || n > (int64_t(1) << 24)) {
-    set_error("madicp_builder_build: bad arguments (1 <= n <= 2^24 points)");
+// A batch of scans -> their trees, built as one forest (build_forest): what Pipeline.prefetch feeds.
+int madtree_gpu_build_batch(madicp_ctx_t* c, const void* const* clouds, const int64_t* n_points, int is_f32, int count,
+                            double b_max, double b_min, madtree_gpu_t** out) {
+  if (!c || !clouds || !n_points || !out || count < 1 || count > kMaxBatch) {
+    set_error("madtree_gpu_build_batch: bad arguments (1..64 clouds)");
     return MADICP_ERR_INVALID;
   }
   MADICP_TRY
-  madicp_ctx* c = b->ctx;
+  int offs[kMaxBatch + 1];
+  offs[0] = 0;
+  for (int b = 0; b < count; ++b) {
+    if (!clouds[b] || n_points[b] <= 0 || n_points[b] > (int64_t(1) << 24) || int64_t(offs[b]) + n_points[b] > (int64_t(1) << 26)) {
+      set_error("madtree_gpu_build_batch: empty cloud, or more than 2^26 points in the batch");
+      return MADICP_ERR_INVALID;
+    }
+    offs[b + 1] = offs[b] + int(n_points[b]);
+  }
   CK(cudaSetDevice(c->device));
   BuildState* bs = nullptr;
-  int rc = ensure_state(&b->state, b->stream, size_t(n), &bs);
+  int rc = ensure_state(c, size_t(offs[count]), &bs);
   if (rc) return rc;
-  bs->threads = 1;  // lanes are the parallelism here: every lane serves its own libm calls
-  const size_t raw_bytes = size_t(n) * 3 * (is_f32 ? sizeof(float) : sizeof(double));
-  double S[9];
+  cudaStream_t st = c->stream;
+  const size_t elt = is_f32 ? sizeof(float) : sizeof(double);
+  char* dst = is_f32 ? static_cast<char*>(bs->d_raw) : reinterpret_cast<char*>(bs->P[0]);
+  for (int b = 0; b < count; ++b)
+    CK(cudaMemcpyAsync(dst + size_t(offs[b]) * 3 * elt, clouds[b], size_t(n_points[b]) * 3 * elt, cudaMemcpyHostToDevice, st));
   if (is_f32) {
-    CK(cudaMemcpyAsync(bs->d_raw, xyz, raw_bytes, cudaMemcpyHostToDevice, b->stream));
-    k_ingest<<<blocks(n), kBlock, 0, b->stream>>>(bs->d_raw, 1, nullptr, nullptr, bs->d_poses, int(n), bs->P[0]);
+    k_ingest<<<blocks(offs[count]), kBlock, 0, st>>>(bs->d_raw, 1, nullptr, nullptr, bs->d_poses, offs[count], bs->P[0]);
     c->launches++;
-    root_sums_host(static_cast<const float*>(xyz), n, S);
-  } else {
-    CK(cudaMemcpyAsync(bs->P[0], xyz, raw_bytes, cudaMemcpyHostToDevice, b->stream));
-    root_sums_host(static_cast<const double*>(xyz), n, S);
   }
-  bs->n_resident = n;
-  rc = build_resident(c, bs, b->stream, n, b_max, b_min, S, out);
-  if (rc) return rc;
-  CK(cudaStreamSynchronize(b->stream));  // the tree is complete when the call returns: any stream may use it
-  return MADICP_OK;
-  MADICP_CATCH("madicp_builder_build")
+  bs->n_resident = 0;  // the concatenated clouds are not "the resident cloud" of madtree_gpu_build_resident
+  bs->has_root_S = false;
+  double S[9];
+  const double* root = nullptr;
+  if (count == 1) {  // one tree: the host has the points in hand while they are being copied up (see root_sums_host)
+    if (is_f32) root_sums_host(static_cast<const float*>(clouds[0]), n_points[0], S);
+    else root_sums_host(static_cast<const double*>(clouds[0]), n_points[0], S);
+    root = S;
+  }
+  return build_forest(c, bs, st, count, offs, b_max, b_min, root, out);
+  MADICP_CATCH("madtree_gpu_build_batch")
 }
 
 int madtree_gpu_build(madicp_ctx_t* c, const double* points_xyz, int64_t n, double b_max, double b_min,

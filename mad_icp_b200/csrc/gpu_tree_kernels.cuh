@@ -42,6 +42,7 @@ struct Nodes {
   int* pp;      // plane predecessor handed down from above (-1: none)          mad_tree.cpp:90-93
   int* anc;     // nearest ancestor with >= 3 points, or the root               mad_tree.cpp:68-73
   int* link;    // left child id, or -1 for a leaf
+  int* tree;    // which tree of the batch the node belongs to (a batch is built as a forest)
   double* full; // 16 per node: mean 3, eigenvectors 9 (column-major), bbox 3, num_points
 };
 
@@ -374,6 +375,7 @@ k_decide(const Work W) {
           N.parent[gl + s] = g;
           N.pp[gl + s] = pp;
           N.anc[gl + s] = anc;
+          N.tree[gl + s] = N.tree[g];
         }
         atomicAdd(&s_active, npts);
       } else {
@@ -640,7 +642,64 @@ k_split_scatter(const Work W) {
   owner_next[d] = child_of[j] + (dest < c.m ? 0 : 1);
 }
 
-// (9) records.  getLeafs ordinal of a leaf = number of leaves whose point range starts before its own.
+// (9) records.  A batch of scans is built as ONE forest (the level loop above never looks at which tree a node belongs
+// to; the nodes of a level are grouped by tree, in tree order, because children are created in parent order).  The
+// last step hands every tree its own breadth-first records: with F[b][d] the forest index of tree b's first node of
+// depth d and Loff[b][d] the tree's own level offset, node g of tree b and depth d is record Loff[b][d] + (g - F[b][d]).
+// getLeafs ordinal of a leaf = number of leaves OF ITS TREE whose point range starts before its own.
+struct TreeOut {
+  madtree_rec_t* recs;
+  int* leaf_of;
+  int first_point;  // the tree's first position in the concatenated cloud
+  int pad;
+};
+constexpr int kMaxBatch = 64;
+
+__device__ __forceinline__ int forest_depth(const int* __restrict__ lvl, int n_levels, int g) {
+  int lo = 0, hi = n_levels;  // invariant: lvl[lo] <= g < lvl[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (lvl[mid] <= g) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+// roots of the forest + owner of every point
+__global__ void __launch_bounds__(kBlock)
+k_init_forest(const Work W, int n_trees, const int* __restrict__ offs /* n_trees + 1 */, double b_max, double b_min) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  const int n = offs[n_trees];
+  if (i == 0) {
+    Lvl* l = W.lvl;
+    l->depth = 0; l->g0 = 0; l->cur = 0; l->n_points = n; l->b_max = b_max; l->b_min = b_min;
+    W.count[0] = n_trees;
+  }
+  if (i < n_trees) {
+    W.N.lo[i] = offs[i];
+    W.N.hi[i] = offs[i + 1];
+    W.N.parent[i] = -1;
+    W.N.pp[i] = -1;
+    W.N.anc[i] = i;
+    W.N.link[i] = -1;
+    W.N.tree[i] = i;
+  }
+  if (i < n) {
+    int lo = 0, hi = n_trees;  // offs[lo] <= i < offs[hi]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (offs[mid] <= i) lo = mid; else hi = mid;
+    }
+    W.owner[0][i] = lo;
+  }
+}
+__global__ void __launch_bounds__(kBlock)
+k_tree_level_counts(Nodes N, int n_nodes, const int* __restrict__ lvl, int n_levels, int stride, int* __restrict__ tcnt,
+                    int* __restrict__ tleaf) {
+  const int g = blockIdx.x * kBlock + threadIdx.x;
+  if (g >= n_nodes) return;
+  const int b = N.tree[g];
+  atomicAdd(tcnt + size_t(b) * stride + forest_depth(lvl, n_levels, g), 1);
+  if (N.link[g] < 0) atomicAdd(tleaf + b, 1);
+}
 __global__ void __launch_bounds__(kBlock)
 k_mark_leaf_starts(Nodes N, int n_nodes, int n_points, unsigned char* __restrict__ flag) {
   const int g = blockIdx.x * kBlock + threadIdx.x;
@@ -650,9 +709,16 @@ k_mark_leaf_starts(Nodes N, int n_nodes, int n_points, unsigned char* __restrict
 }
 __global__ void __launch_bounds__(kBlock)
 k_records(Nodes N, int n_nodes, int n_points, const int* __restrict__ G, const int* __restrict__ tile_off,
-          madtree_rec_t* __restrict__ recs, int* __restrict__ leaf_of) {
+          const int* __restrict__ lvl, int n_levels, int stride, const int* __restrict__ F, const int* __restrict__ Loff,
+          const TreeOut* __restrict__ out) {
   const int g = blockIdx.x * kBlock + threadIdx.x;
   if (g >= n_nodes) return;
+  const int b = N.tree[g];
+  const int d = forest_depth(lvl, n_levels, g);
+  const int* Fb = F + size_t(b) * stride;
+  const int* Lb = Loff + size_t(b) * stride;
+  const int local = Lb[d] + (g - Fb[d]);
+  const TreeOut o = out[b];
   const double* full = N.full + size_t(g) * 16;
   madtree_rec_t r;
   r.mean[0] = full[0]; r.mean[1] = full[1]; r.mean[2] = full[2];
@@ -661,15 +727,16 @@ k_records(Nodes N, int n_nodes, int n_points, const int* __restrict__ G, const i
   const int link = N.link[g];
   if (link >= 0) {
     r.dir[0] = full[9]; r.dir[1] = full[10]; r.dir[2] = full[11];  // eigenvectors.col(2): split direction
-    r.link = link;
+    r.link = Lb[d + 1] + (link - Fb[d + 1]);
   } else {
     r.dir[0] = full[3]; r.dir[1] = full[4]; r.dir[2] = full[5];    // eigenvectors.col(0): surface normal
     const int lo = N.lo[g];
-    const int ord = (lo < n_points) ? G[lo] + tile_off[lo >> 10] : 0;
+    const int base = G[o.first_point] + tile_off[o.first_point >> 10];
+    const int ord = (lo < n_points) ? (G[lo] + tile_off[lo >> 10]) - base : 0;
     r.link = -1 - ord;
-    leaf_of[ord] = g;
+    o.leaf_of[ord] = local;
   }
-  recs[g] = r;
+  o.recs[local] = r;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -171,6 +171,17 @@ class Registrar:
                   "madtree_gpu_build")
         return DeviceTree(h, self)
 
+    def build_trees(self, clouds, b_max=0.2, b_min=0.1):
+        """Several scans at once (all float32 or all float64): one forest build, a DeviceTree per scan."""
+        f32 = all(np.asarray(c).dtype == np.float32 for c in clouds)
+        arrs = [np.ascontiguousarray(c, dtype=np.float32 if f32 else np.float64) for c in clouds]
+        k = len(arrs)
+        ptrs = (C.c_void_p * k)(*[a.ctypes.data for a in arrs])
+        ns = (C.c_int64 * k)(*[a.shape[0] for a in arrs])
+        out = (C.c_void_p * k)()
+        check(capi.lib().madtree_gpu_build_batch(self._h, ptrs, ns, int(f32), k, b_max, b_min, out), "madtree_gpu_build_batch")
+        return [DeviceTree(C.c_void_p(out[i]), self) for i in range(k)]
+
     def ingest(self, xyz, deskew=False, T_prev=None, T_now=None, sensor_hz=10.0, num_threads=1, want_points=False):
         """Raw scan -> device-resident float64 cloud (optionally deskewed, Pipeline::deskew)."""
         a = np.ascontiguousarray(xyz)

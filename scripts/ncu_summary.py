@@ -28,9 +28,12 @@ for k, row in enumerate(rows[2:]):
     rd = num("dram__bytes_read.sum") * scale.get(units[hdr.index("dram__bytes_read.sum")], 1.0)
     wr = num("dram__bytes_write.sum") * scale.get(units[hdr.index("dram__bytes_write.sum")], 1.0)
     traffic = int(rd + wr)
+    l2_sectors = num("lts__t_sectors_srcunit_tex_op_read.sum")
+    su = units[hdr.index("lts__t_sectors_srcunit_tex_op_read.sum")] if "lts__t_sectors_srcunit_tex_op_read.sum" in hdr else "sector"
+    l2_bytes = int(l2_sectors * {"sector": 1.0, "Ksector": 1e3, "Msector": 1e6}.get(su, 1.0) * 32)
 open(out, "w").write("\n".join(lines) + "\n")
 if traffic is not None:
-    json.dump({"dram_bytes_per_launch": traffic,
+    json.dump({"dram_bytes_per_launch": traffic, "l2_to_l1_bytes_per_launch": l2_bytes,
                "source": f"{out}: dram__bytes_read.sum + dram__bytes_write.sum of the last captured k_gn_loop launch, ncu --set full "
                          f"(cold L2: ncu flushes caches before the replayed launch)"}, open("profiles/gn_loop_traffic.json", "w"))
 print(out, "traffic bytes", traffic)

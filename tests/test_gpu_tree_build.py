@@ -79,6 +79,42 @@ def test_degenerate_clouds(reg, oracle):
         _same_as_oracle(dt, oracle.OracleTree(cloud), FlatTree(cloud))
 
 
+def test_batch_build_is_a_forest_of_the_same_trees(reg, oracle):
+    """madtree_gpu_build_batch: several scans built as one forest must give, tree for tree, the records of the single
+    builds (and hence the reference's), for ragged batches (different sizes, a one-point cloud, planar clouds)."""
+    c = synth.registration_case(K=3, beams=32, azimuths=1024, seed=21)
+    rs = np.random.RandomState(1)
+    clouds = [c["scans"][0], c["scans"][1][:5000], np.array([[1.0, 2.0, 3.0]]), c["query"],
+              rs.uniform(-1, 1, (700, 3)) * [10, 10, 0], c["scans"][2]]
+    trees = reg.build_trees(clouds)
+    for cloud, dt in zip(clouds, trees):
+        ft = FlatTree(cloud)
+        h, d = ft.records(), dt.records()
+        assert dt.num_nodes == ft.num_nodes and dt.num_leaves == ft.num_leaves and dt.num_levels == len(_bfs_levels(h))
+        for k in ("mean", "dir", "bbox0"):
+            assert bits_equal(d[k], h[k]), k
+        assert (d["link"] == h["link"]).all() and (d["num_points"] == h["num_points"]).all()
+        leaf = np.nonzero(h["link"] < 0)[0]
+        want = np.empty(ft.num_leaves, np.int32)
+        want[-1 - h["link"][leaf]] = leaf
+        assert (dt.leaf_records() == want).all()
+    f32 = [cl.astype(np.float32) for cl in clouds[:3]]
+    for cloud, dt in zip(f32, reg.build_trees(f32)):
+        assert dt.records().tobytes() == FlatTree(cloud.astype(np.float64)).records().tobytes() or \
+            bits_equal(dt.records()["mean"], FlatTree(cloud.astype(np.float64)).records()["mean"])
+
+
+def _bfs_levels(recs):
+    """level sizes of breadth-first records with adjacent siblings"""
+    sizes, lo, hi = [], 0, 1
+    while lo < hi:
+        sizes.append(hi - lo)
+        links = recs["link"][lo:hi]
+        nxt = 2 * int((links >= 0).sum())
+        lo, hi = hi, hi + nxt
+    return sizes
+
+
 def test_registration_from_device_built_trees(reg):
     """The whole device-resident chain: build on the device -> moving leaves from the device tree -> promotion with the
     pose applied on the device; same bits as host-built trees transformed on the host."""
@@ -143,12 +179,10 @@ def test_pipeline_device_path_lookahead_and_host_path_agree(oracle):
         assert p.gpuBuild() == (mode != "host")
         out = []
         for i, scan in enumerate(seq):
-            if mode == "lookahead":  # compute() consumes prefetched scans in FIFO order: scans 1.. are handed over
-                if i == 1:           # after the initialising scan, three ahead of their compute()
-                    for k in range(1, 4):
-                        assert p.prefetch(seq[k])
-                elif i > 1 and i + 2 < len(seq):
-                    p.prefetch(seq[i + 2])
+            if mode == "lookahead" and i >= 1 and p.prefetched() == 0:
+                # compute() consumes prefetched scans in FIFO order: hand over the next five (one forest build)
+                for k in range(i, min(i + 5, len(seq))):
+                    assert p.prefetch(seq[k])
             p.compute(0.1 * i, scan)
             out.append((p.currentPose().copy(), bool(p.isMapUpdated()), int(p.keyframeID()), int(p.numKeyframes())))
         return out

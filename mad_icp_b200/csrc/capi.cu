@@ -291,8 +291,6 @@ int madicp_create(madicp_ctx_t** out, int device, int max_keyframes) {
   for (int i = 0; i < madicp_ctx::kXformRing; ++i) CK(cudaEventCreateWithFlags(&c->xform_done[i], cudaEventDisableTiming));
   CK(cudaMallocHost(&c->h_pinned, sizeof(double) * 64));
   CK(cudaMallocHost(&c->h_state, sizeof(GnState)));
-  CK(cudaMallocHost(&c->h_in, size_t(madicp_ctx::kInRing) * 128));
-  for (int i = 0; i < madicp_ctx::kInRing; ++i) CK(cudaEventCreateWithFlags(&c->in_done[i], cudaEventDisableTiming));
   CK(cudaMallocHost(&c->h_matched, kMatchedCap));
   if (const char* e = getenv("MADICP_NO_MEMO")) c->use_memo = (atoi(e) == 0);
   int threads = 1024, ctas = 1;
@@ -348,9 +346,6 @@ void madicp_destroy(madicp_ctx_t* c) {
   cudaFreeHost(c->h_lvl);
   cudaFreeHost(c->h_pinned);
   cudaFreeHost(c->h_state);
-  cudaFreeHost(c->h_in);
-  for (int i = 0; i < madicp_ctx::kInRing; ++i)
-    if (c->in_done[i]) cudaEventDestroy(c->in_done[i]);
   for (int i = 0; i < madicp_ctx::kXformRing; ++i)
     if (c->xform_done[i]) cudaEventDestroy(c->xform_done[i]);
   cudaFreeHost(c->h_matched);
@@ -649,7 +644,7 @@ void madtree_gpu_free(madtree_gpu_t* t) {
   cudaEventRecord(c->tree_free_ev, c->stream);
   {
     std::lock_guard<std::mutex> lk(c->tree_mu);
-    if (c->tree_cache.size() < 24) {
+    if (c->tree_cache.size() < 96) {
       c->tree_cache.push_back(t);
       return;
     }

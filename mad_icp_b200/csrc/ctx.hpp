@@ -103,11 +103,6 @@ struct madicp_ctx {
   madicp::CommBlock* d_comm = nullptr;
   double* h_pinned = nullptr;       // 12 + 36 + 6 + ... staging
   madicp::GnState* h_state = nullptr;  // pinned mirror (results)
-  // pinned ring of launch headers (control words + initial pose): a header may only be rewritten once the
-  // copy that reads it has executed, so back-to-back asynchronous registrations stay correct
-  static constexpr int kInRing = 16;
-  unsigned char* h_in = nullptr;
-  cudaEvent_t in_done[kInRing] = {};
   unsigned char* h_matched = nullptr;
   int gn_grid = 0;
   bool gn_auto = true;  // pick the shape per launch from the item count (pick_shape)

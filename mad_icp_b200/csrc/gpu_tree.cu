@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <functional>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -22,7 +23,8 @@
 using namespace madicp;
 using namespace madicp::gtb;
 
-// ingest.cpp (host half of the ingest, host libm service)
+// ingest.cpp (host half of the ingest, host libm service, a parallel-for on the library's host pool)
+void madicp_host_for(int n, int num_threads, const std::function<void(int)>& fn);
 int madicp_deskew_plan(const void* xyz, int is_f32, int64_t n, const double T_prev[12], const double T_now[12],
                        double sensor_hz, int num_threads, int32_t* perm, uint16_t* chunk, double* poses, int* n_poses);
 void madicp_host_trig(const double* args, double* res, int n, int num_threads);
@@ -39,7 +41,8 @@ struct BuildState {
   double* S = nullptr;
   Eig3Mid* mid = nullptr;
   long long* box = nullptr;
-  int *cnt = nullptr, *imin = nullptr, *child_of = nullptr;
+  int *cnt = nullptr, *imin = nullptr, *child_of = nullptr, *dtile = nullptr;
+  double* dres = nullptr;
   unsigned long long* dmin = nullptr;
   // whole build
   Nodes N{};
@@ -71,7 +74,7 @@ struct BuildState {
   bool has_root_S = false;
   int64_t n_resident = 0;  // points of the cloud madicp_ingest left in P[0]
   uint64_t seq = 0;        // builds so far (madtree_gpu_export is valid for the latest one only)
-  int threads = 8;
+  int threads = 16;
   std::vector<void*> dev_allocs, host_allocs;
 };
 
@@ -134,6 +137,8 @@ int ensure_state(void** slot, cudaStream_t stream, size_t n, BuildState** out) {
   if (!rc) rc = dev_alloc(bs, &bs->cnt, lvl);
   if (!rc) rc = dev_alloc(bs, &bs->imin, lvl);
   if (!rc) rc = dev_alloc(bs, &bs->child_of, lvl);
+  if (!rc) rc = dev_alloc(bs, &bs->dtile, lvl / 1024 + 4);
+  if (!rc) rc = dev_alloc(bs, &bs->dres, 2 * lvl);
   if (!rc) rc = dev_alloc(bs, &bs->dmin, lvl);
   if (!rc) rc = dev_alloc(bs, &bs->N.lo, nodes);
   if (!rc) rc = dev_alloc(bs, &bs->N.hi, nodes);
@@ -174,7 +179,7 @@ int ensure_state(void** slot, cudaStream_t stream, size_t n, BuildState** out) {
   if (!rc) rc = host_alloc(bs, &bs->h_perm, cap);
   if (!rc) rc = host_alloc(bs, &bs->h_chunk, cap);
   if (!rc) rc = host_alloc(bs, &bs->h_poses, size_t(65536) * 12);
-  if (!rc) rc = host_alloc(bs, &bs->h_root, 16);
+  if (!rc) rc = host_alloc(bs, &bs->h_root, size_t(kMaxBatch) * 9);
   if (rc) {
     release(bs);
     delete bs;
@@ -185,6 +190,7 @@ int ensure_state(void** slot, cudaStream_t stream, size_t n, BuildState** out) {
   W.owner[0] = bs->owner[0]; W.owner[1] = bs->owner[1];
   W.flag = bs->flag; W.G = bs->G; W.tile = bs->tile; W.XF = bs->XF; W.BP = bs->BP;
   W.S = bs->S; W.mid = bs->mid; W.box = bs->box; W.cnt = bs->cnt; W.imin = bs->imin; W.child_of = bs->child_of;
+  W.dtile = bs->dtile; W.dres = bs->dres;
   W.dmin = bs->dmin; W.N = bs->N; W.count = bs->d_count; W.lvl = bs->d_lvl;
   W.args = bs->h_args; W.res = bs->h_res; W.ctl = bs->h_ctl;
   *slot = bs;
@@ -212,7 +218,7 @@ int blocks(int64_t n, int per = kBlock) { return int(std::max<int64_t>(1, (n + p
 
 // Builds the trees of the n_trees clouds that lie back to back in bs->P[0] (tree b = points [offs[b], offs[b+1])) on
 // stream `st`, as ONE forest: the level loop is the same for one tree or sixteen, and so is its latency (the in-order
-// sums are dependent-add chains; sixteen roots are sixteen chains side by side).  root_S (nullable, single tree only):
+// sums are dependent-add chains; sixteen roots are sixteen chains side by side).  root_S (nullable):
 // the root's sums, already computed by the host.
 int build_forest(madicp_ctx* c, BuildState* bs, cudaStream_t st, int n_trees, const int* offs, double b_max, double b_min,
                  const double* root_S, madtree_gpu** out) {
@@ -234,22 +240,24 @@ int build_forest(madicp_ctx* c, BuildState* bs, cudaStream_t st, int n_trees, co
   const auto t_start = now();
   double t_sync = 0, t_trig = 0;
   std::string per_level;
-  if (root_S && n_trees == 1) {
-    memcpy(bs->h_root, root_S, 9 * sizeof(double));
-    CK(cudaMemcpyAsync(bs->S, bs->h_root, 9 * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (root_S) {
+    memcpy(bs->h_root, root_S, size_t(n_trees) * 9 * sizeof(double));
+    CK(cudaMemcpyAsync(bs->S, bs->h_root, size_t(n_trees) * 9 * sizeof(double), cudaMemcpyHostToDevice, st));
   }
   const Work& W = bs->W;
   const int cap_pblocks = blocks(int64_t(bs->cap));          // per-point kernels: sized by the lane's capacity and
   const int cap_tiles = int((bs->cap + kTile - 1) / kTile);  // bounded by Lvl::n_points inside -> one graph fits all scans
   constexpr int kNodeBlocks = 64, kBigBlocks = 1024, kSmallBlocks = 592;  // grid-stride over the nodes of a level
-  // The fourteen kernels between two host round trips, captured once per lane: what follows the libm values of
+  // The sixteen kernels between two host round trips, captured once per lane: what follows the libm values of
   // level d (eigenvectors ... split), the state update, and the sums + eigen preparation of level d + 1.
   if (!bs->level_graph) {
     cudaGraph_t g = nullptr;
     CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     k_eig_finish<<<kNodeBlocks, kBlock, 0, st>>>(W);
     k_bbox_flags<<<cap_pblocks, kBlock, 0, st>>>(W);
-    k_decide<<<1, 1024, 0, st>>>(W);
+    k_decide_mark<<<kNodeBlocks, 1024, 0, st>>>(W);
+    k_decide_scan<<<1, 1024, 0, st>>>(W);
+    k_decide_apply<<<kNodeBlocks, 1024, 0, st>>>(W);
     k_leaf_dist<<<cap_pblocks, kBlock, 0, st>>>(W);
     k_leaf_pick<<<cap_pblocks, kBlock, 0, st>>>(W);
     k_leaf_set<<<kNodeBlocks, kBlock, 0, st>>>(W);
@@ -277,7 +285,7 @@ int build_forest(madicp_ctx* c, BuildState* bs, cudaStream_t st, int n_trees, co
   memcpy(bs->h_offs, offs, size_t(n_trees + 1) * sizeof(int));
   CK(cudaMemcpyAsync(bs->d_offs, bs->h_offs, size_t(n_trees + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
   k_init_forest<<<blocks(std::max(n, n_trees)), kBlock, 0, st>>>(W, n_trees, bs->d_offs, b_max, b_min);
-  if (!(root_S && n_trees == 1)) {
+  if (!root_S) {
     k_sums_big<<<n_trees, kSumsBlock, 0, st>>>(W);
     k_sums_small<<<blocks(int64_t(n_trees) * 9, kSumsBlock), kSumsBlock, 0, st>>>(W);
     c->launches += 2;
@@ -312,8 +320,9 @@ int build_forest(madicp_ctx* c, BuildState* bs, cudaStream_t st, int n_trees, co
       t_trig += us(ts1, now());
       per_level += " " + std::to_string(nl) + ":" + std::to_string(int(us(ts0, ts1)));
     }
+    CK(cudaMemcpyAsync(bs->dres, bs->h_res, size_t(nl) * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaGraphLaunch(bs->level_graph, st));  // level `depth` to its end + sums / eigen preparation of the next
-    c->launches += 14;
+    c->launches += 16;
     g0 += nl;
     ++depth;
     bs->h_lvl[depth] = g0;
@@ -437,14 +446,18 @@ int madtree_gpu_build_batch(madicp_ctx_t* c, const void* const* clouds, const in
   }
   bs->n_resident = 0;  // the concatenated clouds are not "the resident cloud" of madtree_gpu_build_resident
   bs->has_root_S = false;
-  double S[9];
-  const double* root = nullptr;
-  if (count == 1) {  // one tree: the host has the points in hand while they are being copied up (see root_sums_host)
-    if (is_f32) root_sums_host(static_cast<const float*>(clouds[0]), n_points[0], S);
-    else root_sums_host(static_cast<const double*>(clouds[0]), n_points[0], S);
-    root = S;
-  }
-  return build_forest(c, bs, st, count, offs, b_max, b_min, root, out);
+  // the roots' sums on the host, one scan per host thread, while the clouds are being copied up (see root_sums_host)
+  std::vector<double> S(size_t(count) * 9);
+  madicp_host_for(count, bs->threads, [&](int b) {
+    if (is_f32) root_sums_host(static_cast<const float*>(clouds[b]), n_points[b], S.data() + size_t(b) * 9);
+    else root_sums_host(static_cast<const double*>(clouds[b]), n_points[b], S.data() + size_t(b) * 9);
+  });
+  const auto tb0 = std::chrono::steady_clock::now();
+  rc = build_forest(c, bs, st, count, offs, b_max, b_min, S.data(), out);
+  if (getenv("MADICP_BUILD_TIMING"))
+    fprintf(stderr, "madtree_gpu_build_batch: %d scans, forest build %.0f us\n", count,
+            std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tb0).count());
+  return rc;
   MADICP_CATCH("madtree_gpu_build_batch")
 }
 

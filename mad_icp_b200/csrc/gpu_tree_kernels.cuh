@@ -73,6 +73,8 @@ struct Work {
   Eig3Mid* mid;
   long long* box;
   int *cnt, *imin, *child_of;
+  int* dtile;   // per tile of 1024 nodes of the level: number of internal nodes (k_decide_*)
+  double* dres; // device copy of the libm results (cos, sin per node)
   unsigned long long* dmin;
   Nodes N;
   int* count;   // nodes per level
@@ -224,7 +226,7 @@ k_eig_finish(const Work W) {
   const Lvl L = *W.lvl;
   const int n_level = W.count[L.depth];
   const Nodes N = W.N;
-  const double* __restrict__ res = W.res;  // mapped host: cos, sin per node
+  const double* __restrict__ res = W.dres;  // cos, sin per node (copied up by the host before the launch)
   long long* __restrict__ box = W.box;
   int* __restrict__ cnt = W.cnt;
   unsigned long long* __restrict__ dmin = W.dmin;
@@ -302,109 +304,139 @@ k_bbox_flags(const Work W) {
   }
 }
 
-// (5) leaf test, children, inheritance of the plane predecessor / ancestor; ONE CTA walks the level in tiles.
-__global__ void __launch_bounds__(1024)
-k_decide(const Work W) {
-  __shared__ int s_warp[32];
-  __shared__ int s_carry, s_leaves, s_active;
-  const Lvl L = *W.lvl;
-  const Nodes N = W.N;
-  const int g0 = L.g0;
-  const double b_max = L.b_max, b_min = L.b_min;
-  const long long* __restrict__ box = W.box;
-  const int* __restrict__ cnt = W.cnt;
-  int* __restrict__ child_of = W.child_of;  // level-local: first child (level-local in the next level) or -1
-  Ctl* __restrict__ ctl = W.ctl + L.depth;  // mapped host
-  int* n_next = W.count + L.depth + 1;
-  const int n = W.count[L.depth];
-  const int g1 = g0 + n;  // first node of the next level
+// (5) leaf test, children, inheritance of the plane predecessor / ancestor.  Children are numbered in parent order, i.e.
+// by an exclusive prefix sum of "is internal" over the level: k_decide_mark (per tile of 1024 nodes: flags + tile count),
+// k_decide_scan (one CTA: prefix over the tile counts, totals for the host), k_decide_apply (per tile: the rest).
+__device__ __forceinline__ int block_excl_scan_1024(int v, int* s_warp, int& total) {  // all 1024 threads call it
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_carry = s_leaves = s_active = 0;
-  __syncthreads();
-  for (int base = 0; base < n; base += 1024) {
-    const int j = base + threadIdx.x;
-    int internal = 0, npts = 0;
-    double bbox[3] = {0, 0, 0};
-    int g = g0 + j;
-    if (j < n) {
-      double* full = N.full + size_t(g) * 16;
+  int incl = v;
 #pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        const double lo = -__longlong_as_double(box[size_t(j) * 6 + a]);
-        const double hi = __longlong_as_double(box[size_t(j) * 6 + 3 + a]);
-        bbox[a] = sub_(hi, lo);
-        full[12 + a] = bbox[a];
-      }
-      npts = N.hi[g] - N.lo[g];
-      internal = (bbox[2] < b_max) ? 0 : 1;
-    }
-    // exclusive scan of `internal` over the tile
-    int incl = internal;
+  for (int off = 1; off < 32; off <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += u;
+  }
+  __syncthreads();  // s_warp may still be read from the previous call
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = s_warp[lane];
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, off);
-      if (lane >= off) incl += v;
+      const int u = __shfl_up_sync(0xffffffffu, w, off);
+      if (lane >= off) w += u;
     }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      int w = s_warp[lane];
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, w, off);
-        if (lane >= off) w += v;
-      }
-      s_warp[lane] = w;
-    }
-    __syncthreads();
-    const int rank = s_carry + (warp ? s_warp[warp - 1] : 0) + (incl - internal);
+    s_warp[lane] = w;
+  }
+  __syncthreads();
+  total = s_warp[31];
+  return (warp ? s_warp[warp - 1] : 0) + incl - v;
+}
+
+__global__ void __launch_bounds__(1024)
+k_decide_mark(const Work W) {
+  __shared__ int s_warp[32];
+  const Lvl L = *W.lvl;
+  const Nodes N = W.N;
+  const int n = W.count[L.depth];
+  for (int base = blockIdx.x * 1024; base < n; base += gridDim.x * 1024) {
+    const int j = base + threadIdx.x;
+    int internal = 0;
     if (j < n) {
-      if (internal) {
-        const int cl = 2 * rank;  // level-local ids of the children in the next level
-        const int gl = g1 + cl;
-        const int lo = N.lo[g], hi = N.hi[g], m = cnt[j];
-        N.link[g] = gl;
-        child_of[j] = cl;
-        int pp = N.pp[g];
-        if (pp < 0 && bbox[0] < b_min) pp = g;  // this node becomes the plane predecessor of its subtree
-        const int anc = (npts >= 3 || N.parent[g] < 0) ? g : N.anc[g];
+      double* full = N.full + size_t(L.g0 + j) * 16;
+      double bbox2 = 0.0;
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          N.lo[gl + s] = s ? lo + m : lo;
-          N.hi[gl + s] = s ? hi : lo + m;
-          N.parent[gl + s] = g;
-          N.pp[gl + s] = pp;
-          N.anc[gl + s] = anc;
-          N.tree[gl + s] = N.tree[g];
-        }
-        atomicAdd(&s_active, npts);
-      } else {
-        N.link[g] = -1;
-        child_of[j] = -1;
-        // leaf normal (mad_tree.cpp:65-74): the plane predecessor's, else (fewer than 3 points) the nearest
-        // ancestor's with >= 3 points; both are internal nodes, whose eigenvectors are final
-        double* full = N.full + size_t(g) * 16;
-        const int pp = N.pp[g];
-        int src = -1;
-        if (pp >= 0) src = pp;
-        else if (npts < 3 && N.parent[g] >= 0) src = N.anc[g];
-        if (src >= 0) {
-          const double* o = N.full + size_t(src) * 16;
-          full[3] = o[3]; full[4] = o[4]; full[5] = o[5];
-        }
-        atomicAdd(&s_leaves, 1);
+      for (int a = 0; a < 3; ++a) {
+        const double lo = -__longlong_as_double(W.box[size_t(j) * 6 + a]);
+        const double hi = __longlong_as_double(W.box[size_t(j) * 6 + 3 + a]);
+        const double bb = sub_(hi, lo);
+        full[12 + a] = bb;
+        if (a == 2) bbox2 = bb;
       }
+      internal = (bbox2 < L.b_max) ? 0 : 1;
+      W.child_of[j] = internal;
     }
+    int total;
+    (void) block_excl_scan_1024(internal, s_warp, total);
+    if (threadIdx.x == 0) W.dtile[base >> 10] = total;
+  }
+}
+__global__ void __launch_bounds__(1024)
+k_decide_scan(const Work W) {  // one CTA
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  const Lvl L = *W.lvl;
+  const int n = W.count[L.depth];
+  const int n_tiles = (n + 1023) >> 10;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_tiles; base += 1024) {
+    const int t = base + threadIdx.x;
+    const int v = (t < n_tiles) ? W.dtile[t] : 0;
+    int total;
+    const int excl = block_excl_scan_1024(v, s_warp, total);
+    if (t < n_tiles) W.dtile[t] = s_carry + excl;
     __syncthreads();
-    if (threadIdx.x == 1023) s_carry = rank + internal;
+    if (threadIdx.x == 0) s_carry += total;
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    *n_next = 2 * s_carry;
+    Ctl* ctl = W.ctl + L.depth;  // mapped host memory
+    W.count[L.depth + 1] = 2 * s_carry;
     ctl->n_next = 2 * s_carry;
-    ctl->n_leaves = s_leaves;
-    ctl->n_active = s_active;
+    ctl->n_leaves = n - s_carry;
+    ctl->n_active = 0;
     __threadfence_system();
+  }
+}
+__global__ void __launch_bounds__(1024)
+k_decide_apply(const Work W) {
+  __shared__ int s_warp[32];
+  const Lvl L = *W.lvl;
+  const Nodes N = W.N;
+  const int g0 = L.g0;
+  const int n = W.count[L.depth];
+  const int g1 = g0 + n;  // first node of the next level
+  for (int base = blockIdx.x * 1024; base < n; base += gridDim.x * 1024) {
+    const int j = base + threadIdx.x;
+    const int internal = (j < n) ? W.child_of[j] : 0;
+    int total;
+    const int rank = W.dtile[base >> 10] + block_excl_scan_1024(internal, s_warp, total);
+    if (j >= n) continue;
+    const int g = g0 + j;
+    double* full = N.full + size_t(g) * 16;
+    const int npts = N.hi[g] - N.lo[g];
+    if (internal) {
+      const int cl = 2 * rank;  // level-local ids of the children in the next level
+      const int gl = g1 + cl;
+      const int lo = N.lo[g], hi = N.hi[g], m = W.cnt[j];
+      N.link[g] = gl;
+      W.child_of[j] = cl;
+      int pp = N.pp[g];
+      if (pp < 0 && full[12] < L.b_min) pp = g;  // this node becomes the plane predecessor of its subtree
+      const int anc = (npts >= 3 || N.parent[g] < 0) ? g : N.anc[g];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        N.lo[gl + s] = s ? lo + m : lo;
+        N.hi[gl + s] = s ? hi : lo + m;
+        N.parent[gl + s] = g;
+        N.pp[gl + s] = pp;
+        N.anc[gl + s] = anc;
+        N.tree[gl + s] = N.tree[g];
+      }
+    } else {
+      N.link[g] = -1;
+      W.child_of[j] = -1;
+      // leaf normal (mad_tree.cpp:65-74): the plane predecessor's, else (fewer than 3 points) the nearest
+      // ancestor's with >= 3 points; both are internal nodes, whose eigenvectors are final
+      const int pp = N.pp[g];
+      int src = -1;
+      if (pp >= 0) src = pp;
+      else if (npts < 3 && N.parent[g] >= 0) src = N.anc[g];
+      if (src >= 0) {
+        const double* o = N.full + size_t(src) * 16;
+        full[3] = o[3]; full[4] = o[4]; full[5] = o[5];
+      }
+    }
   }
 }
 

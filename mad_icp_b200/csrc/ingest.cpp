@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <functional>
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
@@ -302,6 +303,12 @@ void madicp_host_trig(const double* args, double* res, int n, int num_threads) {
       res[2 * j] = std::cos(theta);
       res[2 * j + 1] = std::sin(theta);
     }
+  });
+}
+
+void madicp_host_for(int n, int num_threads, const std::function<void(int)>& fn) {
+  for_chunks(std::max(1, std::min(num_threads, 64)), size_t(n), 1, [&](size_t c0, size_t c1) {
+    for (size_t i = c0; i < c1; ++i) fn(int(i));
   });
 }
 

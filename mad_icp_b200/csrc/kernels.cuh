@@ -109,8 +109,8 @@ struct GnState {
                   // clear-before-the-last-round, pipeline.cpp:172-176; 0: a budget-limited loop that never cleared)
   int n_matched;  // matched moving leaves in the last round
   int error;      // set by the kernel when a peer never answered (multi-GPU); cleared by the host before a launch
-  double X_in[12];  // initial pose: [ticket .. X_in] is ONE host-to-device copy per registration
-  double X_out[12]; // final pose:   [ticket .. b] is ONE device-to-host copy per registration
+  double X_in[12];  // (unused since the initial pose travels in the kernel arguments; keeps the result block's layout)
+  double X_out[12]; // final pose:   [ticket .. weight] is ONE device-to-host copy per registration
   double H[36];     // last round; H[r*6+c] = sum (scale*J_r)*J_c, both triangles accumulated independently
   double b[6];
   double weight;    // det(H^-1) of the last round's H (Frame::weight_, odometry/pipeline.cpp:223)

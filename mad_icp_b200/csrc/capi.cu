@@ -315,10 +315,8 @@ void madicp_destroy(madicp_ctx_t* c) {
   for (int r = 0; r < c->world; ++r)
     if (c->world > 1 && r != c->rank && c->peer_comm[r]) cudaIpcCloseMemHandle(c->peer_comm[r]);
   madicp_gpu_build_release(c);
-  for (madtree_gpu* t : c->tree_cache) {
-    cudaFree(t->block);
-    delete t;
-  }
+  for (madtree_gpu* t : c->tree_cache) delete t;  // (trees still held by the caller are the caller's to free first)
+  for (void* slab : c->tree_slabs) cudaFree(slab);
   cudaFree(c->d_pool_recs);
   cudaFree(c->d_pool_child0);
   cudaFree(c->d_pool_rec_of);
@@ -567,38 +565,44 @@ int64_t madicp_kernel_launches(const madicp_ctx_t* c) { return c ? c->launches.l
 // ------------------------------------------------------------------------------ device-resident trees
 }  // extern "C"
 
-// One allocation per tree, carved: records | level table | getLeafs table.  Freed trees keep it (a streamed
-// sequence allocates one tree per scan and frees one per scan).
+// Tree memory comes in slabs of 16 trees (records | level table | getLeafs table each): cudaMalloc costs milliseconds
+// on a busy context, and a streamed sequence holds a few dozen trees at a time (frame window, keyframes, the look-ahead
+// batch).  Freed trees go back to a per-context cache; slabs are released with the context.
 int madicp_tree_alloc(madicp_ctx* c, size_t cap_nodes, madtree_gpu** out) {
   madtree_gpu* t = nullptr;
-  {
-    std::lock_guard<std::mutex> lk(c->tree_mu);
-    for (size_t i = 0; i < c->tree_cache.size(); ++i)
-      if (c->tree_cache[i]->cap_nodes >= cap_nodes) {
-        t = c->tree_cache[i];
-        c->tree_cache.erase(c->tree_cache.begin() + long(i));
-        break;
-      }
-  }
+  std::lock_guard<std::mutex> lk(c->tree_mu);
+  for (size_t i = 0; i < c->tree_cache.size(); ++i)
+    if (c->tree_cache[i]->cap_nodes >= cap_nodes) {
+      t = c->tree_cache[i];
+      c->tree_cache.erase(c->tree_cache.begin() + long(i));
+      break;
+    }
   if (!t) {
-    t = new madtree_gpu;
-    t->ctx = c;
     size_t cap = size_t(1) << 16;
     while (cap < cap_nodes) cap <<= 1;
-    const size_t bytes = cap * sizeof(madtree_rec_t) + size_t(kMaxLevels + 1) * sizeof(int) + cap * sizeof(int);
-    cudaError_t e = cudaMalloc(&t->block, bytes);
+    const size_t one = ((cap * sizeof(madtree_rec_t) + size_t(kMaxLevels + 1) * sizeof(int) + cap * sizeof(int)) + 255) & ~size_t(255);
+    const int per_slab = cap <= (size_t(1) << 17) ? 16 : 1;
+    void* slab = nullptr;
+    cudaError_t e = cudaMalloc(&slab, one * size_t(per_slab));
     if (e != cudaSuccess) {
-      delete t;
       set_error(std::string("device tree allocation: ") + cudaGetErrorString(e));
       return MADICP_ERR_NOMEM;
     }
-    t->cap_nodes = cap;
-    t->recs = static_cast<madtree_rec_t*>(t->block);
-    t->lvl = reinterpret_cast<int*>(t->recs + cap);
-    t->leaf_of = t->lvl + (kMaxLevels + 1);
+    c->tree_slabs.push_back(slab);
+    for (int k = 0; k < per_slab; ++k) {
+      madtree_gpu* n = new madtree_gpu;
+      n->ctx = c;
+      n->block = static_cast<char*>(slab) + size_t(k) * one;
+      n->cap_nodes = cap;
+      n->recs = static_cast<madtree_rec_t*>(n->block);
+      n->lvl = reinterpret_cast<int*>(n->recs + cap);
+      n->leaf_of = n->lvl + (kMaxLevels + 1);
+      if (k == 0) t = n; else c->tree_cache.push_back(n);
+    }
   }
   t->n_nodes = t->n_leaves = t->n_levels = 0;
   t->h_lvl.clear();
+  t->full = nullptr;
   *out = t;
   return MADICP_OK;
 }
@@ -642,17 +646,8 @@ void madtree_gpu_free(madtree_gpu_t* t) {
   // free; a builder that picks the memory up writes it from ANOTHER stream, so it first waits for that work)
   cudaSetDevice(c->device);
   cudaEventRecord(c->tree_free_ev, c->stream);
-  {
-    std::lock_guard<std::mutex> lk(c->tree_mu);
-    if (c->tree_cache.size() < 96) {
-      c->tree_cache.push_back(t);
-      return;
-    }
-  }
-  cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
-  cudaFree(t->block);
-  delete t;
+  std::lock_guard<std::mutex> lk(c->tree_mu);
+  c->tree_cache.push_back(t);  // (its memory belongs to a slab: released with the context)
 }
 int madtree_gpu_num_nodes(const madtree_gpu_t* t) { return t ? t->n_nodes : MADICP_ERR_INVALID; }
 int madtree_gpu_num_leaves(const madtree_gpu_t* t) { return t ? t->n_leaves : MADICP_ERR_INVALID; }

@@ -73,6 +73,7 @@ struct madicp_ctx {
   cudaEvent_t xform_done[kXformRing] = {};
   uint32_t xform_seq = 0;
   std::vector<madtree_gpu*> tree_cache;  // freed device trees keep their memory for the next scan
+  std::vector<void*> tree_slabs;         // the allocations the trees are carved from
   cudaEvent_t tree_free_ev = nullptr;    // recorded on the context's stream at every madtree_gpu_free
   std::mutex tree_mu;                    // ... builders on other host threads allocate from it too
   void* build_state = nullptr;           // gpu_tree.cu: working memory of the device build (lazily created)

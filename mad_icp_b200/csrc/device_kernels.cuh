@@ -522,9 +522,15 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
         double mx, my, mz;
         iso_apply(s_X, m.px, m.py, m.pz, mx, my, mz);
         int leaf = -1;
+        Rec f;
+        double ww = 0.0;
         if (it > 0 && A.use_memo) {
           const float have = memo_margin[t];
           const int last = memo_leaf[t];
+          // the remembered leaf's record is requested BEFORE the margin is checked: in the rounds where nearly every
+          // pair keeps its leaf this takes one dependent memory round trip out of every item
+          f = load_rec(A.model.recs + last);
+          ww = __ldg(A.model.ww + last);
           double bx, by, bz;
           iso_apply(s_Xp, m.px, m.py, m.pz, bx, by, bz);
           const double dx = mx - bx, dy = my - by, dz = mz - bz;
@@ -547,9 +553,9 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
             memo_margin[t] = margin;
           }
           ++n_walked;
+          ww = __ldg(A.model.ww + leaf);  // (1 - bbox0/min_ball)^2 of the leaf, mad_icp.cpp:97-98
+          f = load_rec(A.model.recs + leaf);
         }
-        const double ww = __ldg(A.model.ww + leaf);  // (1 - bbox0/min_ball)^2 of the leaf, mad_icp.cpp:97-98
-        const Rec f = load_rec(A.model.recs + leaf);
         if (linearize_one(s_X, A.P.rho_ker_sqrt, m, mx, my, mz, f, ww, v) && it >= A.clear_from) {
           if (multi) {
             for (int r = 0; r < A.peers.world; ++r) A.peer_matched[r][q] = 1;

@@ -428,10 +428,22 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
   unsigned p_lo[kPieces], p_n[kPieces];
   unsigned n_b = 0;  // moving leaves of this CTA
 #pragma unroll
+  // CTA 0 also folds the tiles of the round and solves: it gets 5/8 of a share, so that it is done with its own items
+  // early and has the other CTAs' tiles in hand when the last one arrives (weights in eighths; grids below 8 CTAs: equal).
+  const unsigned G = gridDim.x;
+  const unsigned light = (G >= 8u) ? 3u : 0u;
+  const uint64_t W8 = 8ull * G - light;
   for (unsigned p = 0; p < kPieces; ++p) {
-    const unsigned r = p * gridDim.x + ((p & 1u) ? (gridDim.x - 1u - blockIdx.x) : blockIdx.x);
-    p_lo[p] = unsigned((uint64_t(L) * r) / (uint64_t(kPieces) * gridDim.x));
-    p_n[p] = unsigned((uint64_t(L) * (r + 1)) / (uint64_t(kPieces) * gridDim.x)) - p_lo[p];
+    const unsigned s = (p & 1u) ? (G - 1u - blockIdx.x) : blockIdx.x;  // position of this CTA inside piece p
+    auto cum8 = [&](unsigned pos) -> uint64_t {                         // weight of the positions before `pos`
+      if (p & 1u) return (pos >= G) ? W8 : 8ull * pos;                  // odd pieces: CTA 0 sits last
+      return pos ? 8ull * pos - light : 0ull;                           // even pieces: CTA 0 sits first
+    };
+    const uint64_t p0 = (uint64_t(L) * p) / kPieces, p1 = (uint64_t(L) * (p + 1)) / kPieces;
+    const unsigned lo = unsigned(p0 + ((p1 - p0) * cum8(s)) / W8);
+    const unsigned hi = unsigned(p0 + ((p1 - p0) * cum8(s + 1u)) / W8);
+    p_lo[p] = lo;
+    p_n[p] = hi - lo;
     n_b += p_n[p];
   }
   const unsigned t_total = unsigned(A.model.K) * n_b;  // CTA-local items

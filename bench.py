@@ -297,7 +297,7 @@ def stream_block(a, scans, rank, world, dev):
     pipe.compute(0.0, scans[0])  # initialise: keyframe 0 (also first-touch allocations)
     traj, kf = [], []
     torch.cuda.synchronize(dev)
-    depth = int(os.environ.get("MADICP_BENCH_LOOKAHEAD", "16"))  # scans handed over ahead of their turn: their trees are built in batches (0: none)
+    depth = int(os.environ.get("MADICP_BENCH_LOOKAHEAD", "32"))  # scans handed over ahead of their turn: their trees are built in batches (0: none)
     t0 = time.perf_counter()
     for i in range(1, n):
         if depth > 0 and pipe.prefetched() == 0:  # hand over the next `depth` scans: one forest build

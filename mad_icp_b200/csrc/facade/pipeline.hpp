@@ -239,7 +239,7 @@ class Pipeline {
   bool prefetch(const void* xyz, size_t n, bool is_f32, std::shared_ptr<void> keepalive = nullptr) {
     if (!gpu_build_ || deskew_ || !xyz || n == 0) return false;
     if (!lookahead_) {
-      int batch = 16;
+      int batch = 32;
       if (const char* e = std::getenv("MADICP_LOOKAHEAD")) batch = std::atoi(e);
       if (batch < 1) return false;
       lookahead_.reset(new Lookahead(icp_.context(), b_max_, b_min_, std::min(batch, 64)));

@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ctx.hpp"
@@ -119,7 +120,11 @@ int ensure_state(void** slot, cudaStream_t stream, size_t n, BuildState** out) {
   size_t cap = size_t(1) << 17;
   while (cap < n) cap <<= 1;
   bs->cap = cap;
-  if (const char* e = getenv("MADICP_HOST_THREADS")) bs->threads = std::max(1, atoi(e));
+  {  // host threads for the libm calls and the roots' sums: half the cores, 4..32 (MADICP_HOST_THREADS overrides)
+    const int hw = int(std::thread::hardware_concurrency());
+    bs->threads = std::max(4, std::min(32, hw / 2));
+    if (const char* e = getenv("MADICP_HOST_THREADS")) bs->threads = std::max(1, atoi(e));
+  }
   const size_t nodes = 2 * cap + 2, lvl = cap + 2;
   int rc = 0;
   for (int k = 0; k < 2 && !rc; ++k) {

@@ -299,11 +299,12 @@ def stream_block(a, scans, rank, world, dev):
     torch.cuda.synchronize(dev)
     depth = int(os.environ.get("MADICP_BENCH_LOOKAHEAD", "32"))  # scans handed over ahead of their turn: their trees are built in batches (0: none)
     t0 = time.perf_counter()
+    for k in range(1, min(1 + depth, n)):  # the scans in flight ahead of the one being registered
+        pipe.prefetch(scans[k])
     for i in range(1, n):
-        if depth > 0 and pipe.prefetched() == 0:  # hand over the next `depth` scans: one forest build
-            for k in range(i, min(i + depth, n)):
-                pipe.prefetch(scans[k])
         pipe.compute(0.1 * i, scans[i])
+        if depth > 0 and i + depth < n:  # a scan arrives: it goes up now, its tree is built with the next batch
+            pipe.prefetch(scans[i + depth])
         traj.append(pipe.currentPose()[:3, 3].copy())
         kf.append((bool(pipe.isMapUpdated()), int(pipe.keyframeID())))
     t_gpu = time.perf_counter() - t0

@@ -145,6 +145,14 @@ int madtree_gpu_build_resident(madicp_ctx_t* ctx, double b_max, double b_min, ma
  * batch runs side by side, so sixteen trees cost little more than one.  out[count]. */
 int madtree_gpu_build_batch(madicp_ctx_t* ctx, const void* const* clouds, const int64_t* n_points, int is_f32, int count,
                             double b_max, double b_min, madtree_gpu_t** out);
+/* Early upload for the NEXT madtree_gpu_build_batch: starts copying `cloud` (host memory, n_points x 3 float32 or
+ * float64; it must stay valid and unchanged until that batch call returns) to the device now, on a copy stream of its
+ * own, so that the copy runs under the registrations of earlier scans.  Staged clouds lie back to back in the build
+ * lane's working buffer: the batch call uses the longest prefix of its clouds[] that was staged in this order (same
+ * pointers and sizes) and copies the rest itself; any other build / ingest call on the context discards what was
+ * staged.  reserve_points: total points the batch will hold (sizes the lane on first use; 0 = this cloud only).
+ * Returns MADICP_OK whether or not the cloud could be staged. */
+int madicp_stage_cloud(madicp_ctx_t* ctx, const void* cloud, int64_t n_points, int is_f32, int64_t reserve_points);
 /* Upload of a host-built tree (records + tables), asynchronous. */
 int madtree_gpu_upload(madicp_ctx_t* ctx, const madtree_t* tree, madtree_gpu_t** out);
 void madtree_gpu_free(madtree_gpu_t* t);

@@ -108,7 +108,10 @@ class Lookahead {
     for (auto& j : fifo_)
       if (j.tree) madtree_gpu_free(j.tree);
   }
-  void push(Job&& j) { fifo_.push_back(std::move(j)); }
+  void push(Job&& j) {
+    fifo_.push_back(std::move(j));
+    stageQueued();
+  }
   bool empty() const { return fifo_.empty(); }
   size_t size() const { return fifo_.size(); }
   // tree of the oldest prefetched scan
@@ -117,6 +120,7 @@ class Lookahead {
     madtree_gpu_t* t = fifo_.front().tree;
     fifo_.front().tree = nullptr;
     fifo_.pop_front();
+    --built_;
     return t;
   }
 
@@ -134,6 +138,8 @@ class Lookahead {
     std::vector<madtree_gpu_t*> out(ptr.size(), nullptr);
     check(madtree_gpu_build_batch(ctx_, ptr.data(), n.data(), f32 ? 1 : 0, int(ptr.size()), b_max_, b_min_, out.data()),
           "madtree_gpu_build_batch");
+    built_ = out.size();
+    staged_ = 0;  // (the batch call consumed or discarded every early upload)
     for (size_t i = 0; i < out.size(); ++i) {
       Job& j = fifo_[i];
       j.tree = out[i];
@@ -141,10 +147,22 @@ class Lookahead {
       j.f64 = std::vector<double>();
       j.f32 = std::vector<float>();
     }
+    stageQueued();
+  }
+  // Early upload (madicp_stage_cloud) of the queued scans whose trees are not built yet, oldest first, up to one
+  // batch: the copies run while the device registers the scans before them.
+  void stageQueued() {
+    while (staged_ < size_t(batch_) && built_ + staged_ < fifo_.size()) {
+      const Job& j = fifo_[built_ + staged_];
+      if (j.is_f32 != fifo_[built_].is_f32) break;
+      check(madicp_stage_cloud(ctx_, j.data(), int64_t(j.n), j.is_f32 ? 1 : 0, int64_t(batch_) * int64_t(j.n)), "madicp_stage_cloud");
+      ++staged_;
+    }
   }
   madicp_ctx_t* ctx_;
   double b_max_, b_min_;
   int batch_;
+  size_t built_ = 0, staged_ = 0;  // the first built_ queued scans have their trees; the next staged_ are on their way up
   std::deque<Job> fifo_;
 };
 

@@ -76,6 +76,13 @@ struct BuildState {
   int64_t n_resident = 0;  // points of the cloud madicp_ingest left in P[0]
   uint64_t seq = 0;        // builds so far (madtree_gpu_export is valid for the latest one only)
   int threads = 16;
+  // early uploads for the next batch (madicp_stage_cloud): clouds already on their way into P[0] / d_raw, back to back
+  struct Staged { const void* ptr; int64_t n; };
+  std::vector<Staged> staged;
+  int64_t staged_points = 0;
+  bool staged_f32 = false, stage_closed = false;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_ev = nullptr, idle_ev = nullptr;  // copies done / the working buffers are free again
   std::vector<void*> dev_allocs, host_allocs;
 };
 
@@ -95,6 +102,14 @@ int host_alloc(BuildState* bs, T** p, size_t count) {
 void release(BuildState* bs) {
   if (bs->level_graph) cudaGraphExecDestroy(bs->level_graph);
   bs->level_graph = nullptr;
+  if (bs->copy_stream) {
+    cudaStreamSynchronize(bs->copy_stream);
+    cudaStreamDestroy(bs->copy_stream);
+  }
+  if (bs->copy_ev) cudaEventDestroy(bs->copy_ev);
+  if (bs->idle_ev) cudaEventDestroy(bs->idle_ev);
+  bs->copy_stream = nullptr;
+  bs->copy_ev = bs->idle_ev = nullptr;
   for (void* p : bs->dev_allocs) cudaFree(p);
   for (void* p : bs->host_allocs) cudaFreeHost(p);
   bs->dev_allocs.clear();
@@ -185,6 +200,9 @@ int ensure_state(void** slot, cudaStream_t stream, size_t n, BuildState** out) {
   if (!rc) rc = host_alloc(bs, &bs->h_chunk, cap);
   if (!rc) rc = host_alloc(bs, &bs->h_poses, size_t(65536) * 12);
   if (!rc) rc = host_alloc(bs, &bs->h_root, size_t(kMaxBatch) * 9);
+  if (!rc && cudaStreamCreateWithFlags(&bs->copy_stream, cudaStreamNonBlocking) != cudaSuccess) rc = MADICP_ERR_CUDA;
+  if (!rc && cudaEventCreateWithFlags(&bs->copy_ev, cudaEventDisableTiming) != cudaSuccess) rc = MADICP_ERR_CUDA;
+  if (!rc && cudaEventCreateWithFlags(&bs->idle_ev, cudaEventDisableTiming) != cudaSuccess) rc = MADICP_ERR_CUDA;
   if (rc) {
     release(bs);
     delete bs;
@@ -203,6 +221,25 @@ int ensure_state(void** slot, cudaStream_t stream, size_t n, BuildState** out) {
   return MADICP_OK;
 }
 int ensure_state(madicp_ctx* c, size_t n, BuildState** out) { return ensure_state(&c->build_state, c->stream, n, out); }
+
+// Whatever was staged for a batch (madicp_stage_cloud) is given up: `st` waits for the copies in flight, which write
+// into the buffers the caller is about to use.
+int drop_staged(BuildState* bs, cudaStream_t st) {
+  if (!bs || (bs->staged.empty() && !bs->stage_closed)) return MADICP_OK;
+  if (!bs->staged.empty()) {
+    CK(cudaEventRecord(bs->copy_ev, bs->copy_stream));
+    CK(cudaStreamWaitEvent(st, bs->copy_ev, 0));
+  }
+  bs->staged.clear();
+  bs->staged_points = 0;
+  bs->stage_closed = false;
+  return MADICP_OK;
+}
+// the working buffers are free for early uploads once everything queued on `st` so far has run
+int mark_idle(BuildState* bs, cudaStream_t st) {
+  CK(cudaEventRecord(bs->idle_ev, st));
+  return MADICP_OK;
+}
 
 // Sigma x, Sigma x x^T of the whole cloud in array order (tools/utils.h:55-73) on the calling host thread: the root's
 // nine chains are the longest dependent-add chains of the build (n adds each; a CPU core retires one per ~1 ns, the
@@ -394,6 +431,7 @@ int build_forest(madicp_ctx* c, BuildState* bs, cudaStream_t st, int n_trees, co
                        cudaMemcpyHostToDevice, st));
   c->launches += 2;
   CK(cudaGetLastError());
+  if (int e = mark_idle(bs, st)) return e;
   if (timing)
     fprintf(stderr, "madtree_gpu_build: n=%d levels=%d nodes=%d total %.0f us (waiting for the device %.0f, host libm %.0f); "
             "per level nodes:wait_us%s\n", n, n_levels, n_nodes, us(t_start, now()), t_sync, t_trig, per_level.c_str());
@@ -437,14 +475,26 @@ int madtree_gpu_build_batch(madicp_ctx_t* c, const void* const* clouds, const in
     offs[b + 1] = offs[b] + int(n_points[b]);
   }
   CK(cudaSetDevice(c->device));
-  BuildState* bs = nullptr;
+  BuildState* bs = static_cast<BuildState*>(c->build_state);
+  cudaStream_t st = c->stream;
+  if (bs && bs->cap < size_t(offs[count])) {  // the lane is about to be re-allocated: early uploads are lost
+    int e = drop_staged(bs, st);
+    if (e) return e;
+  }
   int rc = ensure_state(c, size_t(offs[count]), &bs);
   if (rc) return rc;
-  cudaStream_t st = c->stream;
   const auto ta0 = std::chrono::steady_clock::now();
   const size_t elt = is_f32 ? sizeof(float) : sizeof(double);
   char* dst = is_f32 ? static_cast<char*>(bs->d_raw) : reinterpret_cast<char*>(bs->P[0]);
-  for (int b = 0; b < count; ++b)
+  // clouds uploaded ahead of time (madicp_stage_cloud): the longest prefix of this batch that was staged in this order
+  int n_staged = 0;
+  if (!bs->staged.empty() && bs->staged_f32 == (is_f32 != 0))
+    while (n_staged < count && n_staged < int(bs->staged.size()) && bs->staged[size_t(n_staged)].ptr == clouds[n_staged] &&
+           bs->staged[size_t(n_staged)].n == n_points[n_staged])
+      ++n_staged;
+  rc = drop_staged(bs, st);  // (st waits for every early copy, used or not: they all write into dst)
+  if (rc) return rc;
+  for (int b = n_staged; b < count; ++b)
     CK(cudaMemcpyAsync(dst + size_t(offs[b]) * 3 * elt, clouds[b], size_t(n_points[b]) * 3 * elt, cudaMemcpyHostToDevice, st));
   if (is_f32) {
     k_ingest<<<blocks(offs[count]), kBlock, 0, st>>>(bs->d_raw, 1, nullptr, nullptr, bs->d_poses, offs[count], bs->P[0]);
@@ -470,6 +520,38 @@ int madtree_gpu_build_batch(madicp_ctx_t* c, const void* const* clouds, const in
   MADICP_CATCH("madtree_gpu_build_batch")
 }
 
+int madicp_stage_cloud(madicp_ctx_t* c, const void* cloud, int64_t n, int is_f32, int64_t reserve_points) {
+  if (!c || !cloud || n <= 0 || n > (int64_t(1) << 24) || reserve_points > (int64_t(1) << 26)) {
+    set_error("madicp_stage_cloud: bad arguments");
+    return MADICP_ERR_INVALID;
+  }
+  MADICP_TRY
+  CK(cudaSetDevice(c->device));
+  BuildState* bs = static_cast<BuildState*>(c->build_state);
+  if (bs && bs->stage_closed) return MADICP_OK;
+  if (!bs || bs->staged.empty()) {
+    int rc = ensure_state(c, size_t(std::max(reserve_points, n)), &bs);
+    if (rc) return rc;
+    CK(cudaEventRecord(bs->idle_ev, c->stream));  // whatever is queued on the context's stream may still use the buffers
+    CK(cudaStreamWaitEvent(bs->copy_stream, bs->idle_ev, 0));
+    bs->staged_f32 = is_f32 != 0;
+    bs->staged_points = 0;
+    bs->n_resident = 0;  // the cloud madicp_ingest left is about to be overwritten
+    bs->has_root_S = false;
+  }
+  if (bs->staged_f32 != (is_f32 != 0) || size_t(bs->staged_points + n) > bs->cap || int(bs->staged.size()) >= kMaxBatch) {
+    bs->stage_closed = true;  // staged clouds lie back to back: nothing after a gap
+    return MADICP_OK;
+  }
+  const size_t elt = is_f32 ? sizeof(float) : sizeof(double);
+  char* dst = is_f32 ? static_cast<char*>(bs->d_raw) : reinterpret_cast<char*>(bs->P[0]);
+  CK(cudaMemcpyAsync(dst + size_t(bs->staged_points) * 3 * elt, cloud, size_t(n) * 3 * elt, cudaMemcpyHostToDevice, bs->copy_stream));
+  bs->staged.push_back({cloud, n});
+  bs->staged_points += n;
+  return MADICP_OK;
+  MADICP_CATCH("madicp_stage_cloud")
+}
+
 int madtree_gpu_build(madicp_ctx_t* c, const double* points_xyz, int64_t n, double b_max, double b_min,
                       madtree_gpu_t** out) {
   if (!c || !points_xyz || !out || n <= 0 || n > (int64_t(1) << 24)) {
@@ -479,7 +561,8 @@ int madtree_gpu_build(madicp_ctx_t* c, const double* points_xyz, int64_t n, doub
   MADICP_TRY
   CK(cudaSetDevice(c->device));
   BuildState* bs = nullptr;
-  int rc = ensure_state(c, size_t(n), &bs);
+  int rc = drop_staged(static_cast<BuildState*>(c->build_state), c->stream);
+  if (!rc) rc = ensure_state(c, size_t(n), &bs);
   if (rc) return rc;
   CK(cudaMemcpyAsync(bs->P[0], points_xyz, size_t(n) * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   bs->n_resident = n;
@@ -498,6 +581,7 @@ int madtree_gpu_build_resident(madicp_ctx_t* c, double b_max, double b_min, madt
     return MADICP_ERR_STATE;
   }
   CK(cudaSetDevice(c->device));
+  if (int e = drop_staged(bs, c->stream)) return e;
   return build_resident(c, bs, c->stream, bs->n_resident, b_max, b_min, bs->has_root_S ? bs->root_S : nullptr, out);
   MADICP_CATCH("madtree_gpu_build_resident")
 }
@@ -535,7 +619,8 @@ int madicp_ingest(madicp_ctx_t* c, const void* xyz, int64_t n, int is_f32, int d
   MADICP_TRY
   CK(cudaSetDevice(c->device));
   BuildState* bs = nullptr;
-  int rc = ensure_state(c, size_t(n), &bs);
+  int rc = drop_staged(static_cast<BuildState*>(c->build_state), c->stream);
+  if (!rc) rc = ensure_state(c, size_t(n), &bs);
   if (rc) return rc;
   const size_t raw_bytes = size_t(n) * 3 * (is_f32 ? sizeof(float) : sizeof(double));
   cudaStream_t st = c->stream;

@@ -119,6 +119,7 @@ class Registrar:
         h = C.c_void_p()
         check(capi.lib().madicp_create(C.byref(h), device, max_keyframes), "madicp_create")
         self._h = h
+        self._staged_keepalive = []
         self.device = device
         self.max_keyframes = max_keyframes
         self.L = 0
@@ -171,6 +172,16 @@ class Registrar:
                   "madtree_gpu_build")
         return DeviceTree(h, self)
 
+    def stage_cloud(self, cloud, reserve_points=0):
+        """Early upload of a scan of the NEXT build_trees call (madicp_stage_cloud).  The array (float32 or float64,
+        C-contiguous N x 3) is read in place: pass the same object to build_trees, unchanged."""
+        a = np.asarray(cloud)
+        if a.dtype not in (np.float32, np.float64) or not a.flags.c_contiguous or a.ndim != 2 or a.shape[1] != 3:
+            raise ValueError("stage_cloud: a C-contiguous N x 3 float32 / float64 array")
+        self._staged_keepalive.append(a)
+        check(capi.lib().madicp_stage_cloud(self._h, C.c_void_p(a.ctypes.data), a.shape[0], int(a.dtype == np.float32),
+                                            int(reserve_points)), "madicp_stage_cloud")
+
     def build_trees(self, clouds, b_max=0.2, b_min=0.1):
         """Several scans at once (all float32 or all float64): one forest build, a DeviceTree per scan."""
         f32 = all(np.asarray(c).dtype == np.float32 for c in clouds)
@@ -180,6 +191,7 @@ class Registrar:
         ns = (C.c_int64 * k)(*[a.shape[0] for a in arrs])
         out = (C.c_void_p * k)()
         check(capi.lib().madtree_gpu_build_batch(self._h, ptrs, ns, int(f32), k, b_max, b_min, out), "madtree_gpu_build_batch")
+        self._staged_keepalive.clear()
         return [DeviceTree(C.c_void_p(out[i]), self) for i in range(k)]
 
     def ingest(self, xyz, deskew=False, T_prev=None, T_now=None, sensor_hz=10.0, num_threads=1, want_points=False):

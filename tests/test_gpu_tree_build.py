@@ -104,6 +104,43 @@ def test_batch_build_is_a_forest_of_the_same_trees(reg, oracle):
             bits_equal(dt.records()["mean"], FlatTree(cloud.astype(np.float64)).records()["mean"])
 
 
+def test_staged_clouds_build_the_same_forest(reg, oracle):
+    """madicp_stage_cloud: early uploads change where the copy happens, never the trees: a full prefix, a partial one,
+    a staged cloud the batch does not start with, and a single build in between (which discards what was staged)."""
+    c = synth.registration_case(K=3, beams=32, azimuths=1024, seed=23)
+    clouds = [np.ascontiguousarray(x) for x in (c["scans"][0], c["scans"][1][:7000], c["query"], c["scans"][2])]
+    want = [FlatTree(cl).records() for cl in clouds]
+
+    def same(d, h):
+        return all(bits_equal(d[k], h[k]) for k in ("mean", "dir", "bbox0")) and (d["link"] == h["link"]).all() and \
+            (d["num_points"] == h["num_points"]).all()
+
+    def check(trees, idx):
+        for dt, i in zip(trees, idx):
+            assert same(dt.records(), want[i]), i
+
+    total = sum(cl.shape[0] for cl in clouds)
+    for cl in clouds:  # everything staged, in order
+        reg.stage_cloud(cl, total)
+    check(reg.build_trees(clouds), range(4))
+    for cl in clouds[:2]:  # a prefix only
+        reg.stage_cloud(cl, total)
+    check(reg.build_trees(clouds), range(4))
+    reg.stage_cloud(clouds[1], total)  # staged, but the batch starts with another cloud
+    reg.stage_cloud(clouds[0], total)
+    check(reg.build_trees([clouds[0], clouds[1], clouds[3]]), [0, 1, 3])
+    reg.stage_cloud(clouds[2], total)  # a single build in between discards the staged cloud
+    assert same(reg.build_tree(clouds[3]).records(), want[3])
+    check(reg.build_trees([clouds[2], clouds[0]]), [2, 0])
+    f32 = [np.ascontiguousarray(cl[:3000].astype(np.float32)) for cl in clouds[:3]]
+    for cl in f32:
+        reg.stage_cloud(cl, 9000)
+    for cl, dt in zip(f32, reg.build_trees(f32)):
+        assert same(dt.records(), FlatTree(cl.astype(np.float64)).records())
+    reg.stage_cloud(f32[0], 0)  # float32 staged, float64 batch
+    check(reg.build_trees(clouds[:2]), [0, 1])
+
+
 def _bfs_levels(recs):
     """level sizes of breadth-first records with adjacent siblings"""
     sizes, lo, hi = [], 0, 1

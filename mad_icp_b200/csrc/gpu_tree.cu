@@ -289,13 +289,13 @@ int build_forest(madicp_ctx* c, BuildState* bs, cudaStream_t st, int n_trees, co
   const Work& W = bs->W;
   const int cap_pblocks = blocks(int64_t(bs->cap));          // per-point kernels: sized by the lane's capacity and
   const int cap_tiles = int((bs->cap + kTile - 1) / kTile);  // bounded by Lvl::n_points inside -> one graph fits all scans
-  constexpr int kNodeBlocks = 64, kBigBlocks = 1024, kSmallBlocks = 592;  // grid-stride over the nodes of a level
+  constexpr int kNodeBlocks = 64, kEigBlocks = 1184, kBigBlocks = 1776, kSmallBlocks = 1776;  // grid-stride over the nodes of a level
   // The sixteen kernels between two host round trips, captured once per lane: what follows the libm values of
   // level d (eigenvectors ... split), the state update, and the sums + eigen preparation of level d + 1.
   if (!bs->level_graph) {
     cudaGraph_t g = nullptr;
     CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    k_eig_finish<<<kNodeBlocks, kBlock, 0, st>>>(W);
+    k_eig_finish<<<kEigBlocks, kBlock, 0, st>>>(W);
     k_bbox_flags<<<cap_pblocks, kBlock, 0, st>>>(W);
     k_decide_mark<<<kNodeBlocks, 1024, 0, st>>>(W);
     k_decide_scan<<<1, 1024, 0, st>>>(W);
@@ -310,7 +310,7 @@ int build_forest(madicp_ctx* c, BuildState* bs, cudaStream_t st, int n_trees, co
     k_advance<<<1, 32, 0, st>>>(W);
     k_sums_big<<<kBigBlocks, kSumsBlock, 0, st>>>(W);
     k_sums_small<<<kSmallBlocks, kSumsBlock, 0, st>>>(W);
-    k_eig_prep<<<kNodeBlocks, kBlock, 0, st>>>(W);
+    k_eig_prep<<<kEigBlocks, kBlock, 0, st>>>(W);
     cudaError_t e = cudaStreamEndCapture(st, &g);
     if (e != cudaSuccess || !g) {
       set_error(std::string("madtree_gpu_build: graph capture: ") + cudaGetErrorString(e));
@@ -329,7 +329,7 @@ int build_forest(madicp_ctx* c, BuildState* bs, cudaStream_t st, int n_trees, co
   k_init_forest<<<blocks(std::max(n, n_trees)), kBlock, 0, st>>>(W, n_trees, bs->d_offs, b_max, b_min);
   if (!root_S) {
     k_sums_big<<<n_trees, kSumsBlock, 0, st>>>(W);
-    k_sums_small<<<blocks(int64_t(n_trees) * 9, kSumsBlock), kSumsBlock, 0, st>>>(W);
+    k_sums_small<<<blocks(int64_t(n_trees) * 32, kSumsBlock), kSumsBlock, 0, st>>>(W);
     c->launches += 2;
   }
   k_eig_prep<<<1, kBlock, 0, st>>>(W);

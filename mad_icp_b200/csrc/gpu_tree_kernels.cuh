@@ -27,10 +27,8 @@ namespace madicp {
 namespace gtb {
 
 constexpr int kBlock = 256;
-// The in-order sums are the long-running kernels of a build (one dependent FP64 add per point and chain).  Their CTAs
-// are kept at 128 threads x 32 registers = 4096 registers so that one fits NEXT TO a 768-thread x 80-register CTA of the
-// persistent registration kernel on the same SM: a build lane running ahead never keeps the registration of the
-// current scan from becoming resident.
+// The in-order sums are the long-running kernels of a build (one dependent FP64 add per point and chain): small CTAs,
+// many per SM, so that every node (k_sums_big) / every four nodes (k_sums_small) of a level have a CTA of their own.
 constexpr int kSumsBlock = 128;
 constexpr int kTile = 1024;  // positions per CTA of the flag scan
 
@@ -90,16 +88,36 @@ __device__ __forceinline__ long long dbits(double v) { return __double_as_longlo
 // adds (~19 cycles each on this part: scripts/fp64_probe.cu) and cannot be cut; what can be done is keep the adds fed:
 //   k_sums_big    one CTA per node of >= kBigNode points: warps 1-3 stream the node's points through two shared-memory
 //                 tiles (coalesced, one tile ahead) while nine lanes of warp 0 run the nine chains out of the other tile;
-//   k_sums_small  one thread per (node, chain) for the short ranges of the lower levels.
+//   k_sums_small  one warp per node for the short ranges of the lower levels: same scheme, one 32-point tile per warp.
 constexpr int kBigNode = 512;
-constexpr int kSumTile = 64;   // points per shared-memory tile (2 x 1.5 KB: fits beside the registration kernel's carve-out)
+constexpr int kSumTile = 256;  // points per shared-memory tile of k_sums_big: 256 dependent adds (~2.5 us) outlast the load of the next tile
 
 __device__ __forceinline__ void chain_coords(int c, int& u, int& v) {  // term = p[v] * p[u], u == 3: p[v] itself
   u = (c < 3) ? 3 : (c < 6 ? 0 : (c < 8 ? 1 : 2));
   v = (c < 3) ? c : (c < 6 ? c - 3 : (c < 8 ? c - 5 : 2));
 }
 
-__global__ void __launch_bounds__(kSumsBlock, 16)  // <= 32 registers: 128 x 32 = the 4096 the registration CTA leaves free
+// `cnt` points of a shared-memory tile added to chain (u, v), in order, products of 8 points issued ahead of the adds
+__device__ __forceinline__ double chain_tile(const double* t, int cnt, int u, int v, double s) {
+  int i = 0;
+  for (; i + 8 <= cnt; i += 8) {
+    double term[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const double a = t[3 * (i + q) + v];
+      term[q] = (u == 3) ? a : mul_(a, t[3 * (i + q) + u]);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s = add_(s, term[q]);
+  }
+  for (; i < cnt; ++i) {
+    const double a = t[3 * i + v];
+    s = add_(s, (u == 3) ? a : mul_(a, t[3 * i + u]));
+  }
+  return s;
+}
+
+__global__ void __launch_bounds__(kSumsBlock, 12)
 k_sums_big(const Work W) {
   __shared__ double tile[2][kSumTile * 3];
   const Lvl L = *W.lvl;
@@ -127,23 +145,7 @@ k_sums_big(const Work W) {
     if (tid >= 32) {
       if (k + 1 < n_tiles) load_tile(k + 1);
     } else if (tid < 9) {
-      const double* t = tile[k & 1];
-      const int cnt = min(kSumTile, e - (b + k * kSumTile));
-      int i = 0;
-      for (; i + 8 <= cnt; i += 8) {
-        double term[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const double a = t[3 * (i + q) + v];
-          term[q] = (u == 3) ? a : mul_(a, t[3 * (i + q) + u]);
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) s = add_(s, term[q]);
-      }
-      for (; i < cnt; ++i) {
-        const double a = t[3 * i + v];
-        s = add_(s, (u == 3) ? a : mul_(a, t[3 * i + u]));
-      }
+      s = chain_tile(tile[k & 1], min(kSumTile, e - (b + k * kSumTile)), u, v, s);
     }
     __syncthreads();
   }
@@ -152,37 +154,43 @@ k_sums_big(const Work W) {
   }
 }
 
-__global__ void __launch_bounds__(kSumsBlock, 16)
+// One WARP per node of < kBigNode points: all lanes fetch the next 32 points (coalesced, one tile ahead, in registers)
+// while lanes 0..8 run the nine chains out of the warp's shared-memory tile.
+__global__ void __launch_bounds__(kSumsBlock, 12)
 k_sums_small(const Work W) {
+  constexpr int kWarps = kSumsBlock / 32;
+  __shared__ double tile[kWarps][32 * 3];
   const Lvl L = *W.lvl;
   const int n_level = W.count[L.depth];
   const double* __restrict__ P = W.P[L.cur];
   double* __restrict__ S = W.S;
-  for (int t = blockIdx.x * kSumsBlock + threadIdx.x; t < n_level * 9; t += gridDim.x * kSumsBlock) {
-  const int j = t / 9, c = t - j * 9;
-  const int b = W.N.lo[L.g0 + j], e = W.N.hi[L.g0 + j];
-  if (e - b >= kBigNode) continue;
-  int u, v;
-  chain_coords(c, u, v);
-  double s = 0.0;
-  int i = b;
-  for (; i + 8 <= e; i += 8) {  // loads and products of 8 points are issued ahead of the dependent adds
-    double term[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const double* p = P + 3 * size_t(i + k);
-      const double a = __ldg(p + v);
-      term[k] = (u == 3) ? a : mul_(a, __ldg(p + u));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* t = tile[warp];
+  int u = 3, v = 0;
+  if (lane < 9) chain_coords(lane, u, v);
+  for (int j = blockIdx.x * kWarps + warp; j < n_level; j += gridDim.x * kWarps) {
+    const int b = W.N.lo[L.g0 + j], e = W.N.hi[L.g0 + j];
+    const int npts = e - b;
+    if (npts >= kBigNode) continue;  // (warp-uniform)
+    const double* src = P + 3 * size_t(b);
+    const int total = 3 * npts;
+    double r0, r1, r2;
+    auto fetch = [&](int k) {
+      const int i = 96 * k + lane;
+      r0 = (i < total) ? __ldg(src + i) : 0.0;
+      r1 = (i + 32 < total) ? __ldg(src + i + 32) : 0.0;
+      r2 = (i + 64 < total) ? __ldg(src + i + 64) : 0.0;
+    };
+    fetch(0);
+    double s = 0.0;
+    for (int k = 0; 32 * k < npts; ++k) {
+      __syncwarp();  // the chains are done with the previous tile
+      t[lane] = r0; t[lane + 32] = r1; t[lane + 64] = r2;
+      __syncwarp();
+      if (32 * (k + 1) < npts) fetch(k + 1);
+      if (lane < 9) s = chain_tile(t, min(32, npts - 32 * k), u, v, s);
     }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) s = add_(s, term[k]);
-  }
-  for (; i < e; ++i) {
-    const double* p = P + 3 * size_t(i);
-    const double a = __ldg(p + v);
-    s = add_(s, (u == 3) ? a : mul_(a, __ldg(p + u)));
-  }
-  S[size_t(j) * 9 + c] = s;
+    if (lane < 9) S[size_t(j) * 9 + lane] = s;
   }
 }
 
@@ -292,6 +300,39 @@ k_bbox_flags(const Work W) {
         hi3[a] = (hi3[a] < h) ? h : hi3[a];
       }
     }
+  }
+  // a block whose positions all belong to ONE node (every block of the upper levels): one set of atomics per block
+  __shared__ int s_j;
+  __shared__ double s_lo[kBlock / 32][3], s_hi[kBlock / 32][3];
+  __shared__ int s_np[kBlock / 32];
+  if (threadIdx.x == 0) s_j = j;
+  __syncthreads();
+  const bool uniform = __syncthreads_and(j == s_j) != 0 && s_j >= 0;
+  if (uniform) {
+    const int w = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { s_lo[w][a] = lo3[a]; s_hi[w][a] = hi3[a]; }
+      s_np[w] = npass;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+      const int a = threadIdx.x % 3;
+      const bool is_hi = threadIdx.x >= 3;
+      double m = 0.0;
+#pragma unroll
+      for (int q = 0; q < kBlock / 32; ++q) {
+        const double x = is_hi ? s_hi[q][a] : -s_lo[q][a];
+        m = (m < x) ? x : m;
+      }
+      if (m > 0.0) atomicMax(box + size_t(j) * 6 + threadIdx.x, dbits(m));
+    } else if (threadIdx.x == 6) {
+      int np = 0;
+#pragma unroll
+      for (int q = 0; q < kBlock / 32; ++q) np += s_np[q];
+      if (np) atomicAdd(cnt + j, np);
+    }
+    return;
   }
   if (j >= 0 && lane == first) {
     long long* b = box + size_t(j) * 6;
@@ -727,10 +768,19 @@ __global__ void __launch_bounds__(kBlock)
 k_tree_level_counts(Nodes N, int n_nodes, const int* __restrict__ lvl, int n_levels, int stride, int* __restrict__ tcnt,
                     int* __restrict__ tleaf) {
   const int g = blockIdx.x * kBlock + threadIdx.x;
-  if (g >= n_nodes) return;
-  const int b = N.tree[g];
-  atomicAdd(tcnt + size_t(b) * stride + forest_depth(lvl, n_levels, g), 1);
-  if (N.link[g] < 0) atomicAdd(tleaf + b, 1);
+  const bool in = g < n_nodes;
+  const int b = in ? N.tree[g] : -1;
+  const int d = in ? forest_depth(lvl, n_levels, g) : 0;
+  const int leaf = (in && N.link[g] < 0) ? 1 : 0;
+  // neighbouring nodes mostly share (tree, level): one atomic per group of lanes instead of one per node
+  const int key = in ? b * (n_levels + 1) + d : -1;
+  const unsigned peers = __match_any_sync(0xffffffffu, key);
+  const unsigned lane = threadIdx.x & 31;
+  const int n_leaf = __popc(__ballot_sync(0xffffffffu, leaf) & peers);
+  if (in && lane == unsigned(__ffs(int(peers))) - 1u) {
+    atomicAdd(tcnt + size_t(b) * stride + d, __popc(peers));
+    if (n_leaf) atomicAdd(tleaf + b, n_leaf);
+  }
 }
 __global__ void __launch_bounds__(kBlock)
 k_mark_leaf_starts(Nodes N, int n_nodes, int n_points, unsigned char* __restrict__ flag) {

@@ -9,7 +9,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <array>
 #include <chrono>
+#include <future>
 #include <functional>
 #include <cstdio>
 #include <cstdlib>
@@ -77,7 +79,11 @@ struct BuildState {
   uint64_t seq = 0;        // builds so far (madtree_gpu_export is valid for the latest one only)
   int threads = 16;
   // early uploads for the next batch (madicp_stage_cloud): clouds already on their way into P[0] / d_raw, back to back
-  struct Staged { const void* ptr; int64_t n; };
+  struct Staged {
+    const void* ptr;
+    int64_t n;
+    std::shared_future<std::array<double, 9>> root;  // the root's sums, running on a host thread since the cloud was staged
+  };
   std::vector<Staged> staged;
   int64_t staged_points = 0;
   bool staged_f32 = false, stage_closed = false;
@@ -492,6 +498,8 @@ int madtree_gpu_build_batch(madicp_ctx_t* c, const void* const* clouds, const in
     while (n_staged < count && n_staged < int(bs->staged.size()) && bs->staged[size_t(n_staged)].ptr == clouds[n_staged] &&
            bs->staged[size_t(n_staged)].n == n_points[n_staged])
       ++n_staged;
+  std::vector<std::shared_future<std::array<double, 9>>> early;
+  for (int b = 0; b < n_staged; ++b) early.push_back(bs->staged[size_t(b)].root);
   rc = drop_staged(bs, st);  // (st waits for every early copy, used or not: they all write into dst)
   if (rc) return rc;
   for (int b = n_staged; b < count; ++b)
@@ -505,10 +513,15 @@ int madtree_gpu_build_batch(madicp_ctx_t* c, const void* const* clouds, const in
   const auto ta1 = std::chrono::steady_clock::now();
   // the roots' sums on the host, one scan per host thread, while the clouds are being copied up (see root_sums_host)
   std::vector<double> S(size_t(count) * 9);
-  madicp_host_for(count, bs->threads, [&](int b) {
+  if (count > n_staged) madicp_host_for(count - n_staged, bs->threads, [&](int k) {
+    const int b = n_staged + k;
     if (is_f32) root_sums_host(static_cast<const float*>(clouds[b]), n_points[b], S.data() + size_t(b) * 9);
     else root_sums_host(static_cast<const double*>(clouds[b]), n_points[b], S.data() + size_t(b) * 9);
   });
+  for (int b = 0; b < n_staged; ++b) {
+    const std::array<double, 9> r = early[size_t(b)].get();
+    memcpy(S.data() + size_t(b) * 9, r.data(), sizeof(r));
+  }
   const auto tb0 = std::chrono::steady_clock::now();
   rc = build_forest(c, bs, st, count, offs, b_max, b_min, S.data(), out);
   if (getenv("MADICP_BUILD_TIMING"))
@@ -546,7 +559,14 @@ int madicp_stage_cloud(madicp_ctx_t* c, const void* cloud, int64_t n, int is_f32
   const size_t elt = is_f32 ? sizeof(float) : sizeof(double);
   char* dst = is_f32 ? static_cast<char*>(bs->d_raw) : reinterpret_cast<char*>(bs->P[0]);
   CK(cudaMemcpyAsync(dst + size_t(bs->staged_points) * 3 * elt, cloud, size_t(n) * 3 * elt, cudaMemcpyHostToDevice, bs->copy_stream));
-  bs->staged.push_back({cloud, n});
+  // the root's sums (root_sums_host) start now too, on a thread of their own: the caller is about to wait for the device
+  auto sums = std::async(std::launch::async, [cloud, n, is_f32]() {
+    std::array<double, 9> S{};
+    if (is_f32) root_sums_host(static_cast<const float*>(cloud), n, S.data());
+    else root_sums_host(static_cast<const double*>(cloud), n, S.data());
+    return S;
+  }).share();
+  bs->staged.push_back({cloud, n, std::move(sums)});
   bs->staged_points += n;
   return MADICP_OK;
   MADICP_CATCH("madicp_stage_cloud")

@@ -223,8 +223,7 @@ k_eig_prep(const Work W) {
   Eig3Mid m;
   eig3_prepare(c, m);
   mid[j] = m;
-  args[2 * size_t(j)] = m.sq;
-  args[2 * size_t(j) + 1] = m.half_b;
+  reinterpret_cast<double2*>(args)[j] = make_double2(m.sq, m.half_b);  // one 16-byte store: whole PCIe payloads per warp
   }
 }
 

@@ -295,7 +295,7 @@ int build_forest(madicp_ctx* c, BuildState* bs, cudaStream_t st, int n_trees, co
   const Work& W = bs->W;
   const int cap_pblocks = blocks(int64_t(bs->cap));          // per-point kernels: sized by the lane's capacity and
   const int cap_tiles = int((bs->cap + kTile - 1) / kTile);  // bounded by Lvl::n_points inside -> one graph fits all scans
-  constexpr int kNodeBlocks = 64, kEigBlocks = 1184, kBigBlocks = 1776, kSmallBlocks = 1776;  // grid-stride over the nodes of a level
+  constexpr int kNodeBlocks = 64, kEigBlocks = 1184, kBigBlocks = 1776, kSmallBlocks = 1776, kLeafBlocks = 2368;  // grid-stride over the nodes of a level
   // The sixteen kernels between two host round trips, captured once per lane: what follows the libm values of
   // level d (eigenvectors ... split), the state update, and the sums + eigen preparation of level d + 1.
   if (!bs->level_graph) {
@@ -306,8 +306,8 @@ int build_forest(madicp_ctx* c, BuildState* bs, cudaStream_t st, int n_trees, co
     k_decide_mark<<<kNodeBlocks, 1024, 0, st>>>(W);
     k_decide_scan<<<1, 1024, 0, st>>>(W);
     k_decide_apply<<<kNodeBlocks, 1024, 0, st>>>(W);
-    k_leaf_dist<<<cap_pblocks, kBlock, 0, st>>>(W);
-    k_leaf_pick<<<cap_pblocks, kBlock, 0, st>>>(W);
+    k_leaf_dist<<<std::min(cap_pblocks, kLeafBlocks), kBlock, 0, st>>>(W);
+    k_leaf_pick<<<std::min(cap_pblocks, kLeafBlocks), kBlock, 0, st>>>(W);
     k_leaf_set<<<kNodeBlocks, kBlock, 0, st>>>(W);
     k_scan_tiles_lvl<<<cap_tiles, kTile, 0, st>>>(W);
     k_scan_tile_sums_lvl<<<1, 1024, 0, st>>>(W);

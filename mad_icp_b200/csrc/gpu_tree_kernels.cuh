@@ -59,6 +59,7 @@ struct Ctl {
 struct Lvl {
   int depth, g0, cur, n_points;
   double b_max, b_min;
+  int n_leaves, pad;  // leaves found on the current level (k_decide_scan): the leaf kernels of a level without any return at once
 };
 struct Eig3MidFwd;
 // All device pointers of a build lane (by value in every kernel).
@@ -283,11 +284,27 @@ k_bbox_flags(const Work W) {
     }
   }
   if (i < n) flag[i] = (unsigned char) pass;
-  // segmented reduction over the lanes of the same node (positions of a node are contiguous)
+  // reduction over the lanes of the same node (positions of a node are contiguous)
   const unsigned peers = __match_any_sync(0xffffffffu, j);
   const unsigned last = 31u - unsigned(__clz(int(peers)));
   const unsigned first = unsigned(__ffs(int(peers))) - 1u;
   const int npass = __popc(__ballot_sync(0xffffffffu, pass) & peers);
+  if (peers == 0xffffffffu) {
+    // the whole warp is one node (every warp of the upper levels): the six values are non-negative doubles (-lo, hi),
+    // whose bit patterns order like unsigned integers -> two 32-bit REDUX.MAX per value instead of ten shuffles
+    if (j >= 0) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        const double x = (a < 3) ? ((lo3[a] < 0.0) ? -lo3[a] : 0.0) : hi3[a - 3];
+        const unsigned long long bits = (unsigned long long) dbits(x);
+        const unsigned hi = unsigned(bits >> 32), lo = unsigned(bits);
+        const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+        const double m = __longlong_as_double((long long) ((((unsigned long long) mh) << 32) | ml));
+        if (a < 3) lo3[a] = -m; else hi3[a - 3] = m;
+      }
+    }
+  } else {
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
 #pragma unroll
@@ -299,6 +316,7 @@ k_bbox_flags(const Work W) {
         hi3[a] = (hi3[a] < h) ? h : hi3[a];
       }
     }
+  }
   }
   // a block whose positions all belong to ONE node (every block of the upper levels): one set of atomics per block
   __shared__ int s_j;
@@ -425,6 +443,7 @@ k_decide_scan(const Work W) {  // one CTA
     ctl->n_next = 2 * s_carry;
     ctl->n_leaves = n - s_carry;
     ctl->n_active = 0;
+    W.lvl->n_leaves = n - s_carry;
     __threadfence_system();
   }
 }
@@ -489,13 +508,14 @@ k_leaf_dist(const Work W) {
   const Nodes N = W.N;
   const int g0 = L.g0;
   unsigned long long* __restrict__ dmin = W.dmin;
-  const int i = blockIdx.x * kBlock + threadIdx.x;
-  if (i >= L.n_points) return;
-  const int j = owner[i];
-  if (j < 0 || N.link[g0 + j] >= 0) return;
-  const double* full = N.full + size_t(g0 + j) * 16;
-  const double d = norm3(sub_(P[3 * size_t(i)], full[0]), sub_(P[3 * size_t(i) + 1], full[1]), sub_(P[3 * size_t(i) + 2], full[2]));
-  if (d < 1.7976931348623157e308) atomicMin(dmin + j, (unsigned long long) dbits(d));  // d >= 0: bits order like the values
+  if (L.n_leaves == 0) return;
+  for (int i = blockIdx.x * kBlock + threadIdx.x; i < L.n_points; i += gridDim.x * kBlock) {
+    const int j = owner[i];
+    if (j < 0 || N.link[g0 + j] >= 0) continue;
+    const double* full = N.full + size_t(g0 + j) * 16;
+    const double d = norm3(sub_(P[3 * size_t(i)], full[0]), sub_(P[3 * size_t(i) + 1], full[1]), sub_(P[3 * size_t(i) + 2], full[2]));
+    if (d < 1.7976931348623157e308) atomicMin(dmin + j, (unsigned long long) dbits(d));  // d >= 0: bits order like the values
+  }
 }
 __global__ void __launch_bounds__(kBlock)
 k_leaf_pick(const Work W) {
@@ -506,13 +526,14 @@ k_leaf_pick(const Work W) {
   const int g0 = L.g0;
   const unsigned long long* __restrict__ dmin = W.dmin;
   int* __restrict__ imin = W.imin;
-  const int i = blockIdx.x * kBlock + threadIdx.x;
-  if (i >= L.n_points) return;
-  const int j = owner[i];
-  if (j < 0 || N.link[g0 + j] >= 0) return;
-  const double* full = N.full + size_t(g0 + j) * 16;
-  const double d = norm3(sub_(P[3 * size_t(i)], full[0]), sub_(P[3 * size_t(i) + 1], full[1]), sub_(P[3 * size_t(i) + 2], full[2]));
-  if (d < 1.7976931348623157e308 && (unsigned long long) dbits(d) == dmin[j]) atomicMin(imin + j, i);
+  if (L.n_leaves == 0) return;
+  for (int i = blockIdx.x * kBlock + threadIdx.x; i < L.n_points; i += gridDim.x * kBlock) {
+    const int j = owner[i];
+    if (j < 0 || N.link[g0 + j] >= 0) continue;
+    const double* full = N.full + size_t(g0 + j) * 16;
+    const double d = norm3(sub_(P[3 * size_t(i)], full[0]), sub_(P[3 * size_t(i) + 1], full[1]), sub_(P[3 * size_t(i) + 2], full[2]));
+    if (d < 1.7976931348623157e308 && (unsigned long long) dbits(d) == dmin[j]) atomicMin(imin + j, i);
+  }
 }
 __global__ void __launch_bounds__(kBlock)
 k_leaf_set(const Work W) {

@@ -31,6 +31,7 @@ void madicp_host_for(int n, int num_threads, const std::function<void(int)>& fn)
 int madicp_deskew_plan(const void* xyz, int is_f32, int64_t n, const double T_prev[12], const double T_now[12],
                        double sensor_hz, int num_threads, int32_t* perm, uint16_t* chunk, double* poses, int* n_poses);
 void madicp_host_trig(const double* args, double* res, int n, int num_threads);
+void madicp_host_hot(int on);
 
 namespace {
 
@@ -280,6 +281,10 @@ int build_forest(madicp_ctx* c, BuildState* bs, cudaStream_t st, int n_trees, co
   }
   const int n = offs[n_trees];
   bs->seq++;
+  struct Hot {  // the levels' libm sections follow each other within a few hundred microseconds
+    Hot() { madicp_host_hot(1); }
+    ~Hot() { madicp_host_hot(0); }
+  } hot;
   const bool timing = getenv("MADICP_BUILD_TIMING") != nullptr;
   auto now = []() { return std::chrono::steady_clock::now(); };
   auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {

@@ -62,30 +62,44 @@ public:
       for (size_t i = 0; i < n; ++i) fn(i);
       return;
     }
-    task_ = [&fn](size_t i) { fn(i); };
-    n_ = n;
-    next_.store(0, std::memory_order_relaxed);
-    done_.store(0, std::memory_order_relaxed);
+    // One Job object per call, handed to the workers by shared_ptr: the call returns when all n TASKS are done, not
+    // when all workers have reported -- a worker the OS wakes late (busy host) finds nothing left and goes back to
+    // waiting, instead of holding the whole section up; it can never touch the next call's job.
+    auto job = std::make_shared<Job>();
+    job->fn = [&fn](size_t i) { fn(i); };
+    job->n = n;
+    job->blocked = blocked_;
+    job->shares = workers_.size() + 1;
     {
       std::lock_guard<std::mutex> lk(mu_);
+      job_ = job;
       gen_.fetch_add(1, std::memory_order_release);
     }
     cv_.notify_all();
-    drain(0);
-    const int w = int(workers_.size());
-    for (int spin = 0; done_.load(std::memory_order_acquire) != w; ++spin)
+    work(*job, 0);
+    for (int spin = 0; job->finished.load(std::memory_order_acquire) != n; ++spin)
       if (spin > 1500) std::this_thread::yield(); else _mm_pause();
   }
 
 private:
-  void drain(int me) {
-    if (blocked_) {
-      const size_t W = workers_.size() + 1;
-      for (size_t i = n_ * size_t(me) / W, e = n_ * size_t(me + 1) / W; i < e; ++i) task_(i);
+  struct Job {
+    std::function<void(size_t)> fn;  // set before the job is published, never changed afterwards
+    size_t n = 0, shares = 1;
+    bool blocked = false;
+    std::atomic<size_t> next{0}, finished{0};
+  };
+  static void work(Job& j, int me) {
+    if (j.blocked) {  // (every share has an owner: a blocked section does wait for its slowest worker)
+      for (size_t i = j.n * size_t(me) / j.shares, e = j.n * size_t(me + 1) / j.shares; i < e; ++i) {
+        j.fn(i);
+        j.finished.fetch_add(1, std::memory_order_release);
+      }
       return;
     }
-    for (size_t i = next_.fetch_add(1, std::memory_order_relaxed); i < n_; i = next_.fetch_add(1, std::memory_order_relaxed))
-      task_(i);
+    for (size_t i = j.next.fetch_add(1, std::memory_order_relaxed); i < j.n; i = j.next.fetch_add(1, std::memory_order_relaxed)) {
+      j.fn(i);
+      j.finished.fetch_add(1, std::memory_order_release);
+    }
   }
   void loop(int me) {
     uint64_t seen = 0;
@@ -107,21 +121,22 @@ private:
           }
         }
       }
-      seen = gen_.load(std::memory_order_acquire);
-      if (stop_) return;
-      drain(me);
-      done_.fetch_add(1, std::memory_order_release);
+      std::shared_ptr<Job> job;
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        seen = gen_.load(std::memory_order_acquire);
+        job = job_;
+        if (stop_) return;
+      }
+      if (job) work(*job, me);
     }
   }
   static constexpr long kSpinNs = 500000;
   std::vector<std::thread> workers_;
   std::mutex mu_;
   std::condition_variable cv_;
-  std::function<void(size_t)> task_;
-  size_t n_ = 0;
+  std::shared_ptr<Job> job_;  // the current section (guarded by mu_)
   bool blocked_ = false;
-  std::atomic<size_t> next_{0};
-  std::atomic<int> done_{0};
   std::atomic<uint64_t> gen_{0};
   bool stop_ = false;
 };

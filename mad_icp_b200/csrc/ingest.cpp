@@ -306,6 +306,9 @@ void madicp_host_trig(const double* args, double* res, int n, int num_threads) {
   });
 }
 
+// > 0 while a device build strings its per-level libm sections together: the pool's workers keep spinning between them
+void madicp_host_hot(int on) { madicp_host::g_hot.fetch_add(on ? 1 : -1, std::memory_order_relaxed); }
+
 void madicp_host_for(int n, int num_threads, const std::function<void(int)>& fn) {
   for_chunks(std::max(1, std::min(num_threads, 64)), size_t(n), 1, [&](size_t c0, size_t c1) {
     for (size_t i = c0; i < c1; ++i) fn(int(i));

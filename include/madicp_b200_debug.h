@@ -17,6 +17,12 @@ int madicp_debug_timing(madicp_ctx_t* ctx, int enable, int64_t* out, int max_rou
 /* Item-phase cycles of every CTA for the rounds of the last launch (rounds x grid int64, debug timing
  * must be on).  Returns the grid size. */
 int madicp_debug_cta_cycles(madicp_ctx_t* ctx, int64_t* out, int cap);
+/* Plane 1..4 of the per-CTA stamps of the last launch (rounds x grid int64, debug timing on): %globaltimer in ns at the
+ * start of the round's items, at their end, and after the CTA's tile went out (plane 0 = madicp_debug_cta_cycles).
+ * Rows 6 and 7 of madicp_debug_timing are on the same clock: all tiles folded, next pose handed out.  Plane 4, first
+ * 16 entries of a round: CTA 0's fold trace in SM cycles ([0] entry, [1..12] end of thread 0's sweeps, [13] done,
+ * [14] number of sweeps). */
+int madicp_debug_cta_stamps(madicp_ctx_t* ctx, int plane, int64_t* out, int cap);
 /* Shape of the persistent kernel: threads per CTA and resident CTAs per SM; supported pairs are
  * (1024,1) default, (768,1), (512,1), (512,2), (256,2), (256,3), (256,4); env MADICP_GN_SHAPE="t,c"
  * selects one at create time.  By default the library picks among the one-CTA-per-SM shapes per

@@ -84,6 +84,7 @@ SYMBOLS = {
     "madicp_debug_cta_cycles": (C.c_int, [vp, C.POINTER(C.c_int64), C.c_int]),
     "madicp_set_gn_grid": (C.c_int, [vp, C.c_int, C.c_int]),
     "madicp_debug_set_memo": (C.c_int, [vp, C.c_int]),
+    "madicp_debug_cta_stamps": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int64), C.c_int]),
 }
 
 REC_DTYPE = np.dtype([("mean", "<f8", 3), ("dir", "<f8", 3), ("bbox0", "<f8"), ("link", "<i4"), ("num_points", "<i4")])

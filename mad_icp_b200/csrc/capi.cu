@@ -1168,7 +1168,8 @@ int madicp_debug_timing(madicp_ctx_t* c, int enable, int64_t* out, int max_round
   if (enable && !c->d_dbg) {
     CK(cudaMalloc(&c->d_dbg, MADICP_MAX_ITERS * 8 * sizeof(long long)));
     CK(cudaMemset(c->d_dbg, 0, MADICP_MAX_ITERS * 8 * sizeof(long long)));
-    CK(cudaMalloc(&c->d_dbg_cta, size_t(MADICP_MAX_ITERS) * c->sm_count * 8 * sizeof(long long)));
+    CK(cudaMalloc(&c->d_dbg_cta, size_t(MADICP_MAX_ITERS) * c->sm_count * 8 * 4 * sizeof(long long)));  // 4 planes, <= 8 CTAs/SM
+    CK(cudaMemset(c->d_dbg_cta, 0, size_t(MADICP_MAX_ITERS) * c->sm_count * 8 * 4 * sizeof(long long)));
   } else if (!enable && c->d_dbg) {
     cudaFree(c->d_dbg);
     cudaFree(c->d_dbg_cta);
@@ -1184,6 +1185,18 @@ int madicp_debug_cta_cycles(madicp_ctx_t* c, int64_t* out, int cap) {
   CK(cudaStreamSynchronize(c->stream));
   const int n = std::min(cap, c->last_iters * c->gn_grid);
   CK(cudaMemcpy(out, c->d_dbg_cta, size_t(n) * sizeof(long long), cudaMemcpyDeviceToHost));
+  return c->gn_grid;
+}
+
+// plane p (1..3) of the per-CTA stamps: %globaltimer (ns) at the start of the round's items, at their end, after the
+// CTA's tile went out; rounds x grid int64 of the last launch.  Returns the grid size.
+int madicp_debug_cta_stamps(madicp_ctx_t* c, int plane, int64_t* out, int cap) {
+  if (!c || !out || !c->d_dbg_cta || plane < 0 || plane > 4) return MADICP_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  const int n = std::min(cap, c->last_iters * c->gn_grid);
+  CK(cudaMemcpy(out, c->d_dbg_cta + size_t(plane) * MADICP_MAX_ITERS * c->gn_grid, size_t(n) * sizeof(long long),
+                cudaMemcpyDeviceToHost));
   return c->gn_grid;
 }
 

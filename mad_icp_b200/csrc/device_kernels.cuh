@@ -378,8 +378,15 @@ struct GnArgs {
   int walk_buf;                            // which half of GnState::walked this call counts into
   int use_memo;                            // 0: every item is walked in every round (probe / A-B measurement)
   long long* dbg;                          // nullable: per-round SM-clock stamps (madicp_debug_timing)
-  long long* dbg_cta;                      // nullable: [round][CTA] item-phase cycles
+  long long* dbg_cta;                      // nullable: [plane][round][CTA]: item-phase cycles; %globaltimer at the start of
+                                           // the round's items, at their end, after the tile went out (planes 1..3);
+                                           // plane 4, first 16 entries of a round: CTA 0's fold trace (fold_tiles)
 };
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // Persistent cooperative grid (all CTAs co-resident), one software grid barrier per round: CTAs
 // publish their partial, take a release-ticket, the last one folds / exchanges / solves and
@@ -501,8 +508,7 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
         const uint32_t ep = A.pose_epoch + uint32_t(it);
         uint32_t lo, hi, f0, f1;
         do {
-          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1)
-                       : "l"(&st->X_ll[threadIdx.x]) : "memory");
+          ll_load(&st->X_ll[threadIdx.x], lo, f0, hi, f1);
         } while (f0 != ep || f1 != ep);
         x = __hiloint2double(int(hi), int(lo));
       }
@@ -516,6 +522,8 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
     double c0 = 0.0, c1 = 0.0;
     long long t_begin = 0;
     if (A.dbg && threadIdx.x == 0) t_begin = clock64();
+    const size_t dbg_plane = size_t(MADICP_MAX_ITERS) * gridDim.x, dbg_at = size_t(it) * gridDim.x + blockIdx.x;
+    if (A.dbg_cta && threadIdx.x == 0) A.dbg_cta[dbg_plane + dbg_at] = global_ns();
 
     // One pass in the static item order (the order of the sums is fixed).  From round 1 on an item keeps the leaf
     // of its last walk when its query has moved, since that walk, by less than the smallest margin of the walk
@@ -583,7 +591,10 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
     if (A.dbg && threadIdx.x == 0 && blockIdx.x == 0) A.dbg[it * 8 + 0] = clock64() - t_begin;  // item phase, CTA 0
     if (A.dbg_cta) {  // per-CTA item phase (slowest warp) + this warp's own time
       __syncthreads();
-      if (threadIdx.x == 0) A.dbg_cta[size_t(it) * gridDim.x + blockIdx.x] = clock64() - t_begin;
+      if (threadIdx.x == 0) {
+        A.dbg_cta[dbg_at] = clock64() - t_begin;
+        A.dbg_cta[2 * dbg_plane + dbg_at] = global_ns();
+      }
       if (threadIdx.x == 0 && blockIdx.x == 0) A.dbg[it * 8 + 5] = s_qn;
     }
     __syncthreads();  // every warp is done with its staging tile: s_red aliases them
@@ -594,14 +605,17 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
     const uint32_t ep_round = A.pose_epoch + uint32_t(it);
     block_reduce_publish<WARPS>(c0, c1, s_red, A.tiles + size_t(blockIdx.x) * kAcc, ep_round,
                                 /*fence: matched flags of this round must be visible before the tile*/ it >= A.clear_from, multi);
+    if (A.dbg_cta && threadIdx.x == 0) A.dbg_cta[3 * dbg_plane + dbg_at] = global_ns();
     if (blockIdx.x == 0) {
       long long t0 = 0, t1 = 0, t2 = 0;
       if (A.dbg && threadIdx.x == 0) t0 = clock64();
-      fold_tiles<THREADS>(A.tiles, gridDim.x, ep_round, s_red, s_tot);
+      fold_tiles<THREADS>(A.tiles, gridDim.x, ep_round, s_red, s_tot,
+                          (A.dbg_cta && gridDim.x >= 16) ? A.dbg_cta + 4 * dbg_plane + size_t(it) * gridDim.x : nullptr);
       if (A.dbg && threadIdx.x == 0) {
         t1 = clock64();
         A.dbg[it * 8 + 1] = t1 - t_begin;  // round start -> all tiles folded
         A.dbg[it * 8 + 2] = t1 - t0;       // of which: waiting for / folding the tiles after CTA 0's own items
+        A.dbg[it * 8 + 6] = global_ns();   // all tiles folded (same clock as the per-CTA stamps)
       }
       if (multi) {
         if (last_round) __threadfence_system();
@@ -611,12 +625,29 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
       if (last_round) {  // count matched moving leaves (every writer fenced before its tile, and the tiles are in)
         __threadfence();
         int c = 0;
-        for (int q = threadIdx.x; q < A.L; q += THREADS) c += (__ldcv(A.matched + q) != 0);
+        {  // 16 flags per load (each 0 or 1; the bytes between L and the next multiple of 16 were zeroed with the buffer)
+          const uint4* m16 = reinterpret_cast<const uint4*>(A.matched);
+          for (int q = threadIdx.x; q < (A.L + 15) / 16; q += THREADS) {
+            const uint4 w = __ldcv(m16 + q);
+            c += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+          }
+        }
         for (int off = 16; off > 0; off >>= 1) c += __shfl_down_sync(0xffffffffu, c, off);
         if (lane == 0) s_count[warp] = c;
       }
       if (threadIdx.x < 6) s_b[threadIdx.x] = s_tot[threadIdx.x * 8 + 6];
       __syncthreads();
+      if (last_round && threadIdx.x >= 32) {
+        // the last round's other results leave on three other warps while thread 0 solves (on thread 0 they added
+        // 4.5k cycles to every registration: profiles/r03b_variant_probe.txt, variants 1 -> 3)
+        if (threadIdx.x == 32) unpack_Hb(s_tot, st->H, st->b);
+        if (threadIdx.x == 64) st->weight = inv_det6_dev(s_tot, 8);
+        if (threadIdx.x == 96) {
+          int c = 0;
+          for (int w2 = 0; w2 < WARPS; ++w2) c += s_count[w2];
+          st->n_matched = c;
+        }
+      }
       if (threadIdx.x == 0) {
         if (A.dbg) t2 = clock64();
         double Xn[12];
@@ -624,25 +655,18 @@ k_gn_loop(const __grid_constant__ GnArgs A) {
         if (!last_round) {
           const uint32_t ep = ep_round + 1u;
 #pragma unroll
-          for (int i = 0; i < 12; ++i)
-            asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(&st->X_ll[i]),
-                         "r"(uint32_t(__double2loint(Xn[i]))), "r"(ep), "r"(uint32_t(__double2hiint(Xn[i]))), "r"(ep)
-                         : "memory");
+          for (int i = 0; i < 12; ++i) ll_store(&st->X_ll[i], Xn[i], ep);
         }
 #pragma unroll
         for (int i = 0; i < 12; ++i) st->X_trace[(it + 1) * 12 + i] = Xn[i];
         if (last_round) {
 #pragma unroll
           for (int i = 0; i < 12; ++i) st->X_out[i] = Xn[i];
-          unpack_Hb(s_tot, st->H, st->b);
-          st->weight = inv_det6_dev(s_tot, 8);
-          int c = 0;
-          for (int w2 = 0; w2 < WARPS; ++w2) c += s_count[w2];
-          st->n_matched = c;
         }
         if (A.dbg) {
           A.dbg[it * 8 + 3] = t2 - t1;         // peer exchange + matched count
           A.dbg[it * 8 + 4] = clock64() - t2;  // solve + pose update + publish
+          A.dbg[it * 8 + 7] = global_ns();     // pose handed out
         }
       }
     }

@@ -103,6 +103,17 @@ struct __align__(16) LLCell {
   uint32_t lo, flag_lo, hi, flag_hi;
 };
 
+// One LL cell (tiles of the round, pose of the next round): value and flag in one 16-byte access.  (`volatile` is
+// system scope, SASS LDG/STG.E.128.STRONG.SYS; GPU scope for the cells only this GPU touches measured the same:
+// profiles/r03c_variant_probe.txt, variant 7.)
+__device__ __forceinline__ void ll_store(LLCell* p, double v, uint32_t epoch) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(uint32_t(__double2loint(v))), "r"(epoch),
+               "r"(uint32_t(__double2hiint(v))), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ void ll_load(const LLCell* p, uint32_t& lo, uint32_t& f0, uint32_t& hi, uint32_t& f1) {
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(p) : "memory");
+}
+
 struct GnState {
   int ticket;     // monotonically increasing arrival counter (reset by the host before a launch)
   int clear_from; // first round whose gate passes are recorded in the matched flags (iters-1: the reference's
@@ -182,14 +193,18 @@ static __device__ __noinline__ bool side_exact(const madtree_rec_t* rec, double 
 // evaluation (3 subtractions, 3 products, 2 additions: < 8 * 2^-53 * (|q|_1 + |mean|_1) in absolute terms).
 // A query this close to a plane (it failed the FP32 filter) still keeps its leaf in later rounds, when the pose
 // moves by nanometres.  NaN (one-point nodes never reach here; defensive): margin 0, the item is walked again.
-static __device__ __noinline__ bool side_exact_m(const madtree_rec_t* rec, double qx, double qy, double qz, float* margin) {
+// The result travels in ONE register: |return| = margin, sign bit = left (-0.0f for "left, margin 0").  (An out
+// parameter made the caller keep its margin in local memory: one STL per node visit of every walk, 1.8 M sectors per
+// registration in profiles/r02_gn_loop_summary.txt, for a value the rare call alone needs.)
+static __device__ __noinline__ float side_exact_m(const madtree_rec_t* rec, double qx, double qy, double qz) {
   const Rec r = load_rec(rec);
   const double s = plane_side(qx, qy, qz, r.mx, r.my, r.mz, r.dx, r.dy, r.dz);
   const double l1 = ((fabs(qx) + fabs(qy)) + fabs(qz)) + ((fabs(r.mx) + fabs(r.my)) + fabs(r.mz));
   const double m = fabs(s) * (1.0 - 1e-9) - 2e-15 * l1;
-  *margin = (m > 0.0) ? __double2float_rd(m) : 0.0f;
-  return !(s < 0.0);
+  const float mg = (m > 0.0) ? __double2float_rd(m) : 0.0f;
+  return (s < 0.0) ? -mg : mg;
 }
+__device__ __forceinline__ bool exact_right(float r) { return __float_as_int(r) >= 0; }
 
 // FP32 query of a walk: rounded coordinates + the query part of the error bound.
 struct QueryF {
@@ -261,7 +276,11 @@ __device__ __forceinline__ int descend_t(const ModelView& M, int k, double qx, d
     bool s0 = f0.right;
     if (MEMO) {
       float mg = f0.margin;
-      if (!f0.decided) s0 = side_exact_m(M.recs + bfs0, qx, qy, qz, &mg);
+      if (!f0.decided) {
+        const float r = side_exact_m(M.recs + bfs0, qx, qy, qz);
+        s0 = exact_right(r);
+        mg = fabsf(r);
+      }
       margin = fminf(margin, mg);
     } else if (!f0.decided) {
       s0 = side_exact(M.recs + bfs0, qx, qy, qz);
@@ -275,8 +294,11 @@ __device__ __forceinline__ int descend_t(const ModelView& M, int k, double qx, d
     bool s1 = f1.right;
     if (MEMO) {
       float mg = f1.margin;
-      if (!f1.decided)
-        s1 = side_exact_m(M.recs + (M.broot[k] + load_rec_link(M.recs + bfs0) + (s0 ? 1 : 0)), qx, qy, qz, &mg);
+      if (!f1.decided) {
+        const float r = side_exact_m(M.recs + (M.broot[k] + load_rec_link(M.recs + bfs0) + (s0 ? 1 : 0)), qx, qy, qz);
+        s1 = exact_right(r);
+        mg = fabsf(r);
+      }
       margin = fminf(margin, mg);
     } else if (!f1.decided) {
       s1 = side_exact(M.recs + (M.broot[k] + load_rec_link(M.recs + bfs0) + (s0 ? 1 : 0)), qx, qy, qz);
@@ -395,8 +417,7 @@ __device__ __forceinline__ void block_reduce_publish(double c0, double c1, doubl
     if (fence) {
       if (system_scope) __threadfence_system(); else __threadfence();
     }
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(out + threadIdx.x), "r"(uint32_t(__double2loint(s))),
-                 "r"(epoch), "r"(uint32_t(__double2hiint(s))), "r"(epoch) : "memory");
+    ll_store(out + threadIdx.x, s, epoch);
   }
 }
 
@@ -404,7 +425,10 @@ __device__ __forceinline__ void block_reduce_publish(double c0, double c1, doubl
 // index, combined in strand order; within a strand the tiles are added in ascending CTA order (fixed => the sums
 // are reproducible).  Every thread first issues the loads of all its cells, then re-polls only the missing ones.
 template <int THREADS>
-__device__ __forceinline__ void fold_tiles(const LLCell* tiles, int nblk, uint32_t epoch, double (*s_red)[64], double* s_tot) {
+__device__ __forceinline__ void fold_tiles(const LLCell* tiles, int nblk, uint32_t epoch, double (*s_red)[64], double* s_tot,
+                                           long long* trace = nullptr) {  // trace (debug): clock at entry, after each sweep of thread 0, at the end
+  int n_sweeps = 0;
+  if (trace && threadIdx.x == 0) trace[0] = clock64();
   constexpr int STRANDS = THREADS / kAcc > 16 ? 16 : THREADS / kAcc;  // (s_red has room for WARPS >= 16 rows of 64)
   constexpr int kPer = 10;  // cells per thread in flight at a time: all loads of a batch are issued BEFORE any is looked at
   const int j = (threadIdx.x < STRANDS * kAcc) ? int(threadIdx.x % kAcc) : 64, g = threadIdx.x / kAcc;
@@ -423,9 +447,15 @@ __device__ __forceinline__ void fold_tiles(const LLCell* tiles, int nblk, uint32
         uint32_t lo[kPer], hi[kPer], f0[kPer], f1[kPer];
 #pragma unroll
         for (int i = 0; i < kPer; ++i) {
-          const int blk = (missing & (1u << i)) ? blk0 + i * STRANDS : blk0;  // (a present cell again: harmless)
-          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo[i]), "=r"(f0[i]), "=r"(hi[i]), "=r"(f1[i])
-                       : "l"(tiles + size_t(blk) * kAcc + j) : "memory");
+          // only cells still missing are asked for again (a sweep over all 148 tiles is 113 KB through one SM's L2
+          // port, ~1.7k cycles: profiles/r03c_variant_probe.txt)
+          f0[i] = f1[i] = ~epoch;
+          lo[i] = hi[i] = 0;
+          if (missing & (1u << i)) ll_load(tiles + size_t(blk0 + i * STRANDS) * kAcc + j, lo[i], f0[i], hi[i], f1[i]);
+        }
+        if (trace && threadIdx.x == 0) {
+          if (n_sweeps < 12) trace[1 + n_sweeps] = clock64();
+          ++n_sweeps;
         }
 #pragma unroll
         for (int i = 0; i < kPer; ++i)
@@ -447,6 +477,10 @@ __device__ __forceinline__ void fold_tiles(const LLCell* tiles, int nblk, uint32
     s_tot[threadIdx.x] = s;
   }
   __syncthreads();
+  if (trace && threadIdx.x == 0) {
+    trace[13] = clock64();
+    trace[14] = n_sweeps;
+  }
 }
 
 __device__ __forceinline__ double ld_relaxed_f64(const double* p) {

@@ -115,6 +115,8 @@ MADICP_HD void ldlt6_solve_neg(const double* H, int ld, const double* b, double*
 // det(H^-1) as 1 / det(H) by partial-pivot LU (reference: odometry/pipeline.cpp:223 computes
 // H_adder_.inverse().determinant(); the C++ facade uses the same form).  H row-major 6x6, stride ld.
 MADICP_HD double inv_det6(const double* H, int ld) {
+  // static indices only (the row exchange is a chain of selects): on the device the 6x6 stays in registers -- indexed
+  // at run time it lived in local memory and the routine cost 4.6k cycles at the end of every registration
   double A[6][6];
 #pragma unroll
   for (int r = 0; r < 6; ++r)
@@ -124,18 +126,26 @@ MADICP_HD double inv_det6(const double* H, int ld) {
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
     int p = k;
+    double best = fabs(A[k][k]);
 #pragma unroll
-    for (int i = k + 1; i < 6; ++i)
-      if (i > k && fabs(A[i][k]) > fabs(A[p][k])) p = i;
-    if (p != k) {
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        const double u = A[k][c];
-        A[k][c] = A[p][c];
-        A[p][c] = u;
+    for (int i = k + 1; i < 6; ++i) {  // first maximum of |A[i][k]|, i >= k
+      const double a = fabs(A[i][k]);
+      if (a > best) {
+        best = a;
+        p = i;
       }
-      det = -det;
     }
+#pragma unroll
+    for (int i = k + 1; i < 6; ++i) {  // rows k <-> p (columns left of k are never read again)
+      const bool sw = (p == i);
+#pragma unroll
+      for (int c = k; c < 6; ++c) {
+        const double u = A[k][c], w = A[i][c];
+        A[k][c] = sw ? w : u;
+        A[i][c] = sw ? u : w;
+      }
+    }
+    if (p != k) det = -det;
     det = mul_(det, A[k][k]);
 #pragma unroll
     for (int i = k + 1; i < 6; ++i) {

@@ -338,6 +338,11 @@ class Registrar:
         grid = check(capi.lib().madicp_debug_cta_cycles(self._h, buf.ctypes.data_as(C.POINTER(C.c_int64)), buf.size))
         return buf[:rounds * grid].reshape(rounds, grid)
 
+    def debug_cta_stamps(self, plane, rounds):
+        buf = np.zeros(rounds * 148 * 8, np.int64)
+        grid = check(capi.lib().madicp_debug_cta_stamps(self._h, plane, buf.ctypes.data_as(C.POINTER(C.c_int64)), buf.size))
+        return buf[:rounds * grid].reshape(rounds, grid)
+
     def set_memo(self, enable=True):
         check(capi.lib().madicp_debug_set_memo(self._h, int(enable)))
 

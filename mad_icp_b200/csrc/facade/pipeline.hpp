@@ -186,8 +186,9 @@ class Pipeline {
   ~Pipeline() {
     if (timing_ && timed_scans_ > 0)
       std::fprintf(stderr, "Pipeline phases, mean over %d scans [ms]: deskew %.3f  tree build %.3f  set moving %.3f  "
-                   "register (incl. keyframe upload) %.3f  rest %.3f\n", timed_scans_, t_ph_[0] / timed_scans_,
-                   t_ph_[1] / timed_scans_, t_ph_[2] / timed_scans_, t_ph_[3] / timed_scans_, t_ph_[4] / timed_scans_);
+                   "register (incl. keyframe upload) %.3f  rest %.3f  | prefetch (outside compute) %.3f\n", timed_scans_,
+                   t_ph_[0] / timed_scans_, t_ph_[1] / timed_scans_, t_ph_[2] / timed_scans_, t_ph_[3] / timed_scans_,
+                   t_ph_[4] / timed_scans_, t_prefetch_ / timed_scans_);
   }
 
   // the reference's constructor has no device argument: MADICP_DEVICE selects the GPU (default 0)
@@ -256,6 +257,11 @@ class Pipeline {
   // the scan; without it the cloud is copied.
   bool prefetch(const void* xyz, size_t n, bool is_f32, std::shared_ptr<void> keepalive = nullptr) {
     if (!gpu_build_ || deskew_ || !xyz || n == 0) return false;
+    const auto p0 = clk();
+    struct Tick {  // (the hand-over runs on the thread that launches the registrations: its cost is part of the scan's)
+      Pipeline* p; std::chrono::steady_clock::time_point t0;
+      ~Tick() { if (p->timing_) p->t_prefetch_ += ms(t0, clk()); }
+    } tick{this, p0};
     if (!lookahead_) {
       int batch = 32;
       if (const char* e = std::getenv("MADICP_LOOKAHEAD")) batch = std::atoi(e);
@@ -412,7 +418,7 @@ class Pipeline {
   }
   bool timing_ = false;  // MADICP_PIPELINE_TIMING: per-phase host wall clock, printed by the destructor
   int timed_scans_ = 0;
-  double t_ph_[5] = {0, 0, 0, 0, 0};
+  double t_ph_[5] = {0, 0, 0, 0, 0}, t_prefetch_ = 0;
   double sensor_hz_;
   bool deskew_;
   double b_max_, p_th_, b_min_;

@@ -11,7 +11,10 @@
 #include <algorithm>
 #include <array>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
 #include <future>
+#include <mutex>
 #include <functional>
 #include <cstdio>
 #include <cstdlib>
@@ -261,6 +264,51 @@ void root_sums_host(const T* p, int64_t n, double* S) {
     s6 += y * y; s7 += z * y; s8 += z * z;
   }
   S[0] = s0; S[1] = s1; S[2] = s2; S[3] = s3; S[4] = s4; S[5] = s5; S[6] = s6; S[7] = s7; S[8] = s8;
+}
+
+// A few resident host threads for work that is handed over and collected later (the roots' sums of staged clouds).
+// std::async(std::launch::async) creates a thread per call: in a process with CUDA and a large address space that
+// is tens to hundreds of microseconds ON THE CALLING THREAD per staged scan -- the thread that is about to launch
+// the next registration (profiles/r03ab: up to 0.33 ms per scan of the stream outside Pipeline.compute).
+// Leaked on purpose (detached workers may still wait on it at exit); created at first use, i.e. after any fork()
+// the caller did before touching CUDA.
+class Background {
+ public:
+  using Result = std::array<double, 9>;
+  explicit Background(int threads) {
+    for (int i = 0; i < threads; ++i) std::thread([this]() { loop(); }).detach();
+  }
+  std::shared_future<Result> submit(std::function<Result()> fn) {
+    std::packaged_task<Result()> task(std::move(fn));
+    std::shared_future<Result> f = task.get_future().share();
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      q_.push_back(std::move(task));
+    }
+    cv_.notify_one();
+    return f;
+  }
+
+ private:
+  void loop() {
+    for (;;) {
+      std::packaged_task<Result()> task;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [this]() { return !q_.empty(); });
+        task = std::move(q_.front());
+        q_.pop_front();
+      }
+      task();
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<std::packaged_task<Result()>> q_;
+};
+Background& background() {
+  static Background* bg = new Background(4);
+  return *bg;
 }
 
 int blocks(int64_t n, int per = kBlock) { return int(std::max<int64_t>(1, (n + per - 1) / per)); }
@@ -564,13 +612,13 @@ int madicp_stage_cloud(madicp_ctx_t* c, const void* cloud, int64_t n, int is_f32
   const size_t elt = is_f32 ? sizeof(float) : sizeof(double);
   char* dst = is_f32 ? static_cast<char*>(bs->d_raw) : reinterpret_cast<char*>(bs->P[0]);
   CK(cudaMemcpyAsync(dst + size_t(bs->staged_points) * 3 * elt, cloud, size_t(n) * 3 * elt, cudaMemcpyHostToDevice, bs->copy_stream));
-  // the root's sums (root_sums_host) start now too, on a thread of their own: the caller is about to wait for the device
-  auto sums = std::async(std::launch::async, [cloud, n, is_f32]() {
+  // the root's sums (root_sums_host) start now too, on a background thread: the caller is about to wait for the device
+  auto sums = background().submit([cloud, n, is_f32]() {
     std::array<double, 9> S{};
     if (is_f32) root_sums_host(static_cast<const float*>(cloud), n, S.data());
     else root_sums_host(static_cast<const double*>(cloud), n, S.data());
     return S;
-  }).share();
+  });
   bs->staged.push_back({cloud, n, std::move(sums)});
   bs->staged_points += n;
   return MADICP_OK;

@@ -64,7 +64,10 @@ def workload_name(a, n):
 
 # --------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """Polls NVML (SM clock + clock-event reasons) while the timed region runs."""
+    """Polls NVML (SM clock + clock-event reasons) while the timed region runs.  (The polling period is not what costs
+    the host-timed `e2e` its efficiency at N > 1: 2, 10 and 50 ms measured the same within the run-to-run spread at N=2,
+    profiles/r03_sampler_period_2gpu.txt.)"""
+    PERIOD_S = float(os.environ.get("MADICP_BENCH_SAMPLER_MS", "2")) * 1e-3
     BITS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
             0x80: "hw_power_brake_slowdown"}
 
@@ -97,7 +100,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.002)
+            time.sleep(self.PERIOD_S)
 
     def summary(self):
         if not self.ok or not self.samples:

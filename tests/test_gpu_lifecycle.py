@@ -186,3 +186,29 @@ def test_path_memo_changes_nothing(oracle):
         reg.set_memo(False)
         b2 = reg.register(b["X"], iters=5)
         assert bits_equal(a["X"], b2["X"]) and bits_equal(a["H"], b2["H"])
+
+
+def test_round_timeline_stamps(case, host_path):
+    """madicp_debug_cta_stamps: every CTA's items start before they end, the tile goes out after them, CTA 0 has folded
+    after the last tile went out and hands the pose out after that; the next round starts after the pose is out.  The
+    instrumented launches return the same registration as the plain ones."""
+    reg, _ = host_path
+    iters = 6
+    plain = reg.register(case["T_guess"], iters=iters)
+    reg.debug_timing(True, fetch=False)
+    try:
+        out = reg.register(case["T_guess"], iters=iters)
+        d = reg.debug_timing(True)
+        start, end, pub = (reg.debug_cta_stamps(p, iters) for p in (1, 2, 3))
+        trace = reg.debug_cta_stamps(4, iters)[:, :16]
+    finally:
+        reg.debug_timing(False, fetch=False)
+    for k in ("X", "H", "b"):
+        assert bits_equal(out[k], plain[k]), k
+    assert d.shape[0] == iters and start.shape == end.shape == pub.shape and start.shape[0] == iters
+    assert (start > 0).all() and (start <= end).all() and (end <= pub).all()
+    folded, handed = d[:, 6], d[:, 7]
+    assert (folded >= pub.max(axis=1) - 1024).all()  # (the timer ticks every few hundred ns)
+    assert (handed >= folded).all()
+    assert (start[1:].min(axis=1) >= handed[:-1] - 1024).all()
+    assert (trace[:, 13] > trace[:, 0]).all() and (trace[:, 14] >= 1).all()

@@ -153,6 +153,9 @@ int madtree_gpu_build_batch(madicp_ctx_t* ctx, const void* const* clouds, const 
  * staged.  reserve_points: total points the batch will hold (sizes the lane on first use; 0 = this cloud only).
  * Returns MADICP_OK whether or not the cloud could be staged. */
 int madicp_stage_cloud(madicp_ctx_t* ctx, const void* cloud, int64_t n_points, int is_f32, int64_t reserve_points);
+/* Gives up whatever madicp_stage_cloud staged and returns once nothing reads the staged host buffers any more (their
+ * uploads and the background sums of their roots): call it before releasing a staged cloud that was never built. */
+int madicp_stage_discard(madicp_ctx_t* ctx);
 /* Upload of a host-built tree (records + tables), asynchronous. */
 int madtree_gpu_upload(madicp_ctx_t* ctx, const madtree_t* tree, madtree_gpu_t** out);
 void madtree_gpu_free(madtree_gpu_t* t);

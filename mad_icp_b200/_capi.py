@@ -46,6 +46,7 @@ SYMBOLS = {
     "madtree_gpu_build_batch": (C.c_int, [vp, C.POINTER(vp), C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_double, C.c_double,
                                           C.POINTER(vp)]),
     "madicp_stage_cloud": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.c_int64]),
+    "madicp_stage_discard": (C.c_int, [vp]),
     "madtree_gpu_upload": (C.c_int, [vp, vp, C.POINTER(vp)]),
     "madtree_gpu_free": (None, [vp]),
     "madtree_gpu_num_nodes": (C.c_int, [vp]),

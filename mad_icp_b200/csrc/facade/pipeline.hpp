@@ -105,6 +105,7 @@ class Lookahead {
   };
   Lookahead(madicp_ctx_t* ctx, double b_max, double b_min, int batch) : ctx_(ctx), b_max_(b_max), b_min_(b_min), batch_(batch) {}
   ~Lookahead() {
+    madicp_stage_discard(ctx_);  // uploads and background sums may still be reading the queued clouds
     for (auto& j : fifo_)
       if (j.tree) madtree_gpu_free(j.tree);
   }

@@ -110,6 +110,8 @@ int host_alloc(BuildState* bs, T** p, size_t count) {
 }
 
 void release(BuildState* bs) {
+  for (const BuildState::Staged& sg : bs->staged) sg.root.wait();  // (background sums still reading staged clouds)
+  bs->staged.clear();
   if (bs->level_graph) cudaGraphExecDestroy(bs->level_graph);
   bs->level_graph = nullptr;
   if (bs->copy_stream) {
@@ -240,6 +242,9 @@ int drop_staged(BuildState* bs, cudaStream_t st) {
     CK(cudaEventRecord(bs->copy_ev, bs->copy_stream));
     CK(cudaStreamWaitEvent(st, bs->copy_ev, 0));
   }
+  // the background sums read the CALLER's buffers: nothing may still be running when the staging is given up (the
+  // caller is free to release a cloud once the call that discards it returns)
+  for (const BuildState::Staged& sg : bs->staged) sg.root.wait();
   bs->staged.clear();
   bs->staged_points = 0;
   bs->stage_closed = false;
@@ -623,6 +628,20 @@ int madicp_stage_cloud(madicp_ctx_t* c, const void* cloud, int64_t n, int is_f32
   bs->staged_points += n;
   return MADICP_OK;
   MADICP_CATCH("madicp_stage_cloud")
+}
+
+int madicp_stage_discard(madicp_ctx_t* c) {
+  if (!c) return MADICP_ERR_INVALID;
+  MADICP_TRY
+  BuildState* bs = static_cast<BuildState*>(c->build_state);
+  if (!bs) return MADICP_OK;
+  CK(cudaSetDevice(c->device));
+  const bool copies = !bs->staged.empty();
+  int rc = drop_staged(bs, c->stream);
+  if (rc) return rc;
+  if (copies) CK(cudaStreamSynchronize(bs->copy_stream));  // the uploads read the host buffers too
+  return MADICP_OK;
+  MADICP_CATCH("madicp_stage_discard")
 }
 
 int madtree_gpu_build(madicp_ctx_t* c, const double* points_xyz, int64_t n, double b_max, double b_min,

@@ -182,6 +182,10 @@ class Registrar:
         check(capi.lib().madicp_stage_cloud(self._h, C.c_void_p(a.ctypes.data), a.shape[0], int(a.dtype == np.float32),
                                             int(reserve_points)), "madicp_stage_cloud")
 
+    def stage_discard(self):
+        """Gives up the staged clouds; returns once nothing reads their host buffers (madicp_stage_discard)."""
+        check(capi.lib().madicp_stage_discard(self._h), "madicp_stage_discard")
+
     def build_trees(self, clouds, b_max=0.2, b_min=0.1):
         """Several scans at once (all float32 or all float64): one forest build, a DeviceTree per scan."""
         f32 = all(np.asarray(c).dtype == np.float32 for c in clouds)

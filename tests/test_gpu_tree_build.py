@@ -139,6 +139,16 @@ def test_staged_clouds_build_the_same_forest(reg, oracle):
         assert same(dt.records(), FlatTree(cl.astype(np.float64)).records())
     reg.stage_cloud(f32[0], 0)  # float32 staged, float64 batch
     check(reg.build_trees(clouds[:2]), [0, 1])
+    # staged, then given up (madicp_stage_discard): the buffers may go away at once, the next batch is unaffected
+    gone = [cl.copy() for cl in clouds[:2]]
+    for cl in gone:
+        reg.stage_cloud(cl, total)
+    reg.stage_discard()
+    for cl in gone:
+        cl[:] = np.nan
+    del gone
+    reg.stage_discard()  # nothing staged: a no-op
+    check(reg.build_trees(clouds), range(4))
 
 
 def _bfs_levels(recs):

@@ -109,6 +109,39 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def _sibling_sets(cores):
+    """Hardware threads of `cores` grouped by physical core (sorted by their lowest CPU number)."""
+    seen, sets = set(), []
+    for c in sorted(cores):
+        if c in seen:
+            continue
+        sib = {c}
+        try:
+            with open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list") as f:
+                for part in f.read().strip().split(","):
+                    lo, _, hi = part.partition("-")
+                    sib.update(range(int(lo), int(hi or lo) + 1))
+        except (OSError, ValueError):
+            pass
+        sib &= set(cores)
+        sib.add(c)
+        seen |= sib
+        sets.append(sorted(sib))
+    return sets
+
+
+def share_of_cores(cores, k, m, sibling_sets=None):
+    """The k-th of m shares of `cores`, in WHOLE physical cores: the ranks next to one socket must not end up on each
+    other's hyperthreads.  (Until the second half of round 2 the sorted CPU list was cut into m runs: on a 2 x 32-core
+    host numbered [0..31 | 64..95] per socket that gave rank 0 the CPUs 0-15 and rank 2 their siblings 64-79, two
+    spinning driver threads per physical core -- the host-timed `e2e` ran at 0.76 of N x the single-GPU rate at N=8
+    while the device-timed `value` scaled 0.99.)"""
+    sets = sibling_sets if sibling_sets is not None else _sibling_sets(cores)
+    per = max(1, len(sets) // m)
+    mine = sets[k * per:(k + 1) * per] or sets
+    return sorted(c for s0 in mine for c in s0)
+
+
 def pin_to_gpu(dev, local_rank, world):
     """Keeps this process (and the pinned buffers it is about to allocate) on the CPU cores next to its GPU: with one
     process per GPU the host side of a step is a handful of latency-bound driver calls, and a remote NUMA node or a core
@@ -122,17 +155,17 @@ def pin_to_gpu(dev, local_rank, world):
         cores = [i for i in range(ncpu) if (words[i // 64] >> (i % 64)) & 1]
         if not cores:
             return None
-        if world > 1:  # ranks whose GPUs share a node split its cores between them
+        note = ""
+        if world > 1:  # ranks whose GPUs share a node split its physical cores between them
             peers = []
             for d in range(world):
                 w2 = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(d), (ncpu + 63) // 64)
                 if list(w2) == list(words):
                     peers.append(d)
-            k, m = peers.index(dev), len(peers)
-            share = max(4, len(cores) // m)
-            cores = cores[k * share:(k + 1) * share] or cores
+            cores = share_of_cores(cores, peers.index(dev), len(peers))
+            note = ", whole physical cores"
         os.sched_setaffinity(0, cores)
-        return f"{len(cores)} cores next to GPU {dev} ({cores[0]}-{cores[-1]})"
+        return f"{len(cores)} hardware threads next to GPU {dev} ({cores[0]}-{cores[-1]}{note})"
     except Exception as e:  # noqa: BLE001  (no NVML / no permission: run unpinned)
         return f"unpinned ({type(e).__name__})"
 

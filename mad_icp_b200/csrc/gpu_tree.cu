@@ -7,6 +7,7 @@
 // mapping.  Everything else of a level is stream-ordered kernels.  No CPU fallback: the host never sees the points
 // again after the upload.
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <array>
@@ -147,8 +148,12 @@ int ensure_state(void** slot, cudaStream_t stream, size_t n, BuildState** out) {
   size_t cap = size_t(1) << 17;
   while (cap < n) cap <<= 1;
   bs->cap = cap;
-  {  // host threads for the libm calls and the roots' sums: half the cores, 4..32 (MADICP_HOST_THREADS overrides)
-    const int hw = int(std::thread::hardware_concurrency());
+  {  // host threads for the libm calls and the roots' sums: half the CPUs this process may run on (its affinity mask,
+    // not the machine: eight ranks pinned to 16 CPUs each must not start 32 threads apiece), 4..32
+    // (MADICP_HOST_THREADS overrides)
+    int hw = int(std::thread::hardware_concurrency());
+    cpu_set_t mask;
+    if (sched_getaffinity(0, sizeof(mask), &mask) == 0 && CPU_COUNT(&mask) > 0) hw = std::min(hw > 0 ? hw : 1 << 20, CPU_COUNT(&mask));
     bs->threads = std::max(4, std::min(32, hw / 2));
     if (const char* e = getenv("MADICP_HOST_THREADS")) bs->threads = std::max(1, atoi(e));
   }

@@ -20,7 +20,7 @@ def timed(iters, cold, n=20):
         a.record(st); reg.register_async(X0, iters); b.record(st); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b) * 1e3)
     return np.median(ts)
-for shape in ((768, 1), (1024, 1), (512, 1)):
+for shape in tuple(tuple(int(v) for v in a.split(',')) for a in sys.argv[1:]) or ((768, 1), (704, 1), (1024, 1)):
     reg.set_gn_grid(*shape)
     for memo in (True, False):
         reg.set_memo(memo)

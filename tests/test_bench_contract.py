@@ -41,3 +41,24 @@ def test_product_arm_needs_a_gpu(built):
     p = _run("--steps", "1", "--warmup", "1", "--beams", "8", "--azimuths", "256", "--no-cpu-baseline")
     assert p.returncode != 0
     assert "CUDA" in (p.stderr + p.stdout)
+
+
+def test_ranks_next_to_one_socket_get_whole_physical_cores():
+    """bench.pin_to_gpu: four ranks next to a 32-core / 64-thread socket numbered [0..31 | 64..95] must not sit on each
+    other's hyperthreads (the sorted CPU list cut into four runs did exactly that)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    cores = list(range(0, 32)) + list(range(64, 96))
+    sets = [[c, c + 64] for c in range(32)]
+    shares = [bench.share_of_cores(cores, k, 4, sibling_sets=sets) for k in range(4)]
+    assert shares[0] == list(range(0, 8)) + list(range(64, 72))
+    assert sorted(c for sh in shares for c in sh) == sorted(cores)
+    phys = [{c % 64 for c in sh} for sh in shares]
+    for a in range(4):
+        assert len(shares[a]) == 16
+        for b in range(a + 1, 4):
+            assert not (phys[a] & phys[b])
+    # no SMT / topology unreadable: every CPU is its own core; more ranks than cores: everybody keeps the whole set
+    assert bench.share_of_cores([0, 1, 2, 3], 1, 2, sibling_sets=[[0], [1], [2], [3]]) == [2, 3]
+    assert bench.share_of_cores([0, 1], 2, 4, sibling_sets=[[0], [1]]) == [0, 1]
+    assert bench._sibling_sets(sorted(os.sched_getaffinity(0)))  # reads /sys without raising

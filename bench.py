@@ -131,11 +131,14 @@ def _sibling_sets(cores):
 
 
 def share_of_cores(cores, k, m, sibling_sets=None):
-    """The k-th of m shares of `cores`, in WHOLE physical cores: the ranks next to one socket must not end up on each
-    other's hyperthreads.  (Until the second half of round 2 the sorted CPU list was cut into m runs: on a 2 x 32-core
-    host numbered [0..31 | 64..95] per socket that gave rank 0 the CPUs 0-15 and rank 2 their siblings 64-79, two
-    spinning driver threads per physical core -- the host-timed `e2e` ran at 0.76 of N x the single-GPU rate at N=8
-    while the device-timed `value` scaled 0.99.)"""
+    """The k-th of m shares of `cores`, in WHOLE physical cores: ranks next to one socket should not end up on each
+    other's hyperthreads.  (The sorted CPU list cut into m runs does that on a host numbered [0..31 | 64..95] per socket:
+    rank 0 gets the CPUs 0-15 and rank 2 their siblings 64-79.  At N=2 the two cuts measure the same,
+    profiles/r03_pinning_2gpu.txt; whether it is what the host-timed `e2e` loses at N=8 -- 0.76 of N x the single-GPU
+    rate against 0.99 for the device-timed `value` -- could not be measured in round 2.)"""
+    if os.environ.get("MADICP_BENCH_PIN_LEGACY"):  # the old cut, for A/B runs (profiles/r03_pinning_2gpu.txt)
+        share = max(4, len(cores) // m)
+        return sorted(cores)[k * share:(k + 1) * share] or sorted(cores)
     sets = sibling_sets if sibling_sets is not None else _sibling_sets(cores)
     per = max(1, len(sets) // m)
     mine = sets[k * per:(k + 1) * per] or sets

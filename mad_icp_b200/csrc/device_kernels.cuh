@@ -388,12 +388,13 @@ __device__ __forceinline__ long long global_ns() {
   return t;
 }
 
-// Persistent cooperative grid (all CTAs co-resident), one software grid barrier per round: CTAs
-// publish their partial, take a release-ticket, the last one folds / exchanges / solves and
-// publishes the new pose as 12 epoch-tagged LL cells (value and flag in one 16-byte store); twelve
-// threads of every other CTA spin on one cell each with a volatile 16-byte load, so the wake-up is a
-// single L2 round trip.  No acquire fence is ever executed in the loop, so L1 is not invalidated between
-// rounds; everything that crosses SMs (partials, pose) is read with L2-coherent loads.
+// Persistent cooperative grid (all CTAs co-resident), one software grid barrier per round, without a ticket: every
+// CTA publishes its 48-value tile as epoch-tagged LL cells (value and flag in one 16-byte store); CTA 0 -- the fixed
+// folder, with a lighter share of the items -- polls the tiles, adds them in a fixed order, exchanges across GPUs when
+// sharded, solves and publishes the new pose the same way; twelve threads of every other CTA spin on one pose cell each,
+// so the wake-up is a single L2 round trip.  No acquire fence is executed inside the loop (only in the last round, for the
+// matched flags), so L1 keeps the tree across rounds; everything that crosses SMs is read with L2-coherent loads.
+// DESIGN.md 4.1.1 has the round on one clock.
 //
 // Work distribution.  CTA b owns the moving leaves [L*b/G, L*(b+1)/G) -- a contiguous stretch of the
 // scan's own tree in DFS order, i.e. one spatial region -- and registers them against EVERY keyframe:

@@ -22,8 +22,9 @@
 //     is loaded and one memory round trip resolves two binary decisions.
 //   * Each CTA owns a few contiguous stretches of the scan's leaves (DFS order = spatially compact) and
 //     registers them against every keyframe: balanced across SMs, and the lanes of a warp / the warps of
-//     an SM share the upper levels in L1.  The inter-round barrier uses release-only atomics and
-//     L2-coherent loads, so L1 is never invalidated between rounds.
+//     an SM share the upper levels in L1.  The inter-round barrier is ticket-free (epoch-tagged LL cells read with
+//     L2-coherent loads, no acquire fence), so L1 is never invalidated between rounds.
+//   * PATH MEMO.  From round 1 on a walk is skipped when the query provably cannot have left its leaf (descend_t).
 // No tcgen05: there is no dense contraction.  The only tensor-pipe use is the FP64 DMMA fold of the
 // per-correspondence outer products (warp_accumulate), which exists to save registers.
 // Compiled with -fmad=false; exact predicates use __d*_rn intrinsics (arith.h).

@@ -204,6 +204,41 @@ def algorithmic_bytes(reg, depth_tables, trace, iters, L):
 
 
 # --------------------------------------------------------------------------------------------
+def latency_model(walked, visits, iters, K, L, measured_s, sm=148, warps_per_sm=24):
+    """Latency floor of one k_gn_loop launch (what bounds the kernel): an SM runs its warp-items in passes
+    of `warps_per_sm` resident warps, and a pass cannot be shorter than the chain of DEPENDENT operations of one item:
+      * memory: a walk is one L2 round trip per two tree levels + the leaf record; a remembered item the memo word + the
+        leaf record;
+      * arithmetic (added in the second half of round 2; `floor_memory_only_ms` keeps the earlier definition): the FP64
+        operations of one item that depend on each other -- pose applied (4), displacement, norm, square root and margin
+        of the memo check (17), gate, error, Jacobian and scale (13), counted in kernels.cuh / device_kernels.cuh -- at the
+        ~19 cycles a dependent FP64 operation takes on this part (scripts/fp64_probe.cu), and the 8 dependent DMMAs of the
+        fold at ~30;
+    and every round ends with the fold (one L2 round trip), the 6x6 solve + exponential map (~150 dependent FP64
+    operations) and the pose hand-over (one L2 round trip).  Nothing here is a tuning constant of the kernel."""
+    clk_ghz, l2_lat, fp64_lat, dmma_lat = 1.92, 250.0, 19.0, 30.0
+    chain_ops = 4 + 17 + 13
+    items_sm = K * L / sm / 32.0
+    passes = int(np.ceil(items_sm / float(warps_per_sm)))
+    dbar = visits / max(1, iters * K * L)  # mean nodes visited per walk (internal + leaf)
+    mem_cycles = arith_cycles = 0.0
+    for w in walked:
+        frac_w = w / float(K * L)
+        trips = frac_w * (dbar / 2.0 + 1.0) + (1.0 - frac_w) * 2.0
+        mem_cycles += passes * trips * l2_lat + (2 * l2_lat + 150 * fp64_lat)
+        arith_cycles += passes * (chain_ops * fp64_lat + 8 * dmma_lat)
+    mem_s, floor_s = mem_cycles / (clk_ghz * 1e9), (mem_cycles + arith_cycles) / (clk_ghz * 1e9)
+    return {"floor_ms": floor_s * 1e3, "floor_memory_only_ms": mem_s * 1e3, "measured_ms": measured_s * 1e3,
+            "frac": floor_s / measured_s, "frac_memory_only": mem_s / measured_s, "passes_per_round": passes,
+            "mean_nodes_per_walk": dbar, "walked_pairs_per_round": list(walked),
+            "assumed": {"l2_hit_latency_cycles": l2_lat, "fp64_dependent_latency_cycles": fp64_lat,
+                        "dmma_dependent_latency_cycles": dmma_lat, "dependent_fp64_ops_per_item": chain_ops,
+                        "sm_ghz": clk_ghz, "resident_warps_per_sm": warps_per_sm},
+            "note": "lower bound on the launch time if every dependent load were an L2 hit, every dependent FP64 operation "
+                    "issued the cycle its operand arrived and nothing else cost time; frac = floor / measured (1.0 = at the "
+                    "latency floor); frac_memory_only is the figure reported until the first half of round 2"}
+
+
 def cpu_reference_leg(a, steps, warmup, budget_s=None):
     """Times the reference's OpenMP registration loop on the host cores.  Two CPU builds exist: the reference's
     own sources compiled against an Eigen stand-in (oracle/_ref, kind "reference") and the Eigen-free
@@ -581,28 +616,7 @@ def main():
               "peak": l2_peak, "unit": "GB/s", "frac": (l2_bytes / avg_launch_s / 1e9 / l2_peak) if l2_bytes else None,
               "source": "lts__t_sectors_srcunit_tex_op_read.sum x 32 B of the committed ncu capture (profiles/); peak = "
                         "torch sum over a 48 MiB L2-resident buffer, measured in this run"}
-        # Latency model (what actually bounds the kernel): an SM runs its warp-items in passes of W
-        # resident warps; a pass cannot be shorter than the chain of DEPENDENT memory round trips of one item -- a walk
-        # is one L2 round trip per two tree levels + the leaf record, a remembered item the memo word + the leaf
-        # record -- and every round ends with the fold (one L2 round trip), the 6x6 solve (~150 dependent FP64
-        # operations at ~19 cycles each on this part) and the pose hand-over (one L2 round trip).
-        sm, clk_ghz, l2_lat, fp64_lat = 148, 1.92, 250.0, 19.0
-        warps = max(1, launches and 24)
-        items_sm = K_MODEL * L / sm / 32.0
-        passes = int(np.ceil(items_sm / 24.0))
-        dbar = visits / max(1, a.iters * K_MODEL * L)  # mean nodes visited per walk (internal + leaf)
-        floor_cycles = 0.0
-        for w in walked:
-            frac_w = w / float(K_MODEL * L)
-            trips = frac_w * (dbar / 2.0 + 1.0) + (1.0 - frac_w) * 2.0
-            floor_cycles += passes * trips * l2_lat + (2 * l2_lat + 150 * fp64_lat)
-        floor_s = floor_cycles / (clk_ghz * 1e9)
-        lat = {"floor_ms": floor_s * 1e3, "measured_ms": avg_launch_s * 1e3, "frac": floor_s / avg_launch_s,
-               "passes_per_round": passes, "mean_nodes_per_walk": dbar, "walked_pairs_per_round": walked,
-               "assumed": {"l2_hit_latency_cycles": l2_lat, "fp64_dependent_latency_cycles": fp64_lat, "sm_ghz": clk_ghz,
-                           "resident_warps_per_sm": 24},
-               "note": "lower bound on the launch time if every dependent load were an L2 hit and nothing else cost time; "
-                       "frac = floor / measured (1.0 = at the latency floor)"}
+        lat = latency_model(walked, visits, a.iters, K_MODEL, L, avg_launch_s)
         rf = {"kernel": "k_gn_loop (persistent: search + linearize + reduce + solve, all GN rounds)", "bound": "hbm",
               "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
               "traffic": prof.get("dram_bytes_per_launch"),

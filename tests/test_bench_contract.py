@@ -62,3 +62,19 @@ def test_ranks_next_to_one_socket_get_whole_physical_cores():
     assert bench.share_of_cores([0, 1, 2, 3], 1, 2, sibling_sets=[[0], [1], [2], [3]]) == [2, 3]
     assert bench.share_of_cores([0, 1], 2, 4, sibling_sets=[[0], [1]]) == [0, 1]
     assert bench._sibling_sets(sorted(os.sched_getaffinity(0)))  # reads /sys without raising
+
+
+def test_latency_model_is_a_pure_function_of_the_walk_counts():
+    """bench.latency_model on the numbers of profiles/r03f_bench.json: the memory-only floor is the figure the earlier
+    bench lines carried (0.0312 ms, frac 0.183); the full floor adds the dependent FP64 chain of every pass."""
+    sys.path.insert(0, ROOT)
+    import bench
+    walked = [307232, 281829, 107440, 14523, 1799, 206, 9, 0, 0, 0]
+    m = bench.latency_model(walked, 46436884, 10, 16, 19202, 0.1703627222031355e-3)
+    assert m["passes_per_round"] == 3 and abs(m["mean_nodes_per_walk"] - 15.1146) < 1e-3
+    assert abs(m["floor_memory_only_ms"] - 0.031205134883585593) < 1e-9
+    assert abs(m["frac_memory_only"] - 0.18316879702343278) < 1e-9
+    extra_cycles = 10 * 3 * (34 * 19.0 + 8 * 30.0)
+    assert abs(m["floor_ms"] - (m["floor_memory_only_ms"] + extra_cycles / 1.92e9 * 1e3)) < 1e-12
+    assert m["floor_memory_only_ms"] < m["floor_ms"] < m["measured_ms"] and 0 < m["frac"] < 1
+    json.dumps(m)  # goes into the bench line as it is
